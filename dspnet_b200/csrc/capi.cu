@@ -1,0 +1,96 @@
+// Library-wide pieces of the C ABI: error state, libm-compatibility mode, status read-back, self-test hooks.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace dspmb {
+
+static thread_local char g_error[512] = "";
+static int g_libm_mode = -1;
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return DSPMB_ERR_CUDA;
+}
+
+// glibc's ifunc resolvers for expf/logf pick the FMA build iff the CPU has usable FMA and AVX2
+// (sysdeps/x86_64/fpu/multiarch/ifunc-fma.h); mirror that test for the host this process runs on.
+static int detect_host_libm_mode() {
+#if defined(__x86_64__)
+  __builtin_cpu_init();
+  return (__builtin_cpu_supports("fma") && __builtin_cpu_supports("avx2")) ? 1 : 0;
+#else
+  return 0;
+#endif
+}
+
+int libm_fma_mode() {
+  if (g_libm_mode < 0) g_libm_mode = detect_host_libm_mode();
+  return g_libm_mode;
+}
+
+namespace {
+__global__ void test_expf_kernel(const float *x, float *y, long n, int fma_build) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = libm::expf_glibc(x[i], fma_build != 0);
+}
+__global__ void test_logf_kernel(const float *x, float *y, long n, int fma_build) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = libm::logf_glibc(x[i], fma_build != 0);
+}
+}  // namespace
+}  // namespace dspmb
+
+using namespace dspmb;
+
+extern "C" int dspmb_version(void) { return DSPMB_VERSION; }
+
+extern "C" const char *dspmb_last_error(void) { return g_error; }
+
+extern "C" int dspmb_set_libm_mode(int mode) {
+  g_libm_mode = mode < 0 ? detect_host_libm_mode() : (mode ? 1 : 0);
+  return g_libm_mode;
+}
+
+extern "C" int dspmb_status(const void *workspace, void *stream) {
+  if (!workspace) {
+    set_error("dspmb_status: workspace is NULL");
+    return DSPMB_ERR_WORKSPACE;
+  }
+  int status = 0;
+  DSPMB_CUDA_TRY(cudaMemcpyAsync(&status, workspace, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DSPMB_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  switch (status) {
+    case DSPMB_OK:
+      break;
+    case DSPMB_ERR_LABEL_PADDING:
+      set_error("MultiBoxTarget: first padding label row is not all -1 (multibox_target.cc:98-101)");
+      break;
+    case DSPMB_ERR_MINING_CANDIDATES:
+      set_error("MultiBoxTarget: fewer mining candidates than num_negative (multibox_target.cc:236)");
+      break;
+    default:
+      set_error("device status %d", status);
+  }
+  return status;
+}
+
+extern "C" int dspmb_test_expf(const float *x, float *y, long n, void *stream) {
+  test_expf_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(x, y, n, libm_fma_mode());
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_test_logf(const float *x, float *y, long n, void *stream) {
+  test_logf_kernel<<<kNumSMs * 4, 256, 0, (cudaStream_t)stream>>>(x, y, n, libm_fma_mode());
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}

@@ -1,0 +1,582 @@
+// MultiBoxDetection for sm_100a.
+//
+// Reference semantics (CPU operator, the parity target): operator/multibox_detection-inl.h:81-107 (`out = -1`)
+// and operator/multibox_detection.cc:53-169:
+//   pass 1 (:79-128)  per anchor ascending: (score,id) = max/argmax over classes 1..C-1 (strict >, from -1),
+//                     score < threshold => background; survivors are decoded (variances, expf, clip) and
+//                     appended in ANCHOR ORDER at row valid_count++;
+//   sort   (:130-151) if valid_count >= 1 and 0 < nms_threshold <= 1: stable sort by score descending;
+//                     only rows [0, nkeep) (nkeep = min(V, nms_topk>0 ? nms_topk : V)) are rewritten in sorted
+//                     order, rows [nkeep, V) KEEP their pass-1 content;
+//   NMS    (:153-167) greedy over all V rows in that order, same class (or force_suppress), iou >= threshold
+//                     overwrites only the id with -1.
+// The reference's own GPU kernel (operator/multibox_detection.cu:52-207) is one block per image with an
+// atomicAdd compaction (non-deterministic order), a global-memory merge sort and one __syncthreads per NMS
+// candidate, and it diverges from the CPU semantics; it is not followed.
+//
+// Structure here (three launches, all images in every grid):
+//   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread,
+//                      fills `out` with -1 (128-bit stores), decodes the survivors and writes them in anchor
+//                      order into per-tile record slots (block scan => deterministic order).
+//   det_sort_kernel    one CTA per image: prefix over tile counts, 64-bit keys (~score_order | rank) => a bitonic
+//                      sort in shared memory (global scratch above 16K candidates) reproduces stable_sort; emits
+//                      the V rows in the reference's order (sorted head + anchor-ordered tail) and per-class
+//                      segment offsets.
+//   det_nms_kernel     one CTA per (image, class) segment (one per image with force_suppress): ordered member
+//                      list, boxes staged in shared memory, greedy NMS in 64-row chunks: 64x64 ballot mask +
+//                      64-bit serial resolve + parallel sweep of the later rows against the surviving pivots.
+#include "common.cuh"
+
+namespace dspmb {
+namespace {
+
+constexpr int kStreamThreads = 128;
+constexpr int kSortThreads = 1024;
+constexpr int kNmsThreads = 256;
+constexpr int kSortSmemKeys = 16384;  // 128 KB of 64-bit keys
+constexpr int kNmsSmemRows = 2048;    // rows of one NMS segment staged in shared memory
+constexpr int kRecFloats = 8;         // score, id, x1, y1, x2, y2, dist, pad
+
+struct DetWorkspace {
+  WsHeader *header;
+  int *tile_count;  // (B, T)
+  int *valid;       // (B) V
+  int *nms_rows;    // (B) rows taking part in NMS (0 = skipped)
+  int *seg_off;     // (B, C+1) first row-list position of each class segment
+  int *slot_of_rank;  // (B, Apad)
+  int *seg_list;    // (B, A) member rows of the segments
+  float *rec;       // (B, Apad, 8)
+  float4 *seg_box;  // (B, A) spill for segments larger than kNmsSmemRows
+  unsigned char *seg_dead;  // (B, A)
+  unsigned long long *sort_keys;  // (B, npad) spill for more than kSortSmemKeys candidates
+  size_t bytes;
+};
+
+inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Layout is a pure function of (B, A, C); T and Apad are bounded with the smallest tile (128 anchors).
+DetWorkspace carve(void *base, int B, int A, int C) {
+  DetWorkspace w;
+  const size_t Tmax = (size_t)ceil_div(A, kStreamThreads);
+  const size_t Apad = (size_t)A + 4 * kStreamThreads;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return (char *)base + o;
+  };
+  w.header = (WsHeader *)take(sizeof(WsHeader));
+  w.tile_count = (int *)take(sizeof(int) * B * Tmax);
+  w.valid = (int *)take(sizeof(int) * B);
+  w.nms_rows = (int *)take(sizeof(int) * B);
+  w.seg_off = (int *)take(sizeof(int) * B * (C + 1));
+  w.slot_of_rank = (int *)take(sizeof(int) * B * Apad);
+  w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
+  w.rec = (float *)take(sizeof(float) * kRecFloats * B * Apad);
+  w.seg_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
+  w.seg_dead = (unsigned char *)take((size_t)B * A);
+  const int npad = next_pow2(A);
+  w.sort_keys = (unsigned long long *)take(npad > kSortSmemKeys ? sizeof(unsigned long long) * (size_t)B * npad : 0);
+  w.bytes = off;
+  return w;
+}
+
+struct StreamArgs {
+  const float *cls_prob, *loc_pred, *anchors;
+  float *out;
+  int *tile_count;
+  float *rec;
+  int A, C, T, Apad;
+  float threshold;
+  int clip;
+  float vx, vy, vw, vh;
+  int fma_build;
+};
+
+__device__ __forceinline__ float clip01(float v) {
+  // std::max(0, std::min(1, v)) of multibox_detection.cc:121-125
+  const float m = v < 1.f ? v : 1.f;
+  return 0.f < m ? m : 0.f;
+}
+
+// Decode one surviving anchor (multibox_detection.cc:98-125) into a record.
+__device__ __forceinline__ void decode_record(const StreamArgs &a, const float *loc, int i, int id, float score,
+                                              float *rec) {
+  const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i);
+  const float aw = fsub(an.z, an.x);
+  const float ah = fsub(an.w, an.y);
+  const float ax = fdiv(fadd(an.x, an.z), 2.f);
+  const float ay = fdiv(fadd(an.y, an.w), 2.f);
+  const float *lp = loc + (size_t)i * 5;
+  const float px = __ldg(lp), py = __ldg(lp + 1), pw = __ldg(lp + 2), ph = __ldg(lp + 3), pz = __ldg(lp + 4);
+  const float ox = fadd(fmul(fmul(px, a.vx), aw), ax);
+  const float oy = fadd(fmul(fmul(py, a.vy), ah), ay);
+  const float ow = fdiv(fmul(libm::expf_glibc(fmul(pw, a.vw), a.fma_build), aw), 2.f);
+  const float oh = fdiv(fmul(libm::expf_glibc(fmul(ph, a.vh), a.fma_build), ah), 2.f);
+  const float oz = __double2float_rn(__dmul_rn((double)pz, 0.1));
+  float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
+  if (a.clip) {
+    x1 = clip01(x1);
+    y1 = clip01(y1);
+    x2 = clip01(x2);
+    y2 = clip01(y2);
+    z = clip01(z);
+  }
+  float4 *r4 = reinterpret_cast<float4 *>(rec);
+  r4[0] = make_float4(score, (float)(id - 1), x1, y1);
+  r4[1] = make_float4(x2, y2, z, 0.f);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid_constant__ StreamArgs a) {
+  __shared__ int scan_smem[kStreamThreads / 32 + 1];
+  const int b = blockIdx.y, t = blockIdx.x;
+  constexpr int kTile = kStreamThreads * VEC;
+  const int tile_begin = t * kTile;
+  const int i0 = tile_begin + threadIdx.x * VEC;
+  const int A = a.A;
+  const float *cp = a.cls_prob + (size_t)b * a.C * A;
+
+  // ---- `out = -1` for this tile's rows (multibox_detection-inl.h:103) ----
+  {
+    float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
+    const int rows = min(kTile, A - tile_begin);
+    const int nfl = rows * 7;
+    if constexpr (VEC == 4) {
+      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+      for (int q = threadIdx.x * 4; q < nfl; q += kStreamThreads * 4) *reinterpret_cast<float4 *>(ob + q) = m1;
+    } else {
+      for (int q = threadIdx.x; q < nfl; q += kStreamThreads) ob[q] = -1.f;
+    }
+  }
+
+  // ---- class max / argmax over the foreground channels ----
+  float score[VEC];
+  int id[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    score[k] = -1.f;
+    id[k] = 0;
+  }
+  if (i0 < A) {
+#pragma unroll 5
+    for (int j = 1; j < a.C; ++j) {
+      float v[VEC];
+      if constexpr (VEC == 4) {
+        const float4 q = ld_stream_f4(cp + (size_t)j * A + i0);
+        v[0] = q.x;
+        v[1] = q.y;
+        v[2] = q.z;
+        v[3] = q.w;
+      } else {
+        v[0] = ld_stream_f1(cp + (size_t)j * A + i0);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        if (v[k] > score[k]) {
+          score[k] = v[k];
+          id[k] = j;
+        }
+    }
+  }
+  int nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    if (id[k] > 0 && score[k] < a.threshold) id[k] = 0;
+    nvalid += id[k] > 0;
+  }
+
+  // ---- ordered compaction inside the tile ----
+  int total;
+  int pos = block_scan_excl(nvalid, scan_smem, &total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  if (nvalid) {
+    const float *loc = a.loc_pred + (size_t)b * A * 5;
+    float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k)
+      if (id[k] > 0) {
+        decode_record(a, loc, i0 + k, id[k], score[k], rec + (size_t)pos * kRecFloats);
+        ++pos;
+      }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
+// global memory (generic addressing).
+__device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int q = threadIdx.x; q < (n >> 1); q += blockDim.x) {
+        // q-th compare-exchange pair of this stage
+        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const unsigned long long x = keys[lo], y = keys[hi];
+        if ((x > y) == up) {
+          keys[lo] = y;
+          keys[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+struct SortArgs {
+  float *out;
+  const int *tile_count;
+  const float *rec;
+  int *slot_of_rank;
+  int *valid, *nms_rows, *seg_off;
+  unsigned long long *sort_keys;
+  int *valid_count_out;
+  WsHeader *header;
+  int A, C, T, Apad, tile, npad_max;
+  float nms_threshold;
+  int force_suppress, nms_topk;
+};
+
+__global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ int scan_smem[kSortThreads / 32 + 1];
+  __shared__ int carry_smem;
+  const int b = blockIdx.x;
+  const int T = a.T, tile = a.tile;
+  // dynamic smem: [keys: key_cap u64][tile_off: T+1 int][hist: C+1 int]
+  const int key_cap = min(a.npad_max, kSortSmemKeys);
+  unsigned long long *skeys = reinterpret_cast<unsigned long long *>(dyn_smem);
+  int *tile_off = reinterpret_cast<int *>(skeys + key_cap);
+  int *hist = tile_off + (T + 1);
+  if (b == 0 && threadIdx.x == 0) a.header->status = DSPMB_OK;
+
+  // 1. exclusive prefix over the tile counts -> rank of every record in anchor order
+  if (threadIdx.x == 0) carry_smem = 0;
+  for (int c = threadIdx.x; c <= a.C; c += blockDim.x) hist[c] = 0;
+  __syncthreads();
+  const int *cnt = a.tile_count + (size_t)b * T;
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    const int v = t < T ? cnt[t] : 0;
+    int total;
+    const int ex = block_scan_excl(v, scan_smem, &total);
+    const int carry = carry_smem;
+    if (t < T) tile_off[t] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_smem = carry + total;
+    __syncthreads();
+  }
+  const int V = carry_smem;
+  if (threadIdx.x == 0) {
+    tile_off[T] = V;
+    a.valid[b] = V;
+    if (a.valid_count_out) a.valid_count_out[b] = V;
+  }
+  const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;  // multibox_detection.cc:130
+  if (threadIdx.x == 0) a.nms_rows[b] = do_sort ? V : 0;
+  if (V == 0) return;
+  __syncthreads();
+
+  // 2. rank -> slot map and sort keys
+  int npad = 2;
+  while (npad < V) npad <<= 1;
+  unsigned long long *keys = npad <= key_cap ? skeys : a.sort_keys + (size_t)b * a.npad_max;
+  const float *rec = a.rec + (size_t)b * a.Apad * kRecFloats;
+  int *slot_of_rank = a.slot_of_rank + (size_t)b * a.Apad;
+  for (int slot = threadIdx.x; slot < T * tile; slot += blockDim.x) {
+    const int t = slot / tile, r = slot - t * tile;
+    const int first = tile_off[t];
+    if (r < tile_off[t + 1] - first) {
+      const int p = first + r;
+      slot_of_rank[p] = slot;
+      if (do_sort) {
+        const float score = rec[(size_t)slot * kRecFloats];
+        keys[p] = ((unsigned long long)(~float_order_key(score)) << 32) | (unsigned)p;
+      }
+    }
+  }
+  int nkeep = 0;
+  if (do_sort) {
+    for (int p = V + threadIdx.x; p < npad; p += blockDim.x) keys[p] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(keys, npad);  // ends with __syncthreads()
+    nkeep = V;
+    if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;  // multibox_detection.cc:142-145
+  } else {
+    __syncthreads();
+  }
+
+  // 3. emit the V rows: sorted head [0, nkeep), anchor-ordered tail [nkeep, V) (multibox_detection.cc:146-151)
+  float *out = a.out + (size_t)b * a.A * 7;
+  for (int r = threadIdx.x; r < V; r += blockDim.x) {
+    const int p = r < nkeep ? (int)(unsigned)(keys[r] & 0xffffffffull) : r;
+    const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)slot_of_rank[p] * kRecFloats);
+    const float4 s0 = src[0], s1 = src[1];
+    float *o = out + (size_t)r * 7;
+    o[0] = s0.y;  // id
+    o[1] = s0.x;  // score
+    o[2] = s0.z;
+    o[3] = s0.w;
+    o[4] = s1.x;
+    o[5] = s1.y;
+    o[6] = s1.z;
+    if (do_sort && !a.force_suppress) atomicAdd(&hist[(int)s0.y], 1);
+  }
+  __syncthreads();
+  // 4. class segment offsets for the NMS launch
+  if (threadIdx.x == 0 && do_sort) {
+    int *so = a.seg_off + (size_t)b * (a.C + 1);
+    int acc = 0;
+    if (a.force_suppress) {
+      so[0] = 0;
+      so[1] = V;
+    } else {
+      for (int c = 0; c < a.C; ++c) {
+        so[c] = acc;
+        acc += hist[c];
+      }
+      so[a.C] = acc;
+    }
+  }
+}
+
+struct NmsArgs {
+  float *out;
+  const int *nms_rows, *seg_off;
+  int *seg_list;
+  float4 *seg_box;
+  unsigned char *seg_dead;
+  int A, C;
+  float nms_threshold;
+  int force_suppress;
+};
+
+__global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
+  __shared__ float4 sm_box[kNmsSmemRows];
+  __shared__ unsigned char sm_dead[kNmsSmemRows];
+  __shared__ unsigned long long sm_word[64];
+  __shared__ unsigned sm_deadbits[2];
+  __shared__ unsigned long long sm_alive, sm_deadmask;
+  __shared__ int scan_smem[kNmsThreads / 32 + 1];
+  __shared__ int carry_smem;
+
+  const int b = blockIdx.y, seg = blockIdx.x;
+  const int V = a.nms_rows[b];
+  if (V == 0) return;
+  const int *so = a.seg_off + (size_t)b * (a.C + 1);
+  const int seg_base = so[seg];
+  const int n = so[seg + 1] - seg_base;
+  if (n < 2) return;
+  float *out = a.out + (size_t)b * a.A * 7;
+  int *list = a.seg_list + (size_t)b * a.A + seg_base;
+
+  // ---- ordered member list of this class (row order == NMS order) ----
+  if (!a.force_suppress) {
+    if (threadIdx.x == 0) carry_smem = 0;
+    __syncthreads();
+    const float cls = (float)seg;
+    for (int base = 0; base < V; base += blockDim.x) {
+      const int r = base + threadIdx.x;
+      const int hit = (r < V && out[(size_t)r * 7] == cls) ? 1 : 0;
+      int total;
+      const int ex = block_scan_excl(hit, scan_smem, &total);
+      const int carry = carry_smem;
+      if (hit) list[carry + ex] = r;
+      __syncthreads();
+      if (threadIdx.x == 0) carry_smem = carry + total;
+      __syncthreads();
+    }
+  }
+  float4 *boxes;
+  unsigned char *dead;
+  if (n <= kNmsSmemRows) {
+    boxes = sm_box;
+    dead = sm_dead;
+  } else {
+    boxes = a.seg_box + (size_t)b * a.A + seg_base;
+    dead = a.seg_dead + (size_t)b * a.A + seg_base;
+  }
+  for (int q = threadIdx.x; q < n; q += blockDim.x) {
+    const int r = a.force_suppress ? q : list[q];
+    const float *row = out + (size_t)r * 7;
+    boxes[q] = make_float4(row[2], row[3], row[4], row[5]);
+    dead[q] = 0;
+  }
+  __syncthreads();
+
+  const float thr = a.nms_threshold;
+  const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
+  for (int c0 = 0; c0 < n; c0 += 64) {
+    const int m = min(64, n - c0);
+    // (1) 64x64 upper-triangular suppression mask of the chunk, one row per warp iteration
+    if (warp < 2) {
+      const int t = warp * 32 + lane;
+      const unsigned bal = __ballot_sync(kFullMask, t < m && dead[c0 + t]);
+      if (lane == 0) sm_deadbits[warp] = bal;
+    }
+    for (int i = warp; i < m; i += nwarps) {
+      unsigned lo = 0, hi = 0;
+      if (!dead[c0 + i]) {
+        const float4 bi = boxes[c0 + i];
+        const int j0 = lane, j1 = lane + 32;
+        const bool s0 = j0 > i && j0 < m && iou_detection(bi, boxes[c0 + j0]) >= thr;
+        const bool s1 = j1 > i && j1 < m && iou_detection(bi, boxes[c0 + j1]) >= thr;
+        lo = __ballot_sync(kFullMask, s0);
+        hi = __ballot_sync(kFullMask, s1);
+      }
+      if (lane == 0) sm_word[i] = ((unsigned long long)hi << 32) | lo;
+    }
+    __syncthreads();
+    // (2) serial greedy resolve inside the chunk on 64-bit words
+    if (threadIdx.x == 0) {
+      unsigned long long dm = ((unsigned long long)sm_deadbits[1] << 32) | sm_deadbits[0];
+      unsigned long long alive = 0;
+      for (int t = 0; t < m; ++t)
+        if (!((dm >> t) & 1ull)) {
+          alive |= 1ull << t;
+          dm |= sm_word[t];
+        }
+      sm_alive = alive;
+      sm_deadmask = dm;
+    }
+    __syncthreads();
+    const unsigned long long alive = sm_alive;
+    if ((int)threadIdx.x < m) dead[c0 + threadIdx.x] = (unsigned char)((sm_deadmask >> threadIdx.x) & 1ull);
+    // (3) sweep every later row against the surviving pivots of this chunk
+    for (int j = c0 + 64 + threadIdx.x; j < n; j += blockDim.x) {
+      if (dead[j]) continue;
+      const float4 bj = boxes[j];
+      unsigned long long rem = alive;
+      while (rem) {
+        const int t = __ffsll((long long)rem) - 1;
+        rem &= rem - 1;
+        if (iou_detection(boxes[c0 + t], bj) >= thr) {
+          dead[j] = 1;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- suppressed rows: only the id field is overwritten (multibox_detection.cc:163) ----
+  for (int q = threadIdx.x; q < n; q += blockDim.x)
+    if (dead[q]) {
+      const int r = a.force_suppress ? q : list[q];
+      out[(size_t)r * 7] = -1.f;
+    }
+}
+
+}  // namespace
+}  // namespace dspmb
+
+using namespace dspmb;
+
+extern "C" size_t dspmb_detection_workspace_bytes(int B, int A, int C) {
+  if (B <= 0 || A <= 0 || C <= 0) return 0;
+  return carve(nullptr, B, A, C).bytes;
+}
+
+extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const float *anchors, float *out,
+                                   int B, int A, int C, float threshold, int clip, const float *variances,
+                                   float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out,
+                                   void *workspace, size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  // Shape CHECKs of MultiBoxDetectionProp::InferShape (multibox_detection-inl.h:149-171).
+  DSPMB_REQUIRE(B >= 0 && A > 0 && C > 0, "MultiBoxDetection: bad shape B=%d A=%d C=%d", B, A, C);
+  DSPMB_REQUIRE(cls_prob && loc_pred && anchors && out && variances, "MultiBoxDetection: NULL tensor");
+  DSPMB_REQUIRE(B <= 65535, "MultiBoxDetection: batch > 65535 not supported in one call");
+  DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxDetection: anchors must be 16-byte aligned");
+  if (B == 0) return DSPMB_OK;
+  const size_t need = carve(nullptr, B, A, C).bytes;
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+    set_error("MultiBoxDetection: workspace must be 256-byte aligned and >= %zu bytes (got %zu)", need, workspace_bytes);
+    return DSPMB_ERR_WORKSPACE;
+  }
+  DetWorkspace w = carve(workspace, B, A, C);
+
+  const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out) & 15) == 0;
+  const int tile = kStreamThreads * (vec4 ? 4 : 1);
+  const int T = ceil_div(A, tile);
+  const int Apad = A + 4 * kStreamThreads;
+
+  StreamArgs sa;
+  sa.cls_prob = cls_prob;
+  sa.loc_pred = loc_pred;
+  sa.anchors = anchors;
+  sa.out = out;
+  sa.tile_count = w.tile_count;
+  sa.rec = w.rec;
+  sa.A = A;
+  sa.C = C;
+  sa.T = T;
+  sa.Apad = Apad;
+  sa.threshold = threshold;
+  sa.clip = clip;
+  sa.vx = variances[0];
+  sa.vy = variances[1];
+  sa.vw = variances[2];
+  sa.vh = variances[3];
+  sa.fma_build = libm_fma_mode();
+  dim3 grid1(T, B);
+  if (vec4)
+    det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
+  else
+    det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
+  DSPMB_CUDA_TRY(cudaGetLastError());
+
+  SortArgs so;
+  so.out = out;
+  so.tile_count = w.tile_count;
+  so.rec = w.rec;
+  so.slot_of_rank = w.slot_of_rank;
+  so.valid = w.valid;
+  so.nms_rows = w.nms_rows;
+  so.seg_off = w.seg_off;
+  so.sort_keys = w.sort_keys;
+  so.valid_count_out = valid_count_out;
+  so.header = w.header;
+  so.A = A;
+  so.C = C;
+  so.T = T;
+  so.Apad = Apad;
+  so.tile = tile;
+  so.npad_max = next_pow2(A);
+  so.nms_threshold = nms_threshold;
+  so.force_suppress = force_suppress;
+  so.nms_topk = nms_topk;
+  const int key_cap = so.npad_max < kSortSmemKeys ? so.npad_max : kSortSmemKeys;
+  const size_t smem2 = sizeof(unsigned long long) * key_cap + sizeof(int) * (T + 1 + C + 1);
+  DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxDetection: too many tiles/classes for the sort kernel (A=%d C=%d)", A, C);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  det_sort_kernel<<<B, kSortThreads, smem2, stream>>>(so);
+  DSPMB_CUDA_TRY(cudaGetLastError());
+
+  if (nms_threshold > 0.f && nms_threshold <= 1.f) {
+    NmsArgs na;
+    na.out = out;
+    na.nms_rows = w.nms_rows;
+    na.seg_off = w.seg_off;
+    na.seg_list = w.seg_list;
+    na.seg_box = w.seg_box;
+    na.seg_dead = w.seg_dead;
+    na.A = A;
+    na.C = C;
+    na.nms_threshold = nms_threshold;
+    na.force_suppress = force_suppress;
+    dim3 grid3(force_suppress ? 1 : (C > 1 ? C - 1 : 1), B);
+    if (C > 1 || force_suppress) {
+      det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
+      DSPMB_CUDA_TRY(cudaGetLastError());
+    }
+  }
+  return DSPMB_OK;
+}

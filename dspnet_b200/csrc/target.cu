@@ -1,0 +1,639 @@
+// MultiBoxTarget for sm_100a.
+//
+// Reference semantics (CPU operator, the parity target): operator/multibox_target-inl.h:89-171 (output init
+// :121-124, IoU planes :137-161) and operator/multibox_target.cc:72-284:
+//   G            (:95-105)  number of leading label rows with cls != -1;
+//   bipartite    (:113-149) repeatedly take the global argmax IoU (> 1e-6, first in (anchor, gt) scan order)
+//                           over unmatched anchors x unmatched gts;
+//   threshold    (:151-180) every other anchor: first-max gt; positive iff max IoU > overlap_threshold;
+//   mining       (:182-241) num_negative = (int)(num_positive * ratio) clamped to A - num_positive; candidates are
+//                           non-positive anchors with max IoU < negative_mining_thresh; stable sort by background
+//                           softmax probability ascending (ties: lower anchor first); first num_negative -> 0;
+//   write        (:251-281) positives: cls+1, mask 1x5, 5-wide encoding; negatives: 0; rest: ignore_label.
+// The reference materialises 11 broadcast planes of B*A*L floats for the IoU (4 GB at SSD-512, B=64); its GPU
+// kernels (operator/multibox_target.cu) diverge from the CPU semantics and are not followed.
+//
+// Structure here (memset + two launches, all images in every grid):
+//   target_stream_kernel  HBM-bound.  One thread per 4 consecutive anchors; ground truths staged in shared
+//                         memory; fused IoU / first-max row argmax / column argmax (packed 64-bit keys: warp
+//                         shuffle max -> shared atomicMax -> one global atomicMax per CTA and gt); exact two-pass
+//                         softmax of the background logit (glibc-bit-exact expf in fp64); writes loc_target,
+//                         loc_mask, provisional cls_target and the 32-bit mining key of every anchor.
+//   target_match_kernel   one CTA per image: lazy greedy bipartite matching on the cached column maxima (a stale
+//                         maximum is an upper bound, so it is recomputed only when it reaches the top), output
+//                         fix-up of the <= G matched anchors, then an MSB-first radix select (4 x 8 bit) of the
+//                         num_negative smallest (probability, anchor) keys with an ordered tie pass.
+#include "common.cuh"
+
+namespace dspmb {
+namespace {
+
+constexpr int kStreamThreads = 128;
+constexpr int kMatchThreads = 1024;
+constexpr unsigned kKeySentinel = 0xffffffffu;  // "not a mining candidate"
+
+struct TargetWorkspace {
+  WsHeader *header;
+  int *gcount;     // (B) valid ground truths
+  int *thr_count;  // (B) threshold-stage positives (zeroed per call)
+  unsigned long long *colbest;  // (B, L) best (iou, anchor) per gt (zeroed per call)
+  unsigned *key;   // (B, A) mining keys
+  size_t zero_begin, zero_bytes;
+  size_t bytes;
+};
+
+TargetWorkspace carve(void *base, int B, int A, int L) {
+  TargetWorkspace w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return (char *)base + o;
+  };
+  w.header = (WsHeader *)take(sizeof(WsHeader));
+  w.zero_begin = 0;
+  w.gcount = (int *)take(sizeof(int) * B);
+  w.thr_count = (int *)take(sizeof(int) * B);
+  w.colbest = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * L);
+  w.zero_bytes = off;
+  w.key = (unsigned *)take(sizeof(unsigned) * (size_t)B * A);
+  w.bytes = off;
+  return w;
+}
+
+struct TargetArgs {
+  const float *anchors, *labels, *cls_preds;
+  float *loc_target, *loc_mask, *cls_target;
+  int32_t *match_out, *stats_out;
+  WsHeader *header;
+  int *gcount, *thr_count;
+  unsigned long long *colbest;
+  unsigned *key;
+  int B, A, L, W, C, T;
+  float overlap_threshold, ignore_label, mining_ratio, mining_thresh;
+  float vx, vy, vw, vh;
+  int fma_build;
+};
+
+// 5-wide box encoding, operator/multibox_target.cc:30-56.
+__device__ __forceinline__ void encode_loc(float4 an, const float *lab, const TargetArgs &a, float *dst) {
+  const float aw = fsub(an.z, an.x);
+  const float ah = fsub(an.w, an.y);
+  const float ax = fmul(fadd(an.x, an.z), 0.5f);  // (al + ar) * 0.5 in double and back: exact either way
+  const float ay = fmul(fadd(an.y, an.w), 0.5f);
+  const float gl = lab[1], gt = lab[2], gr = lab[3], gb = lab[4], gz = lab[5];
+  const float gw = fsub(gr, gl);
+  const float gh = fsub(gb, gt);
+  const float gx = fmul(fadd(gl, gr), 0.5f);
+  const float gy = fmul(fadd(gt, gb), 0.5f);
+  dst[0] = fdiv(fdiv(fsub(gx, ax), aw), a.vx);
+  dst[1] = fdiv(fdiv(fsub(gy, ay), ah), a.vy);
+  dst[2] = fdiv(libm::logf_glibc(fdiv(gw, aw), a.fma_build), a.vw);
+  dst[3] = fdiv(libm::logf_glibc(fdiv(gh, ah), a.fma_build), a.vh);
+  dst[4] = __double2float_rn(__ddiv_rn((double)gz, 0.1));  // DType(gz) / 0.1 is a double division
+}
+
+__device__ __forceinline__ unsigned long long col_key(float iou, int anchor) {
+  // larger IoU wins, then the lower anchor index (scan order of multibox_target.cc:117-134)
+  return ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(0xffffffffu - (unsigned)anchor);
+}
+
+// Number of leading valid label rows (multibox_target.cc:95-105).  All threads of the CTA must call.
+__device__ int count_valid_gt(const float *lab, int L, int W, int *smem_min) {
+  if (threadIdx.x == 0) *smem_min = L;
+  __syncthreads();
+  int first = L;
+  for (int l = threadIdx.x; l < L; l += blockDim.x)
+    if (lab[(size_t)l * W] == -1.0f) {
+      first = l;
+      break;
+    }
+  if (first < L) atomicMin(smem_min, first);
+  __syncthreads();
+  return *smem_min;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __grid_constant__ TargetArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ int sm_int;
+  __shared__ int sm_pos;
+  float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);                                  // [L]
+  unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + a.L);       // [L]
+
+  const int b = blockIdx.y, t = blockIdx.x;
+  constexpr int kTile = kStreamThreads * VEC;
+  const int A = a.A, W = a.W;
+  const int i0 = t * kTile + threadIdx.x * VEC;
+  const float *lab = a.labels + (size_t)b * a.L * W;
+
+  const int G = count_valid_gt(lab, a.L, W, &sm_int);
+  if (t == 0 && threadIdx.x == 0) {
+    a.gcount[b] = G;
+    if (G < a.L) {  // CHECK_EQ on the first padding row, multibox_target.cc:98-101
+      const float *row = lab + (size_t)G * W;
+      if (row[1] != -1.0f || row[2] != -1.0f || row[3] != -1.0f || row[4] != -1.0f)
+        atomicMin(&a.header->status, DSPMB_ERR_LABEL_PADDING);
+    }
+  }
+  for (int k = threadIdx.x; k < G; k += blockDim.x) {
+    const float *row = lab + (size_t)k * W;
+    sm_gt[k] = make_float4(row[1], row[2], row[3], row[4]);
+    sm_col[k] = 0ull;
+  }
+  if (threadIdx.x == 0) sm_pos = 0;
+  __syncthreads();
+
+  const bool mining = a.mining_ratio > 0.f;
+  float best_iou[VEC];
+  int best_k[VEC];
+  float4 an[VEC];
+  const bool active = i0 < A;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    best_iou[v] = -1.0f;
+    best_k[v] = -1;
+    an[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (active) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) an[v] = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i0 + v);
+  }
+
+  // ---- fused IoU + row first-max + column max (multibox_target-inl.h:137-161, .cc:113-134,158-166) ----
+  for (int k = 0; k < G; ++k) {
+    const float4 g = sm_gt[k];
+    unsigned long long tkey = 0ull;
+    if (active) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        const float iou = iou_target(an[v], g);
+        if (iou > best_iou[v]) {
+          best_iou[v] = iou;
+          best_k[v] = k;
+        }
+        if (iou > 1e-6f) {
+          const unsigned long long ck = col_key(iou, i0 + v);
+          tkey = ck > tkey ? ck : tkey;
+        }
+      }
+    }
+    if (__any_sync(kFullMask, tkey != 0ull)) {
+      const unsigned long long wk = warp_max_u64(tkey);
+      if (lane_id() == 0) atomicMax(&sm_col[k], wk);
+    }
+  }
+
+  // ---- threshold-stage positives + mining keys ----
+  bool pos[VEC];
+  unsigned key[VEC];
+  int npos = 0;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) {
+    pos[v] = active && G > 0 && a.overlap_threshold > 0.f && best_k[v] >= 0 && best_iou[v] > a.overlap_threshold;
+    npos += pos[v];
+    key[v] = kKeySentinel;
+  }
+  if (mining && G > 0 && active) {
+    const float *cp = a.cls_preds + (size_t)b * a.C * A + i0;
+    float mx[VEC], sum[VEC], p0[VEC];
+    // pass 1: running max over the classes (multibox_target.cc:220-224); pass 2: sum of expf in class order
+    // (:225-229).  The second pass re-reads the same lines (L1/L2 resident).
+#pragma unroll 4
+    for (int c = 0; c < a.C; ++c) {
+      float x[VEC];
+      if constexpr (VEC == 4) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
+        x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+      } else {
+        x[0] = __ldg(cp + (size_t)c * A);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (c == 0) {
+          mx[v] = x[v];
+          p0[v] = x[v];
+        } else if (x[v] > mx[v]) {
+          mx[v] = x[v];
+        }
+      }
+    }
+    bool cand[VEC];
+    bool any_cand = false;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      cand[v] = !pos[v] && best_iou[v] < a.mining_thresh;
+      any_cand |= cand[v];
+      sum[v] = 0.f;
+    }
+    if (any_cand) {
+#pragma unroll 2
+      for (int c = 0; c < a.C; ++c) {
+        float x[VEC];
+        if constexpr (VEC == 4) {
+          const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
+          x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+        } else {
+          x[0] = __ldg(cp + (size_t)c * A);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v)
+          if (cand[v]) sum[v] = fadd(sum[v], libm::expf_glibc(fsub(x[v], mx[v]), a.fma_build));
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v)
+        if (cand[v]) {
+          const float prob = fdiv(libm::expf_glibc(fsub(p0[v], mx[v]), a.fma_build), sum[v]);
+          key[v] = __float_as_uint(prob);
+        }
+    }
+  }
+
+  // ---- outputs ----
+  if (active) {
+    const size_t row0 = (size_t)b * A + i0;
+    float ct[VEC];
+    float lt[VEC * 5], lm[VEC * 5];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      if (pos[v]) {
+        const float *lrow = lab + (size_t)best_k[v] * W;
+        ct[v] = fadd(lrow[0], 1.0f);
+        encode_loc(an[v], lrow, a, lt + v * 5);
+#pragma unroll
+        for (int c = 0; c < 5; ++c) lm[v * 5 + c] = 1.0f;
+      } else {
+        ct[v] = (G > 0 && !mining) ? 0.0f : a.ignore_label;  // multibox_target.cc:242-249 vs -inl.h:123
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          lt[v * 5 + c] = 0.f;
+          lm[v * 5 + c] = 0.f;
+        }
+      }
+    }
+    float *plt = a.loc_target + row0 * 5, *plm = a.loc_mask + row0 * 5;
+    if constexpr (VEC == 4) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        reinterpret_cast<float4 *>(plt)[q] = make_float4(lt[4 * q], lt[4 * q + 1], lt[4 * q + 2], lt[4 * q + 3]);
+        reinterpret_cast<float4 *>(plm)[q] = make_float4(lm[4 * q], lm[4 * q + 1], lm[4 * q + 2], lm[4 * q + 3]);
+      }
+      *reinterpret_cast<float4 *>(a.cls_target + row0) = make_float4(ct[0], ct[1], ct[2], ct[3]);
+      *reinterpret_cast<uint4 *>(a.key + row0) = make_uint4(key[0], key[1], key[2], key[3]);
+      if (a.match_out)
+        *reinterpret_cast<int4 *>(a.match_out + row0) =
+            make_int4(pos[0] ? best_k[0] : -1, pos[1] ? best_k[1] : -1, pos[2] ? best_k[2] : -1, pos[3] ? best_k[3] : -1);
+    } else {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        plt[c] = lt[c];
+        plm[c] = lm[c];
+      }
+      a.cls_target[row0] = ct[0];
+      a.key[row0] = key[0];
+      if (a.match_out) a.match_out[row0] = pos[0] ? best_k[0] : -1;
+    }
+  }
+
+  // ---- publish the CTA's column maxima and positive count ----
+  npos = warp_sum_i32(npos);
+  if (lane_id() == 0 && npos) atomicAdd(&sm_pos, npos);
+  __syncthreads();
+  if (threadIdx.x == 0 && sm_pos) atomicAdd(&a.thr_count[b], sm_pos);
+  unsigned long long *gcol = a.colbest + (size_t)b * a.L;
+  for (int k = threadIdx.x; k < G; k += blockDim.x) {
+    const unsigned long long ck = sm_col[k];
+    if (ck) atomicMax(&gcol[k], ck);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v, unsigned long long *smem) {
+  v = warp_max_u64(v);
+  const unsigned w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) smem[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    unsigned long long x = l < nw ? smem[l] : 0ull;
+    x = warp_max_u64(x);
+    if (l == 0) smem[0] = x;
+  }
+  __syncthreads();
+  return smem[0];
+}
+
+enum { kStateDone = 0, kStateRecompute = 1 };
+
+__global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __grid_constant__ TargetArgs a) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ unsigned long long red_smem[kMatchThreads / 32];
+  __shared__ int scan_smem[kMatchThreads / 32 + 1];
+  __shared__ unsigned hist[256];
+  __shared__ int sm_state, sm_arg, sm_nmatch, sm_dup, sm_carry;
+  __shared__ unsigned sm_prefix;
+  __shared__ int sm_need;
+
+  const int b = blockIdx.x;
+  const int A = a.A, L = a.L, W = a.W;
+  const int G = a.gcount[b];
+  int32_t *stats = a.stats_out ? a.stats_out + 4 * b : nullptr;
+  if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values
+    if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    return;
+  }
+  // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
+  float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);
+  unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + L);
+  int *m_anchor = reinterpret_cast<int *>(sm_col + L);
+  int *m_gt = m_anchor + L;
+  unsigned char *done = reinterpret_cast<unsigned char *>(m_gt + L);
+  unsigned *bits = reinterpret_cast<unsigned *>(done + ((L + 15) / 16) * 16);
+  const int nwords = (A + 31) / 32;
+
+  const float *lab = a.labels + (size_t)b * L * W;
+  const float4 *anchors = reinterpret_cast<const float4 *>(a.anchors);
+  unsigned long long *gcol = a.colbest + (size_t)b * L;
+  for (int k = threadIdx.x; k < G; k += blockDim.x) {
+    const float *row = lab + (size_t)k * W;
+    sm_gt[k] = make_float4(row[1], row[2], row[3], row[4]);
+    sm_col[k] = gcol[k];
+    done[k] = 0;
+  }
+  for (int w = threadIdx.x; w < nwords; w += blockDim.x) bits[w] = 0u;
+  if (threadIdx.x == 0) {
+    sm_nmatch = 0;
+    sm_dup = 0;
+  }
+  __syncthreads();
+
+  // ---- bipartite stage (multibox_target.cc:113-149) ----
+  while (true) {
+    if (warp_id() == 0) {
+      const unsigned lane = lane_id();
+      while (true) {
+        // best cached (iou, anchor) over the unmatched gts; ties on both go to the lower gt index
+        unsigned long long best = 0ull;
+        int bk = -1;
+        for (int k = lane; k < G; k += 32) {
+          const unsigned long long ck = sm_col[k];
+          if (!done[k] && ck > best) {
+            best = ck;
+            bk = k;
+          }
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          const unsigned long long ob = shfl_xor_u64(best, m);
+          const int ok = __shfl_xor_sync(kFullMask, bk, m);
+          if (ob > best || (ob == best && ob != 0ull && ok < bk)) {
+            best = ob;
+            bk = ok;
+          }
+        }
+        int state = -1;
+        if (bk < 0) {
+          state = kStateDone;  // no remaining pair above 1e-6 (:136-138) or every gt matched
+        } else {
+          const int j = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
+          if ((bits[j >> 5] >> (j & 31)) & 1u) {
+            state = kStateRecompute;  // cached maximum points at an anchor that has been taken since
+          } else if (lane == 0) {
+            const int n = sm_nmatch;
+            m_anchor[n] = j;
+            m_gt[n] = bk;
+            sm_nmatch = n + 1;
+            done[bk] = 1;
+            bits[j >> 5] |= 1u << (j & 31);
+          }
+        }
+        __syncwarp();
+        if (state >= 0) {
+          if (lane == 0) {
+            sm_state = state;
+            sm_arg = bk;
+          }
+          break;
+        }
+      }
+    }
+    __syncthreads();
+    if (sm_state == kStateDone) break;
+    // recompute the column maximum of gt sm_arg over the anchors that are still unmatched
+    const int k = sm_arg;
+    const float4 g = sm_gt[k];
+    unsigned long long tkey = 0ull;
+    for (int j = threadIdx.x; j < A; j += blockDim.x) {
+      if ((bits[j >> 5] >> (j & 31)) & 1u) continue;
+      const float iou = iou_target(__ldg(anchors + j), g);
+      if (iou > 1e-6f) {
+        const unsigned long long ck = col_key(iou, j);
+        tkey = ck > tkey ? ck : tkey;
+      }
+    }
+    const unsigned long long bm = block_max_u64(tkey, red_smem);
+    if (threadIdx.x == 0) sm_col[k] = bm;
+    __syncthreads();
+  }
+  const int nmatch = sm_nmatch;
+
+  // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
+  for (int q = threadIdx.x; q < nmatch; q += blockDim.x) {
+    const int j = m_anchor[q], k = m_gt[q];
+    const float4 an = __ldg(anchors + j);
+    float max_iou = -1.0f;
+    for (int kk = 0; kk < G; ++kk) {
+      const float iou = iou_target(an, sm_gt[kk]);
+      if (iou > max_iou) max_iou = iou;
+    }
+    if (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) atomicAdd(&sm_dup, 1);  // counted by the stream kernel
+    const size_t row = (size_t)b * A + j;
+    const float *lrow = lab + (size_t)k * W;
+    float enc[5];
+    encode_loc(an, lrow, a, enc);
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      a.loc_target[row * 5 + c] = enc[c];
+      a.loc_mask[row * 5 + c] = 1.0f;
+    }
+    a.cls_target[row] = fadd(lrow[0], 1.0f);
+    a.key[row] = kKeySentinel;
+    if (a.match_out) a.match_out[row] = k;
+  }
+  __syncthreads();
+  const int num_positive = a.thr_count[b] + nmatch - sm_dup;
+
+  // ---- hard-negative mining (multibox_target.cc:182-241) ----
+  int num_negative = 0;
+  if (a.mining_ratio > 0.f) {
+    num_negative = (int)fmul((float)num_positive, a.mining_ratio);
+    if (num_negative > A - num_positive) num_negative = A - num_positive;
+    if (num_negative < 0) num_negative = 0;
+  }
+  if (stats && threadIdx.x == 0) {
+    stats[0] = G;
+    stats[1] = num_positive;
+    stats[2] = a.mining_ratio > 0.f ? num_negative : A - num_positive;
+    stats[3] = nmatch;
+  }
+  if (num_negative <= 0) return;
+
+  const unsigned *keys = a.key + (size_t)b * A;
+  // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
+  // (larger than the bits of any probability), so they are only reached if there are too few candidates.
+  if (threadIdx.x == 0) {
+    sm_prefix = 0u;
+    sm_need = num_negative;
+  }
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    __syncthreads();
+    const unsigned prefix = sm_prefix;
+    for (int base = 0; base < A; base += blockDim.x) {
+      const int j = base + threadIdx.x;
+      const unsigned kv = j < A ? keys[j] : kKeySentinel;
+      const bool hit = j < A && (kv & mask) == prefix;
+      // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
+      const unsigned digit = (kv >> shift) & 0xffu;
+      const unsigned active = __ballot_sync(kFullMask, hit);
+      if (hit) {
+        const unsigned peers = __match_any_sync(active, digit);
+        if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
+      unsigned acc = 0;
+      int d = 0;
+      for (; d < 255; ++d) {
+        if ((int)(acc + hist[d]) >= need) break;
+        acc += hist[d];
+      }
+      sm_need = need - (int)acc;
+      sm_prefix = prefix | ((unsigned)d << shift);
+    }
+    __syncthreads();
+  }
+  const unsigned thr_key = sm_prefix;
+  const int need_eq = sm_need;
+  if (thr_key == kKeySentinel) {
+    // the num_negative-th smallest key is a non-candidate: CHECK_GE(temp.size(), num_negative) fails
+    // (multibox_target.cc:236)
+    if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_MINING_CANDIDATES);
+    return;
+  }
+  // ordered final pass: keys below the pivot, plus the first need_eq keys equal to it in anchor order
+  if (threadIdx.x == 0) sm_carry = 0;
+  __syncthreads();
+  float *ct = a.cls_target + (size_t)b * A;
+  for (int base = 0; base < A; base += blockDim.x) {
+    const int j = base + threadIdx.x;
+    const unsigned kv = j < A ? keys[j] : kKeySentinel;
+    const int eq = kv == thr_key ? 1 : 0;
+    int total;
+    const int ex = block_scan_excl(eq, scan_smem, &total);
+    const int carry = sm_carry;
+    if (kv < thr_key || (eq && carry + ex < need_eq)) ct[j] = 0.0f;
+    __syncthreads();
+    if (threadIdx.x == 0) sm_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+}  // namespace
+}  // namespace dspmb
+
+using namespace dspmb;
+
+extern "C" size_t dspmb_target_workspace_bytes(int B, int A, int L, int C) {
+  (void)C;
+  if (B <= 0 || A <= 0 || L <= 0) return 0;
+  return carve(nullptr, B, A, L).bytes;
+}
+
+extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const float *cls_preds,
+                                float *loc_target, float *loc_mask, float *cls_target, int B, int A, int L,
+                                int label_width, int C, float overlap_threshold, float ignore_label,
+                                float negative_mining_ratio, float negative_mining_thresh,
+                                int minimum_negative_samples, const float *variances, int32_t *match_out,
+                                int32_t *stats_out, void *workspace, size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  (void)minimum_negative_samples;  // declared but never read by the CPU operator (multibox_target.cc:182-241)
+  // Shape CHECKs of MultiBoxTargetProp::InferShape (multibox_target-inl.h:213-238).
+  DSPMB_REQUIRE(B >= 0 && A > 0 && L > 0 && C > 0, "MultiBoxTarget: bad shape B=%d A=%d L=%d C=%d", B, A, L, C);
+  DSPMB_REQUIRE(label_width >= 6, "MultiBoxTarget: label width must be >= 6 [cls,xmin,ymin,xmax,ymax,dist]");
+  DSPMB_REQUIRE(anchors && labels && cls_preds && loc_target && loc_mask && cls_target && variances,
+                "MultiBoxTarget: NULL tensor");
+  DSPMB_REQUIRE(B <= 65535, "MultiBoxTarget: batch > 65535 not supported in one call");
+  DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxTarget: anchors must be 16-byte aligned");
+  if (negative_mining_ratio > 0.f && !(negative_mining_thresh > 0.f)) {  // multibox_target.cc:184
+    set_error("MultiBoxTarget: negative_mining_thresh must be > 0 when mining is enabled");
+    return DSPMB_ERR_MINING_THRESH;
+  }
+  if (B == 0) return DSPMB_OK;
+  const size_t need = carve(nullptr, B, A, L).bytes;
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+    set_error("MultiBoxTarget: workspace must be 256-byte aligned and >= %zu bytes (got %zu)", need, workspace_bytes);
+    return DSPMB_ERR_WORKSPACE;
+  }
+  TargetWorkspace w = carve(workspace, B, A, L);
+  DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
+
+  const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
+                             (uintptr_t)cls_target | (uintptr_t)match_out;
+  const bool vec4 = (A % 4 == 0) && (align_or & 15) == 0;
+  const int tile = kStreamThreads * (vec4 ? 4 : 1);
+
+  TargetArgs ta;
+  ta.anchors = anchors;
+  ta.labels = labels;
+  ta.cls_preds = cls_preds;
+  ta.loc_target = loc_target;
+  ta.loc_mask = loc_mask;
+  ta.cls_target = cls_target;
+  ta.match_out = match_out;
+  ta.stats_out = stats_out;
+  ta.header = w.header;
+  ta.gcount = w.gcount;
+  ta.thr_count = w.thr_count;
+  ta.colbest = w.colbest;
+  ta.key = w.key;
+  ta.B = B;
+  ta.A = A;
+  ta.L = L;
+  ta.W = label_width;
+  ta.C = C;
+  ta.T = ceil_div(A, tile);
+  ta.overlap_threshold = overlap_threshold;
+  ta.ignore_label = ignore_label;
+  ta.mining_ratio = negative_mining_ratio;
+  ta.mining_thresh = negative_mining_thresh;
+  ta.vx = variances[0];
+  ta.vy = variances[1];
+  ta.vw = variances[2];
+  ta.vh = variances[3];
+  ta.fma_build = libm_fma_mode();
+
+  const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long)) * (size_t)L;
+  const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
+                       (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((A + 31) / 32);
+  DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 24);
+  DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  dim3 grid1(ta.T, B);
+  if (vec4)
+    target_stream_kernel<4><<<grid1, kStreamThreads, smem1, stream>>>(ta);
+  else
+    target_stream_kernel<1><<<grid1, kStreamThreads, smem1, stream>>>(ta);
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  target_match_kernel<<<B, kMatchThreads, smem2, stream>>>(ta);
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}

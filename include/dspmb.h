@@ -1,0 +1,138 @@
+/*
+ * dspmb.h -- C ABI of the B200-native multibox hot path (libdspmb.so).
+ *
+ * Drop-in boundary for the three MXNet contrib operators the reference patches into MXNet
+ * (operator/multibox_{prior,target,detection}{-inl.h,.cc,.cu}) and for the Cython NMS helpers
+ * (cython/{cpu_nms.pyx,gpu_nms.pyx,nms_kernel.cu,gpu_nms.hpp}).  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain C types only; `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - unless marked HOST, pointers are device pointers on the current CUDA device, caller-owned,
+ *     contiguous fp32 in exactly the reference's layouts; outputs are fully overwritten;
+ *   - calls are asynchronous on `stream` (except the *_host entry) and allocate nothing: scratch comes
+ *     from the caller via the *_workspace_bytes queries (the analogue of ResourceRequest::kTempSpace,
+ *     operator/multibox_target-inl.h:258-261, multibox_detection-inl.h:183-186);
+ *   - return value: 0 on success, a negative DSPMB_ERR_* code otherwise (the reference aborts through
+ *     CHECK_* -> dmlc::Error; here the failure is a code plus dspmb_last_error()).  Data-dependent CHECKs
+ *     (label padding, mining candidates) are evaluated on the device and latched in the workspace; read
+ *     them with dspmb_status().
+ *   - there is no CPU fallback: without a CUDA device every compute entry returns DSPMB_ERR_CUDA.
+ */
+#ifndef DSPMB_H_
+#define DSPMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSPMB_VERSION 100
+
+#define DSPMB_OK 0
+#define DSPMB_ERR_BAD_ARG -1           /* shape / parameter CHECKs of the Param ctors and InferShape       */
+#define DSPMB_ERR_LABEL_PADDING -2     /* operator/multibox_target.cc:98-101                                */
+#define DSPMB_ERR_MINING_CANDIDATES -3 /* operator/multibox_target.cc:236 CHECK_GE(temp.size(), num_neg)    */
+#define DSPMB_ERR_MINING_THRESH -4     /* operator/multibox_target.cc:184 CHECK_GT(negative_mining_thresh)  */
+#define DSPMB_ERR_WORKSPACE -5         /* workspace pointer NULL / too small / misaligned                   */
+#define DSPMB_ERR_CUDA -6              /* CUDA runtime error (message in dspmb_last_error)                  */
+
+int dspmb_version(void);
+
+/* Thread-local description of the last failure in this thread ("" if none). */
+const char *dspmb_last_error(void);
+
+/*
+ * The reference's CPU operators call the host libm (std::exp / std::log on float,
+ * operator/multibox_target.cc:53-54,228,230 and multibox_detection.cc:117-118).  The kernels evaluate
+ * glibc's expf/logf algorithm bit-for-bit in fp64; glibc selects an FMA or a non-FMA build of it at load
+ * time from the CPU flags.  mode: 0 = non-FMA (sse2) variant, 1 = FMA variant, -1 = detect from this host.
+ * Default is -1.  Returns the mode now in effect.
+ */
+int dspmb_set_libm_mode(int mode);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MultiBoxPrior -- replaces MultiBoxPriorOp::Forward (operator/multibox_prior-inl.h:97-129) and
+ * MultiBoxPriorForward (operator/multibox_prior.cc:29-71, .cu:61-101).
+ * out: (in_height*in_width*(num_sizes+num_ratios-1), 4).  sizes/ratios: HOST arrays (op parameters).
+ * steps <= 0 select the automatic 1/H, 1/W steps.  One launch for all anchor kinds.
+ * ------------------------------------------------------------------------------------------------- */
+int dspmb_prior_f32(float *out, int in_height, int in_width, const float *sizes, int num_sizes,
+                    const float *ratios, int num_ratios, float step_y, float step_x, float offset_y,
+                    float offset_x, int clip, void *stream);
+
+/* All feature maps of a head in ONE launch, written back to back into out (sum_i H_i*W_i*K_i, 4) -- the
+ * MultiBoxPrior-per-scale + Flatten + Concat of symbol/common.py:415-432.  All arrays HOST; sizes/ratios are
+ * the per-map lists concatenated, with num_sizes[i]/num_ratios[i] entries for map i; steps holds (y, x) pairs
+ * and offsets (y, x) pairs per map.  At most DSPMB_MAX_MAPS maps, DSPMB_MAX_KINDS sizes+ratios in total. */
+#define DSPMB_MAX_MAPS 16
+#define DSPMB_MAX_KINDS 128
+int dspmb_prior_multi_f32(float *out, int num_maps, const int *heights, const int *widths, const float *sizes,
+                          const int *num_sizes, const float *ratios, const int *num_ratios, const float *steps,
+                          const float *offsets, int clip, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MultiBoxTarget -- replaces MultiBoxTargetOp::Forward (operator/multibox_target-inl.h:89-171) and
+ * MultiBoxTargetForward (operator/multibox_target.cc:72-284; CPU semantics, not the divergent .cu ones).
+ * anchors (A,4) | labels (B,L,label_width>=6) [cls,xmin,ymin,xmax,ymax,dist,...] | cls_preds (B,C,A)
+ * -> loc_target (B,A*5), loc_mask (B,A*5), cls_target (B,A).
+ * variances: HOST float[4].  Optional device outputs (NULL to skip):
+ *   match_out (B,A) int32 : ground-truth index each positive anchor was matched to, -1 otherwise;
+ *   stats_out (B,4) int32 : num_valid_gt, num_positive, num_negative, num_bipartite_matches.
+ * ------------------------------------------------------------------------------------------------- */
+size_t dspmb_target_workspace_bytes(int B, int A, int L, int C);
+int dspmb_target_f32(const float *anchors, const float *labels, const float *cls_preds, float *loc_target,
+                     float *loc_mask, float *cls_target, int B, int A, int L, int label_width, int C,
+                     float overlap_threshold, float ignore_label, float negative_mining_ratio,
+                     float negative_mining_thresh, int minimum_negative_samples, const float *variances,
+                     int32_t *match_out, int32_t *stats_out, void *workspace, size_t workspace_bytes,
+                     void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * MultiBoxDetection -- replaces MultiBoxDetectionOp::Forward (operator/multibox_detection-inl.h:81-107)
+ * and MultiBoxDetectionForward (operator/multibox_detection.cc:53-169; CPU semantics).
+ * cls_prob (B,C,A) | loc_pred (B,A*5) | anchors (A,4) -> out (B,A,7) [id,score,xmin,ymin,xmax,ymax,dist].
+ * Optional device output valid_count_out (B) int32 = rows emitted by pass 1 per image.
+ * ------------------------------------------------------------------------------------------------- */
+size_t dspmb_detection_workspace_bytes(int B, int A, int C);
+int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const float *anchors, float *out, int B,
+                        int A, int C, float threshold, int clip, const float *variances, float nms_threshold,
+                        int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
+                        size_t workspace_bytes, void *stream);
+
+/* Synchronises `stream` and returns the data-dependent status latched by the last target/detection call
+ * that used `workspace` (0 or a DSPMB_ERR_* code). */
+int dspmb_status(const void *workspace, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Standalone NMS -- replaces cpu_nms (cython/cpu_nms.pyx:17-68), gpu_nms (cython/gpu_nms.pyx:16-31) and
+ * _nms (cython/nms_kernel.cu:91-144).  Pixel "+1" IoU convention.
+ * mode 0: suppress iff (double)iou >= thresh  (cpu_nms);  mode 1: suppress iff iou > (float)thresh (gpu_nms,
+ * detect/nms.py::nms).  dets (N,dim>=5) rows [x1,y1,x2,y2,score,(class)...].
+ * class_col >= 5 restricts suppression to boxes with equal dets[:,class_col] (force_suppress off);
+ * class_col < 0 is the reference's single-class behaviour.
+ * presorted != 0: rows are already in descending score order (the _nms contract); otherwise the library sorts
+ * on the device (score descending; ties -> higher index first, i.e. a stable argsort()[::-1]).
+ * keep (N) int32 receives kept ORIGINAL row indices in score order, num_keep (1) int32 their count.
+ * ------------------------------------------------------------------------------------------------- */
+size_t dspmb_nms_workspace_bytes(int N);
+int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, int mode, int class_col, int presorted,
+                  int32_t *keep, int32_t *num_keep, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Binary-compatible with `void _nms(int*, int*, const float*, int, int, float, int)` of cython/gpu_nms.hpp:1-2
+ * apart from the int return: HOST pointers, boxes sorted by descending score, synchronous, selects
+ * device_id, strict-greater rule.  keep_out receives sorted positions. */
+int dspmb_nms_host(int *keep_out, int *num_out, const float *boxes_host, int boxes_num, int boxes_dim,
+                   float nms_overlap_thresh, int device_id);
+
+/* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same
+ * glibc-compatible routines the kernels use.  x, y device pointers. */
+int dspmb_test_expf(const float *x, float *y, long n, void *stream);
+int dspmb_test_logf(const float *x, float *y, long n, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPMB_H_ */

@@ -1,0 +1,205 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes front-end of the CPU oracle (oracle/multibox_oracle.cc).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module.  The product package (dspnet_b200/) never does.
+
+Functions mirror the reference operator names and keyword arguments
+(operator/multibox_{prior,target,detection}-inl.h Param structs) and work on numpy arrays.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle_multibox.so")
+_lib = None
+
+ERRORS = {
+    0: "ok",
+    -1: "bad argument",
+    -2: "label padding row is not all -1 (multibox_target.cc:98-101)",
+    -3: "fewer mining candidates than num_negative (multibox_target.cc:236)",
+    -4: "negative_mining_thresh must be > 0 (multibox_target.cc:184)",
+}
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code):
+        super().__init__("oracle: %s (code %d)" % (ERRORS.get(code, "?"), code))
+        self.code = code
+
+
+def build(force=False):
+    """Compile the restatement with the flags SURVEY.md section 8c prescribes."""
+    src = os.path.join(_HERE, "multibox_oracle.cc")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle_multibox.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        fp = ctypes.POINTER(ctypes.c_float)
+        ip = ctypes.POINTER(ctypes.c_int32)
+        L.oracle_multibox_prior.argtypes = [fp, ctypes.c_int, ctypes.c_int, fp, ctypes.c_int, fp, ctypes.c_int,
+                                            ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                            ctypes.c_int]
+        L.oracle_multibox_prior.restype = ctypes.c_int
+        L.oracle_target_iou.argtypes = [fp, ctypes.c_int, fp, ctypes.c_int, ctypes.c_int, fp]
+        L.oracle_target_iou.restype = None
+        L.oracle_multibox_target.argtypes = [fp, fp, fp, fp, fp, fp] + [ctypes.c_int] * 5 + [ctypes.c_float] * 4 + [
+            ctypes.c_int, fp, ip, fp, ctypes.POINTER(ctypes.c_int8), ip, ctypes.c_int]
+        L.oracle_multibox_target.restype = ctypes.c_int
+        L.oracle_multibox_detection.argtypes = [fp, fp, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_float, ctypes.c_int, fp, ctypes.c_float, ctypes.c_int,
+                                                ctypes.c_int, ip, ctypes.c_int]
+        L.oracle_multibox_detection.restype = ctypes.c_int
+        L.oracle_cpu_nms.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                     ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
+        L.oracle_cpu_nms.restype = ctypes.c_int
+        L.oracle_expf_array.argtypes = [fp, fp, ctypes.c_long]
+        L.oracle_logf_array.argtypes = [fp, fp, ctypes.c_long]
+        _lib = L
+    return _lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a, ty=ctypes.c_float):
+    return a.ctypes.data_as(ctypes.POINTER(ty)) if a is not None else None
+
+
+def multibox_prior(in_height, in_width, sizes=(1.0,), ratios=(1.0,), clip=False, steps=(-1.0, -1.0),
+                   offsets=(0.5, 0.5)):
+    """operator/multibox_prior.cc:29-71; returns (1, H*W*(S+R-1), 4) like InferShape (-inl.h:171-193)."""
+    sizes = _f32(sizes)
+    ratios = _f32(ratios)
+    n = in_height * in_width * (len(sizes) + len(ratios) - 1)
+    out = np.empty((1, n, 4), np.float32)
+    rc = lib().oracle_multibox_prior(_p(out), in_height, in_width, _p(sizes), len(sizes), _p(ratios), len(ratios),
+                                     float(steps[0]), float(steps[1]), float(offsets[0]), float(offsets[1]),
+                                     int(bool(clip)))
+    if rc:
+        raise OracleError(rc)
+    return out
+
+
+def target_iou(anchors, gts):
+    anchors = _f32(anchors).reshape(-1, 4)
+    gts = _f32(gts).reshape(-1, 4)
+    out = np.empty((anchors.shape[0], gts.shape[0]), np.float32)
+    lib().oracle_target_iou(_p(anchors), anchors.shape[0], _p(gts), gts.shape[0], 4, _p(out))
+    return out
+
+
+def multibox_target(anchor, label, cls_pred, overlap_threshold=0.5, ignore_label=-1.0, negative_mining_ratio=-1.0,
+                    negative_mining_thresh=0.5, minimum_negative_samples=0, variances=(0.1, 0.1, 0.2, 0.2),
+                    debug=False, nthreads=1):
+    """operator/multibox_target-inl.h:89-171 + multibox_target.cc:72-284.
+
+    Returns [loc_target (B, A*5), loc_mask (B, A*5), cls_target (B, A)]; with debug=True also a dict with
+    match_gt, match_iou, anchor_flags, stats (num_valid_gt, num_positive, num_negative, num_bipartite).
+    """
+    anchor = _f32(anchor)
+    label = _f32(label)
+    cls_pred = _f32(cls_pred)
+    assert anchor.ndim == 3 and anchor.shape[0] == 1 and anchor.shape[2] == 4
+    assert label.ndim == 3 and cls_pred.ndim == 3 and cls_pred.shape[2] == anchor.shape[1]
+    B, L, W = label.shape
+    A = anchor.shape[1]
+    C = cls_pred.shape[1]
+    var = _f32(variances)
+    loc_target = np.empty((B, A * 5), np.float32)
+    loc_mask = np.empty((B, A * 5), np.float32)
+    cls_target = np.empty((B, A), np.float32)
+    match_gt = np.empty((B, A), np.int32) if debug else None
+    match_iou = np.empty((B, A), np.float32) if debug else None
+    flags = np.empty((B, A), np.int8) if debug else None
+    stats = np.zeros((B, 4), np.int32)
+    rc = lib().oracle_multibox_target(_p(anchor), _p(label), _p(cls_pred), _p(loc_target), _p(loc_mask),
+                                      _p(cls_target), B, A, L, W, C, overlap_threshold, ignore_label,
+                                      negative_mining_ratio, negative_mining_thresh, minimum_negative_samples,
+                                      _p(var), _p(match_gt, ctypes.c_int32), _p(match_iou),
+                                      _p(flags, ctypes.c_int8), _p(stats, ctypes.c_int32), nthreads)
+    if rc:
+        raise OracleError(rc)
+    outs = [loc_target, loc_mask, cls_target]
+    if debug:
+        return outs, dict(match_gt=match_gt, match_iou=match_iou, anchor_flags=flags, stats=stats)
+    return outs
+
+
+def multibox_detection(cls_prob, loc_pred, anchor, clip=True, threshold=0.01, background_id=0, nms_threshold=0.5,
+                       force_suppress=False, variances=(0.1, 0.1, 0.2, 0.2), nms_topk=-1, return_valid=False,
+                       nthreads=1):
+    """operator/multibox_detection-inl.h:81-107 + multibox_detection.cc:53-169.  Returns (B, A, 7)."""
+    cls_prob = _f32(cls_prob)
+    loc_pred = _f32(loc_pred)
+    anchor = _f32(anchor)
+    B, C, A = cls_prob.shape
+    assert loc_pred.shape == (B, A * 5) and anchor.shape == (1, A, 4)
+    var = _f32(variances)
+    out = np.empty((B, A, 7), np.float32)
+    valid = np.zeros((B,), np.int32)
+    rc = lib().oracle_multibox_detection(_p(cls_prob), _p(loc_pred), _p(anchor), _p(out), B, A, C, threshold,
+                                         int(bool(clip)), _p(var), nms_threshold, int(bool(force_suppress)),
+                                         nms_topk, _p(valid, ctypes.c_int32), nthreads)
+    if rc:
+        raise OracleError(rc)
+    return (out, valid) if return_valid else out
+
+
+def cpu_nms(dets, thresh, mode="cpu"):
+    """cython/cpu_nms.pyx:17-68 (mode='cpu', suppress iff double(ovr) >= thresh) or the strict-greater rule
+    of cython/nms_kernel.cu:71 and detect/nms.py:55 (mode='gpu').  Returns kept indices in score order."""
+    dets = _f32(dets)
+    n, dim = dets.shape
+    order = np.ascontiguousarray(dets[:, 4].argsort()[::-1], dtype=np.int64)
+    keep = np.empty((n,), np.int64)
+    k = lib().oracle_cpu_nms(_p(dets), n, dim, _p(order, ctypes.c_int64), float(thresh),
+                             0 if mode == "cpu" else 1, _p(keep, ctypes.c_int64))
+    return [int(i) for i in keep[:k]]
+
+
+def py_nms(dets, thresh):
+    """detect/nms.py:24-58 restated with numpy (keeps ovr <= thresh)."""
+    x1, y1, x2, y2, scores = (dets[:, i] for i in range(5))
+    areas = (x2 - x1 + 1) * (y2 - y1 + 1)
+    order = scores.argsort()[::-1]
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        rest = order[1:]
+        xx1 = np.maximum(x1[i], x1[rest])
+        yy1 = np.maximum(y1[i], y1[rest])
+        xx2 = np.minimum(x2[i], x2[rest])
+        yy2 = np.minimum(y2[i], y2[rest])
+        w = np.maximum(0.0, xx2 - xx1 + 1)
+        h = np.maximum(0.0, yy2 - yy1 + 1)
+        inter = w * h
+        ovr = inter / (areas[i] + areas[rest] - inter)
+        order = rest[np.where(ovr <= thresh)[0]]
+    return keep
+
+
+def expf(x):
+    x = _f32(x).ravel()
+    y = np.empty_like(x)
+    lib().oracle_expf_array(_p(x), _p(y), x.size)
+    return y
+
+
+def logf(x):
+    x = _f32(x).ravel()
+    y = np.empty_like(x)
+    lib().oracle_logf_array(_p(x), _p(y), x.size)
+    return y

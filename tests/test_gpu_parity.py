@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via dspnet_b200.ops) against the CPU oracle on the same
+seeded inputs.  Discrete outputs (ids, match indices, mining masks, kept rows) must be identical; on this build
+the float outputs are bit-identical too (glibc-exact expf/logf, no FMA contraction), which is stricter than the
+1e-5 relative tolerance BASELINE.json's north_star asks for -- REL_TOL below is that documented bound and is what
+a failure of the bit-exact check is reported against."""
+import numpy as np
+import pytest
+import torch
+
+from dspnet_b200 import presets, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+def _t(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+@pytest.mark.parametrize("preset", sorted(presets.PRESETS))
+def test_prior_per_map_and_concat(oracle, cuda, preset):
+    from dspnet_b200 import MultiBoxPrior
+    from dspnet_b200.symbol import multibox_anchors
+    p = presets.PRESETS[preset]
+    for fm in p.maps:
+        want = oracle.multibox_prior(fm.height, fm.width, fm.sizes, fm.ratios, False, (fm.step, fm.step))
+        got = MultiBoxPrior((1, 8, fm.height, fm.width), sizes=fm.sizes, ratios=fm.ratios, steps=(fm.step, fm.step))
+        util.assert_bit_equal(got.cpu().numpy(), want, "prior %s %dx%d" % (preset, fm.height, fm.width))
+    util.assert_bit_equal(multibox_anchors(preset).cpu().numpy(), util.oracle_anchors(oracle, preset), "concat")
+
+
+def test_prior_clip_offsets_strings(oracle, cuda):
+    from dspnet_b200 import MultiBoxPrior
+    want = oracle.multibox_prior(5, 7, (0.4, 0.9), (1, 2, 0.5, 3), True, (0.21, 0.13), (0.3, 0.8))
+    got = MultiBoxPrior(torch.empty(2, 3, 5, 7, device=cuda), sizes="(0.4,0.9)", ratios="(1,2,0.5,3)", clip=True,
+                        steps="(0.21, 0.13)", offsets=(0.3, 0.8))
+    util.assert_bit_equal(got.cpu().numpy(), want, "prior clip")
+
+
+def test_libm_compat_on_device(oracle, cuda):
+    from dspnet_b200 import _lib
+    import ctypes
+    rng = np.random.default_rng(7)
+    x = np.concatenate([rng.uniform(-110, 95, 2_000_000), rng.normal(0, 3, 2_000_000),
+                        np.array([0, -0.0, np.inf, -np.inf, 88.0, 88.72284, -103.9, -103.3, -104, 1e-30, -1e-30])]).astype(np.float32)
+    xd = _t(x, cuda)
+    yd = torch.empty_like(xd)
+    _lib.check(_lib.lib().dspmb_test_expf(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(yd.data_ptr()), x.size, None))
+    torch.cuda.synchronize()
+    util.assert_bit_equal(yd.cpu().numpy(), oracle.expf(x), "expf")
+    xl = np.concatenate([np.exp(rng.uniform(-80, 80, 2_000_000)), rng.uniform(0, 4, 2_000_000),
+                         np.array([0, 1, 1e-42, np.inf, 0.5, 2.0])]).astype(np.float32)
+    xd = _t(xl, cuda)
+    yd = torch.empty_like(xd)
+    _lib.check(_lib.lib().dspmb_test_logf(ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(yd.data_ptr()), xl.size, None))
+    torch.cuda.synchronize()
+    util.assert_bit_equal(yd.cpu().numpy(), oracle.logf(xl), "logf")
+
+
+def _check_detection(oracle, cuda, anchors, prob, lp, **kw):
+    from dspnet_b200 import MultiBoxDetection
+    want, want_valid = oracle.multibox_detection(prob, lp, anchors, return_valid=True, **kw)
+    got, got_valid = MultiBoxDetection(_t(prob, cuda), _t(lp, cuda), _t(anchors, cuda), return_valid_count=True, **kw)
+    got = got.cpu().numpy()
+    util.assert_bit_equal(got_valid.cpu().numpy(), want_valid, "valid_count")
+    util.assert_bit_equal(got[:, :, 0], want[:, :, 0], "detection ids / kept rows")
+    np.testing.assert_allclose(got, want, rtol=REL_TOL, atol=0, err_msg="detection values")
+    util.assert_bit_equal(got, want, "detection (bit-exact)")
+    return want_valid
+
+
+@pytest.mark.parametrize("preset,batch", [("ssd300", 1), ("ssd512", 4), ("dspnet_cs", 2)])
+@pytest.mark.parametrize("force", [False, True])
+def test_detection_presets(oracle, cuda, preset, batch, force):
+    anchors, prob, lp = util.detection_inputs(oracle, preset, batch, config_id=11)
+    valid = _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, force_suppress=force, nms_topk=400)
+    assert (valid > 400).any(), "inputs should exercise the nms_topk tail quirk"
+
+
+@pytest.mark.parametrize("kw", [
+    dict(nms_threshold=0.5, nms_topk=-1),
+    dict(nms_threshold=0.3, nms_topk=10, force_suppress=True),
+    dict(nms_threshold=0.0),            # NMS skipped: rows stay in anchor order
+    dict(nms_threshold=1.5, nms_topk=5),
+    dict(nms_threshold=1.0, clip=False),
+    dict(threshold=0.5, nms_threshold=0.45, nms_topk=400),
+    dict(threshold=2.0),                # nothing survives
+    dict(threshold=-5.0, nms_threshold=0.45, nms_topk=100, variances=(0.2, 0.1, 0.3, 0.25)),
+])
+def test_detection_parameters(oracle, cuda, kw):
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=12)
+    _check_detection(oracle, cuda, anchors, prob, lp, **kw)
+
+
+def test_detection_dense_and_ties(oracle, cuda):
+    # every anchor valid (V = A > 16384 sort keys in shared memory -> global sort path, large NMS segments)
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd512", 1, config_id=13, dense=True)
+    _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=400)
+    # duplicate scores: stable order must fall back to the anchor index
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=14)
+    prob = np.round(prob * 64) / 64
+    _check_detection(oracle, cuda, anchors, prob.astype(np.float32), lp, nms_threshold=0.45, nms_topk=400)
+    _check_detection(oracle, cuda, anchors, prob.astype(np.float32), lp, nms_threshold=0.45, nms_topk=-1, force_suppress=True)
+
+
+def test_detection_odd_anchor_count(oracle, cuda):
+    # A % 4 != 0 -> scalar load path
+    rng = np.random.default_rng(3)
+    A, C, B = 1001, 5, 3
+    xy = rng.uniform(0, 0.8, (A, 2))
+    wh = rng.uniform(0.05, 0.4, (A, 2))
+    anchors = np.concatenate([xy, xy + wh], axis=1).reshape(1, A, 4).astype(np.float32)
+    prob = synth.cls_prob(15, B, C, A)
+    lp = synth.loc_pred(15, B, A)
+    _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=50)
+
+
+def _check_target(oracle, cuda, anchors, lab, cp, **kw):
+    from dspnet_b200 import MultiBoxTarget
+    want, dbg = oracle.multibox_target(anchors, lab, cp, debug=True, **kw)
+    got = MultiBoxTarget(_t(anchors, cuda), _t(lab, cuda), _t(cp, cuda), return_match=True, return_stats=True, **kw)
+    loc_t, loc_m, cls_t, match, stats = [g.cpu().numpy() for g in got]
+    util.assert_bit_equal(stats, dbg["stats"], "stats [G, num_pos, num_neg, bipartite]")
+    want_match = np.where(dbg["anchor_flags"] == 1, dbg["match_gt"], -1)
+    util.assert_bit_equal(match, want_match, "match indices")
+    util.assert_bit_equal(cls_t, want[2], "cls_target (mining mask)")
+    util.assert_bit_equal(loc_m, want[1], "loc_mask")
+    np.testing.assert_allclose(loc_t, want[0], rtol=REL_TOL, atol=0, err_msg="loc_target")
+    util.assert_bit_equal(loc_t, want[0], "loc_target (bit-exact)")
+    return dbg
+
+
+@pytest.mark.parametrize("preset,batch,max_gt", [("ssd300", 3, 8), ("ssd512", 4, 8), ("dspnet_cs", 3, 50)])
+def test_target_presets(oracle, cuda, preset, batch, max_gt):
+    anchors, lab, cp = util.target_inputs(oracle, preset, batch, config_id=21, max_gt=max_gt)
+    dbg = _check_target(oracle, cuda, anchors, lab, cp, overlap_threshold=0.5, ignore_label=-1, negative_mining_ratio=3,
+                        negative_mining_thresh=0.5, minimum_negative_samples=0, variances=(0.1, 0.1, 0.2, 0.2))
+    assert dbg["stats"][1, 0] == 0 and dbg["stats"][2, 0] == lab.shape[1]  # G = 0 and G = L edge images
+
+
+@pytest.mark.parametrize("kw", [
+    dict(),                                                    # defaults: mining disabled -> all negatives
+    dict(negative_mining_ratio=3, overlap_threshold=0.3),
+    dict(negative_mining_ratio=1.5, negative_mining_thresh=0.3, ignore_label=-7),
+    dict(negative_mining_ratio=3, overlap_threshold=0.0),      # threshold stage skipped
+    dict(negative_mining_ratio=3, minimum_negative_samples=500),  # ignored by the CPU operator
+    dict(negative_mining_ratio=0.4, variances=(0.3, 0.2, 0.1, 0.5)),
+    dict(negative_mining_ratio=1000.0),                        # clamps to A - num_positive or raises
+])
+def test_target_parameters(oracle, cuda, kw):
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 4, config_id=22)
+    try:
+        oracle.multibox_target(anchors, lab, cp, **kw)
+    except oracle.OracleError as e:
+        from dspnet_b200 import MultiBoxTarget, DspmbError
+        with pytest.raises(DspmbError) as ei:
+            MultiBoxTarget(_t(anchors, cuda), _t(lab, cuda), _t(cp, cuda), **kw)
+        assert ei.value.code == e.code
+        return
+    _check_target(oracle, cuda, anchors, lab, cp, **kw)
+
+
+def test_target_adversarial_matching(oracle, cuda):
+    """Duplicate ground truths and gts sharing their best anchor force the bipartite stage to re-evaluate column
+    maxima; quantised logits create probability ties at the mining cut."""
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 4, config_id=23)
+    lab[0, 1] = lab[0, 0]                       # exact duplicate gt
+    lab[0, 2, 1:5] = lab[0, 0, 1:5] + 1e-3      # near duplicate
+    lab[3, :6] = lab[3, 0]                      # six identical gts
+    lab[3, :6, 0] = np.arange(6)
+    cp = (np.round(cp * 2) / 2).astype(np.float32)  # heavy ties in the softmax probabilities
+    _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+    # tiny gts that overlap no anchor above 1e-6 and gts outside the image
+    lab2 = lab.copy()
+    lab2[1, 0, 1:5] = (0.5, 0.5, 0.5, 0.5)
+    lab2[0, 3, 1:5] = (0.2, 0.2, 0.2000001, 0.2000001)
+    _check_target(oracle, cuda, anchors, lab2, cp, negative_mining_ratio=3)
+
+
+def test_target_label_padding_check(oracle, cuda):
+    from dspnet_b200 import MultiBoxTarget, DspmbError
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 2, config_id=24)
+    g = int((lab[0, :, 0] != -1).sum())
+    lab[0, g] = (-1, 0.1, -1, -1, -1, -1)   # first padding row is not all -1
+    with pytest.raises(oracle.OracleError):
+        oracle.multibox_target(anchors, lab, cp, negative_mining_ratio=3)
+    with pytest.raises(DspmbError) as ei:
+        MultiBoxTarget(_t(anchors, cuda), _t(lab, cuda), _t(cp, cuda), negative_mining_ratio=3)
+    assert ei.value.code == -2
+
+
+def test_target_odd_anchor_count(oracle, cuda):
+    rng = np.random.default_rng(5)
+    A, C, B, L = 777, 4, 3, 9
+    xy = rng.uniform(0, 0.8, (A, 2))
+    wh = rng.uniform(0.05, 0.4, (A, 2))
+    anchors = np.concatenate([xy, xy + wh], axis=1).reshape(1, A, 4).astype(np.float32)
+    lab = synth.labels(25, B, L, C, max_gt=6, edge_cases=False)
+    cp = synth.cls_preds(25, B, C, A)
+    _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+
+
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 1000, 5000])
+@pytest.mark.parametrize("rule", ["ge", "gt"])
+def test_nms_sweep(oracle, cuda, n, rule):
+    from dspnet_b200 import nms as N
+    dets = synth.nms_boxes(100 + n, n)
+    want = oracle.cpu_nms(dets, 0.45, mode="cpu" if rule == "ge" else "gpu")
+    got = (N.cpu_nms if rule == "ge" else N.gpu_nms)(dets, 0.45)
+    assert got == want
+    if rule == "gt":
+        assert N.nms(dets, 0.45) == oracle.py_nms(dets, 0.45) == want
+
+
+def test_nms_threshold_is_double(oracle, cuda):
+    """cpu_nms compares float32 iou promoted to double against a double threshold: an IoU of float32(0.45) is NOT
+    >= 0.45."""
+    from dspnet_b200 import nms as N
+    dets = synth.nms_boxes(9, 3000)
+    for thr in (0.45, float(np.float32(0.45)), 0.3, 0.7):
+        assert N.cpu_nms(dets, thr) == oracle.cpu_nms(dets, thr, mode="cpu")
+
+
+def test_nms_per_class_and_host_abi(oracle, cuda):
+    import ctypes
+    from dspnet_b200 import nms as N, _lib
+    dets = synth.nms_boxes(77, 4000, with_class=True, num_classes=7)
+    keep, num = N.nms_device(torch.from_numpy(dets).to(cuda), 0.45, rule="ge", class_col=5)
+    got = keep[: int(num.item())].cpu().tolist()
+    # oracle: cpu_nms per class, kept indices merged in score order
+    kept = []
+    for c in range(7):
+        idx = np.nonzero(dets[:, 5] == c)[0]
+        kept += [int(idx[i]) for i in oracle.cpu_nms(dets[idx, :5], 0.45)]
+    kept.sort(key=lambda i: -dets[i, 4])
+    assert got == kept
+    # _nms-compatible host entry (cython/gpu_nms.hpp:1-2): sorted boxes in, sorted positions out
+    d5 = dets[:, :5]
+    order = d5[:, 4].argsort()[::-1]
+    sd = np.ascontiguousarray(d5[order])
+    keep_out = np.zeros(len(sd), np.int32)
+    num_out = ctypes.c_int(0)
+    rc = _lib.lib().dspmb_nms_host(keep_out.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.byref(num_out),
+                                   sd.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), len(sd), 5, 0.45, 0)
+    assert rc == 0
+    assert list(order[keep_out[: num_out.value]]) == oracle.cpu_nms(d5, 0.45, mode="gpu")
+
+
+def test_host_buffer_round_trip(oracle, cuda):
+    """numpy in -> numpy out: the reference-facing call with host buffers (what bench.py times as e2e)."""
+    from dspnet_b200 import MultiBoxDetection, MultiBoxTarget
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=31)
+    got = MultiBoxDetection(prob, lp, anchors, nms_threshold=0.45, nms_topk=400)
+    assert isinstance(got, np.ndarray)
+    util.assert_bit_equal(got, oracle.multibox_detection(prob, lp, anchors, nms_threshold=0.45, nms_topk=400), "host det")
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 2, config_id=32)
+    got = MultiBoxTarget(anchors, lab, cp, negative_mining_ratio=3)
+    want = oracle.multibox_target(anchors, lab, cp, negative_mining_ratio=3)
+    for g, w, n in zip(got, want, ("loc_target", "loc_mask", "cls_target")):
+        util.assert_bit_equal(g, w, "host " + n)
