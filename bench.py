@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""Benchmark of the multibox hot path (BASELINE.json: "SSD-512 multibox target+detect images/s at 1/2/4/8 B200;
+% of HBM peak").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+A step is one pass of MultiBoxDetection (decode + threshold + top-k sort + per-class NMS) over one batch of 32
+synthetic SSD-512 VOC head tensors per GPU (BASELINE.json configs[1]); with N > 1 every rank processes its own 32
+images (weak scaling, images are independent) and the compacted detections are all-gathered over NCCL, overlapped
+with the next step's kernels.  Inputs rotate over several resident copies whose total footprint exceeds the 126 MB
+L2, so every step streams from HBM.  One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PRESET = "ssd512"
+BATCH = 32
+CONFIG_ID = 2
+DET_PARAMS = dict(threshold=0.01, clip=True, nms_threshold=0.45, force_suppress=False, nms_topk=400,
+                  variances=(0.1, 0.1, 0.2, 0.2))
+TGT_PARAMS = dict(overlap_threshold=0.5, ignore_label=-1.0, negative_mining_ratio=3.0, negative_mining_thresh=0.5,
+                  minimum_negative_samples=0, variances=(0.1, 0.1, 0.2, 0.2))
+ROTATE = 4  # resident input/output sets cycled through: 4 x ~104 MB > 126 MB L2
+
+
+def det_algorithmic_bytes(B, A, C):
+    """4*B*C*A + 4*B*A*5 + 16*A read, 28*B*A written."""
+    return 4 * B * C * A + 20 * B * A + 16 * A + 28 * B * A
+
+
+def tgt_algorithmic_bytes(B, A, C, L):
+    return 16 * A + 24 * B * L + 4 * B * C * A + 44 * B * A
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled in a side process while the GPU is under load."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.tmp,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.proc.wait()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = max(mx, float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        sm.sort()
+        # the median of the upper half approximates "under load" when idle samples are mixed in
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(first_image, B):
+    """Seeded synthetic SSD-512 head tensors (numpy, host)."""
+    import numpy as np
+    from dspnet_b200 import presets, synth
+    p = presets.PRESETS[PRESET]
+    A = presets.num_anchors(p)
+    prob = synth.cls_prob(CONFIG_ID, B, p.num_classes, A, first_image=first_image)
+    loc = synth.loc_pred(CONFIG_ID, B, A, first_image=first_image)
+    lab = synth.labels(CONFIG_ID, B, p.label_slots, p.num_classes, first_image=first_image)
+    logits = synth.cls_preds(CONFIG_ID, B, p.num_classes, A, first_image=first_image)
+    return dict(prob=prob, loc=loc, lab=lab, logits=logits, A=A, C=p.num_classes, L=p.label_slots), np
+
+
+def oracle_anchors():
+    import numpy as np
+    from dspnet_b200 import presets
+    from oracle import oracle as O
+    p = presets.PRESETS[PRESET]
+    return np.concatenate([O.multibox_prior(fm.height, fm.width, fm.sizes, fm.ratios, False, (fm.step, fm.step))
+                           for fm in p.maps], axis=1)
+
+
+def cpu_baseline(inputs, threads, repeats=3):
+    """Times the CPU oracle (restated reference CPU operator) on the host cores: one B=32 detection batch per
+    repeat, image-parallel over `threads` threads (the reference loop itself is single-threaded)."""
+    from oracle import oracle as O
+    anchors = oracle_anchors()
+    times = []
+    for _ in range(repeats + 1):
+        t0 = time.perf_counter()
+        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+        times.append(time.perf_counter() - t0)
+    times = sorted(times[1:])
+    return BATCH / times[len(times) // 2]
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: MXNet cannot be installed
+    here) on all host threads; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    inputs, _ = make_inputs(0, BATCH)
+    from oracle import oracle as O
+    anchors = oracle_anchors()
+    for _ in range(max(args.warmup, 1)):
+        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+    dt = time.perf_counter() - t0
+    value = BATCH * args.steps / dt
+    kind = "port"
+    line = {
+        "impl": "reference", "metric": "ssd512_multibox_detection_images_per_s", "value": value, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "ssd512_voc21_multibox_detection_nms_batch32", "preset": PRESET, "batch_per_gpu": BATCH,
+                   "anchors": inputs["A"], "classes": inputs["C"], **{k: v for k, v in DET_PARAMS.items()}},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": "%d steps x one B=32 SSD-512 detection batch, one image per thread" % args.steps},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-soak", action="store_true", help="skip the 1.5 s clock soak (for runs under ncu)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dspnet_b200 import _lib
+    from dspnet_b200.plan import DetectionPlan, TargetPlan
+    from dspnet_b200.symbol import multibox_anchors
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    inputs, _ = make_inputs(rank * BATCH, BATCH)
+    A, C, L = inputs["A"], inputs["C"], inputs["L"]
+    anchors = multibox_anchors(PRESET, device=dev)
+    plan = DetectionPlan(BATCH, A, C, dev, **DET_PARAMS)
+    # resident rotating sets (same values, distinct addresses) so that consecutive steps do not hit in L2
+    prob_sets = [torch.from_numpy(inputs["prob"]).to(dev) for _ in range(ROTATE)]
+    loc_sets = [torch.from_numpy(inputs["loc"]).to(dev) for _ in range(ROTATE)]
+    out_sets = [plan.new_output() for _ in range(ROTATE)]
+    gatherer = None
+    if world > 1:
+        from dspnet_b200.dist import DetectionGatherer
+        gatherer = DetectionGatherer(BATCH, A, DET_PARAMS["nms_topk"], dev, world)
+
+    def step(i):
+        s = i % ROTATE
+        plan.run(prob_sets[s], loc_sets[s], anchors, out_sets[s])
+        if gatherer is not None:
+            gatherer.submit(out_sets[s], i)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # warm-up: W steps as asked, then keep the GPU busy for ~1.5 s so clocks and the sampler reach steady state
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    t_end = time.perf_counter() + (0.0 if args.no_soak else 1.5)
+    i = args.warmup
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step(i)
+            i += 1
+        torch.cuda.synchronize()
+    if gatherer is not None:
+        gatherer.drain()
+
+    # ---- timed region: exactly K steps, device-timed, max over ranks ----
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    if gatherer is not None:
+        gatherer.drain()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = args.steps * (plan.launches_per_run + (gatherer.launches_per_submit if gatherer else 0))
+
+    # ---- per-kernel durations: a second pass of K steps with cudaEvent pairs around every kernel ----
+    lib = _lib.lib()
+    lib.dspmb_profile_enable(1)
+    for i in range(args.steps):
+        s = i % ROTATE
+        plan.run(prob_sets[s], loc_sets[s], anchors, out_sets[s])
+    torch.cuda.synchronize()
+    import ctypes
+    kms = (ctypes.c_float * 16)()
+    kcnt = (ctypes.c_int * 16)()
+    nslots = lib.dspmb_profile_read(kms, kcnt, 16)
+    lib.dspmb_profile_enable(0)
+    kernels = {lib.dspmb_profile_kernel_name(k).decode(): (kms[k] / max(kcnt[k], 1)) for k in range(nslots) if kcnt[k]}
+
+    # ---- end to end through the public operator with HOST buffers (pinned in, result read back) ----
+    from dspnet_b200 import MultiBoxDetection
+    pin_prob = torch.from_numpy(inputs["prob"]).pin_memory()
+    pin_loc = torch.from_numpy(inputs["loc"]).pin_memory()
+    pin_out = torch.empty((BATCH, A, 7), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        d_prob = pin_prob.to(dev, non_blocking=True)
+        d_loc = pin_loc.to(dev, non_blocking=True)
+        out = MultiBoxDetection(d_prob, d_loc, anchors, **DET_PARAMS)
+        pin_out.copy_(out, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+
+    # ---- secondary figure: MultiBoxTarget with hard-negative mining (BASELINE.json configs[2]) ----
+    tgt = None
+    try:
+        TB = 64 // world if world > 1 else 64
+        tin, _ = make_inputs(rank * TB, TB)
+        tplan = TargetPlan(TB, A, L, C, dev, **TGT_PARAMS)
+        lab_d = torch.from_numpy(tin["lab"]).to(dev)
+        logit_sets = [torch.from_numpy(tin["logits"]).to(dev) for _ in range(2)]
+        touts = [tplan.new_outputs() for _ in range(2)]
+        for i in range(5):
+            tplan.run(anchors, lab_d, logit_sets[i % 2], touts[i % 2])
+        barrier()
+        ev0.record()
+        tsteps = max(10, min(args.steps, 100))
+        for i in range(tsteps):
+            tplan.run(anchors, lab_d, logit_sets[i % 2], touts[i % 2])
+        ev1.record()
+        barrier()
+        tms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([tms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tms = float(t.item())
+        tplan.status()
+        lib.dspmb_profile_enable(1)
+        for i in range(tsteps):
+            tplan.run(anchors, lab_d, logit_sets[i % 2], touts[i % 2])
+        torch.cuda.synchronize()
+        kms2 = (ctypes.c_float * 16)()
+        kcnt2 = (ctypes.c_int * 16)()
+        lib.dspmb_profile_read(kms2, kcnt2, 16)
+        lib.dspmb_profile_enable(0)
+        tk = {lib.dspmb_profile_kernel_name(k).decode(): (kms2[k] / max(kcnt2[k], 1)) for k in range(nslots) if kcnt2[k]}
+        peak, _ = measured_peaks()
+        tbytes = tgt_algorithmic_bytes(TB, A, C, L)
+        tgt = {"workload": "ssd512_multibox_target_mining3_batch64_%s" % ("sharded" if world > 1 else "1gpu"),
+               "images_per_s": TB * world * tsteps / (tms * 1e-3), "ms_per_step": tms / tsteps,
+               "kernel_ms": tk,
+               "stream_kernel_gbs": tbytes / (tk.get("target_stream_kernel", float("nan")) * 1e-3) / 1e9,
+               "stream_kernel_frac_of_hbm": tbytes / (tk.get("target_stream_kernel", float("nan")) * 1e-3) / 1e9 / peak,
+               "scaling": "strong"}
+    except Exception as e:  # the headline must still print
+        tgt = {"error": repr(e)}
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        abytes = det_algorithmic_bytes(BATCH, A, C)
+        k_ms = kernels.get("det_stream_kernel", float("nan"))
+        achieved = abytes / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": "ssd512_multibox_detection_images_per_s", "value": BATCH * world * args.steps / (ms * 1e-3),
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "ssd512_voc21_multibox_detection_nms_batch32", "preset": PRESET,
+                       "batch_per_gpu": BATCH, "anchors": A, "classes": C,
+                       "l2": "inputs/outputs rotate over %d resident sets (%d MB total) > 126 MB L2" % (
+                           ROTATE, ROTATE * abytes // 2 ** 20),
+                       "parallelism": "images sharded, %d per GPU" % BATCH, **DET_PARAMS},
+            "roofline": {"bound": "hbm", "kernel": "det_stream_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": abytes, "kernel_ms": k_ms,
+                         "timing": "cudaEvent pair around each kernel, second pass of K steps right after the timed region",
+                         "all_kernels_ms": kernels,
+                         "whole_op_frac": abytes / (ms / args.steps * 1e-3) / 1e9 / peak},
+            "e2e": {"value": BATCH * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(pin_prob.numel() * 4 + pin_loc.numel() * 4),
+                    "d2h_bytes_per_step": int(pin_out.numel() * 4), "steps": e2e_steps,
+                    "api": "dspnet_b200.MultiBoxDetection on pinned host tensors, result copied back"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "target": tgt,
+        }
+        traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(traffic_path):
+            with open(traffic_path) as f:
+                line["roofline"]["traffic"] = json.load(f).get("det_stream_kernel")
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            v = cpu_baseline(inputs, threads)
+            v1 = cpu_baseline(inputs, 1, repeats=1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                    "sample": "one B=32 SSD-512 detection batch, median of 3 after 1 warm-up, one image "
+                                              "per thread; single thread: %.1f images/s" % v1}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

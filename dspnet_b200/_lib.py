@@ -23,7 +23,7 @@ EXPORTS = (
     "dspmb_version", "dspmb_last_error", "dspmb_set_libm_mode", "dspmb_prior_f32", "dspmb_prior_multi_f32",
     "dspmb_target_workspace_bytes", "dspmb_target_f32", "dspmb_detection_workspace_bytes", "dspmb_detection_f32",
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
-    "dspmb_test_logf",
+    "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32",
 )
 
 
@@ -66,12 +66,17 @@ def lib():
     L.dspmb_detection_workspace_bytes.restype = c_size_t
     L.dspmb_detection_f32.argtypes = [c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, fp, c_float, c_int, c_int,
                                                                      c_void_p, c_void_p, c_size_t, c_void_p]
+    L.dspmb_detection_compact_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.dspmb_status.argtypes = [c_void_p, c_void_p]
     L.dspmb_nms_workspace_bytes.argtypes = [c_int]
     L.dspmb_nms_workspace_bytes.restype = c_size_t
     L.dspmb_nms_f32.argtypes = [c_void_p, c_int, c_int, c_double, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_size_t, c_void_p]
     L.dspmb_nms_host.argtypes = [ip, ip, fp, c_int, c_int, c_float, c_int]
+    L.dspmb_profile_enable.argtypes = [c_int]
+    L.dspmb_profile_read.argtypes = [fp, ip, c_int]
+    L.dspmb_profile_kernel_name.argtypes = [c_int]
+    L.dspmb_profile_kernel_name.restype = ctypes.c_char_p
     L.dspmb_test_expf.argtypes = [c_void_p, c_void_p, c_long, c_void_p]
     L.dspmb_test_logf.argtypes = [c_void_p, c_void_p, c_long, c_void_p]
     for name in EXPORTS:

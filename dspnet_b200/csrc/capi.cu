@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace dspmb {
@@ -35,6 +38,38 @@ static int detect_host_libm_mode() {
 int libm_fma_mode() {
   if (g_libm_mode < 0) g_libm_mode = detect_host_libm_mode();
   return g_libm_mode;
+}
+
+bool g_profile_on = false;
+namespace {
+struct ProfileRecord {
+  int slot;
+  cudaEvent_t begin, end;
+};
+std::mutex g_profile_mutex;
+std::vector<ProfileRecord> g_profile_records;
+const char *const kSlotNames[kNumKernelSlots] = {
+    "prior_kernel",        "det_stream_kernel", "det_sort_kernel", "det_nms_kernel",  "target_stream_kernel",
+    "target_match_kernel", "nms_sort_kernel",   "nms_gather_kernel", "nms_mask_kernel", "nms_scan_kernel",
+    "det_compact_kernel"};
+}  // namespace
+
+void profile_mark(int slot, cudaStream_t stream, bool begin) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  if (begin) {
+    ProfileRecord r;
+    r.slot = slot;
+    cudaEventCreate(&r.begin);
+    cudaEventCreate(&r.end);
+    cudaEventRecord(r.begin, stream);
+    g_profile_records.push_back(r);
+  } else {
+    for (size_t i = g_profile_records.size(); i-- > 0;)
+      if (g_profile_records[i].slot == slot) {
+        cudaEventRecord(g_profile_records[i].end, stream);
+        break;
+      }
+  }
 }
 
 namespace {
@@ -81,6 +116,31 @@ extern "C" int dspmb_status(const void *workspace, void *stream) {
       set_error("device status %d", status);
   }
   return status;
+}
+
+extern "C" int dspmb_profile_enable(int on) {
+  g_profile_on = on != 0;
+  return g_profile_on ? 1 : 0;
+}
+
+extern "C" int dspmb_profile_read(float *ms, int *launches, int max_slots) {
+  std::lock_guard<std::mutex> lock(g_profile_mutex);
+  for (ProfileRecord &r : g_profile_records) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.end) == cudaSuccess && cudaEventElapsedTime(&t, r.begin, r.end) == cudaSuccess &&
+        r.slot < max_slots) {
+      if (ms) ms[r.slot] += t;
+      if (launches) launches[r.slot] += 1;
+    }
+    cudaEventDestroy(r.begin);
+    cudaEventDestroy(r.end);
+  }
+  g_profile_records.clear();
+  return kNumKernelSlots;
+}
+
+extern "C" const char *dspmb_profile_kernel_name(int slot) {
+  return slot >= 0 && slot < kNumKernelSlots ? kSlotNames[slot] : "";
 }
 
 extern "C" int dspmb_test_expf(const float *x, float *y, long n, void *stream) {

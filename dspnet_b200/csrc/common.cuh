@@ -33,6 +33,34 @@ int libm_fma_mode();  // 0 / 1, resolved from dspmb_set_libm_mode / host CPU fla
     }                               \
   } while (0)
 
+// ---- per-kernel event timing (capi.cu) ----------------------------------------------------------------
+enum KernelSlot {
+  kSlotPrior = 0,
+  kSlotDetStream,
+  kSlotDetSort,
+  kSlotDetNms,
+  kSlotTargetStream,
+  kSlotTargetMatch,
+  kSlotNmsSort,
+  kSlotNmsGather,
+  kSlotNmsMask,
+  kSlotNmsScan,
+  kSlotDetCompact,
+  kNumKernelSlots
+};
+extern bool g_profile_on;
+void profile_mark(int slot, cudaStream_t stream, bool begin);
+struct ProfileScope {  // brackets one kernel launch when profiling is enabled
+  int slot;
+  cudaStream_t stream;
+  ProfileScope(int s, cudaStream_t st) : slot(s), stream(st) {
+    if (g_profile_on) profile_mark(slot, stream, true);
+  }
+  ~ProfileScope() {
+    if (g_profile_on) profile_mark(slot, stream, false);
+  }
+};
+
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

@@ -471,10 +471,59 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     }
 }
 
+// Ordered compaction of the surviving rows (id >= 0) of every image into (B, K, 7), padded with -1, plus the
+// per-image count: the `det[:, 0] >= 0` filter every consumer of the op applies on the host
+// (detect/multitask_detector.py:268-271, multi_solver.py:419-432), done on the device so that only K rows per
+// image have to cross NVLink / PCIe.
+__global__ void __launch_bounds__(256) det_compact_kernel(const float *__restrict__ out, const int *__restrict__ valid,
+                                                          int A, int K, float *__restrict__ dst, int *__restrict__ counts) {
+  __shared__ int scan_smem[256 / 32 + 1];
+  __shared__ int carry_smem;
+  const int b = blockIdx.x;
+  const float *src = out + (size_t)b * A * 7;
+  float *d = dst + (size_t)b * K * 7;
+  const int V = valid ? min(valid[b], A) : A;
+  if (threadIdx.x == 0) carry_smem = 0;
+  __syncthreads();
+  for (int base = 0; base < V; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    const int keep = (r < V && src[(size_t)r * 7] >= 0.f) ? 1 : 0;
+    int total;
+    const int ex = block_scan_excl(keep, scan_smem, &total);
+    const int carry = carry_smem;
+    const int pos = carry + ex;
+    if (keep && pos < K) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) d[(size_t)pos * 7 + c] = src[(size_t)r * 7 + c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_smem = carry + total;
+    __syncthreads();
+    if (carry_smem >= K) break;
+  }
+  const int n = min(carry_smem, K);
+  for (int q = n * 7 + threadIdx.x; q < K * 7; q += blockDim.x) d[q] = -1.f;
+  if (threadIdx.x == 0) counts[b] = n;
+}
+
 }  // namespace
 }  // namespace dspmb
 
 using namespace dspmb;
+
+extern "C" int dspmb_detection_compact_f32(const float *out, const int32_t *valid_count, int B, int A, int K,
+                                           float *dst, int32_t *counts, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSPMB_REQUIRE(B >= 0 && A > 0 && K > 0, "detection_compact: bad shape B=%d A=%d K=%d", B, A, K);
+  DSPMB_REQUIRE(out && dst && counts, "detection_compact: NULL tensor");
+  if (B == 0) return DSPMB_OK;
+  {
+    ProfileScope _p(kSlotDetCompact, stream);
+    det_compact_kernel<<<B, 256, 0, stream>>>(out, valid_count, A, K, dst, counts);
+  }
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}
 
 extern "C" size_t dspmb_detection_workspace_bytes(int B, int A, int C) {
   if (B <= 0 || A <= 0 || C <= 0) return 0;
@@ -523,10 +572,13 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.vh = variances[3];
   sa.fma_build = libm_fma_mode();
   dim3 grid1(T, B);
-  if (vec4)
+  {
+    ProfileScope _p(kSlotDetStream, stream);
+    if (vec4)
     det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
   else
     det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
   SortArgs so;
@@ -557,7 +609,10 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  det_sort_kernel<<<B, kSortThreads, smem2, stream>>>(so);
+  {
+    ProfileScope _p(kSlotDetSort, stream);
+    det_sort_kernel<<<B, kSortThreads, smem2, stream>>>(so);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
   if (nms_threshold > 0.f && nms_threshold <= 1.f) {
@@ -574,7 +629,10 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.force_suppress = force_suppress;
     dim3 grid3(force_suppress ? 1 : (C > 1 ? C - 1 : 1), B);
     if (C > 1 || force_suppress) {
-      det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
+      {
+    ProfileScope _p(kSlotDetNms, stream);
+    det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
+  }
       DSPMB_CUDA_TRY(cudaGetLastError());
     }
   }

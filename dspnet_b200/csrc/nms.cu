@@ -234,19 +234,31 @@ extern "C" int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, i
   if (!presorted) {
     const int npad = next_pow2(N < 2 ? 2 : N);
     const size_t smem = npad <= kSortSmemKeys ? sizeof(unsigned long long) * npad : 0;
+    {
+    ProfileScope _p(kSlotNmsSort, stream);
     nms_sort_kernel<<<1, kSortThreads, smem, stream>>>(dets, N, dim, npad, w.keys, w.order);
+  }
     DSPMB_CUDA_TRY(cudaGetLastError());
     order = w.order;
   }
-  nms_gather_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(dets, N, dim, class_col, order, w.box, w.area, w.cls);
+  {
+    ProfileScope _p(kSlotNmsGather, stream);
+    nms_gather_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(dets, N, dim, class_col, order, w.box, w.area, w.cls);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
   dim3 grid(W, W);
-  if (class_col >= 0)
+  {
+    ProfileScope _p(kSlotNmsMask, stream);
+    if (class_col >= 0)
     nms_mask_kernel<true><<<grid, 64, 0, stream>>>(N, W, thresh, mode, w.box, w.area, w.cls, w.mask);
   else
     nms_mask_kernel<false><<<grid, 64, 0, stream>>>(N, W, thresh, mode, w.box, w.area, w.cls, w.mask);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
-  nms_scan_kernel<<<1, kScanThreads, sizeof(unsigned long long) * W, stream>>>(N, W, w.mask, order, keep, num_keep);
+  {
+    ProfileScope _p(kSlotNmsScan, stream);
+    nms_scan_kernel<<<1, kScanThreads, sizeof(unsigned long long) * W, stream>>>(N, W, w.mask, order, keep, num_keep);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
 }

@@ -103,7 +103,10 @@ int launch(const PriorParams &p, float *out, cudaStream_t stream) {
   const int threads = 256;
   int blocks = ceil_div(p.total_anchors, threads);
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  prior_kernel<<<blocks, threads, 0, stream>>>(p, reinterpret_cast<float4 *>(out));
+  {
+    ProfileScope _p(kSlotPrior, stream);
+    prior_kernel<<<blocks, threads, 0, stream>>>(p, reinterpret_cast<float4 *>(out));
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
 }

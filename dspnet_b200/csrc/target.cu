@@ -628,12 +628,18 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     attr_set = true;
   }
   dim3 grid1(ta.T, B);
-  if (vec4)
+  {
+    ProfileScope _p(kSlotTargetStream, stream);
+    if (vec4)
     target_stream_kernel<4><<<grid1, kStreamThreads, smem1, stream>>>(ta);
   else
     target_stream_kernel<1><<<grid1, kStreamThreads, smem1, stream>>>(ta);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
-  target_match_kernel<<<B, kMatchThreads, smem2, stream>>>(ta);
+  {
+    ProfileScope _p(kSlotTargetMatch, stream);
+    target_match_kernel<<<B, kMatchThreads, smem2, stream>>>(ta);
+  }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
 }

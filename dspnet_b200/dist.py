@@ -1,0 +1,139 @@
+"""Image-sharded multi-GPU execution of the multibox path (one process per GPU, torch.distributed).
+
+Every image is independent in all three operators (per-image loops at operator/multibox_target.cc:92 and
+multibox_detection.cc:74), so a batch is partitioned into contiguous image slices, one per rank, with the anchors
+replicated (regenerated locally by the prior kernel -- no broadcast).  There is no collective on the data path;
+the single exchange step is the all-gather of what the consumers read back on the host in the reference:
+the surviving detection rows (``det[:, 0] >= 0``, detect/multitask_detector.py:268-271) and the per-image target
+statistics (what train/metric.py:35-46 reduces).  Training targets themselves stay on the GPU that owns the image.
+
+``shard_slice`` / ``ShardedMultiBox`` are backend-agnostic host logic (tested on CPU with gloo, world_size 2, with
+the oracle injected as the compute provider); ``DetectionGatherer`` is the CUDA/NCCL pipeline bench.py uses:
+compaction kernel on the compute stream -> all_gather_into_tensor on a side stream, double buffered, so the
+collective of step i overlaps the kernels of step i+1.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_slice(batch, world, rank):
+    """Contiguous image slice [begin, end) of `rank`; the first ``batch % world`` ranks get one extra image."""
+    base, extra = divmod(batch, world)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+class ShardedMultiBox:
+    """Runs MultiBoxTarget / MultiBoxDetection on this rank's image slice and gathers the small results.
+
+    ops: object with ``MultiBoxTarget`` and ``MultiBoxDetection`` callables (default: the CUDA operators of this
+    package).  group: torch.distributed process group (default: WORLD).
+    """
+
+    def __init__(self, ops=None, group=None):
+        if ops is None:
+            from . import ops as _ops
+            ops = _ops
+        self.ops = ops
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def local(self, batch):
+        return shard_slice(batch, self.world, self.rank)
+
+    def _gather_rows(self, local, batch):
+        """All-gather per-image rows whose slice sizes may differ by one across ranks."""
+        if self.world == 1:
+            return local
+        sizes = [shard_slice(batch, self.world, r) for r in range(self.world)]
+        widest = max(e - b for b, e in sizes)
+        pad = torch.zeros((widest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[: local.shape[0]] = local
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        return torch.cat([p[: e - b] for p, (b, e) in zip(parts, sizes)], dim=0)
+
+    def detection(self, cls_prob, loc_pred, anchor, max_rows, **params):
+        """cls_prob / loc_pred hold the FULL batch (only this rank's slice is read).  Returns
+        (rows (B, max_rows, 7), counts (B,)) for the whole batch on every rank, plus this rank's full output."""
+        batch = cls_prob.shape[0]
+        b, e = self.local(batch)
+        out = self.ops.MultiBoxDetection(cls_prob[b:e], loc_pred[b:e], anchor, **params)
+        out_t = torch.as_tensor(out)
+        rows, counts = compact_rows(out_t, max_rows)
+        return self._gather_rows(rows, batch), self._gather_rows(counts, batch), out
+
+    def target(self, anchor, label, cls_pred, **params):
+        """Returns this rank's [loc_target, loc_mask, cls_target] and the gathered per-image statistics
+        (B, 3): [num_positive, num_negative, num_ignored] as train/metric.py derives them from cls_target."""
+        batch = label.shape[0]
+        b, e = self.local(batch)
+        outs = self.ops.MultiBoxTarget(anchor, label[b:e], cls_pred[b:e], **params)
+        ct = torch.as_tensor(outs[2])
+        ignore = params.get("ignore_label", -1.0)
+        stats = torch.stack([(ct > 0).sum(1), (ct == 0).sum(1), (ct == ignore).sum(1)], dim=1).to(torch.int32)
+        return outs, self._gather_rows(stats, batch)
+
+
+def compact_rows(out, max_rows):
+    """Surviving rows (id >= 0) of every image in row order, at most max_rows, padded with -1, and their counts.
+    CUDA tensors go through the det_compact kernel; host tensors (gloo tests) through torch indexing."""
+    B, A, _ = out.shape
+    if out.is_cuda:
+        rows = torch.empty((B, max_rows, 7), dtype=torch.float32, device=out.device)
+        counts = torch.empty((B,), dtype=torch.int32, device=out.device)
+        with torch.cuda.device(out.device):
+            _lib.check(_lib.lib().dspmb_detection_compact_f32(
+                out.data_ptr(), None, B, A, max_rows, rows.data_ptr(), counts.data_ptr(),
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return rows, counts
+    rows = torch.full((B, max_rows, 7), -1.0, dtype=torch.float32)
+    counts = torch.zeros((B,), dtype=torch.int32)
+    for i in range(B):
+        keep = out[i][out[i, :, 0] >= 0][:max_rows]
+        rows[i, : keep.shape[0]] = keep
+        counts[i] = keep.shape[0]
+    return rows, counts
+
+
+class DetectionGatherer:
+    """Double-buffered compaction + NCCL all-gather of the detections, overlapped with the next step's kernels."""
+
+    launches_per_submit = 1  # det_compact_kernel (the NCCL kernel is not ours)
+
+    def __init__(self, batch, anchors, max_rows, device, world, group=None):
+        self.B, self.A, self.K, self.device, self.world, self.group = batch, anchors, max_rows, device, world, group
+        self.lib = _lib.lib()
+        self.comm = torch.cuda.Stream(device)
+        self.rows = [torch.empty((batch, max_rows, 7), dtype=torch.float32, device=device) for _ in range(2)]
+        self.counts = [torch.empty((batch,), dtype=torch.int32, device=device) for _ in range(2)]
+        self.all_rows = [torch.empty((world * batch, max_rows, 7), dtype=torch.float32, device=device) for _ in range(2)]
+        self.all_counts = [torch.empty((world * batch,), dtype=torch.int32, device=device) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.done = [None, None]
+
+    def submit(self, out, step):
+        s = step & 1
+        compute = torch.cuda.current_stream(self.device)
+        if self.done[s] is not None:
+            compute.wait_event(self.done[s])  # the previous collective on this buffer has consumed it
+        _lib.check(self.lib.dspmb_detection_compact_f32(out.data_ptr(), None, self.B, self.A, self.K,
+                                                        self.rows[s].data_ptr(), self.counts[s].data_ptr(),
+                                                        ctypes.c_void_p(compute.cuda_stream)))
+        self.ready[s].record(compute)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(self.ready[s])
+            dist.all_gather_into_tensor(self.all_rows[s], self.rows[s], group=self.group)
+            dist.all_gather_into_tensor(self.all_counts[s], self.counts[s], group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+            self.done[s] = ev
+        return self.all_rows[s], self.all_counts[s]
+
+    def drain(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.comm)

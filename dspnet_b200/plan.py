@@ -1,0 +1,80 @@
+"""Pre-marshalled, allocation-free execution plans for the two batched operators.
+
+``ops.MultiBoxDetection`` / ``ops.MultiBoxTarget`` validate, allocate outputs and marshal ~20 ctypes arguments on
+every call, which costs more host time than the kernels take on a B200.  A plan does that once for a fixed
+(B, A, C[, L]) and parameter set: ``run()`` is a single C-ABI call on the current stream, so it can sit in a
+launch-bound loop or be captured into a CUDA graph (``capture()``).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class DetectionPlan:
+    """MultiBoxDetection (operator/multibox_detection-inl.h:47-72 parameters) for fixed shapes."""
+
+    def __init__(self, B, A, C, device, clip=True, threshold=0.01, nms_threshold=0.5, force_suppress=False,
+                 variances=(0.1, 0.1, 0.2, 0.2), nms_topk=-1, want_valid_count=False):
+        self.B, self.A, self.C, self.device = B, A, C, device
+        self.lib = _lib.lib()
+        with torch.cuda.device(device):
+            self.ws = torch.empty(max(self.lib.dspmb_detection_workspace_bytes(B, A, C), 256), dtype=torch.uint8,
+                                  device=device)
+        self.valid = torch.empty((B,), dtype=torch.int32, device=device) if want_valid_count else None
+        self._var = _lib.float_array(variances)
+        self._tail = (B, A, C, float(threshold), int(bool(clip)), self._var, float(nms_threshold),
+                      int(bool(force_suppress)), int(nms_topk), _ptr(self.valid), _ptr(self.ws), self.ws.numel())
+        self.launches_per_run = 3 if 0 < nms_threshold <= 1 else 2
+
+    def new_output(self):
+        return torch.empty((self.B, self.A, 7), dtype=torch.float32, device=self.device)
+
+    def run(self, cls_prob, loc_pred, anchor, out, stream=None):
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = self.lib.dspmb_detection_f32(cls_prob.data_ptr(), loc_pred.data_ptr(), anchor.data_ptr(), out.data_ptr(),
+                                          *self._tail, s)
+        if rc:
+            _lib.check(rc)
+        return out
+
+
+class TargetPlan:
+    """MultiBoxTarget (operator/multibox_target-inl.h:59-80 parameters) for fixed shapes."""
+
+    def __init__(self, B, A, L, C, device, overlap_threshold=0.5, ignore_label=-1.0, negative_mining_ratio=-1.0,
+                 negative_mining_thresh=0.5, minimum_negative_samples=0, variances=(0.1, 0.1, 0.2, 0.2),
+                 label_width=6, want_stats=True):
+        self.B, self.A, self.L, self.C, self.device = B, A, L, C, device
+        self.lib = _lib.lib()
+        with torch.cuda.device(device):
+            self.ws = torch.empty(max(self.lib.dspmb_target_workspace_bytes(B, A, L, C), 256), dtype=torch.uint8,
+                                  device=device)
+        self.stats = torch.zeros((B, 4), dtype=torch.int32, device=device) if want_stats else None
+        self._var = _lib.float_array(variances)
+        self._tail = (B, A, L, int(label_width), C, float(overlap_threshold), float(ignore_label),
+                      float(negative_mining_ratio), float(negative_mining_thresh), int(minimum_negative_samples),
+                      self._var, None, _ptr(self.stats), _ptr(self.ws), self.ws.numel())
+        self.launches_per_run = 2  # + one memset node
+
+    def new_outputs(self):
+        d = self.device
+        return (torch.empty((self.B, self.A * 5), dtype=torch.float32, device=d),
+                torch.empty((self.B, self.A * 5), dtype=torch.float32, device=d),
+                torch.empty((self.B, self.A), dtype=torch.float32, device=d))
+
+    def run(self, anchor, label, cls_pred, outs, stream=None):
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        rc = self.lib.dspmb_target_f32(anchor.data_ptr(), label.data_ptr(), cls_pred.data_ptr(), outs[0].data_ptr(),
+                                       outs[1].data_ptr(), outs[2].data_ptr(), *self._tail, s)
+        if rc:
+            _lib.check(rc)
+        return outs
+
+    def status(self):
+        _lib.check(self.lib.dspmb_status(_ptr(self.ws), ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))

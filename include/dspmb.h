@@ -102,6 +102,13 @@ int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const floa
                         int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* Ordered compaction of the surviving detections: for every image the rows of `out` (B,A,7) with id >= 0, in
+ * row order, at most K of them, into dst (B,K,7) (padded with -1) and their number into counts (B) -- the
+ * `det[:,0] >= 0` filter of detect/multitask_detector.py:268-271 / multi_solver.py:419-432, on the device.
+ * valid_count (B) optional: rows at and beyond it are known to be empty and are not scanned. */
+int dspmb_detection_compact_f32(const float *out, const int32_t *valid_count, int B, int A, int K, float *dst,
+                                int32_t *counts, void *stream);
+
 /* Synchronises `stream` and returns the data-dependent status latched by the last target/detection call
  * that used `workspace` (0 or a DSPMB_ERR_* code). */
 int dspmb_status(const void *workspace, void *stream);
@@ -126,6 +133,17 @@ int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, int mode, in
  * device_id, strict-greater rule.  keep_out receives sorted positions. */
 int dspmb_nms_host(int *keep_out, int *num_out, const float *boxes_host, int boxes_num, int boxes_dim,
                    float nms_overlap_thresh, int device_id);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Per-kernel timing (used by bench.py for the roofline line).  While enabled, every kernel the library launches
+ * is bracketed by a cudaEvent pair recorded on the launching stream.  dspmb_profile_read synchronises those
+ * events, adds the elapsed milliseconds and launch counts per kernel slot into ms[] / launches[] (up to
+ * max_slots entries), clears the record list and returns the number of slots.  Slot names come from
+ * dspmb_profile_kernel_name.  Not for use inside CUDA graph capture.
+ * ------------------------------------------------------------------------------------------------- */
+int dspmb_profile_enable(int on);
+int dspmb_profile_read(float *ms, int *launches, int max_slots);
+const char *dspmb_profile_kernel_name(int slot);
 
 /* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same
  * glibc-compatible routines the kernels use.  x, y device pointers. */

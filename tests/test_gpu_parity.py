@@ -166,15 +166,17 @@ def test_target_adversarial_matching(oracle, cuda):
     maxima; quantised logits create probability ties at the mining cut."""
     anchors, lab, cp = util.target_inputs(oracle, "ssd300", 4, config_id=23)
     lab[0, 1] = lab[0, 0]                       # exact duplicate gt
-    lab[0, 2, 1:5] = lab[0, 0, 1:5] + 1e-3      # near duplicate
+    lab[0, 2] = lab[0, 0]
+    lab[0, 2, 1:5] += 1e-3                      # near duplicate
     lab[3, :6] = lab[3, 0]                      # six identical gts
     lab[3, :6, 0] = np.arange(6)
     cp = (np.round(cp * 2) / 2).astype(np.float32)  # heavy ties in the softmax probabilities
     _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
     # tiny gts that overlap no anchor above 1e-6 and gts outside the image
     lab2 = lab.copy()
-    lab2[1, 0, 1:5] = (0.5, 0.5, 0.5, 0.5)
-    lab2[0, 3, 1:5] = (0.2, 0.2, 0.2000001, 0.2000001)
+    lab2[0, 0, 1:5] = (0.5, 0.5, 0.5, 0.5)      # zero-area gt: IoU 0 with every anchor
+    lab2[3, 1, 1:5] = (0.2, 0.2, 0.2000001, 0.2000001)
+    lab2[3, 2, 1:5] = (1.5, 1.5, 1.9, 1.9)      # outside the image
     _check_target(oracle, cuda, anchors, lab2, cp, negative_mining_ratio=3)
 
 
