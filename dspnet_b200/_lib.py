@@ -17,13 +17,14 @@ ERR_MINING_CANDIDATES = -3
 ERR_MINING_THRESH = -4
 ERR_WORKSPACE = -5
 ERR_CUDA = -6
+TUNE_DET_BUCKET_CLASSES, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS = range(4)
 
 # every symbol include/dspmb.h declares (tests check that the built library exports all of them)
 EXPORTS = (
     "dspmb_version", "dspmb_last_error", "dspmb_set_libm_mode", "dspmb_prior_f32", "dspmb_prior_multi_f32",
     "dspmb_target_workspace_bytes", "dspmb_target_f32", "dspmb_detection_workspace_bytes", "dspmb_detection_f32",
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
-    "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32",
+    "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32", "dspmb_set_tuning",
 )
 
 
@@ -67,6 +68,7 @@ def lib():
     L.dspmb_detection_f32.argtypes = [c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, fp, c_float, c_int, c_int,
                                                                      c_void_p, c_void_p, c_size_t, c_void_p]
     L.dspmb_detection_compact_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.dspmb_set_tuning.argtypes = [c_int, c_int]
     L.dspmb_status.argtypes = [c_void_p, c_void_p]
     L.dspmb_nms_workspace_bytes.argtypes = [c_int]
     L.dspmb_nms_workspace_bytes.restype = c_size_t

@@ -35,6 +35,10 @@ static int detect_host_libm_mode() {
 #endif
 }
 
+static int g_tuning[4] = {256, 512, 2048, 8192};
+static const int kTuningMax[4] = {256, 512, 2048, 8192};
+int tuning(int knob) { return g_tuning[knob]; }
+
 int libm_fma_mode() {
   if (g_libm_mode < 0) g_libm_mode = detect_host_libm_mode();
   return g_libm_mode;
@@ -93,6 +97,13 @@ extern "C" const char *dspmb_last_error(void) { return g_error; }
 extern "C" int dspmb_set_libm_mode(int mode) {
   g_libm_mode = mode < 0 ? detect_host_libm_mode() : (mode ? 1 : 0);
   return g_libm_mode;
+}
+
+extern "C" int dspmb_set_tuning(int knob, int value) {
+  if (knob < 0 || knob >= 4) return -1;
+  const int old = g_tuning[knob];
+  g_tuning[knob] = value < 0 ? 0 : (value > kTuningMax[knob] ? kTuningMax[knob] : value);
+  return old;
 }
 
 extern "C" int dspmb_status(const void *workspace, void *stream) {

@@ -18,6 +18,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
 int libm_fma_mode();  // 0 / 1, resolved from dspmb_set_libm_mode / host CPU flags
+int tuning(int knob);  // current value of a DSPMB_TUNE_* knob
 
 #define DSPMB_CUDA_TRY(expr)                              \
   do {                                                    \

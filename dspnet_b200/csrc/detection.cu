@@ -33,8 +33,11 @@ namespace {
 constexpr int kStreamThreads = 128;
 constexpr int kSortThreads = 1024;
 constexpr int kNmsThreads = 256;
-constexpr int kSortSmemKeys = 16384;  // 128 KB of 64-bit keys
-constexpr int kNmsSmemRows = 2048;    // rows of one NMS segment staged in shared memory
+constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared memory
+constexpr int kKey32SmemMax = 28672;  // anchors whose 32-bit keys fit in shared memory next to the sort keys
+constexpr int kMaxBucketClasses = 256;  // foreground classes the sort kernel can bucket (32 x nclass table)
+constexpr int kNmsMaskRows = 512;     // NMS segments up to this size use the shared-memory bit mask
+constexpr int kNmsSmemRows = 2048;    // rows of a larger NMS segment staged in shared memory
 constexpr int kRecFloats = 8;         // score, id, x1, y1, x2, y2, dist, pad
 
 struct DetWorkspace {
@@ -49,6 +52,7 @@ struct DetWorkspace {
   float4 *seg_box;  // (B, A) spill for segments larger than kNmsSmemRows
   unsigned char *seg_dead;  // (B, A)
   unsigned long long *sort_keys;  // (B, npad) spill for more than kSortSmemKeys candidates
+  unsigned *key32;  // (B, A) spill for the 32-bit order keys
   size_t bytes;
 };
 
@@ -80,7 +84,8 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.seg_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
   w.seg_dead = (unsigned char *)take((size_t)B * A);
   const int npad = next_pow2(A);
-  w.sort_keys = (unsigned long long *)take(npad > kSortSmemKeys ? sizeof(unsigned long long) * (size_t)B * npad : 0);
+  w.sort_keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * npad);
+  w.key32 = (unsigned *)take(A > kKey32SmemMax ? sizeof(unsigned) * (size_t)B * A : 0);
   w.bytes = off;
   return w;
 }
@@ -208,12 +213,12 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
 
 // ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
-// global memory (generic addressing).
+// global memory (generic addressing).  Shared-memory bandwidth bound (32 B per compare-exchange), so it is only
+// used on the <= nms_topk selected keys, or on everything when no top-k limit applies.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int q = threadIdx.x; q < (n >> 1); q += blockDim.x) {
-        // q-th compare-exchange pair of this stage
         const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
         const int hi = lo | j;
         const bool up = (lo & k) == 0;
@@ -228,16 +233,28 @@ __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
   }
 }
 
+// Warp-aggregated shared-memory histogram increment: lanes with the same bin elect one leader.
+__device__ __forceinline__ void hist_add(unsigned *hist, unsigned bin, bool pred) {
+  const unsigned active = __ballot_sync(kFullMask, pred);
+  if (pred) {
+    const unsigned peers = __match_any_sync(active, bin);
+    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+  }
+}
+
 struct SortArgs {
   float *out;
   const int *tile_count;
   const float *rec;
   int *slot_of_rank;
-  int *valid, *nms_rows, *seg_off;
-  unsigned long long *sort_keys;
+  int *valid, *nms_rows, *seg_off, *seg_list;
+  float4 *seg_box;
+  unsigned *key32;                // (B, A) spill when the keys do not fit in shared memory
+  unsigned long long *sort_keys;  // (B, npad) spill for full sorts above kSortSmemKeys
   int *valid_count_out;
   WsHeader *header;
   int A, C, T, Apad, tile, npad_max;
+  int key32_in_smem, sel_cap, nclass, bucket;  // bucket: class lists are produced here (nclass <= kMaxBucketClasses)
   float nms_threshold;
   int force_suppress, nms_topk;
 };
@@ -245,19 +262,26 @@ struct SortArgs {
 __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ int scan_smem[kSortThreads / 32 + 1];
-  __shared__ int carry_smem;
+  __shared__ unsigned hist256[256];
+  __shared__ int carry_smem, sm_need, sm_count;
+  __shared__ unsigned sm_prefix;
   const int b = blockIdx.x;
-  const int T = a.T, tile = a.tile;
-  // dynamic smem: [keys: key_cap u64][tile_off: T+1 int][hist: C+1 int]
-  const int key_cap = min(a.npad_max, kSortSmemKeys);
-  unsigned long long *skeys = reinterpret_cast<unsigned long long *>(dyn_smem);
-  int *tile_off = reinterpret_cast<int *>(skeys + key_cap);
-  int *hist = tile_off + (T + 1);
+  const int T = a.T, tile = a.tile, A = a.A, nclass = a.nclass;
+  // dynamic smem: [sel: sel_cap u64][key32: A u32 (optional)][tile_off: T+1][chist: nclass+1][coff: nclass+1]
+  //               [crun: nclass][table: 32*nclass (if bucket)]
+  unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
+  unsigned *skey = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
+  int *tile_off = reinterpret_cast<int *>(skey + (a.key32_in_smem ? ((A + 3) & ~3) : 0));
+  unsigned *chist = reinterpret_cast<unsigned *>(tile_off + (T + 1));
+  int *coff = reinterpret_cast<int *>(chist + (nclass + 1));
+  int *crun = coff + (nclass + 1);
+  int *table = crun + nclass;
+  unsigned *key32 = a.key32_in_smem ? skey : a.key32 + (size_t)b * A;
   if (b == 0 && threadIdx.x == 0) a.header->status = DSPMB_OK;
 
   // 1. exclusive prefix over the tile counts -> rank of every record in anchor order
   if (threadIdx.x == 0) carry_smem = 0;
-  for (int c = threadIdx.x; c <= a.C; c += blockDim.x) hist[c] = 0;
+  for (int c = threadIdx.x; c <= nclass; c += blockDim.x) chist[c] = 0;
   __syncthreads();
   const int *cnt = a.tile_count + (size_t)b * T;
   for (int base = 0; base < T; base += blockDim.x) {
@@ -282,65 +306,185 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   if (V == 0) return;
   __syncthreads();
 
-  // 2. rank -> slot map and sort keys
-  int npad = 2;
-  while (npad < V) npad <<= 1;
-  unsigned long long *keys = npad <= key_cap ? skeys : a.sort_keys + (size_t)b * a.npad_max;
+  // 2. rank -> slot map and 32-bit order keys (ascending key == descending score)
   const float *rec = a.rec + (size_t)b * a.Apad * kRecFloats;
   int *slot_of_rank = a.slot_of_rank + (size_t)b * a.Apad;
+  const bool per_class = do_sort && !a.force_suppress;
   for (int slot = threadIdx.x; slot < T * tile; slot += blockDim.x) {
     const int t = slot / tile, r = slot - t * tile;
     const int first = tile_off[t];
     if (r < tile_off[t + 1] - first) {
       const int p = first + r;
       slot_of_rank[p] = slot;
-      if (do_sort) {
-        const float score = rec[(size_t)slot * kRecFloats];
-        keys[p] = ((unsigned long long)(~float_order_key(score)) << 32) | (unsigned)p;
-      }
+      key32[p] = ~float_order_key(rec[(size_t)slot * kRecFloats]);
     }
   }
+  for (int c = threadIdx.x; c < nclass; c += blockDim.x) crun[c] = 0;
+  __syncthreads();
+
+  // 3. the nkeep best keys, sorted (stable_sort + top-k of multibox_detection.cc:132-151)
   int nkeep = 0;
+  unsigned long long *sel = ssel;
   if (do_sort) {
-    for (int p = V + threadIdx.x; p < npad; p += blockDim.x) keys[p] = ~0ull;
-    __syncthreads();
-    bitonic_sort_u64(keys, npad);  // ends with __syncthreads()
     nkeep = V;
-    if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;  // multibox_detection.cc:142-145
+    if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;
+    int npad = 2;
+    while (npad < nkeep) npad <<= 1;
+    if (npad > a.sel_cap) sel = a.sort_keys + (size_t)b * a.npad_max;
+    if (nkeep == V) {
+      for (int p = threadIdx.x; p < npad; p += blockDim.x)
+        sel[p] = p < V ? (((unsigned long long)key32[p] << 32) | (unsigned)p) : ~0ull;
+      __syncthreads();
+    } else {
+      // MSB-first radix select of the nkeep-th smallest key, then an anchor-ordered tie pass
+      if (threadIdx.x == 0) {
+        sm_prefix = 0u;
+        sm_need = nkeep;
+        sm_count = 0;
+        carry_smem = 0;
+      }
+      for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist256[i] = 0u;
+        __syncthreads();
+        const unsigned prefix = sm_prefix;
+        for (int base = 0; base < V; base += blockDim.x) {
+          const int p = base + threadIdx.x;
+          const unsigned kv = p < V ? key32[p] : 0u;
+          hist_add(hist256, (kv >> shift) & 0xffu, p < V && (kv & mask) == prefix);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          const int need = sm_need;
+          unsigned acc = 0;
+          int d = 0;
+          for (; d < 255; ++d) {
+            if ((int)(acc + hist256[d]) >= need) break;
+            acc += hist256[d];
+          }
+          sm_need = need - (int)acc;
+          sm_prefix = prefix | ((unsigned)d << shift);
+        }
+        __syncthreads();
+      }
+      const unsigned pivot = sm_prefix;
+      const int need_eq = sm_need;
+      for (int base = 0; base < V; base += blockDim.x) {
+        const int p = base + threadIdx.x;
+        const unsigned kv = p < V ? key32[p] : 0xffffffffu;
+        const int eq = (p < V && kv == pivot) ? 1 : 0;
+        int total;
+        const int ex = block_scan_excl(eq, scan_smem, &total);
+        const int carry = carry_smem;
+        const bool take = p < V && (kv < pivot || (eq && carry + ex < need_eq));
+        // any slot order will do: the 64-bit keys are unique and get sorted next
+        const unsigned tb = __ballot_sync(kFullMask, take);
+        int wbase = 0;
+        if (lane_id() == 0 && tb) wbase = atomicAdd(&sm_count, __popc(tb));
+        wbase = __shfl_sync(kFullMask, wbase, 0);
+        if (take) sel[wbase + __popc(tb & ((1u << lane_id()) - 1u))] = ((unsigned long long)kv << 32) | (unsigned)p;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_smem = carry + total;
+        __syncthreads();
+      }
+      for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
+      __syncthreads();
+    }
+    bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
   } else {
     __syncthreads();
   }
 
-  // 3. emit the V rows: sorted head [0, nkeep), anchor-ordered tail [nkeep, V) (multibox_detection.cc:146-151)
-  float *out = a.out + (size_t)b * a.A * 7;
-  for (int r = threadIdx.x; r < V; r += blockDim.x) {
-    const int p = r < nkeep ? (int)(unsigned)(keys[r] & 0xffffffffull) : r;
-    const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)slot_of_rank[p] * kRecFloats);
-    const float4 s0 = src[0], s1 = src[1];
-    float *o = out + (size_t)r * 7;
-    o[0] = s0.y;  // id
-    o[1] = s0.x;  // score
-    o[2] = s0.z;
-    o[3] = s0.w;
-    o[4] = s1.x;
-    o[5] = s1.y;
-    o[6] = s1.z;
-    if (do_sort && !a.force_suppress) atomicAdd(&hist[(int)s0.y], 1);
+  // 4. the V output rows are the sorted head [0, nkeep) followed by the anchor-ordered tail [nkeep, V)
+  //    (multibox_detection.cc:146-151): candidates of the head whose rank is >= nkeep appear twice, unselected
+  //    candidates of rank < nkeep not at all.  First sweep: record slot of every row (reusing the key array) and
+  //    the class histogram of the ROWS -> class segment offsets for the NMS launch.
+  int *row_slot = reinterpret_cast<int *>(key32);
+  for (int base = 0; base < V; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    unsigned cls = 0;
+    int slot = 0;
+    if (r < V) {
+      const int p = r < nkeep ? (int)(unsigned)(sel[r] & 0xffffffffull) : r;
+      slot = slot_of_rank[p];
+      cls = (unsigned)rec[(size_t)slot * kRecFloats + 1];
+    }
+    if (r < V) row_slot[r] = slot;
+    if (per_class) hist_add(chist, cls, r < V);
   }
   __syncthreads();
-  // 4. class segment offsets for the NMS launch
-  if (threadIdx.x == 0 && do_sort) {
+  if (threadIdx.x == 0) {
     int *so = a.seg_off + (size_t)b * (a.C + 1);
-    int acc = 0;
-    if (a.force_suppress) {
+    if (!per_class) {
+      coff[0] = 0;
       so[0] = 0;
-      so[1] = V;
+      so[1] = do_sort ? V : 0;
     } else {
-      for (int c = 0; c < a.C; ++c) {
+      int acc = 0;
+      for (int c = 0; c < nclass; ++c) {
+        coff[c] = acc;
         so[c] = acc;
-        acc += hist[c];
+        acc += (int)chist[c];
       }
-      so[a.C] = acc;
+      so[nclass] = acc;
+    }
+  }
+  __syncthreads();
+  // Second sweep, in row order: write the rows and the stable per-class row lists + boxes.
+  float *out = a.out + (size_t)b * A * 7;
+  int *seg_list = a.seg_list + (size_t)b * A;
+  float4 *seg_box = a.seg_box + (size_t)b * A;
+  const bool bucket = per_class && a.bucket;
+  const unsigned warp = warp_id(), lane = lane_id();
+  for (int base = 0; base < V; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    const bool live = r < V;
+    unsigned cls = 0;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)row_slot[r] * kRecFloats);
+      const float4 s0 = src[0], s1 = src[1];
+      float *o = out + (size_t)r * 7;
+      o[0] = s0.y;  // id
+      o[1] = s0.x;  // score
+      o[2] = s0.z;
+      o[3] = s0.w;
+      o[4] = s1.x;
+      o[5] = s1.y;
+      o[6] = s1.z;
+      cls = (unsigned)s0.y;
+      box = make_float4(s0.z, s0.w, s1.x, s1.y);
+    }
+    if (do_sort && a.force_suppress) {
+      if (live) seg_box[r] = box;
+    } else if (bucket) {
+      for (int i = threadIdx.x; i < 32 * nclass; i += blockDim.x) table[i] = 0;
+      __syncthreads();
+      const unsigned active = __ballot_sync(kFullMask, live);
+      int rank_w = 0;
+      if (live) {
+        const unsigned peers = __match_any_sync(active, cls);
+        rank_w = __popc(peers & ((1u << lane) - 1u));
+        if ((int)lane == __ffs(peers) - 1) table[warp * nclass + cls] = __popc(peers);
+      }
+      __syncthreads();
+      for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        int run = crun[c];
+        for (int w = 0; w < 32; ++w) {
+          const int t = table[w * nclass + c];
+          table[w * nclass + c] = run;
+          run += t;
+        }
+        crun[c] = run;
+      }
+      __syncthreads();
+      if (live) {
+        const int pos = coff[cls] + table[warp * nclass + cls] + rank_w;
+        seg_list[pos] = r;
+        seg_box[pos] = box;
+      }
+      __syncthreads();
     }
   }
 }
@@ -353,13 +497,25 @@ struct NmsArgs {
   unsigned char *seg_dead;
   int A, C;
   float nms_threshold;
-  int force_suppress;
+  int force_suppress, lists_ready, mask_rows, smem_rows;
 };
 
+// IoU >= thr test of multibox_detection.cc:44-51,162 with an exact early-out: disjoint boxes have i = 0, hence
+// iou = 0 < thr (thr > 0 whenever NMS runs), so the IEEE division is only paid for overlapping pairs.
+__device__ __forceinline__ bool suppresses(float4 a, float4 b, float thr) {
+  const float w = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
+  const float h = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
+  if (!(w > 0.f) || !(h > 0.f)) return false;
+  const float i = fmul(w, h);
+  const float u = fsub(fadd(fmul(fsub(a.z, a.x), fsub(a.w, a.y)), fmul(fsub(b.z, b.x), fsub(b.w, b.y))), i);
+  return (u <= 0.f ? 0.f : fdiv(i, u)) >= thr;
+}
+
 __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
-  __shared__ float4 sm_box[kNmsSmemRows];
-  __shared__ unsigned char sm_dead[kNmsSmemRows];
-  __shared__ unsigned long long sm_word[64];
+  // shared memory is a union of the two paths:
+  //   small (n <= kNmsMaskRows):  boxes[512] float4 (8 KB) + mask[512 * 8] u64 (32 KB)
+  //   large:                      boxes[2048] float4 (32 KB) + dead[2048] (2 KB) + 64 words
+  __shared__ __align__(16) unsigned char smem_raw[40 * 1024 + 1024];
   __shared__ unsigned sm_deadbits[2];
   __shared__ unsigned long long sm_alive, sm_deadmask;
   __shared__ int scan_smem[kNmsThreads / 32 + 1];
@@ -374,9 +530,13 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   if (n < 2) return;
   float *out = a.out + (size_t)b * a.A * 7;
   int *list = a.seg_list + (size_t)b * a.A + seg_base;
+  float4 *gbox = a.seg_box + (size_t)b * a.A + seg_base;
+  const bool identity = a.force_suppress != 0;  // single segment: row q is list entry q
+  const float thr = a.nms_threshold;
+  const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
 
-  // ---- ordered member list of this class (row order == NMS order) ----
-  if (!a.force_suppress) {
+  if (!a.lists_ready && !identity) {
+    // fallback (more classes than the sort kernel buckets): ordered member list by scanning the rows
     if (threadIdx.x == 0) carry_smem = 0;
     __syncthreads();
     const float cls = (float)seg;
@@ -386,31 +546,87 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
       int total;
       const int ex = block_scan_excl(hit, scan_smem, &total);
       const int carry = carry_smem;
-      if (hit) list[carry + ex] = r;
+      if (hit) {
+        const float *row = out + (size_t)r * 7;
+        list[carry + ex] = r;
+        gbox[carry + ex] = make_float4(row[2], row[3], row[4], row[5]);
+      }
       __syncthreads();
       if (threadIdx.x == 0) carry_smem = carry + total;
       __syncthreads();
     }
   }
+
+  if (n <= a.mask_rows) {
+    // ---------------- small segment: full bit mask in shared memory + word-serial resolve ----------------
+    float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kNmsMaskRows * sizeof(float4));
+    const int W = (n + 63) >> 6;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = gbox[q];
+    __syncthreads();
+    // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  Rows of a warp share the column being tested,
+    // so the column box is a shared-memory broadcast.
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float4 bi = boxes[i];
+      for (int w = 0; w < W; ++w) {
+        unsigned long long bits = 0ull;
+        const int j0 = max(w << 6, i + 1), j1 = min(n, (w + 1) << 6);
+        for (int j = j0; j < j1; ++j)
+          if (suppresses(bi, boxes[j], thr)) bits |= 1ull << (j & 63);
+        mask[i * W + w] = bits;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane w owns word w of the removed set; chunk c is resolved serially on its diagonal words (every lane
+      // redundantly, from broadcast reads), then the rows of its survivors are OR-ed into the later words.
+      unsigned long long remv = 0ull;
+      for (int c = 0; c < W; ++c) {
+        unsigned long long cur = __shfl_sync(kFullMask, remv, c);
+        unsigned long long alive = 0ull;
+        const int m = min(64, n - (c << 6));
+        for (int t = 0; t < m; ++t)
+          if (!((cur >> t) & 1ull)) {
+            alive |= 1ull << t;
+            cur |= mask[((c << 6) + t) * W + c];
+          }
+        if ((int)lane == c) remv = cur;
+        if ((int)lane > c && (int)lane < W) {
+          unsigned long long acc = 0ull, rem = alive;
+          while (rem) {
+            const int t = __ffsll((long long)rem) - 1;
+            rem &= rem - 1;
+            acc |= mask[((c << 6) + t) * W + lane];
+          }
+          remv |= acc;
+        }
+      }
+      // suppressed rows: only the id field is overwritten (multibox_detection.cc:163)
+      for (int w = 0; w < W; ++w) {
+        const unsigned long long word = __shfl_sync(kFullMask, remv, w);
+        for (int half = 0; half < 2; ++half) {
+          const int q = (w << 6) + half * 32 + lane;
+          if (q < n && ((word >> (half * 32 + lane)) & 1ull)) out[(size_t)(identity ? q : list[q]) * 7] = -1.f;
+        }
+      }
+    }
+    return;
+  }
+
+  // ---------------- large segment: 64-row chunks, ballot mask + serial resolve + parallel sweep ----------------
   float4 *boxes;
   unsigned char *dead;
-  if (n <= kNmsSmemRows) {
-    boxes = sm_box;
-    dead = sm_dead;
+  unsigned long long *sm_word = reinterpret_cast<unsigned long long *>(smem_raw + 34 * 1024);
+  if (n <= a.smem_rows) {
+    boxes = reinterpret_cast<float4 *>(smem_raw);
+    dead = smem_raw + 32 * 1024;
+    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = gbox[q];
   } else {
-    boxes = a.seg_box + (size_t)b * a.A + seg_base;
+    boxes = gbox;
     dead = a.seg_dead + (size_t)b * a.A + seg_base;
   }
-  for (int q = threadIdx.x; q < n; q += blockDim.x) {
-    const int r = a.force_suppress ? q : list[q];
-    const float *row = out + (size_t)r * 7;
-    boxes[q] = make_float4(row[2], row[3], row[4], row[5]);
-    dead[q] = 0;
-  }
+  for (int q = threadIdx.x; q < n; q += blockDim.x) dead[q] = 0;
   __syncthreads();
-
-  const float thr = a.nms_threshold;
-  const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
   for (int c0 = 0; c0 < n; c0 += 64) {
     const int m = min(64, n - c0);
     // (1) 64x64 upper-triangular suppression mask of the chunk, one row per warp iteration
@@ -424,8 +640,8 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
       if (!dead[c0 + i]) {
         const float4 bi = boxes[c0 + i];
         const int j0 = lane, j1 = lane + 32;
-        const bool s0 = j0 > i && j0 < m && iou_detection(bi, boxes[c0 + j0]) >= thr;
-        const bool s1 = j1 > i && j1 < m && iou_detection(bi, boxes[c0 + j1]) >= thr;
+        const bool s0 = j0 > i && j0 < m && suppresses(bi, boxes[c0 + j0], thr);
+        const bool s1 = j1 > i && j1 < m && suppresses(bi, boxes[c0 + j1], thr);
         lo = __ballot_sync(kFullMask, s0);
         hi = __ballot_sync(kFullMask, s1);
       }
@@ -455,7 +671,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
       while (rem) {
         const int t = __ffsll((long long)rem) - 1;
         rem &= rem - 1;
-        if (iou_detection(boxes[c0 + t], bj) >= thr) {
+        if (suppresses(boxes[c0 + t], bj, thr)) {
           dead[j] = 1;
           break;
         }
@@ -463,12 +679,8 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     }
     __syncthreads();
   }
-  // ---- suppressed rows: only the id field is overwritten (multibox_detection.cc:163) ----
   for (int q = threadIdx.x; q < n; q += blockDim.x)
-    if (dead[q]) {
-      const int r = a.force_suppress ? q : list[q];
-      out[(size_t)r * 7] = -1.f;
-    }
+    if (dead[q]) out[(size_t)(identity ? q : list[q]) * 7] = -1.f;
 }
 
 // Ordered compaction of the surviving rows (id >= 0) of every image into (B, K, 7), padded with -1, plus the
@@ -601,12 +813,23 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.nms_threshold = nms_threshold;
   so.force_suppress = force_suppress;
   so.nms_topk = nms_topk;
-  const int key_cap = so.npad_max < kSortSmemKeys ? so.npad_max : kSortSmemKeys;
-  const size_t smem2 = sizeof(unsigned long long) * key_cap + sizeof(int) * (T + 1 + C + 1);
-  DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxDetection: too many tiles/classes for the sort kernel (A=%d C=%d)", A, C);
+  so.seg_list = w.seg_list;
+  so.seg_box = w.seg_box;
+  so.key32 = w.key32;
+  const int nclass = C > 1 ? C - 1 : 1;
+  so.nclass = nclass;
+  so.bucket = nclass <= tuning(DSPMB_TUNE_DET_BUCKET_CLASSES) ? 1 : 0;
+  so.key32_in_smem = A <= kKey32SmemMax ? 1 : 0;
+  // sort keys in shared memory: enough for the top-k head, or for everything when no top-k limit applies
+  const int want = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
+  const int smem_keys = tuning(DSPMB_TUNE_SORT_SMEM_KEYS) < 2 ? 2 : tuning(DSPMB_TUNE_SORT_SMEM_KEYS);
+  so.sel_cap = want < smem_keys ? (want < 2 ? 2 : want) : smem_keys;
+  const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (so.key32_in_smem ? sizeof(unsigned) * ((A + 3) & ~3) : 0) +
+                       sizeof(int) * ((size_t)T + 1 + 3 * (nclass + 1) + (so.bucket ? 32 * nclass : 0));
+  DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many tiles/classes for the sort kernel (A=%d C=%d)", A, C);
   static bool attr_set = false;
   if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   {
@@ -627,6 +850,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.C = C;
     na.nms_threshold = nms_threshold;
     na.force_suppress = force_suppress;
+    na.lists_ready = so.bucket;
+    na.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
+    na.smem_rows = tuning(DSPMB_TUNE_NMS_SMEM_ROWS);
     dim3 grid3(force_suppress ? 1 : (C > 1 ? C - 1 : 1), B);
     if (C > 1 || force_suppress) {
       {
