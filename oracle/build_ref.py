@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE ONLY.  Builds oracle/_ref/ from the reference's own sources where they lie under
+/root/reference (nothing is copied into the repository; oracle/_ref/ is git-ignored but travels to the GPU box):
+
+  libmultibox_ref.so   operator/multibox_{prior,target,detection}.cc compiled in place behind oracle/shim/mxnet_shim.h
+                       (the function templates MultiBox*Forward<cpu> are the reference's code, verbatim; the
+                       Forward() glue from the -inl.h headers is restated in oracle/shim/ref_*.cc);
+  cpu_nms_ref*.so      cython/cpu_nms.pyx with the 3-token numpy-2 / Cython-3 patch of SURVEY.md section 8c
+                       (np.int_t -> np.intp_t, dtype=np.int -> np.intp, `np.float thresh` -> `double thresh`),
+                       applied on the fly to a scratch copy under oracle/_ref/.
+
+The reference's own build (MXNet's make/cmake with the operators dropped into src/operator/contrib) cannot be run:
+MXNet is neither vendored nor installable here.
+"""
+import os
+import subprocess
+import sys
+import sysconfig
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("DSPNET_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+CXXFLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-w"]
+
+
+def build_operators():
+    objs = []
+    for op in ("prior", "target", "detection"):
+        obj = os.path.join(OUT, "ref_%s.o" % op)
+        subprocess.check_call(["g++"] + CXXFLAGS + ["-I", os.path.join(HERE, "shim"), "-I", os.path.join(HERE, "shim", "operator"),
+                                                  "-DREF_SOURCE(f)=<%s/operator/f>" % REF, "-c",
+                                                  os.path.join(HERE, "shim", "ref_%s.cc" % op), "-o", obj])
+        objs.append(obj)
+    subprocess.check_call(["g++", "-shared", "-o", os.path.join(OUT, "libmultibox_ref.so")] + objs)
+    for o in objs:
+        os.unlink(o)
+
+
+def build_cpu_nms():
+    import numpy
+    src = open(os.path.join(REF, "cython", "cpu_nms.pyx")).read()
+    patched = src.replace("np.int_t", "np.intp_t").replace("dtype=np.int)", "dtype=np.intp)").replace(
+        "np.float thresh", "double thresh")
+    assert patched != src
+    pyx = os.path.join(OUT, "cpu_nms_ref.pyx")
+    with open(pyx, "w") as f:
+        f.write(patched)
+    subprocess.check_call([sys.executable, "-m", "cython", "-3", "--fast-fail", pyx, "-o", os.path.join(OUT, "cpu_nms_ref.c")])
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+                           "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION", "-I", sysconfig.get_paths()["include"],
+                           "-I", numpy.get_include(), os.path.join(OUT, "cpu_nms_ref.c"), "-o",
+                           os.path.join(OUT, "cpu_nms_ref" + ext)])
+    os.unlink(os.path.join(OUT, "cpu_nms_ref.c"))
+    os.unlink(pyx)
+
+
+def main():
+    if not os.path.isdir(os.path.join(REF, "operator")):
+        print("build_ref: %s not present, keeping the prebuilt oracle/_ref/ (if any)" % REF)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    build_operators()
+    try:
+        build_cpu_nms()
+    except Exception as e:  # Cython missing etc.: the operators are the important part
+        print("build_ref: cpu_nms not built (%r)" % (e,))
+    print("build_ref: ok ->", sorted(os.listdir(OUT)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

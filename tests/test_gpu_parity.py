@@ -261,3 +261,57 @@ def test_host_buffer_round_trip(oracle, cuda):
     want = oracle.multibox_target(anchors, lab, cp, negative_mining_ratio=3)
     for g, w, n in zip(got, want, ("loc_target", "loc_mask", "cls_target")):
         util.assert_bit_equal(g, w, "host " + n)
+
+
+def test_golden_vectors_from_the_reference(cuda):
+    """CUDA path against tests/golden/ (outputs of the reference's own .cc / .pyx compiled in place)."""
+    from dspnet_b200 import MultiBoxDetection, MultiBoxTarget
+    from dspnet_b200.nms import cpu_nms
+    from dspnet_b200.ops import multibox_prior_concat
+    from tests import golden_util
+    z, meta = golden_util.load()
+    gen = golden_util.generator()
+    anchors = multibox_prior_concat([(fm.height, fm.width) for fm in gen.TINY.maps], [fm.sizes for fm in gen.TINY.maps],
+                                    [fm.ratios for fm in gen.TINY.maps])
+    util.assert_bit_equal(anchors.cpu().numpy(), z["tiny_anchors"], "tiny anchors")
+    lt, lm, ct = MultiBoxTarget(anchors, _t(z["tiny_label"], cuda), _t(z["tiny_logits"], cuda), **gen.TARGET_KW)
+    util.assert_bit_equal(lt.cpu().numpy(), z["tiny_loc_target"], "loc_target")
+    util.assert_bit_equal(lm.cpu().numpy(), z["tiny_loc_mask"], "loc_mask")
+    util.assert_bit_equal(ct.cpu().numpy(), z["tiny_cls_target"], "cls_target")
+    det = MultiBoxDetection(_t(z["tiny_prob"], cuda), _t(z["tiny_loc"], cuda), anchors, **gen.DET_KW)
+    util.assert_bit_equal(det.cpu().numpy(), z["tiny_detection"], "detection")
+    det = MultiBoxDetection(_t(z["tiny_prob"], cuda), _t(z["tiny_loc"], cuda), anchors,
+                            **dict(gen.DET_KW, force_suppress=True, nms_topk=20))
+    util.assert_bit_equal(det.cpu().numpy(), z["tiny_detection_force_top20"], "detection force/top20")
+    if z["nms_keep_045"].size:
+        assert cpu_nms(z["nms_dets"], 0.45) == z["nms_keep_045"].tolist()
+    from dspnet_b200.symbol import multibox_anchors
+    for name in presets.PRESETS:
+        assert gen.digest(multibox_anchors(name).cpu().numpy()) == meta["digests"]["anchors_" + name]
+    for name, preset, batch, op, cid, extra in gen.BIG_CASES:
+        a = multibox_anchors(preset)
+        x, y = gen.big_case_inputs(preset, batch, op, cid, extra, a.cpu().numpy())
+        if gen.digest(x, y) != meta["digests"][name]["inputs"]:
+            continue  # numpy generator stream differs from the one the golden inputs were made with
+        if op == "target":
+            res = [r.cpu().numpy() for r in MultiBoxTarget(a, _t(x, cuda), _t(y, cuda), **gen.TARGET_KW)]
+        else:
+            kw = dict(gen.DET_KW, **{k: v for k, v in extra.items() if k != "max_gt"})
+            res = [MultiBoxDetection(_t(x, cuda), _t(y, cuda), a, **kw).cpu().numpy()]
+        assert gen.digest(*res) == meta["digests"][name]["outputs"], name
+
+
+@pytest.mark.parametrize("knobs", [{0: 0}, {1: 0}, {1: 0, 2: 0}, {0: 0, 1: 0}, {3: 2}, {1: 64}])
+def test_detection_forced_code_paths(oracle, cuda, knobs):
+    """Every size-dependent path of the detection pipeline on the same inputs: class lists built by the NMS kernel
+    (knob 0), chunk-sweep NMS with shared / global staging (knobs 1, 2), sort keys spilled to global memory (3)."""
+    from dspnet_b200 import _lib
+    L = _lib.lib()
+    old = {k: L.dspmb_set_tuning(k, v) for k, v in knobs.items()}
+    try:
+        anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=16)
+        _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=400)
+        _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=-1, force_suppress=True)
+    finally:
+        for k, v in old.items():
+            L.dspmb_set_tuning(k, v)
