@@ -16,15 +16,19 @@
 //
 // Structure here (three launches, all images in every grid):
 //   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread,
-//                      fills `out` with -1 (128-bit stores), decodes the survivors and writes them in anchor
-//                      order into per-tile record slots (block scan => deterministic order).
-//   det_sort_kernel    one CTA per image: prefix over tile counts, 64-bit keys (~score_order | rank) => a bitonic
-//                      sort in shared memory (global scratch above 16K candidates) reproduces stable_sort; emits
-//                      the V rows in the reference's order (sorted head + anchor-ordered tail) and per-class
-//                      segment offsets.
+//                      fills `out` with -1 (128-bit stores), decodes the survivors and writes records + 32-bit
+//                      order keys in anchor order into per-tile slots (block scan => deterministic order).
+//   det_sort_kernel    one CTA per image: tile prefix; MSB-first radix select of the nms_topk best keys straight on
+//                      the slot keys in shared memory (ties resolved in slot order through ballot-count tables,
+//                      no atomics on the ordering path); rank sort (<= 1024 keys, barrier-free) or bitonic sort of
+//                      the selection; emits the V rows in the reference's order (sorted head + anchor-ordered
+//                      tail) plus a compact class / box array per row for the NMS launch.
 //   det_nms_kernel     one CTA per (image, class) segment (one per image with force_suppress): ordered member
-//                      list, boxes staged in shared memory, greedy NMS in 64-row chunks: 64x64 ballot mask +
-//                      64-bit serial resolve + parallel sweep of the later rows against the surviving pivots.
+//                      list from ballot-count tables, boxes staged in shared memory, then
+//                        n <= 512: full upper-triangular bit mask built by balanced warp units (4-compare overlap
+//                                  test, IEEE division only for overlapping pairs) + a word-serial resolve that only
+//                                  visits rows that suppress something;
+//                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include "common.cuh"
 
 namespace dspmb {
@@ -34,25 +38,27 @@ constexpr int kStreamThreads = 128;
 constexpr int kSortThreads = 1024;
 constexpr int kNmsThreads = 256;
 constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared memory
-constexpr int kKey32SmemMax = 28672;  // anchors whose 32-bit keys fit in shared memory next to the sort keys
-constexpr int kMaxBucketClasses = 256;  // foreground classes the sort kernel can bucket (32 x nclass table)
+constexpr int kRankSortMax = 1024;    // selections up to this size are rank-sorted (one key per thread)
+constexpr int kKeySmemMax = 28672;    // slot keys (T * tile) that fit in shared memory next to the sort keys
 constexpr int kNmsMaskRows = 512;     // NMS segments up to this size use the shared-memory bit mask
 constexpr int kNmsSmemRows = 2048;    // rows of a larger NMS segment staged in shared memory
 constexpr int kRecFloats = 8;         // score, id, x1, y1, x2, y2, dist, pad
+constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every real key
 
 struct DetWorkspace {
   WsHeader *header;
-  int *tile_count;  // (B, T)
-  int *valid;       // (B) V
-  int *nms_rows;    // (B) rows taking part in NMS (0 = skipped)
-  int *seg_off;     // (B, C+1) first row-list position of each class segment
-  int *slot_of_rank;  // (B, Apad)
-  int *seg_list;    // (B, A) member rows of the segments
-  float *rec;       // (B, Apad, 8)
-  float4 *seg_box;  // (B, A) spill for segments larger than kNmsSmemRows
-  unsigned char *seg_dead;  // (B, A)
-  unsigned long long *sort_keys;  // (B, npad) spill for more than kSortSmemKeys candidates
-  unsigned *key32;  // (B, A) spill for the 32-bit order keys
+  int *tile_count;            // (B, T)
+  int *valid;                 // (B) V
+  int *nms_rows;              // (B) rows taking part in NMS (0 = skipped)
+  int *cursor;                // (B) allocator of seg_list regions for large segments
+  unsigned *keys;             // (B, Apad) order key of every record slot, sentinel where empty
+  float *rec;                 // (B, Apad, 8) decoded records in per-tile slots
+  unsigned short *row_cls;    // (B, Apad) class of every output row
+  float4 *row_box;            // (B, A) box of every output row
+  int *seg_list;              // (B, A) member rows of large segments
+  float4 *seg_box;            // (B, A) boxes of large segments in segment order
+  unsigned char *seg_dead;    // (B, A)
+  unsigned long long *sort_keys;  // (B, npad) spill for selections larger than the shared-memory budget
   size_t bytes;
 };
 
@@ -64,9 +70,10 @@ inline int next_pow2(int v) {
 
 // Layout is a pure function of (B, A, C); T and Apad are bounded with the smallest tile (128 anchors).
 DetWorkspace carve(void *base, int B, int A, int C) {
+  (void)C;
   DetWorkspace w;
   const size_t Tmax = (size_t)ceil_div(A, kStreamThreads);
-  const size_t Apad = (size_t)A + 4 * kStreamThreads;
+  const size_t Apad = (((size_t)A + 3) & ~(size_t)3) + 4 * kStreamThreads;  // multiple of 4: 128-bit key loads
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -77,15 +84,15 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.tile_count = (int *)take(sizeof(int) * B * Tmax);
   w.valid = (int *)take(sizeof(int) * B);
   w.nms_rows = (int *)take(sizeof(int) * B);
-  w.seg_off = (int *)take(sizeof(int) * B * (C + 1));
-  w.slot_of_rank = (int *)take(sizeof(int) * B * Apad);
-  w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
+  w.cursor = (int *)take(sizeof(int) * B);
+  w.keys = (unsigned *)take(sizeof(unsigned) * B * Apad);
   w.rec = (float *)take(sizeof(float) * kRecFloats * B * Apad);
+  w.row_cls = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
+  w.row_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
+  w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
   w.seg_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
   w.seg_dead = (unsigned char *)take((size_t)B * A);
-  const int npad = next_pow2(A);
-  w.sort_keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * npad);
-  w.key32 = (unsigned *)take(A > kKey32SmemMax ? sizeof(unsigned) * (size_t)B * A : 0);
+  w.sort_keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * next_pow2(A));
   w.bytes = off;
   return w;
 }
@@ -94,6 +101,7 @@ struct StreamArgs {
   const float *cls_prob, *loc_pred, *anchors;
   float *out;
   int *tile_count;
+  unsigned *keys;
   float *rec;
   int A, C, T, Apad;
   float threshold;
@@ -139,6 +147,7 @@ __device__ __forceinline__ void decode_record(const StreamArgs &a, const float *
 template <int VEC>
 __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kStreamThreads / 32 + 1];
+  __shared__ __align__(16) unsigned sm_keys[kStreamThreads * VEC];
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kStreamThreads * VEC;
   const int tile_begin = t * kTile;
@@ -166,6 +175,7 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
   for (int k = 0; k < VEC; ++k) {
     score[k] = -1.f;
     id[k] = 0;
+    sm_keys[threadIdx.x * VEC + k] = kKeySentinel;
   }
   if (i0 < A) {
 #pragma unroll 5
@@ -206,15 +216,22 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
     for (int k = 0; k < VEC; ++k)
       if (id[k] > 0) {
         decode_record(a, loc, i0 + k, id[k], score[k], rec + (size_t)pos * kRecFloats);
+        sm_keys[pos] = ~float_order_key(score[k]);  // ascending key == descending score
         ++pos;
       }
+  }
+  __syncthreads();
+  unsigned *gk = a.keys + (size_t)b * a.Apad + tile_begin;
+  if constexpr (VEC == 4) {
+    reinterpret_cast<uint4 *>(gk)[threadIdx.x] = reinterpret_cast<const uint4 *>(sm_keys)[threadIdx.x];
+  } else {
+    gk[threadIdx.x] = sm_keys[threadIdx.x];
   }
 }
 
 // ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
-// global memory (generic addressing).  Shared-memory bandwidth bound (32 B per compare-exchange), so it is only
-// used on the <= nms_topk selected keys, or on everything when no top-k limit applies.
+// global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used above kRankSortMax keys.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -236,25 +253,36 @@ __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
 // Warp-aggregated shared-memory histogram increment: lanes with the same bin elect one leader.
 __device__ __forceinline__ void hist_add(unsigned *hist, unsigned bin, bool pred) {
   const unsigned active = __ballot_sync(kFullMask, pred);
+  if (active == 0u) return;
   if (pred) {
     const unsigned peers = __match_any_sync(active, bin);
     if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
   }
 }
 
+// Unordered append of the lanes with `pred` to a shared list through one atomic per warp.
+__device__ __forceinline__ int warp_append(int *counter, bool pred) {
+  const unsigned m = __ballot_sync(kFullMask, pred);
+  if (m == 0u) return 0;
+  int base = 0;
+  if (lane_id() == 0) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(kFullMask, base, 0);
+  return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+
 struct SortArgs {
   float *out;
   const int *tile_count;
+  const unsigned *keys;
   const float *rec;
-  int *slot_of_rank;
-  int *valid, *nms_rows, *seg_off, *seg_list;
-  float4 *seg_box;
-  unsigned *key32;                // (B, A) spill when the keys do not fit in shared memory
-  unsigned long long *sort_keys;  // (B, npad) spill for full sorts above kSortSmemKeys
+  int *valid, *nms_rows, *cursor;
+  unsigned short *row_cls;
+  float4 *row_box;
+  unsigned long long *sort_keys;
   int *valid_count_out;
   WsHeader *header;
-  int A, C, T, Apad, tile, npad_max;
-  int key32_in_smem, sel_cap, nclass, bucket;  // bucket: class lists are produced here (nclass <= kMaxBucketClasses)
+  int A, C, T, Apad, cls_stride, tile, npad_max, niter;
+  int keys_in_smem, sel_cap;
   float nms_threshold;
   int force_suppress, nms_topk;
 };
@@ -263,25 +291,28 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ int scan_smem[kSortThreads / 32 + 1];
   __shared__ unsigned hist256[256];
-  __shared__ int carry_smem, sm_need, sm_count;
+  __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;
   __shared__ unsigned sm_prefix;
   const int b = blockIdx.x;
-  const int T = a.T, tile = a.tile, A = a.A, nclass = a.nclass;
-  // dynamic smem: [sel: sel_cap u64][key32: A u32 (optional)][tile_off: T+1][chist: nclass+1][coff: nclass+1]
-  //               [crun: nclass][table: 32*nclass (if bucket)]
+  const int T = a.T, tile = a.tile, A = a.A;
+  const int Tt = T * tile;
+  // dynamic smem: [sel: sel_cap u64][skeys: Tt u32 (optional)][tile_off: T+1 int][wtab: niter*32 int]
   unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
-  unsigned *skey = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
-  int *tile_off = reinterpret_cast<int *>(skey + (a.key32_in_smem ? ((A + 3) & ~3) : 0));
-  unsigned *chist = reinterpret_cast<unsigned *>(tile_off + (T + 1));
-  int *coff = reinterpret_cast<int *>(chist + (nclass + 1));
-  int *crun = coff + (nclass + 1);
-  int *table = crun + nclass;
-  unsigned *key32 = a.key32_in_smem ? skey : a.key32 + (size_t)b * A;
+  unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
+  int *tile_off = reinterpret_cast<int *>(skeys + (a.keys_in_smem ? Tt : 0));
+  int *wtab = tile_off + (T + 1);
+  const unsigned *gkeys = a.keys + (size_t)b * a.Apad;
+  const unsigned *keys = a.keys_in_smem ? skeys : gkeys;
+  const unsigned warp = warp_id(), lane = lane_id();
   if (b == 0 && threadIdx.x == 0) a.header->status = DSPMB_OK;
+
+  // 0. stage the slot keys (coalesced 128-bit loads; Tt is a multiple of 128)
+  if (a.keys_in_smem)
+    for (int i = threadIdx.x; i < (Tt >> 2); i += blockDim.x)
+      reinterpret_cast<uint4 *>(skeys)[i] = __ldg(reinterpret_cast<const uint4 *>(gkeys) + i);
 
   // 1. exclusive prefix over the tile counts -> rank of every record in anchor order
   if (threadIdx.x == 0) carry_smem = 0;
-  for (int c = threadIdx.x; c <= nclass; c += blockDim.x) chist[c] = 0;
   __syncthreads();
   const int *cnt = a.tile_count + (size_t)b * T;
   for (int base = 0; base < T; base += blockDim.x) {
@@ -296,33 +327,20 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     __syncthreads();
   }
   const int V = carry_smem;
+  const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;  // multibox_detection.cc:130
   if (threadIdx.x == 0) {
     tile_off[T] = V;
     a.valid[b] = V;
     if (a.valid_count_out) a.valid_count_out[b] = V;
+    a.nms_rows[b] = do_sort ? V : 0;
+    a.cursor[b] = 0;
+    sm_prefix = 0u;
+    sm_count = 0;
+    sm_eq_total = 0;
   }
-  const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;  // multibox_detection.cc:130
-  if (threadIdx.x == 0) a.nms_rows[b] = do_sort ? V : 0;
   if (V == 0) return;
-  __syncthreads();
 
-  // 2. rank -> slot map and 32-bit order keys (ascending key == descending score)
-  const float *rec = a.rec + (size_t)b * a.Apad * kRecFloats;
-  int *slot_of_rank = a.slot_of_rank + (size_t)b * a.Apad;
-  const bool per_class = do_sort && !a.force_suppress;
-  for (int slot = threadIdx.x; slot < T * tile; slot += blockDim.x) {
-    const int t = slot / tile, r = slot - t * tile;
-    const int first = tile_off[t];
-    if (r < tile_off[t + 1] - first) {
-      const int p = first + r;
-      slot_of_rank[p] = slot;
-      key32[p] = ~float_order_key(rec[(size_t)slot * kRecFloats]);
-    }
-  }
-  for (int c = threadIdx.x; c < nclass; c += blockDim.x) crun[c] = 0;
-  __syncthreads();
-
-  // 3. the nkeep best keys, sorted (stable_sort + top-k of multibox_detection.cc:132-151)
+  // 2. the nkeep best keys (stable_sort + top-k of multibox_detection.cc:132-151), as (key << 32 | slot)
   int nkeep = 0;
   unsigned long long *sel = ssel;
   if (do_sort) {
@@ -331,230 +349,299 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     int npad = 2;
     while (npad < nkeep) npad <<= 1;
     if (npad > a.sel_cap) sel = a.sort_keys + (size_t)b * a.npad_max;
-    if (nkeep == V) {
-      for (int p = threadIdx.x; p < npad; p += blockDim.x)
-        sel[p] = p < V ? (((unsigned long long)key32[p] << 32) | (unsigned)p) : ~0ull;
-      __syncthreads();
-    } else {
-      // MSB-first radix select of the nkeep-th smallest key, then an anchor-ordered tie pass
-      if (threadIdx.x == 0) {
-        sm_prefix = 0u;
-        sm_need = nkeep;
-        sm_count = 0;
-        carry_smem = 0;
-      }
+    if (threadIdx.x == 0) sm_need = nkeep;
+    __syncthreads();
+    unsigned pivot = kKeySentinel - 1u;  // nkeep == V: every real key is selected
+    bool ordered_ties = false;
+    int need_eq = 0;
+    if (nkeep < V) {
+      // MSB-first radix select of the nkeep-th smallest key over the slot keys (empty slots are skipped)
       for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
         const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist256[i] = 0u;
         __syncthreads();
         const unsigned prefix = sm_prefix;
-        for (int base = 0; base < V; base += blockDim.x) {
-          const int p = base + threadIdx.x;
-          const unsigned kv = p < V ? key32[p] : 0u;
-          hist_add(hist256, (kv >> shift) & 0xffu, p < V && (kv & mask) == prefix);
+        for (int it = 0; it < a.niter; ++it) {
+          const int s = it * blockDim.x + threadIdx.x;
+          const unsigned kv = s < Tt ? keys[s] : kKeySentinel;
+          hist_add(hist256, (kv >> shift) & 0xffu, kv != kKeySentinel && (kv & mask) == prefix);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-          const int need = sm_need;
-          unsigned acc = 0;
-          int d = 0;
-          for (; d < 255; ++d) {
-            if ((int)(acc + hist256[d]) >= need) break;
-            acc += hist256[d];
+        if (warp == 0) {  // digit search: 8 bins per lane, warp scan
+          unsigned h[8];
+          int tot = 0;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            h[d] = hist256[lane * 8 + d];
+            tot += (int)h[d];
           }
-          sm_need = need - (int)acc;
-          sm_prefix = prefix | ((unsigned)d << shift);
+          const int incl = warp_scan_incl(tot);
+          const int excl = incl - tot;
+          const int need = sm_need;
+          if (excl < need && incl >= need) {
+            int acc = excl;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+              if (acc + (int)h[d] >= need) {
+                sm_need = need - acc;
+                sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
+                sm_eq_total = (int)h[d];
+                break;
+              }
+              acc += (int)h[d];
+            }
+          }
         }
         __syncthreads();
       }
-      const unsigned pivot = sm_prefix;
-      const int need_eq = sm_need;
-      for (int base = 0; base < V; base += blockDim.x) {
-        const int p = base + threadIdx.x;
-        const unsigned kv = p < V ? key32[p] : 0xffffffffu;
-        const int eq = (p < V && kv == pivot) ? 1 : 0;
+      pivot = sm_prefix;
+      need_eq = sm_need;
+      ordered_ties = need_eq < sm_eq_total;  // only some of the keys equal to the pivot make it: lowest slots first
+    }
+    if (ordered_ties) {
+      // ballot counts of the pivot-valued keys per (iteration, warp), scanned in slot order
+      for (int it = 0; it < a.niter; ++it) {
+        const int s = it * blockDim.x + threadIdx.x;
+        const unsigned m = __ballot_sync(kFullMask, s < Tt && keys[s] == pivot);
+        if (lane == 0) wtab[it * 32 + warp] = __popc(m);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) carry_smem = 0;
+      __syncthreads();
+      for (int base = 0; base < a.niter * 32; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < a.niter * 32 ? wtab[i] : 0;
         int total;
-        const int ex = block_scan_excl(eq, scan_smem, &total);
+        const int ex = block_scan_excl(v, scan_smem, &total);
         const int carry = carry_smem;
-        const bool take = p < V && (kv < pivot || (eq && carry + ex < need_eq));
-        // any slot order will do: the 64-bit keys are unique and get sorted next
-        const unsigned tb = __ballot_sync(kFullMask, take);
-        int wbase = 0;
-        if (lane_id() == 0 && tb) wbase = atomicAdd(&sm_count, __popc(tb));
-        wbase = __shfl_sync(kFullMask, wbase, 0);
-        if (take) sel[wbase + __popc(tb & ((1u << lane_id()) - 1u))] = ((unsigned long long)kv << 32) | (unsigned)p;
+        if (i < a.niter * 32) wtab[i] = carry + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry_smem = carry + total;
         __syncthreads();
       }
+    }
+    // gather the selection (any order: the 64-bit keys are unique and get sorted next)
+    for (int it = 0; it < a.niter; ++it) {
+      const int s = it * blockDim.x + threadIdx.x;
+      const unsigned kv = s < Tt ? keys[s] : kKeySentinel;
+      bool take = kv != kKeySentinel && kv <= pivot;
+      if (ordered_ties) {
+        const bool eq = kv == pivot;
+        const unsigned m = __ballot_sync(kFullMask, eq);
+        if (eq) take = wtab[it * 32 + warp] + __popc(m & ((1u << lane) - 1u)) < need_eq;
+      }
+      const int p = warp_append(&sm_count, take);
+      if (take) sel[p] = ((unsigned long long)kv << 32) | (unsigned)s;
+    }
+    __syncthreads();
+    if (nkeep <= kRankSortMax && nkeep <= a.sel_cap) {
+      // rank sort: one key per thread, n broadcast reads, no barriers inside
+      const int n = nkeep;
+      const unsigned long long mine = (int)threadIdx.x < n ? sel[threadIdx.x] : 0ull;
+      int rank = 0;
+      for (int j = 0; j < n; ++j) rank += sel[j] < mine ? 1 : 0;
+      __syncthreads();
+      if ((int)threadIdx.x < n) sel[rank] = mine;
+      __syncthreads();
+    } else {
       for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
       __syncthreads();
+      bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
     }
-    bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
   } else {
     __syncthreads();
   }
 
-  // 4. the V output rows are the sorted head [0, nkeep) followed by the anchor-ordered tail [nkeep, V)
-  //    (multibox_detection.cc:146-151): candidates of the head whose rank is >= nkeep appear twice, unselected
-  //    candidates of rank < nkeep not at all.  First sweep: record slot of every row (reusing the key array) and
-  //    the class histogram of the ROWS -> class segment offsets for the NMS launch.
-  int *row_slot = reinterpret_cast<int *>(key32);
-  for (int base = 0; base < V; base += blockDim.x) {
-    const int r = base + threadIdx.x;
-    unsigned cls = 0;
-    int slot = 0;
-    if (r < V) {
-      const int p = r < nkeep ? (int)(unsigned)(sel[r] & 0xffffffffull) : r;
-      slot = slot_of_rank[p];
-      cls = (unsigned)rec[(size_t)slot * kRecFloats + 1];
-    }
-    if (r < V) row_slot[r] = slot;
-    if (per_class) hist_add(chist, cls, r < V);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int *so = a.seg_off + (size_t)b * (a.C + 1);
-    if (!per_class) {
-      coff[0] = 0;
-      so[0] = 0;
-      so[1] = do_sort ? V : 0;
-    } else {
-      int acc = 0;
-      for (int c = 0; c < nclass; ++c) {
-        coff[c] = acc;
-        so[c] = acc;
-        acc += (int)chist[c];
-      }
-      so[nclass] = acc;
-    }
-  }
-  __syncthreads();
-  // Second sweep, in row order: write the rows and the stable per-class row lists + boxes.
+  // 3. emit the V rows: sorted head [0, nkeep), anchor-ordered tail [nkeep, V) (multibox_detection.cc:146-151),
+  //    plus class and box of every row for the NMS launch.  Four rows per thread in flight.
+  const float *rec = a.rec + (size_t)b * a.Apad * kRecFloats;
   float *out = a.out + (size_t)b * A * 7;
-  int *seg_list = a.seg_list + (size_t)b * A;
-  float4 *seg_box = a.seg_box + (size_t)b * A;
-  const bool bucket = per_class && a.bucket;
-  const unsigned warp = warp_id(), lane = lane_id();
-  for (int base = 0; base < V; base += blockDim.x) {
-    const int r = base + threadIdx.x;
-    const bool live = r < V;
-    unsigned cls = 0;
-    float4 box = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (live) {
-      const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)row_slot[r] * kRecFloats);
-      const float4 s0 = src[0], s1 = src[1];
-      float *o = out + (size_t)r * 7;
-      o[0] = s0.y;  // id
-      o[1] = s0.x;  // score
-      o[2] = s0.z;
-      o[3] = s0.w;
-      o[4] = s1.x;
-      o[5] = s1.y;
-      o[6] = s1.z;
-      cls = (unsigned)s0.y;
-      box = make_float4(s0.z, s0.w, s1.x, s1.y);
-    }
-    if (do_sort && a.force_suppress) {
-      if (live) seg_box[r] = box;
-    } else if (bucket) {
-      for (int i = threadIdx.x; i < 32 * nclass; i += blockDim.x) table[i] = 0;
-      __syncthreads();
-      const unsigned active = __ballot_sync(kFullMask, live);
-      int rank_w = 0;
-      if (live) {
-        const unsigned peers = __match_any_sync(active, cls);
-        rank_w = __popc(peers & ((1u << lane) - 1u));
-        if ((int)lane == __ffs(peers) - 1) table[warp * nclass + cls] = __popc(peers);
-      }
-      __syncthreads();
-      for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
-        int run = crun[c];
-        for (int w = 0; w < 32; ++w) {
-          const int t = table[w * nclass + c];
-          table[w * nclass + c] = run;
-          run += t;
+  unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
+  float4 *row_box = a.row_box + (size_t)b * A;
+  for (int base = 0; base < V; base += 4 * blockDim.x) {
+    float4 s0[4], s1[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = base + u * blockDim.x + threadIdx.x;
+      if (r < V) {
+        int slot;
+        if (r < nkeep) {
+          slot = (int)(unsigned)(sel[r] & 0xffffffffull);
+        } else {  // rank r -> slot: last tile whose first rank is <= r
+          int lo = 0, hi = T - 1;
+          while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (tile_off[mid] <= r) lo = mid; else hi = mid - 1;
+          }
+          slot = lo * tile + (r - tile_off[lo]);
         }
-        crun[c] = run;
+        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)slot * kRecFloats);
+        s0[u] = __ldg(src);
+        s1[u] = __ldg(src + 1);
       }
-      __syncthreads();
-      if (live) {
-        const int pos = coff[cls] + table[warp * nclass + cls] + rank_w;
-        seg_list[pos] = r;
-        seg_box[pos] = box;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = base + u * blockDim.x + threadIdx.x;
+      if (r < V) {
+        float *o = out + (size_t)r * 7;
+        o[0] = s0[u].y;  // id
+        o[1] = s0[u].x;  // score
+        o[2] = s0[u].z;
+        o[3] = s0[u].w;
+        o[4] = s1[u].x;
+        o[5] = s1[u].y;
+        o[6] = s1[u].z;
+        if (do_sort) {
+          row_cls[r] = (unsigned short)s0[u].y;
+          row_box[r] = make_float4(s0[u].z, s0[u].w, s1[u].x, s1[u].y);
+        }
       }
-      __syncthreads();
     }
   }
 }
 
 struct NmsArgs {
   float *out;
-  const int *nms_rows, *seg_off;
+  const int *nms_rows;
+  int *cursor;
+  const unsigned short *row_cls;
+  const float4 *row_box;
   int *seg_list;
   float4 *seg_box;
   unsigned char *seg_dead;
-  int A, C;
+  int A, cls_stride, C;
   float nms_threshold;
-  int force_suppress, lists_ready, mask_rows, smem_rows;
+  int force_suppress, mask_rows, smem_rows;
 };
 
-// IoU >= thr test of multibox_detection.cc:44-51,162 with an exact early-out: disjoint boxes have i = 0, hence
-// iou = 0 < thr (thr > 0 whenever NMS runs), so the IEEE division is only paid for overlapping pairs.
+// IoU >= thr test of multibox_detection.cc:44-51,162.  Disjoint boxes have i = 0, hence iou = 0 < thr (thr > 0
+// whenever NMS runs): the overlap test min(x2) > max(x1) && min(y2) > max(y1) is four compares (a - b > 0 <=> a > b
+// in IEEE arithmetic with gradual underflow), and the division is only paid for overlapping pairs.
 __device__ __forceinline__ bool suppresses(float4 a, float4 b, float thr) {
+  if (!(a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y && a.z > a.x && b.z > b.x && a.w > a.y && b.w > b.y)) return false;
   const float w = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
   const float h = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
-  if (!(w > 0.f) || !(h > 0.f)) return false;
   const float i = fmul(w, h);
   const float u = fsub(fadd(fmul(fsub(a.z, a.x), fsub(a.w, a.y)), fmul(fsub(b.z, b.x), fsub(b.w, b.y))), i);
   return (u <= 0.f ? 0.f : fdiv(i, u)) >= thr;
 }
 
+constexpr int kNmsTab = 1024;  // ballot-count table entries: 128 iterations x 8 warps = 262144 rows per sweep
+
 __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
   // shared memory is a union of the two paths:
-  //   small (n <= kNmsMaskRows):  boxes[512] float4 (8 KB) + mask[512 * 8] u64 (32 KB)
-  //   large:                      boxes[2048] float4 (32 KB) + dead[2048] (2 KB) + 64 words
-  __shared__ __align__(16) unsigned char smem_raw[40 * 1024 + 1024];
+  //   small (n <= mask_rows <= 512): boxes[512] float4 (8 KB) + mask[512 * 8] u64 (32 KB) + list[512] int (2 KB)
+  //   large:                         boxes[2048] float4 (32 KB) + dead[2048] (2 KB) + 64 words
+  __shared__ __align__(16) unsigned char smem_raw[42 * 1024 + 512];
+  __shared__ int wtab[kNmsTab];
+  __shared__ unsigned long long rowany[8];
   __shared__ unsigned sm_deadbits[2];
   __shared__ unsigned long long sm_alive, sm_deadmask;
   __shared__ int scan_smem[kNmsThreads / 32 + 1];
-  __shared__ int carry_smem;
+  __shared__ int carry_smem, sm_base;
 
   const int b = blockIdx.y, seg = blockIdx.x;
   const int V = a.nms_rows[b];
   if (V == 0) return;
-  const int *so = a.seg_off + (size_t)b * (a.C + 1);
-  const int seg_base = so[seg];
-  const int n = so[seg + 1] - seg_base;
-  if (n < 2) return;
   float *out = a.out + (size_t)b * a.A * 7;
-  int *list = a.seg_list + (size_t)b * a.A + seg_base;
-  float4 *gbox = a.seg_box + (size_t)b * a.A + seg_base;
+  const float4 *row_box = a.row_box + (size_t)b * a.A;
   const bool identity = a.force_suppress != 0;  // single segment: row q is list entry q
   const float thr = a.nms_threshold;
   const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
+  const int rows_per_iter = blockDim.x * 8;
+  const int niter = (V + rows_per_iter - 1) / rows_per_iter;
 
-  if (!a.lists_ready && !identity) {
-    // fallback (more classes than the sort kernel buckets): ordered member list by scanning the rows
-    if (threadIdx.x == 0) carry_smem = 0;
-    __syncthreads();
-    const float cls = (float)seg;
-    for (int base = 0; base < V; base += blockDim.x) {
-      const int r = base + threadIdx.x;
-      const int hit = (r < V && out[(size_t)r * 7] == cls) ? 1 : 0;
-      int total;
-      const int ex = block_scan_excl(hit, scan_smem, &total);
-      const int carry = carry_smem;
-      if (hit) {
-        const float *row = out + (size_t)r * 7;
-        list[carry + ex] = r;
-        gbox[carry + ex] = make_float4(row[2], row[3], row[4], row[5]);
+  // ---------------- ordered member list of this class: ballot-count tables, no atomics ----------------
+  int n = V;
+  int *slist = reinterpret_cast<int *>(smem_raw + 40 * 1024);  // small path only
+  int *glist = nullptr;
+  if (!identity) {
+    const uint4 *cls8 = reinterpret_cast<const uint4 *>(a.row_cls + (size_t)b * a.cls_stride);
+    const unsigned short want = (unsigned short)seg;
+    auto hits_of = [&](int it) -> unsigned {  // 8-bit mask of the rows 8*(it*blockDim + tid) .. +7 in this class
+      const int g = it * blockDim.x + threadIdx.x;
+      const int r0 = g * 8;
+      if (r0 >= V) return 0u;
+      const uint4 q = __ldg(cls8 + g);
+      const unsigned w[4] = {q.x, q.y, q.z, q.w};
+      unsigned h = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const unsigned short c = (unsigned short)(w[k >> 1] >> ((k & 1) * 16));
+        if (r0 + k < V && c == want) h |= 1u << k;
+      }
+      return h;
+    };
+    // sweep 1: counts per (iteration, warp)
+    int total_n = 0;
+    for (int it0 = 0; it0 < niter; it0 += kNmsTab / 8) {
+      const int its = min(niter - it0, kNmsTab / 8);
+      for (int it = 0; it < its; ++it) {
+        const int c = warp_sum_i32(__popc(hits_of(it0 + it)));
+        if (lane == 0) wtab[it * nwarps + warp] = c;
       }
       __syncthreads();
-      if (threadIdx.x == 0) carry_smem = carry + total;
+      if (threadIdx.x == 0) carry_smem = 0;
+      __syncthreads();
+      for (int base = 0; base < its * (int)nwarps; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < its * (int)nwarps ? wtab[i] : 0;
+        int total;
+        block_scan_excl(v, scan_smem, &total);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_smem += total;
+        __syncthreads();
+      }
+      total_n += carry_smem;
       __syncthreads();
     }
+    n = total_n;
+    if (n < 2) return;
+    if (n > a.mask_rows) {  // large segment: claim a region of the per-image list buffer
+      if (threadIdx.x == 0) sm_base = atomicAdd(&a.cursor[b], n);
+      __syncthreads();
+      glist = a.seg_list + (size_t)b * a.A + sm_base;
+    }
+    // sweep 2: ordered positions
+    int running = 0;
+    for (int it0 = 0; it0 < niter; it0 += kNmsTab / 8) {
+      const int its = min(niter - it0, kNmsTab / 8);
+      for (int it = 0; it < its; ++it) {
+        const int c = warp_sum_i32(__popc(hits_of(it0 + it)));
+        if (lane == 0) wtab[it * nwarps + warp] = c;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) carry_smem = running;
+      __syncthreads();
+      for (int base = 0; base < its * (int)nwarps; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        const int v = i < its * (int)nwarps ? wtab[i] : 0;
+        int total;
+        const int ex = block_scan_excl(v, scan_smem, &total);
+        const int carry = carry_smem;
+        if (i < its * (int)nwarps) wtab[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_smem = carry + total;
+        __syncthreads();
+      }
+      for (int it = 0; it < its; ++it) {
+        const unsigned h = hits_of(it0 + it);
+        const int c = __popc(h);
+        int pos = wtab[it * nwarps + warp] + warp_scan_incl(c) - c;
+        const int r0 = ((it0 + it) * blockDim.x + threadIdx.x) * 8;
+        for (unsigned m = h; m; m &= m - 1) {
+          const int r = r0 + __ffs(m) - 1;
+          if (glist) glist[pos] = r; else slist[pos] = r;
+          ++pos;
+        }
+      }
+      running = carry_smem;
+      __syncthreads();
+    }
+  } else if (n < 2) {
+    return;
   }
 
   if (n <= a.mask_rows) {
@@ -562,40 +649,49 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
     unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kNmsMaskRows * sizeof(float4));
     const int W = (n + 63) >> 6;
-    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = gbox[q];
+    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = __ldg(row_box + (identity ? q : slist[q]));
+    if (threadIdx.x < 8) rowany[threadIdx.x] = 0ull;
     __syncthreads();
-    // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  Rows of a warp share the column being tested,
-    // so the column box is a shared-memory broadcast.
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const float4 bi = boxes[i];
-      for (int w = 0; w < W; ++w) {
+    // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x one
+    // 64-column word, dealt round-robin to the warps; the column box is a shared-memory broadcast.
+    const int ngroups = (n + 31) >> 5;
+    int unit = 0;
+    for (int rg = 0; rg < ngroups; ++rg) {
+      for (int w = rg >> 1; w < W; ++w, ++unit) {
+        if (unit % (int)nwarps != (int)warp) continue;
+        const int i = (rg << 5) + lane;
         unsigned long long bits = 0ull;
-        const int j0 = max(w << 6, i + 1), j1 = min(n, (w + 1) << 6);
-        for (int j = j0; j < j1; ++j)
-          if (suppresses(bi, boxes[j], thr)) bits |= 1ull << (j & 63);
-        mask[i * W + w] = bits;
+        if (i < n) {
+          const float4 bi = boxes[i];
+          const int j1 = min(n, (w + 1) << 6);
+          for (int j = w << 6; j < j1; ++j)
+            if (j > i && suppresses(bi, boxes[j], thr)) bits |= 1ull << (j & 63);
+          mask[i * W + w] = bits;
+          if (bits) atomicOr(&rowany[i >> 6], 1ull << (i & 63));
+        }
       }
     }
     __syncthreads();
     if (warp == 0) {
-      // lane w owns word w of the removed set; chunk c is resolved serially on its diagonal words (every lane
-      // redundantly, from broadcast reads), then the rows of its survivors are OR-ed into the later words.
+      // lane w owns word w of the removed set.  Chunk c: only rows that suppress something (rowany) need the
+      // serial treatment; every lane resolves them redundantly from broadcast reads, then the rows of the live
+      // suppressors are OR-ed into the later words.
       unsigned long long remv = 0ull;
       for (int c = 0; c < W; ++c) {
         unsigned long long cur = __shfl_sync(kFullMask, remv, c);
-        unsigned long long alive = 0ull;
-        const int m = min(64, n - (c << 6));
-        for (int t = 0; t < m; ++t)
+        unsigned long long live = 0ull;
+        for (unsigned long long cand = rowany[c]; cand; cand &= cand - 1) {
+          const int t = __ffsll((long long)cand) - 1;
           if (!((cur >> t) & 1ull)) {
-            alive |= 1ull << t;
+            live |= 1ull << t;
             cur |= mask[((c << 6) + t) * W + c];
           }
+        }
         if ((int)lane == c) remv = cur;
         if ((int)lane > c && (int)lane < W) {
-          unsigned long long acc = 0ull, rem = alive;
-          while (rem) {
+          unsigned long long acc = 0ull;
+          for (unsigned long long rem = live; rem; rem &= rem - 1) {
             const int t = __ffsll((long long)rem) - 1;
-            rem &= rem - 1;
             acc |= mask[((c << 6) + t) * W + lane];
           }
           remv |= acc;
@@ -606,7 +702,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
         const unsigned long long word = __shfl_sync(kFullMask, remv, w);
         for (int half = 0; half < 2; ++half) {
           const int q = (w << 6) + half * 32 + lane;
-          if (q < n && ((word >> (half * 32 + lane)) & 1ull)) out[(size_t)(identity ? q : list[q]) * 7] = -1.f;
+          if (q < n && ((word >> (half * 32 + lane)) & 1ull)) out[(size_t)(identity ? q : slist[q]) * 7] = -1.f;
         }
       }
     }
@@ -620,12 +716,19 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   if (n <= a.smem_rows) {
     boxes = reinterpret_cast<float4 *>(smem_raw);
     dead = smem_raw + 32 * 1024;
-    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = gbox[q];
   } else {
-    boxes = gbox;
-    dead = a.seg_dead + (size_t)b * a.A + seg_base;
+    // claim scratch in segment order (the list region doubles as the allocator for identity segments)
+    if (identity) {
+      if (threadIdx.x == 0) sm_base = atomicAdd(&a.cursor[b], n);
+      __syncthreads();
+    }
+    boxes = a.seg_box + (size_t)b * a.A + sm_base;
+    dead = a.seg_dead + (size_t)b * a.A + sm_base;
   }
-  for (int q = threadIdx.x; q < n; q += blockDim.x) dead[q] = 0;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) {
+    boxes[q] = __ldg(row_box + (identity ? q : glist[q]));
+    dead[q] = 0;
+  }
   __syncthreads();
   for (int c0 = 0; c0 < n; c0 += 64) {
     const int m = min(64, n - c0);
@@ -680,7 +783,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     __syncthreads();
   }
   for (int q = threadIdx.x; q < n; q += blockDim.x)
-    if (dead[q]) out[(size_t)(identity ? q : list[q]) * 7] = -1.f;
+    if (dead[q]) out[(size_t)(identity ? q : glist[q]) * 7] = -1.f;
 }
 
 // Ordered compaction of the surviving rows (id >= 0) of every image into (B, K, 7), padded with -1, plus the
@@ -750,7 +853,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   // Shape CHECKs of MultiBoxDetectionProp::InferShape (multibox_detection-inl.h:149-171).
   DSPMB_REQUIRE(B >= 0 && A > 0 && C > 0, "MultiBoxDetection: bad shape B=%d A=%d C=%d", B, A, C);
   DSPMB_REQUIRE(cls_prob && loc_pred && anchors && out && variances, "MultiBoxDetection: NULL tensor");
-  DSPMB_REQUIRE(B <= 65535, "MultiBoxDetection: batch > 65535 not supported in one call");
+  DSPMB_REQUIRE(B <= 65535 && C <= 65535, "MultiBoxDetection: batch / classes > 65535 not supported in one call");
   DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxDetection: anchors must be 16-byte aligned");
   if (B == 0) return DSPMB_OK;
   const size_t need = carve(nullptr, B, A, C).bytes;
@@ -763,7 +866,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out) & 15) == 0;
   const int tile = kStreamThreads * (vec4 ? 4 : 1);
   const int T = ceil_div(A, tile);
-  const int Apad = A + 4 * kStreamThreads;
+  const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
 
   StreamArgs sa;
   sa.cls_prob = cls_prob;
@@ -771,6 +874,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.anchors = anchors;
   sa.out = out;
   sa.tile_count = w.tile_count;
+  sa.keys = w.keys;
   sa.rec = w.rec;
   sa.A = A;
   sa.C = C;
@@ -787,20 +891,22 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   {
     ProfileScope _p(kSlotDetStream, stream);
     if (vec4)
-    det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
-  else
-    det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
+      det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
+    else
+      det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
   SortArgs so;
   so.out = out;
   so.tile_count = w.tile_count;
+  so.keys = w.keys;
   so.rec = w.rec;
-  so.slot_of_rank = w.slot_of_rank;
   so.valid = w.valid;
   so.nms_rows = w.nms_rows;
-  so.seg_off = w.seg_off;
+  so.cursor = w.cursor;
+  so.row_cls = w.row_cls;
+  so.row_box = w.row_box;
   so.sort_keys = w.sort_keys;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
@@ -808,25 +914,21 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.C = C;
   so.T = T;
   so.Apad = Apad;
+  so.cls_stride = (Apad + 7) & ~7;
   so.tile = tile;
   so.npad_max = next_pow2(A);
+  so.niter = ceil_div(T * tile, kSortThreads);
   so.nms_threshold = nms_threshold;
   so.force_suppress = force_suppress;
   so.nms_topk = nms_topk;
-  so.seg_list = w.seg_list;
-  so.seg_box = w.seg_box;
-  so.key32 = w.key32;
-  const int nclass = C > 1 ? C - 1 : 1;
-  so.nclass = nclass;
-  so.bucket = nclass <= tuning(DSPMB_TUNE_DET_BUCKET_CLASSES) ? 1 : 0;
-  so.key32_in_smem = A <= kKey32SmemMax ? 1 : 0;
+  so.keys_in_smem = T * tile <= kKeySmemMax ? 1 : 0;
   // sort keys in shared memory: enough for the top-k head, or for everything when no top-k limit applies
-  const int want = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
   const int smem_keys = tuning(DSPMB_TUNE_SORT_SMEM_KEYS) < 2 ? 2 : tuning(DSPMB_TUNE_SORT_SMEM_KEYS);
+  const int want = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
   so.sel_cap = want < smem_keys ? (want < 2 ? 2 : want) : smem_keys;
-  const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (so.key32_in_smem ? sizeof(unsigned) * ((A + 3) & ~3) : 0) +
-                       sizeof(int) * ((size_t)T + 1 + 3 * (nclass + 1) + (so.bucket ? 32 * nclass : 0));
-  DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many tiles/classes for the sort kernel (A=%d C=%d)", A, C);
+  const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (so.keys_in_smem ? sizeof(unsigned) * (size_t)T * tile : 0) +
+                       sizeof(int) * ((size_t)T + 1 + 32 * (size_t)so.niter);
+  DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
   static bool attr_set = false;
   if (!attr_set) {
     DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -838,29 +940,29 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
-  if (nms_threshold > 0.f && nms_threshold <= 1.f) {
+  if (nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress)) {
     NmsArgs na;
     na.out = out;
     na.nms_rows = w.nms_rows;
-    na.seg_off = w.seg_off;
+    na.cursor = w.cursor;
+    na.row_cls = w.row_cls;
+    na.row_box = w.row_box;
     na.seg_list = w.seg_list;
     na.seg_box = w.seg_box;
     na.seg_dead = w.seg_dead;
     na.A = A;
+    na.cls_stride = (Apad + 7) & ~7;
     na.C = C;
     na.nms_threshold = nms_threshold;
     na.force_suppress = force_suppress;
-    na.lists_ready = so.bucket;
     na.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
     na.smem_rows = tuning(DSPMB_TUNE_NMS_SMEM_ROWS);
-    dim3 grid3(force_suppress ? 1 : (C > 1 ? C - 1 : 1), B);
-    if (C > 1 || force_suppress) {
-      {
-    ProfileScope _p(kSlotDetNms, stream);
-    det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
-  }
-      DSPMB_CUDA_TRY(cudaGetLastError());
+    dim3 grid3(force_suppress ? 1 : C - 1, B);
+    {
+      ProfileScope _p(kSlotDetNms, stream);
+      det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
     }
+    DSPMB_CUDA_TRY(cudaGetLastError());
   }
   return DSPMB_OK;
 }
