@@ -35,8 +35,8 @@ static int detect_host_libm_mode() {
 #endif
 }
 
-static int g_tuning[4] = {256, 512, 2048, 8192};
-static const int kTuningMax[4] = {256, 512, 2048, 8192};
+static int g_tuning[4] = {256, 320, 1024, 8192};
+static const int kTuningMax[4] = {256, 320, 1024, 8192};
 int tuning(int knob) { return g_tuning[knob]; }
 
 int libm_fma_mode() {

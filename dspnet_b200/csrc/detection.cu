@@ -40,8 +40,8 @@ constexpr int kNmsThreads = 256;
 constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared memory
 constexpr int kRankSortMax = 1024;    // selections up to this size are rank-sorted (one key per thread)
 constexpr int kKeySmemMax = 28672;    // slot keys (T * tile) that fit in shared memory next to the sort keys
-constexpr int kNmsMaskRows = 512;     // NMS segments up to this size use the shared-memory bit mask
-constexpr int kNmsSmemRows = 2048;    // rows of a larger NMS segment staged in shared memory
+constexpr int kNmsMaskRows = 320;     // NMS segments up to this size use the shared-memory bit mask (5 words/row)
+constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in shared memory
 constexpr int kRecFloats = 8;         // score, id, x1, y1, x2, y2, dist, pad
 constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every real key
 
@@ -58,6 +58,7 @@ struct DetWorkspace {
   int *seg_list;              // (B, A) member rows of large segments
   float4 *seg_box;            // (B, A) boxes of large segments in segment order
   unsigned char *seg_dead;    // (B, A)
+  float *seg_area;            // (B, A) areas of large segments
   unsigned long long *sort_keys;  // (B, npad) spill for selections larger than the shared-memory budget
   size_t bytes;
 };
@@ -92,6 +93,7 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
   w.seg_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
   w.seg_dead = (unsigned char *)take((size_t)B * A);
+  w.seg_area = (float *)take(sizeof(float) * (size_t)B * A);
   w.sort_keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * next_pow2(A));
   w.bytes = off;
   return w;
@@ -287,6 +289,7 @@ struct SortArgs {
   int force_suppress, nms_topk;
 };
 
+template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ int scan_smem[kSortThreads / 32 + 1];
@@ -299,15 +302,16 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   // dynamic smem: [sel: sel_cap u64][skeys: Tt u32 (optional)][tile_off: T+1 int][wtab: niter*32 int]
   unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
   unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
-  int *tile_off = reinterpret_cast<int *>(skeys + (a.keys_in_smem ? Tt : 0));
+  int *tile_off = reinterpret_cast<int *>(skeys + (kKeysInSmem ? Tt : 0));
   int *wtab = tile_off + (T + 1);
   const unsigned *gkeys = a.keys + (size_t)b * a.Apad;
-  const unsigned *keys = a.keys_in_smem ? skeys : gkeys;
+  // explicit address spaces: shared-memory keys must compile to LDS, not to generic loads
+  auto key_at = [&](int s) -> unsigned { return kKeysInSmem ? skeys[s] : gkeys[s]; };
   const unsigned warp = warp_id(), lane = lane_id();
   if (b == 0 && threadIdx.x == 0) a.header->status = DSPMB_OK;
 
   // 0. stage the slot keys (coalesced 128-bit loads; Tt is a multiple of 128)
-  if (a.keys_in_smem)
+  if (kKeysInSmem)
     for (int i = threadIdx.x; i < (Tt >> 2); i += blockDim.x)
       reinterpret_cast<uint4 *>(skeys)[i] = __ldg(reinterpret_cast<const uint4 *>(gkeys) + i);
 
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
         const unsigned prefix = sm_prefix;
         for (int it = 0; it < a.niter; ++it) {
           const int s = it * blockDim.x + threadIdx.x;
-          const unsigned kv = s < Tt ? keys[s] : kKeySentinel;
+          const unsigned kv = s < Tt ? key_at(s) : kKeySentinel;
           hist_add(hist256, (kv >> shift) & 0xffu, kv != kKeySentinel && (kv & mask) == prefix);
         }
         __syncthreads();
@@ -403,7 +407,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
       // ballot counts of the pivot-valued keys per (iteration, warp), scanned in slot order
       for (int it = 0; it < a.niter; ++it) {
         const int s = it * blockDim.x + threadIdx.x;
-        const unsigned m = __ballot_sync(kFullMask, s < Tt && keys[s] == pivot);
+        const unsigned m = __ballot_sync(kFullMask, s < Tt && key_at(s) == pivot);
         if (lane == 0) wtab[it * 32 + warp] = __popc(m);
       }
       __syncthreads();
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     // gather the selection (any order: the 64-bit keys are unique and get sorted next)
     for (int it = 0; it < a.niter; ++it) {
       const int s = it * blockDim.x + threadIdx.x;
-      const unsigned kv = s < Tt ? keys[s] : kKeySentinel;
+      const unsigned kv = s < Tt ? key_at(s) : kKeySentinel;
       bool take = kv != kKeySentinel && kv <= pivot;
       if (ordered_ties) {
         const bool eq = kv == pivot;
@@ -438,11 +442,12 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     if (nkeep <= kRankSortMax && nkeep <= a.sel_cap) {
       // rank sort: one key per thread, n broadcast reads, no barriers inside
       const int n = nkeep;
-      const unsigned long long mine = (int)threadIdx.x < n ? sel[threadIdx.x] : 0ull;
+      const unsigned long long mine = (int)threadIdx.x < n ? ssel[threadIdx.x] : 0ull;  // sel == ssel here
       int rank = 0;
-      for (int j = 0; j < n; ++j) rank += sel[j] < mine ? 1 : 0;
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) rank += ssel[j] < mine ? 1 : 0;
       __syncthreads();
-      if ((int)threadIdx.x < n) sel[rank] = mine;
+      if ((int)threadIdx.x < n) ssel[rank] = mine;
       __syncthreads();
     } else {
       for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
@@ -459,12 +464,20 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   float *out = a.out + (size_t)b * A * 7;
   unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
   float4 *row_box = a.row_box + (size_t)b * A;
-  for (int base = 0; base < V; base += 4 * blockDim.x) {
+  // Rows are staged in shared memory (the key array is dead by now) and written out as one contiguous run of
+  // 128-bit stores per chunk; without a staging area (keys in global memory) each thread stores its 7 floats.
+  float *stage = reinterpret_cast<float *>(skeys);
+  const int stage_rows = kKeysInSmem ? min(4 * (int)blockDim.x, ((Tt * 4) / 28) & ~3) : 0;
+  const int chunk = stage_rows >= 64 ? stage_rows : 4 * (int)blockDim.x;
+  const bool staged = stage_rows >= 64;
+  for (int base = 0; base < V; base += chunk) {
+    const int rows = min(chunk, V - base);
     float4 s0[4], s1[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = base + u * blockDim.x + threadIdx.x;
-      if (r < V) {
+      const int q = u * blockDim.x + threadIdx.x;
+      const int r = base + q;
+      if (q < rows) {
         int slot;
         if (r < nkeep) {
           slot = (int)(unsigned)(sel[r] & 0xffffffffull);
@@ -483,9 +496,10 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = base + u * blockDim.x + threadIdx.x;
-      if (r < V) {
-        float *o = out + (size_t)r * 7;
+      const int q = u * blockDim.x + threadIdx.x;
+      const int r = base + q;
+      if (q < rows) {
+        float *o = staged ? stage + q * 7 : out + (size_t)r * 7;
         o[0] = s0[u].y;  // id
         o[1] = s0[u].x;  // score
         o[2] = s0[u].z;
@@ -499,6 +513,19 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
         }
       }
     }
+    if (staged) {
+      __syncthreads();
+      float *dst = out + (size_t)base * 7;
+      const int nfl = rows * 7;
+      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        for (int i = threadIdx.x; i < (nfl >> 2); i += blockDim.x)
+          reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(stage)[i];
+        for (int i = (nfl & ~3) + threadIdx.x; i < nfl; i += blockDim.x) dst[i] = stage[i];
+      } else {
+        for (int i = threadIdx.x; i < nfl; i += blockDim.x) dst[i] = stage[i];
+      }
+      __syncthreads();
+    }
   }
 }
 
@@ -511,30 +538,60 @@ struct NmsArgs {
   int *seg_list;
   float4 *seg_box;
   unsigned char *seg_dead;
+  float *seg_area;
   int A, cls_stride, C;
   float nms_threshold;
   int force_suppress, mask_rows, smem_rows;
 };
 
-// IoU >= thr test of multibox_detection.cc:44-51,162.  Disjoint boxes have i = 0, hence iou = 0 < thr (thr > 0
-// whenever NMS runs): the overlap test min(x2) > max(x1) && min(y2) > max(y1) is four compares (a - b > 0 <=> a > b
-// in IEEE arithmetic with gradual underflow), and the division is only paid for overlapping pairs.
-__device__ __forceinline__ bool suppresses(float4 a, float4 b, float thr) {
-  if (!(a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y && a.z > a.x && b.z > b.x && a.w > a.y && b.w > b.y)) return false;
+// IoU >= thr test of multibox_detection.cc:44-51,162 on boxes staged by stage_box().
+//  * Disjoint boxes have i = 0, hence iou = 0 < thr (thr > 0 whenever NMS runs).  min(x2) - max(x1) > 0 is four
+//    compares per axis pair (a - b > 0 <=> a > b in IEEE arithmetic with gradual underflow); degenerate boxes were
+//    given x1 = +inf by stage_box so they fail the test.
+//  * For overlapping pairs RN(i/u) >= thr is decided without dividing unless i lies within 2^-20 (relative) of
+//    thr*u: rounding is monotonic, so i/u > thr(1+2^-21) implies RN(i/u) >= thr and i/u < thr(1-2^-21) implies
+//    RN(i/u) < thr; the products thr_hi*u, thr_lo*u carry < 2^-22 relative error.  Only the band in between
+//    (and tiny unions, where those products could underflow) takes the IEEE division.
+struct NmsThr {
+  float thr, lo, hi;
+};
+__device__ __forceinline__ NmsThr make_thr(float thr) {
+  NmsThr t;
+  t.thr = thr;
+  t.lo = fmul(thr, 1.0f - 0x1p-20f);
+  t.hi = fmul(thr, 1.0f + 0x1p-20f);
+  return t;
+}
+__device__ __forceinline__ float4 stage_box(float4 b, float *area) {
+  *area = fmul(fsub(b.z, b.x), fsub(b.w, b.y));  // (a[2]-a[0])*(a[3]-a[1]) of CalculateOverlap
+  if (!(b.z > b.x && b.w > b.y)) b.x = __int_as_float(0x7f800000);
+  return b;
+}
+__device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, NmsThr t) {
+  if (!(a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y)) return false;
   const float w = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
   const float h = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
   const float i = fmul(w, h);
-  const float u = fsub(fadd(fmul(fsub(a.z, a.x), fsub(a.w, a.y)), fmul(fsub(b.z, b.x), fsub(b.w, b.y))), i);
-  return (u <= 0.f ? 0.f : fdiv(i, u)) >= thr;
+  const float u = fsub(fadd(area_a, area_b), i);
+  if (u <= 0.f) return false;
+  if (u >= 1e-30f) {
+    if (i > fmul(t.hi, u)) return true;
+    if (i < fmul(t.lo, u)) return false;
+  }
+  return fdiv(i, u) >= t.thr;
 }
 
-constexpr int kNmsTab = 1024;  // ballot-count table entries: 128 iterations x 8 warps = 262144 rows per sweep
+constexpr int kNmsTab = 512;  // ballot-count table entries: 64 iterations x 8 warps = 131072 rows per sweep
 
 __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
   // shared memory is a union of the two paths:
-  //   small (n <= mask_rows <= 512): boxes[512] float4 (8 KB) + mask[512 * 8] u64 (32 KB) + list[512] int (2 KB)
-  //   large:                         boxes[2048] float4 (32 KB) + dead[2048] (2 KB) + 64 words
-  __shared__ __align__(16) unsigned char smem_raw[42 * 1024 + 512];
+  //   small (n <= mask_rows <= 320): boxes[320] float4 + mask[320 * 5] u64 + list[320] int + areas[320]  (20 KB)
+  //   large:                         boxes[1024] float4 + dead[1024] + 64 words + areas[1024]             (21.5 KB)
+  // kept near 22 KB so that 8 CTAs (all 2048 threads) fit on an SM and the usual grid is a single wave.
+  constexpr int kOffMask = kNmsMaskRows * 16, kOffList = kOffMask + kNmsMaskRows * 5 * 8, kOffArea = kOffList + kNmsMaskRows * 4;
+  constexpr int kOffDead = kNmsSmemRows * 16, kOffWord = kOffDead + kNmsSmemRows, kOffAreaL = kOffWord + 512;
+  __shared__ __align__(16) unsigned char smem_raw[kOffAreaL + kNmsSmemRows * 4];
+  static_assert(kOffArea + kNmsMaskRows * 4 <= kOffAreaL + kNmsSmemRows * 4, "small-path layout exceeds the union");
   __shared__ int wtab[kNmsTab];
   __shared__ unsigned long long rowany[8];
   __shared__ unsigned sm_deadbits[2];
@@ -548,14 +605,14 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   float *out = a.out + (size_t)b * a.A * 7;
   const float4 *row_box = a.row_box + (size_t)b * a.A;
   const bool identity = a.force_suppress != 0;  // single segment: row q is list entry q
-  const float thr = a.nms_threshold;
+  const NmsThr thr = make_thr(a.nms_threshold);
   const unsigned lane = lane_id(), warp = warp_id(), nwarps = blockDim.x >> 5;
   const int rows_per_iter = blockDim.x * 8;
   const int niter = (V + rows_per_iter - 1) / rows_per_iter;
 
   // ---------------- ordered member list of this class: ballot-count tables, no atomics ----------------
   int n = V;
-  int *slist = reinterpret_cast<int *>(smem_raw + 40 * 1024);  // small path only
+  int *slist = reinterpret_cast<int *>(smem_raw + kOffList);  // small path only
   int *glist = nullptr;
   if (!identity) {
     const uint4 *cls8 = reinterpret_cast<const uint4 *>(a.row_cls + (size_t)b * a.cls_stride);
@@ -647,10 +704,11 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   if (n <= a.mask_rows) {
     // ---------------- small segment: full bit mask in shared memory + word-serial resolve ----------------
     float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
-    unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kNmsMaskRows * sizeof(float4));
+    unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kOffMask);
     const int W = (n + 63) >> 6;
-    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = __ldg(row_box + (identity ? q : slist[q]));
-    if (threadIdx.x < 8) rowany[threadIdx.x] = 0ull;
+    float *areas = reinterpret_cast<float *>(smem_raw + kOffArea);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = stage_box(__ldg(row_box + (identity ? q : slist[q])), &areas[q]);
+    if (threadIdx.x < 8) rowany[threadIdx.x] = 0ull;  // W <= 5
     __syncthreads();
     // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x one
     // 64-column word, dealt round-robin to the warps; the column box is a shared-memory broadcast.
@@ -663,9 +721,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
         unsigned long long bits = 0ull;
         if (i < n) {
           const float4 bi = boxes[i];
+          const float ai = areas[i];
           const int j1 = min(n, (w + 1) << 6);
-          for (int j = w << 6; j < j1; ++j)
-            if (j > i && suppresses(bi, boxes[j], thr)) bits |= 1ull << (j & 63);
+          for (int j = max(w << 6, i + 1); j < j1; ++j)
+            if (suppresses(bi, ai, boxes[j], areas[j], thr)) bits |= 1ull << (j & 63);
           mask[i * W + w] = bits;
           if (bits) atomicOr(&rowany[i >> 6], 1ull << (i & 63));
         }
@@ -712,10 +771,12 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   // ---------------- large segment: 64-row chunks, ballot mask + serial resolve + parallel sweep ----------------
   float4 *boxes;
   unsigned char *dead;
-  unsigned long long *sm_word = reinterpret_cast<unsigned long long *>(smem_raw + 34 * 1024);
+  float *areas;
+  unsigned long long *sm_word = reinterpret_cast<unsigned long long *>(smem_raw + kOffWord);
   if (n <= a.smem_rows) {
     boxes = reinterpret_cast<float4 *>(smem_raw);
-    dead = smem_raw + 32 * 1024;
+    dead = smem_raw + kOffDead;
+    areas = reinterpret_cast<float *>(smem_raw + kOffAreaL);
   } else {
     // claim scratch in segment order (the list region doubles as the allocator for identity segments)
     if (identity) {
@@ -724,9 +785,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     }
     boxes = a.seg_box + (size_t)b * a.A + sm_base;
     dead = a.seg_dead + (size_t)b * a.A + sm_base;
+    areas = a.seg_area + (size_t)b * a.A + sm_base;
   }
   for (int q = threadIdx.x; q < n; q += blockDim.x) {
-    boxes[q] = __ldg(row_box + (identity ? q : glist[q]));
+    boxes[q] = stage_box(__ldg(row_box + (identity ? q : glist[q])), &areas[q]);
     dead[q] = 0;
   }
   __syncthreads();
@@ -742,9 +804,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
       unsigned lo = 0, hi = 0;
       if (!dead[c0 + i]) {
         const float4 bi = boxes[c0 + i];
+        const float ai = areas[c0 + i];
         const int j0 = lane, j1 = lane + 32;
-        const bool s0 = j0 > i && j0 < m && suppresses(bi, boxes[c0 + j0], thr);
-        const bool s1 = j1 > i && j1 < m && suppresses(bi, boxes[c0 + j1], thr);
+        const bool s0 = j0 > i && j0 < m && suppresses(bi, ai, boxes[c0 + j0], areas[c0 + j0], thr);
+        const bool s1 = j1 > i && j1 < m && suppresses(bi, ai, boxes[c0 + j1], areas[c0 + j1], thr);
         lo = __ballot_sync(kFullMask, s0);
         hi = __ballot_sync(kFullMask, s1);
       }
@@ -770,11 +833,12 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     for (int j = c0 + 64 + threadIdx.x; j < n; j += blockDim.x) {
       if (dead[j]) continue;
       const float4 bj = boxes[j];
+      const float aj = areas[j];
       unsigned long long rem = alive;
       while (rem) {
         const int t = __ffsll((long long)rem) - 1;
         rem &= rem - 1;
-        if (suppresses(boxes[c0 + t], bj, thr)) {
+        if (suppresses(boxes[c0 + t], areas[c0 + t], bj, aj, thr)) {
           dead[j] = 1;
           break;
         }
@@ -931,12 +995,16 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
   static bool attr_set = false;
   if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   {
     ProfileScope _p(kSlotDetSort, stream);
-    det_sort_kernel<<<B, kSortThreads, smem2, stream>>>(so);
+    if (so.keys_in_smem)
+      det_sort_kernel<true><<<B, kSortThreads, smem2, stream>>>(so);
+    else
+      det_sort_kernel<false><<<B, kSortThreads, smem2, stream>>>(so);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
@@ -950,6 +1018,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.seg_list = w.seg_list;
     na.seg_box = w.seg_box;
     na.seg_dead = w.seg_dead;
+    na.seg_area = w.seg_area;
     na.A = A;
     na.cls_stride = (Apad + 7) & ~7;
     na.C = C;

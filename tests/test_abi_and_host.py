@@ -43,7 +43,7 @@ def test_argument_checks_return_codes_without_gpu():
     assert L.dspmb_nms_workspace_bytes(1000) >= 1000 * 16 * 8
     assert L.dspmb_set_libm_mode(0) == 0 and L.dspmb_set_libm_mode(1) == 1 and L.dspmb_set_libm_mode(-1) in (0, 1)
     old = L.dspmb_set_tuning(_lib.TUNE_NMS_MASK_ROWS, 100000)
-    assert L.dspmb_set_tuning(_lib.TUNE_NMS_MASK_ROWS, old) == 512  # clamped to the compiled maximum
+    assert L.dspmb_set_tuning(_lib.TUNE_NMS_MASK_ROWS, old) == 320  # clamped to the compiled maximum
     assert L.dspmb_set_tuning(99, 1) == -1
 
 
