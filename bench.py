@@ -116,38 +116,60 @@ def oracle_anchors():
                            for fm in p.maps], axis=1)
 
 
-def cpu_baseline(inputs, threads, repeats=3):
-    """Times the CPU oracle (restated reference CPU operator) on the host cores: one B=32 detection batch per
-    repeat, image-parallel over `threads` threads (the reference loop itself is single-threaded)."""
+def cpu_detection(inputs, anchors, threads):
+    """One pass of the reference CPU operator over the batch, one image slice per host thread.  Uses oracle/_ref
+    (the reference's own multibox_detection.cc compiled in place) when it is present, else the oracle port; the two
+    are bit-identical (tests/test_oracle_golden.py).  Returns the kind that ran."""
+    from oracle import ref as R
+    B = inputs["prob"].shape[0]
+    if R.available():
+        from concurrent.futures import ThreadPoolExecutor
+        n = max(1, min(threads, B))
+        bounds = [(i * B // n, (i + 1) * B // n) for i in range(n)]
+
+        def run(be):
+            b, e = be
+            return R.multibox_detection(inputs["prob"][b:e], inputs["loc"][b:e], anchors, **DET_PARAMS)
+        if n == 1:
+            run(bounds[0])
+        else:
+            with ThreadPoolExecutor(n) as ex:
+                list(ex.map(run, bounds))
+        return "reference"
     from oracle import oracle as O
+    O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+    return "port"
+
+
+def cpu_baseline(inputs, threads, repeats=3):
+    """images/s of the CPU operator on one B=32 detection batch (median of `repeats` after one warm-up)."""
     anchors = oracle_anchors()
-    times = []
+    times, kind = [], "port"
     for _ in range(repeats + 1):
         t0 = time.perf_counter()
-        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+        kind = cpu_detection(inputs, anchors, threads)
         times.append(time.perf_counter() - t0)
     times = sorted(times[1:])
-    return BATCH / times[len(times) // 2]
+    return BATCH / times[len(times) // 2], kind
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: MXNet cannot be installed
-    here) on all host threads; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path on all host threads; rank 0 only.
+    (MXNet itself cannot be installed here -- DESIGN.md section 9 -- so the operator body is driven directly.)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     inputs, _ = make_inputs(0, BATCH)
-    from oracle import oracle as O
     anchors = oracle_anchors()
+    kind = "port"
     for _ in range(max(args.warmup, 1)):
-        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+        kind = cpu_detection(inputs, anchors, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.multibox_detection(inputs["prob"], inputs["loc"], anchors, nthreads=threads, **DET_PARAMS)
+        cpu_detection(inputs, anchors, threads)
     dt = time.perf_counter() - t0
     value = BATCH * args.steps / dt
-    kind = "port"
     line = {
         "impl": "reference", "metric": "ssd512_multibox_detection_images_per_s", "value": value, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -155,7 +177,8 @@ def run_reference(args):
         "config": {"workload": "ssd512_voc21_multibox_detection_nms_batch32", "preset": PRESET, "batch_per_gpu": BATCH,
                    "anchors": inputs["A"], "classes": inputs["C"], **{k: v for k, v in DET_PARAMS.items()}},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": kind,
-                         "sample": "%d steps x one B=32 SSD-512 detection batch, one image per thread" % args.steps},
+                         "sample": "%d steps x one B=32 SSD-512 detection batch, image slices over %d host threads"
+                                   % (args.steps, threads)},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -370,9 +393,9 @@ def main():
                 line["roofline"]["traffic"] = json.load(f).get("det_stream_kernel")
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
-            v = cpu_baseline(inputs, threads)
-            v1 = cpu_baseline(inputs, 1, repeats=1)
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+            v, kind = cpu_baseline(inputs, threads)
+            v1, _ = cpu_baseline(inputs, 1, repeats=1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": kind,
                                     "sample": "one B=32 SSD-512 detection batch, median of 3 after 1 warm-up, one image "
                                               "per thread; single thread: %.1f images/s" % v1}
         print(json.dumps(line))
