@@ -35,8 +35,8 @@ static int detect_host_libm_mode() {
 #endif
 }
 
-static int g_tuning[4] = {256, 320, 1024, 8192};
-static const int kTuningMax[4] = {256, 320, 1024, 8192};
+static int g_tuning[5] = {256, 320, 1024, 8192, 7};
+static const int kTuningMax[5] = {256, 320, 1024, 8192, 7};
 int tuning(int knob) { return g_tuning[knob]; }
 
 int libm_fma_mode() {
@@ -100,7 +100,7 @@ extern "C" int dspmb_set_libm_mode(int mode) {
 }
 
 extern "C" int dspmb_set_tuning(int knob, int value) {
-  if (knob < 0 || knob >= 4) return -1;
+  if (knob < 0 || knob >= 5) return -1;
   const int old = g_tuning[knob];
   g_tuning[knob] = value < 0 ? 0 : (value > kTuningMax[knob] ? kTuningMax[knob] : value);
   return old;

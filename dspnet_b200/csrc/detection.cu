@@ -232,6 +232,267 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Register-resident variant for a compile-time number of foreground classes NFG (20 = VOC, 8 = Cityscapes).
+// Every load of the thread -- NFG class rows, the 4 anchors and the 4 loc_pred rows (20 floats) -- is issued
+// before the first compare, so a thread has (NFG + 9) x 16 B in flight, the decode has no dependent memory round
+// trip, and the ~150 registers/thread cap residency at 3 CTAs/SM: the grid runs in several waves whose load and
+// store/decode phases overlap instead of all CTAs being resident and in lockstep.
+template <int NFG>
+__global__ void __launch_bounds__(kStreamThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
+  __shared__ int scan_smem[kStreamThreads / 32 + 1];
+  __shared__ __align__(16) unsigned sm_keys[kStreamThreads * 4];
+  const int b = blockIdx.y, t = blockIdx.x;
+  constexpr int kTile = kStreamThreads * 4;
+  const int tile_begin = t * kTile;
+  const int i0 = tile_begin + threadIdx.x * 4;
+  const int A = a.A;
+  const bool active = i0 < A;
+  const float *cp = a.cls_prob + ((size_t)b * a.C + 1) * A + i0;
+
+  float4 q[NFG], an[4], lp[5];
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < NFG; ++j) q[j] = ld_stream_f4(cp + (size_t)j * A);
+    const float4 *ap = reinterpret_cast<const float4 *>(a.anchors) + i0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) an[k] = __ldg(ap + k);
+    const float *lsrc = a.loc_pred + ((size_t)b * A + i0) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lp[k] = ld_stream_f4(lsrc + 4 * k);
+  }
+  {  // `out = -1` for this tile's rows (multibox_detection-inl.h:103)
+    float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
+    const int nfl = min(kTile, A - tile_begin) * 7;
+    const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+    for (int x = threadIdx.x * 4; x < nfl; x += kStreamThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
+  }
+  float score[4] = {-1.f, -1.f, -1.f, -1.f};
+  int id[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sm_keys[threadIdx.x * 4 + k] = kKeySentinel;
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < NFG; ++j) {
+      const float v[4] = {q[j].x, q[j].y, q[j].z, q[j].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (v[k] > score[k]) {
+          score[k] = v[k];
+          id[k] = j + 1;
+        }
+    }
+  }
+  int nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (id[k] > 0 && score[k] < a.threshold) id[k] = 0;
+    nvalid += id[k] > 0;
+  }
+  int total;
+  int pos = block_scan_excl(nvalid, scan_smem, &total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  if (nvalid) {
+    float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
+    const float lf[20] = {lp[0].x, lp[0].y, lp[0].z, lp[0].w, lp[1].x, lp[1].y, lp[1].z, lp[1].w, lp[2].x, lp[2].y,
+                          lp[2].z, lp[2].w, lp[3].x, lp[3].y, lp[3].z, lp[3].w, lp[4].x, lp[4].y, lp[4].z, lp[4].w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (id[k] > 0) {
+        // decode, multibox_detection.cc:98-125
+        const float aw = fsub(an[k].z, an[k].x), ah = fsub(an[k].w, an[k].y);
+        const float ax = fdiv(fadd(an[k].x, an[k].z), 2.f), ay = fdiv(fadd(an[k].y, an[k].w), 2.f);
+        const float ox = fadd(fmul(fmul(lf[5 * k], a.vx), aw), ax);
+        const float oy = fadd(fmul(fmul(lf[5 * k + 1], a.vy), ah), ay);
+        const float ow = fdiv(fmul(libm::expf_glibc(fmul(lf[5 * k + 2], a.vw), a.fma_build), aw), 2.f);
+        const float oh = fdiv(fmul(libm::expf_glibc(fmul(lf[5 * k + 3], a.vh), a.fma_build), ah), 2.f);
+        const float oz = __double2float_rn(__dmul_rn((double)lf[5 * k + 4], 0.1));
+        float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
+        if (a.clip) {
+          x1 = clip01(x1);
+          y1 = clip01(y1);
+          x2 = clip01(x2);
+          y2 = clip01(y2);
+          z = clip01(z);
+        }
+        float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)pos * kRecFloats);
+        r4[0] = make_float4(score[k], (float)(id[k] - 1), x1, y1);
+        r4[1] = make_float4(x2, y2, z, 0.f);
+        sm_keys[pos] = ~float_order_key(score[k]);
+        ++pos;
+      }
+  }
+  __syncthreads();
+  reinterpret_cast<uint4 *>(a.keys + (size_t)b * a.Apad + tile_begin)[threadIdx.x] =
+      reinterpret_cast<const uint4 *>(sm_keys)[threadIdx.x];
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Persistent, TMA-fed variant of the stream kernel (the default when A % 4 == 0).
+//
+// grid = #SMs x CTAs/SM; every CTA walks tiles of kPipeTile anchors (round-robin over image x tile) through a
+// kStages-deep ring of shared-memory stages.  One elected thread feeds the ring with 1-D bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx: the TMA engine, no registers, no per-thread address math): the C-1
+// foreground class rows of the tile (kPipeTile * 4 B each, contiguous in the (B,C,A) layout) and the tile's
+// loc_pred rows (kPipeTile * 20 B, contiguous).  The copy of tile i + kStages - 1 is issued before tile i is
+// consumed, so HBM stays busy while the CTA does its argmax / compaction / decode / stores -- in the plain kernel
+// all CTAs are resident at once and run their load and compute phases in lockstep, which idles DRAM during
+// the tails.  The block barrier that ends a tile doubles as the "stage free" signal.
+constexpr int kPipeThreads = 128;
+constexpr int kPipeVec = 2;
+constexpr int kPipeTile = kPipeThreads * kPipeVec;  // 256 anchors
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct PipeArgs {
+  StreamArgs s;
+  int num_tiles;    // B * T
+  int stages;       // ring depth (2..4)
+  int stage_floats; // floats per stage: (C-1) * kPipeTile class values + kPipeTile * 5 loc values
+};
+
+__global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __grid_constant__ PipeArgs p) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ __align__(8) unsigned long long full_bar[4];
+  __shared__ int scan_smem[kPipeThreads / 32 + 1];
+  __shared__ __align__(16) unsigned sm_keys[kPipeTile];
+  const StreamArgs &a = p.s;
+  const int A = a.A, T = a.T, nfg = a.C - 1;
+  float *ring = reinterpret_cast<float *>(dyn_smem);
+
+  auto issue = [&](int tile_idx, int stage) {  // one thread: arm the barrier, then the bulk copies of one tile
+    const int b = tile_idx / T, t = tile_idx - b * T;
+    const int tile_begin = t * kPipeTile;
+    const int rows = min(kPipeTile, A - tile_begin);
+    float *dst = ring + (size_t)stage * p.stage_floats;
+    mbar_expect_tx(&full_bar[stage], (unsigned)(rows * 4 * nfg + rows * 20));
+    const float *cp = a.cls_prob + ((size_t)b * a.C + 1) * A + tile_begin;
+    for (int j = 0; j < nfg; ++j) bulk_g2s(dst + j * kPipeTile, cp + (size_t)j * A, rows * 4, &full_bar[stage]);
+    bulk_g2s(dst + nfg * kPipeTile, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar[stage]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages - 1; ++s) {
+      const int idx = blockIdx.x + s * gridDim.x;
+      if (idx < p.num_tiles) issue(idx, s);
+    }
+  }
+
+  int it = 0;
+  for (int tile_idx = blockIdx.x; tile_idx < p.num_tiles; tile_idx += gridDim.x, ++it) {
+    const int stage = it % p.stages;
+    // keep the ring full: the stage freed by the previous iteration receives tile it + stages - 1
+    if (threadIdx.x == 0) {
+      const int ahead = tile_idx + (p.stages - 1) * gridDim.x;
+      if (ahead < p.num_tiles) issue(ahead, (it + p.stages - 1) % p.stages);
+    }
+    const int b = tile_idx / T, t = tile_idx - b * T;
+    const int tile_begin = t * kPipeTile;
+    const int rows = min(kPipeTile, A - tile_begin);
+    const int l0 = threadIdx.x * kPipeVec;  // first anchor of this thread inside the tile
+
+    // `out = -1` for this tile's rows (multibox_detection-inl.h:103); independent of the loads
+    {
+      float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
+      const int nfl = rows * 7;
+      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+      for (int q = threadIdx.x * 4; q < nfl; q += kPipeThreads * 4) *reinterpret_cast<float4 *>(ob + q) = m1;
+    }
+    sm_keys[l0] = kKeySentinel;
+    sm_keys[l0 + 1] = kKeySentinel;
+
+    mbar_wait(&full_bar[stage], (unsigned)((it / p.stages) & 1));
+    const float *cls = ring + (size_t)stage * p.stage_floats;
+    const float *locs = cls + nfg * kPipeTile;
+
+    float score[kPipeVec] = {-1.f, -1.f};
+    int id[kPipeVec] = {0, 0};
+    if (l0 < rows) {
+#pragma unroll 4
+      for (int j = 0; j < nfg; ++j) {
+        const float2 v = *reinterpret_cast<const float2 *>(cls + j * kPipeTile + l0);
+        if (v.x > score[0]) {
+          score[0] = v.x;
+          id[0] = j + 1;
+        }
+        if (v.y > score[1]) {
+          score[1] = v.y;
+          id[1] = j + 1;
+        }
+      }
+    }
+    int nvalid = 0;
+#pragma unroll
+    for (int k = 0; k < kPipeVec; ++k) {
+      if (id[k] > 0 && score[k] < a.threshold) id[k] = 0;
+      nvalid += id[k] > 0;
+    }
+    int total;
+    int pos = block_scan_excl(nvalid, scan_smem, &total);
+    if (threadIdx.x == 0) a.tile_count[(size_t)b * T + t] = total;
+    if (nvalid) {
+      float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
+#pragma unroll
+      for (int k = 0; k < kPipeVec; ++k)
+        if (id[k] > 0) {
+          // decode (multibox_detection.cc:98-125) from the staged loc_pred row
+          const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + tile_begin + l0 + k);
+          const float *lp = locs + (l0 + k) * 5;
+          const float aw = fsub(an.z, an.x), ah = fsub(an.w, an.y);
+          const float ax = fdiv(fadd(an.x, an.z), 2.f), ay = fdiv(fadd(an.y, an.w), 2.f);
+          const float ox = fadd(fmul(fmul(lp[0], a.vx), aw), ax);
+          const float oy = fadd(fmul(fmul(lp[1], a.vy), ah), ay);
+          const float ow = fdiv(fmul(libm::expf_glibc(fmul(lp[2], a.vw), a.fma_build), aw), 2.f);
+          const float oh = fdiv(fmul(libm::expf_glibc(fmul(lp[3], a.vh), a.fma_build), ah), 2.f);
+          const float oz = __double2float_rn(__dmul_rn((double)lp[4], 0.1));
+          float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
+          if (a.clip) {
+            x1 = clip01(x1);
+            y1 = clip01(y1);
+            x2 = clip01(x2);
+            y2 = clip01(y2);
+            z = clip01(z);
+          }
+          float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)pos * kRecFloats);
+          r4[0] = make_float4(score[k], (float)(id[k] - 1), x1, y1);
+          r4[1] = make_float4(x2, y2, z, 0.f);
+          sm_keys[pos] = ~float_order_key(score[k]);
+          ++pos;
+        }
+    }
+    __syncthreads();  // keys complete; every thread is done with this stage -> it may be refilled next iteration
+    reinterpret_cast<uint2 *>(a.keys + (size_t)b * a.Apad + tile_begin)[threadIdx.x] =
+        reinterpret_cast<const uint2 *>(sm_keys)[threadIdx.x];
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
 // global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used above kRankSortMax keys.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
@@ -927,8 +1188,21 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   DetWorkspace w = carve(workspace, B, A, C);
 
-  const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out) & 15) == 0;
-  const int tile = kStreamThreads * (vec4 ? 4 : 1);
+  const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out | (uintptr_t)loc_pred) & 15) == 0;
+  // TMA-fed persistent kernel whenever the ring fits (2..4 stages); plain kernels otherwise
+  const size_t stage_bytes = ((size_t)(C - 1) * kPipeTile + (size_t)kPipeTile * 5) * sizeof(float);
+  int stages = 0, ctas_per_sm = 2;
+  const int variant = tuning(DSPMB_TUNE_DET_STREAM_VARIANT);  // 0 generic, 1 TMA ring, else register-resident
+  if (vec4 && C > 1 && variant == 1) {
+    stages = (int)(100 * 1024 / stage_bytes);
+    if (stages < 2) {
+      ctas_per_sm = 1;
+      stages = (int)(200 * 1024 / stage_bytes);
+    }
+    if (stages > 4) stages = 4;
+    if (stages < 2) stages = 0;
+  }
+  const int tile = stages ? kPipeTile : kStreamThreads * (vec4 ? 4 : 1);
   const int T = ceil_div(A, tile);
   const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
 
@@ -951,10 +1225,32 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.vw = variances[2];
   sa.vh = variances[3];
   sa.fma_build = libm_fma_mode();
-  dim3 grid1(T, B);
-  {
+  const int phases = tuning(DSPMB_TUNE_PHASES);
+  if (!(phases & 1)) {
+    // stream phase skipped (per-phase timing: the workspace still holds the previous call's records)
+  } else if (stages) {
+    PipeArgs pa;
+    pa.s = sa;
+    pa.num_tiles = B * T;
+    pa.stages = stages;
+    pa.stage_floats = (int)(stage_bytes / sizeof(float));
+    static bool pipe_attr_set = false;
+    if (!pipe_attr_set) {
+      DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_stream_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      pipe_attr_set = true;
+    }
+    int grid = kNumSMs * ctas_per_sm;
+    if (grid > pa.num_tiles) grid = pa.num_tiles;
     ProfileScope _p(kSlotDetStream, stream);
-    if (vec4)
+    det_stream_tma_kernel<<<grid, kPipeThreads, stages * stage_bytes, stream>>>(pa);
+  } else {
+    dim3 grid1(T, B);
+    ProfileScope _p(kSlotDetStream, stream);
+    if (vec4 && variant > 1 && C == 21)
+      det_stream_reg_kernel<20><<<grid1, kStreamThreads, 0, stream>>>(sa);
+    else if (vec4 && variant > 1 && C == 9)
+      det_stream_reg_kernel<8><<<grid1, kStreamThreads, 0, stream>>>(sa);
+    else if (vec4)
       det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
     else
       det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
@@ -999,7 +1295,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-  {
+  if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
     if (so.keys_in_smem)
       det_sort_kernel<true><<<B, kSortThreads, smem2, stream>>>(so);
@@ -1008,7 +1304,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
-  if (nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress)) {
+  if ((phases & 4) && nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress)) {
     NmsArgs na;
     na.out = out;
     na.nms_rows = w.nms_rows;

@@ -580,7 +580,8 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     return DSPMB_ERR_WORKSPACE;
   }
   TargetWorkspace w = carve(workspace, B, A, L);
-  DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
+  if (tuning(DSPMB_TUNE_PHASES) & 1)
+    DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
 
   const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
                              (uintptr_t)cls_target | (uintptr_t)match_out;
@@ -627,8 +628,9 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
+  const int phases = tuning(DSPMB_TUNE_PHASES);
   dim3 grid1(ta.T, B);
-  {
+  if (phases & 1) {
     ProfileScope _p(kSlotTargetStream, stream);
     if (vec4)
     target_stream_kernel<4><<<grid1, kStreamThreads, smem1, stream>>>(ta);
@@ -636,7 +638,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     target_stream_kernel<1><<<grid1, kStreamThreads, smem1, stream>>>(ta);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
-  {
+  if (phases & 2) {
     ProfileScope _p(kSlotTargetMatch, stream);
     target_match_kernel<<<B, kMatchThreads, smem2, stream>>>(ta);
   }
