@@ -20,7 +20,9 @@
 
 #ifdef __CUDACC__
 #define DSPMB_HD __host__ __device__ __forceinline__
+#define DSPMB_HDM __host__ __device__ __forceinline__
 #else
+#define DSPMB_HDM inline
 #include <math.h>
 #include <string.h>
 #define DSPMB_HD static inline
@@ -95,7 +97,10 @@ DSPMB_HD uint64_t logf_tab(unsigned i) {
 }
 
 // expf: x*N/ln2 = k + r, exp(x) = 2^(k/N) * (C0 r^3 + C1 r^2 + C2 r + 1), N = 32.
-DSPMB_HD float expf_glibc(float x, bool fma_build) {
+// kFma selects glibc's FMA build; `tab(i)` returns entry i of the 2^(i/32) table (global copy, or a shared-memory
+// copy in the hot kernels).
+template <bool kFma, typename Tab>
+DSPMB_HD float expf_glibc_t(float x, Tab tab) {
   const double kShift = 0x1.8p+52;
   const double kInvLn2N = 0x1.71547652b82fep+5;
   const double kC0 = 0x1.c6af84b912394p-20, kC1 = 0x1.ebfce50fac4f3p-13, kC2 = 0x1.62e42ff0c52d6p-6;
@@ -110,21 +115,21 @@ DSPMB_HD float expf_glibc(float x, bool fma_build) {
   }
   const double xd = (double)x;
   double kd, r;
-  if (fma_build) {
+  if (kFma) {
     kd = dfma(kInvLn2N, xd, kShift);
   } else {
     kd = dadd(dmul(kInvLn2N, xd), kShift);
   }
   const uint64_t ki = dbits(kd);
   kd = dsub(kd, kShift);
-  if (fma_build) {
+  if (kFma) {
     r = dfma(kInvLn2N, xd, -kd);
   } else {
     r = dsub(dmul(kInvLn2N, xd), kd);
   }
-  const double s = dfrom(exp2f_tab((unsigned)(ki & 31)) + (ki << 47));
+  const double s = dfrom(tab((unsigned)(ki & 31)) + (ki << 47));
   double z, r2, y;
-  if (fma_build) {
+  if (kFma) {
     z = dfma(kC0, r, kC1);
     r2 = dmul(r, r);
     y = dfma(kC2, r, 1.0);
@@ -136,6 +141,12 @@ DSPMB_HD float expf_glibc(float x, bool fma_build) {
     y = dadd(dmul(z, r2), y);
   }
   return d2f(dmul(y, s));
+}
+struct GlobalExpTab {
+  DSPMB_HDM uint64_t operator()(unsigned i) const { return exp2f_tab(i); }
+};
+DSPMB_HD float expf_glibc(float x, bool fma_build) {
+  return fma_build ? expf_glibc_t<true>(x, GlobalExpTab()) : expf_glibc_t<false>(x, GlobalExpTab());
 }
 
 // logf: x = 2^k z, z in [OFF, 2 OFF); log(x) = log1p(z/c - 1) + log(c) + k ln2 with c from a 16-entry table.

@@ -38,6 +38,8 @@ struct TargetWorkspace {
   int *thr_count;  // (B) threshold-stage positives (zeroed per call)
   unsigned long long *colbest;  // (B, L) best (iou, anchor) per gt (zeroed per call)
   unsigned *key;   // (B, A) mining keys
+  int *amb_list;      // (B, A) anchors inside the pivot's error band
+  unsigned *amb_key;  // (B, A) their exact keys
   size_t zero_begin, zero_bytes;
   size_t bytes;
 };
@@ -57,6 +59,8 @@ TargetWorkspace carve(void *base, int B, int A, int L) {
   w.colbest = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * L);
   w.zero_bytes = off;
   w.key = (unsigned *)take(sizeof(unsigned) * (size_t)B * A);
+  w.amb_list = (int *)take(sizeof(int) * (size_t)B * A);
+  w.amb_key = (unsigned *)take(sizeof(unsigned) * (size_t)B * A);
   w.bytes = off;
   return w;
 }
@@ -69,6 +73,9 @@ struct TargetArgs {
   int *gcount, *thr_count;
   unsigned long long *colbest;
   unsigned *key;
+  int *amb_list;
+  unsigned *amb_key;
+  float delta;  // relative error bound of the approximate mining keys
   int B, A, L, W, C, T;
   float overlap_threshold, ignore_label, mining_ratio, mining_thresh;
   float vx, vy, vw, vh;
@@ -113,19 +120,95 @@ __device__ int count_valid_gt(const float *lab, int L, int W, int *smem_min) {
   return *smem_min;
 }
 
-template <int VEC>
+// exp(d) for d <= 0 in fp32 through MUFU.EX2: the product d*log2(e) is rounded once (absolute error <= 2^-18 for
+// |d*log2e| < 128, i.e. a relative error of the result <= 2.7e-6) and ex2.approx has a relative error <= 2^-22.
+__device__ __forceinline__ float exp_approx(float d) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmul(d, 1.4426950408889634f)));
+  return r;
+}
+
+// The reference's background probability, bit for bit (multibox_target.cc:220-231): running max, sequential fp32 sum
+// of glibc expf, one division.  Used for the few anchors near the selection pivot and for denormal-range values.
+template <bool kFma>
+__device__ __noinline__ float exact_bg_prob(const float *p_cls, int j, int A, int C) {
+  float mx = __ldg(p_cls + j);
+  for (int k = 1; k < C; ++k) {
+    const float t = __ldg(p_cls + j + (size_t)A * k);
+    if (t > mx) mx = t;
+  }
+  float sum = 0.f;
+  for (int k = 0; k < C; ++k)
+    sum = fadd(sum, libm::expf_glibc_t<kFma>(fsub(__ldg(p_cls + j + (size_t)A * k), mx), libm::GlobalExpTab()));
+  return fdiv(libm::expf_glibc_t<kFma>(fsub(__ldg(p_cls + j), mx), libm::GlobalExpTab()), sum);
+}
+
+struct SmemExpTab {
+  const unsigned long long *t;
+  __device__ __forceinline__ uint64_t operator()(unsigned i) const { return t[i]; }
+};
+
+// IoU of the target operator with the division skipped for disjoint boxes: inter == 0 gives iou == 0 both through
+// safe_divide's union == 0 branch and through 0 / union (multibox_target-inl.h:44-50,153-161).
+__device__ __forceinline__ float iou_target_fast(float4 a, float area_a, float4 g, float area_g) {
+  const float mr = a.z < g.z ? a.z : g.z;
+  const float ml = a.x > g.x ? a.x : g.x;
+  const float mb = a.w < g.w ? a.w : g.w;
+  const float mt = a.y > g.y ? a.y : g.y;
+  const float dw = fsub(mr, ml);
+  const float dh = fsub(mb, mt);
+  if (!(dw > 0.0f) || !(dh > 0.0f)) {
+    // iw or ih is 0 (or -0 * x): inter = +-0 -> iou = 0, except NaN inputs, which the reference does not see
+    return 0.0f;
+  }
+  const float inter = fmul(dw, dh);
+  const float uni = fsub(fadd(area_a, area_g), inter);
+  if (uni == 0.0f) return 0.0f;
+  return fdiv(inter, uni);
+}
+
+// VEC: anchors per thread (4 with 128-bit accesses, 1 for unaligned shapes).  NC > 0: compile-time class count, the
+// thread keeps its NC x VEC logits in registers (one HBM read, no re-load for the second softmax pass); NC == 0:
+// runtime class count, second pass re-reads through L1/L2.  kFma: which glibc build of expf/logf to reproduce.
+template <int VEC, int NC, bool kFma>
 __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ int sm_int;
   __shared__ int sm_pos;
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);                                  // [L]
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + a.L);       // [L]
+  float *sm_garea = reinterpret_cast<float *>(sm_col + a.L);                              // [L]
 
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kStreamThreads * VEC;
   const int A = a.A, W = a.W;
   const int i0 = t * kTile + threadIdx.x * VEC;
   const float *lab = a.labels + (size_t)b * a.L * W;
+  const bool active = i0 < A;
+  const bool mining = a.mining_ratio > 0.f;
+  const int C = NC > 0 ? NC : a.C;
+
+  // ---- issue every global load of this thread first: logits (register-resident when NC > 0) and anchors ----
+  const float *cp = a.cls_preds + (size_t)b * C * A + i0;
+  float xr[NC > 0 ? NC : 1][VEC];
+  float4 an[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) an[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    if (NC > 0 && mining) {
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        if constexpr (VEC == 4) {
+          const float4 q = ld_stream_f4(cp + (size_t)c * A);
+          xr[c][0] = q.x, xr[c][1] = q.y, xr[c][2] = q.z, xr[c][3] = q.w;
+        } else {
+          xr[c][0] = ld_stream_f1(cp + (size_t)c * A);
+        }
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) an[v] = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i0 + v);
+  }
 
   const int G = count_valid_gt(lab, a.L, W, &sm_int);
   if (t == 0 && threadIdx.x == 0) {
@@ -138,36 +221,32 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   }
   for (int k = threadIdx.x; k < G; k += blockDim.x) {
     const float *row = lab + (size_t)k * W;
-    sm_gt[k] = make_float4(row[1], row[2], row[3], row[4]);
+    const float4 g = make_float4(row[1], row[2], row[3], row[4]);
+    sm_gt[k] = g;
+    sm_garea[k] = fmul(fsub(g.z, g.x), fsub(g.w, g.y));
     sm_col[k] = 0ull;
   }
   if (threadIdx.x == 0) sm_pos = 0;
   __syncthreads();
 
-  const bool mining = a.mining_ratio > 0.f;
-  float best_iou[VEC];
+  float best_iou[VEC], area[VEC];
   int best_k[VEC];
-  float4 an[VEC];
-  const bool active = i0 < A;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) {
     best_iou[v] = -1.0f;
     best_k[v] = -1;
-    an[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  if (active) {
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) an[v] = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i0 + v);
+    area[v] = fmul(fsub(an[v].z, an[v].x), fsub(an[v].w, an[v].y));
   }
 
   // ---- fused IoU + row first-max + column max (multibox_target-inl.h:137-161, .cc:113-134,158-166) ----
   for (int k = 0; k < G; ++k) {
     const float4 g = sm_gt[k];
+    const float ga = sm_garea[k];
     unsigned long long tkey = 0ull;
     if (active) {
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float iou = iou_target(an[v], g);
+        const float iou = iou_target_fast(an[v], area[v], g, ga);
         if (iou > best_iou[v]) {
           best_iou[v] = iou;
           best_k[v] = k;
@@ -195,29 +274,12 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     key[v] = kKeySentinel;
   }
   if (mining && G > 0 && active) {
-    const float *cp = a.cls_preds + (size_t)b * a.C * A + i0;
+    // Mining key = background softmax probability (multibox_target.cc:220-231).  The stream kernel computes it in
+    // fp32 with MUFU.EX2 (relative error << a.delta, see approx_softmax_bg); the match kernel selects on these keys
+    // and re-evaluates with the bit-exact glibc expf only the handful of anchors whose key lies within the error
+    // band of the selection pivot, so the chosen SET is exactly the reference's.  Probabilities small enough for
+    // the approximation to lose relative accuracy (denormal range) are evaluated exactly right here.
     float mx[VEC], sum[VEC], p0[VEC];
-    // pass 1: running max over the classes (multibox_target.cc:220-224); pass 2: sum of expf in class order
-    // (:225-229).  The second pass re-reads the same lines (L1/L2 resident).
-#pragma unroll 4
-    for (int c = 0; c < a.C; ++c) {
-      float x[VEC];
-      if constexpr (VEC == 4) {
-        const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
-        x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
-      } else {
-        x[0] = __ldg(cp + (size_t)c * A);
-      }
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        if (c == 0) {
-          mx[v] = x[v];
-          p0[v] = x[v];
-        } else if (x[v] > mx[v]) {
-          mx[v] = x[v];
-        }
-      }
-    }
     bool cand[VEC];
     bool any_cand = false;
 #pragma unroll
@@ -227,23 +289,64 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
       sum[v] = 0.f;
     }
     if (any_cand) {
-#pragma unroll 2
-      for (int c = 0; c < a.C; ++c) {
-        float x[VEC];
-        if constexpr (VEC == 4) {
-          const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
-          x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
-        } else {
-          x[0] = __ldg(cp + (size_t)c * A);
+      if constexpr (NC > 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          mx[v] = xr[0][v];
+          p0[v] = xr[0][v];
         }
 #pragma unroll
-        for (int v = 0; v < VEC; ++v)
-          if (cand[v]) sum[v] = fadd(sum[v], libm::expf_glibc(fsub(x[v], mx[v]), a.fma_build));
+        for (int c = 1; c < NC; ++c)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v)
+            if (xr[c][v] > mx[v]) mx[v] = xr[c][v];
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) sum[v] = fadd(sum[v], exp_approx(fsub(xr[c][v], mx[v])));
+      } else {
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+          float x[VEC];
+          if constexpr (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
+            x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+          } else {
+            x[0] = __ldg(cp + (size_t)c * A);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) {
+            if (c == 0) {
+              mx[v] = x[v];
+              p0[v] = x[v];
+            } else if (x[v] > mx[v]) {
+              mx[v] = x[v];
+            }
+          }
+        }
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+          float x[VEC];
+          if constexpr (VEC == 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
+            x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+          } else {
+            x[0] = __ldg(cp + (size_t)c * A);
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) sum[v] = fadd(sum[v], exp_approx(fsub(x[v], mx[v])));
+        }
       }
 #pragma unroll
       for (int v = 0; v < VEC; ++v)
         if (cand[v]) {
-          const float prob = fdiv(libm::expf_glibc(fsub(p0[v], mx[v]), a.fma_build), sum[v]);
+          const float d0 = fsub(p0[v], mx[v]);
+          float prob;
+          if (d0 < -80.0f) {
+            prob = exact_bg_prob<kFma>(a.cls_preds + (size_t)b * C * A, i0 + v, A, C);  // rare
+          } else {
+            prob = fdiv(exp_approx(d0), sum[v]);
+          }
           key[v] = __float_as_uint(prob);
         }
     }
@@ -275,8 +378,8 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     if constexpr (VEC == 4) {
 #pragma unroll
       for (int q = 0; q < 5; ++q) {
-        reinterpret_cast<float4 *>(plt)[q] = make_float4(lt[4 * q], lt[4 * q + 1], lt[4 * q + 2], lt[4 * q + 3]);
-        reinterpret_cast<float4 *>(plm)[q] = make_float4(lm[4 * q], lm[4 * q + 1], lm[4 * q + 2], lm[4 * q + 3]);
+        st_stream_f4(plt + 4 * q, make_float4(lt[4 * q], lt[4 * q + 1], lt[4 * q + 2], lt[4 * q + 3]));
+        st_stream_f4(plm + 4 * q, make_float4(lm[4 * q], lm[4 * q + 1], lm[4 * q + 2], lm[4 * q + 3]));
       }
       *reinterpret_cast<float4 *>(a.cls_target + row0) = make_float4(ct[0], ct[1], ct[2], ct[3]);
       *reinterpret_cast<uint4 *>(a.key + row0) = make_uint4(key[0], key[1], key[2], key[3]);
@@ -517,29 +620,69 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
     __syncthreads();
   }
-  const unsigned thr_key = sm_prefix;
-  const int need_eq = sm_need;
-  if (thr_key == kKeySentinel) {
+  const unsigned qkey = sm_prefix;  // the num_negative-th smallest APPROXIMATE key
+  if (qkey == kKeySentinel) {
     // the num_negative-th smallest key is a non-candidate: CHECK_GE(temp.size(), num_negative) fails
     // (multibox_target.cc:236)
     if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_MINING_CANDIDATES);
     return;
   }
-  // ordered final pass: keys below the pivot, plus the first need_eq keys equal to it in anchor order
-  if (threadIdx.x == 0) sm_carry = 0;
+  // Keys q approximate the reference's probabilities p with |q - p| <= delta * p, so the exact pivot lies in
+  // [Q/(1+delta), Q/(1-delta)]: keys below Q(1-3 delta) are certainly selected, keys above Q(1+3 delta) certainly
+  // not, and only the band in between is re-evaluated exactly and ranked by (p, anchor) like the stable sort.
+  const float Q = __uint_as_float(qkey);
+  const unsigned klo = __float_as_uint(fmul(Q, 1.0f - 3.0f * a.delta));
+  const unsigned khi = __float_as_uint(fmul(Q, 1.0f + 3.0f * a.delta));
+  if (threadIdx.x == 0) {
+    sm_carry = 0;  // surely selected
+    sm_dup = 0;    // ambiguous
+  }
   __syncthreads();
   float *ct = a.cls_target + (size_t)b * A;
+  int *amb_list = a.amb_list + (size_t)b * A;
+  unsigned *amb_key = a.amb_key + (size_t)b * A;
+  int n_in_local = 0;
   for (int base = 0; base < A; base += blockDim.x) {
     const int j = base + threadIdx.x;
     const unsigned kv = j < A ? keys[j] : kKeySentinel;
-    const int eq = kv == thr_key ? 1 : 0;
-    int total;
-    const int ex = block_scan_excl(eq, scan_smem, &total);
-    const int carry = sm_carry;
-    if (kv < thr_key || (eq && carry + ex < need_eq)) ct[j] = 0.0f;
-    __syncthreads();
-    if (threadIdx.x == 0) sm_carry = carry + total;
-    __syncthreads();
+    if (kv < klo) {
+      ct[j] = 0.0f;
+      ++n_in_local;
+    }
+    const bool amb = kv >= klo && kv <= khi;
+    const unsigned m = __ballot_sync(kFullMask, amb);
+    if (m) {
+      int wbase = 0;
+      if (lane_id() == 0) wbase = atomicAdd(&sm_dup, __popc(m));
+      wbase = __shfl_sync(kFullMask, wbase, 0);
+      if (amb) amb_list[wbase + __popc(m & ((1u << lane_id()) - 1u))] = j;
+    }
+  }
+  n_in_local = warp_sum_i32(n_in_local);
+  if (lane_id() == 0 && n_in_local) atomicAdd(&sm_carry, n_in_local);
+  __syncthreads();
+  const int n_amb = sm_dup;
+  const int need = num_negative - sm_carry;
+  if (need < 0 || need > n_amb) {  // would mean the error bound was violated
+    if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_INTERNAL);
+    return;
+  }
+  const float *p_cls = a.cls_preds + (size_t)b * a.C * A;
+  for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+    const int j = amb_list[q];
+    const float pe = a.fma_build ? exact_bg_prob<true>(p_cls, j, A, a.C) : exact_bg_prob<false>(p_cls, j, A, a.C);
+    amb_key[q] = __float_as_uint(pe);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+    const unsigned kq = amb_key[q];
+    const int jq = amb_list[q];
+    int rank = 0;
+    for (int i = 0; i < n_amb; ++i) {
+      const unsigned ki = amb_key[i];
+      rank += (ki < kq || (ki == kq && amb_list[i] < jq)) ? 1 : 0;
+    }
+    if (rank < need) ct[jq] = 0.0f;
   }
 }
 
@@ -602,6 +745,9 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   ta.thr_count = w.thr_count;
   ta.colbest = w.colbest;
   ta.key = w.key;
+  ta.amb_list = w.amb_list;
+  ta.amb_key = w.amb_key;
+  ta.delta = 1e-4f > (2e-7f * C + 5e-5f) ? 1e-4f : (2e-7f * C + 5e-5f);
   ta.B = B;
   ta.A = A;
   ta.L = L;
@@ -618,10 +764,10 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   ta.vh = variances[3];
   ta.fma_build = libm_fma_mode();
 
-  const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long)) * (size_t)L;
+  const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L;
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((A + 31) / 32);
-  DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 24);
+  DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 28);
   DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
   static bool attr_set = false;
   if (!attr_set) {
@@ -632,10 +778,23 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   dim3 grid1(ta.T, B);
   if (phases & 1) {
     ProfileScope _p(kSlotTargetStream, stream);
-    if (vec4)
-    target_stream_kernel<4><<<grid1, kStreamThreads, smem1, stream>>>(ta);
-  else
-    target_stream_kernel<1><<<grid1, kStreamThreads, smem1, stream>>>(ta);
+    const bool fma = ta.fma_build != 0;
+#define DSPMB_LAUNCH_TS(V, N)                                                          \
+  do {                                                                                 \
+    if (fma)                                                                           \
+      target_stream_kernel<V, N, true><<<grid1, kStreamThreads, smem1, stream>>>(ta);  \
+    else                                                                               \
+      target_stream_kernel<V, N, false><<<grid1, kStreamThreads, smem1, stream>>>(ta); \
+  } while (0)
+    if (vec4 && C == 21)
+      DSPMB_LAUNCH_TS(4, 21);
+    else if (vec4 && C == 9)
+      DSPMB_LAUNCH_TS(4, 9);
+    else if (vec4)
+      DSPMB_LAUNCH_TS(4, 0);
+    else
+      DSPMB_LAUNCH_TS(1, 0);
+#undef DSPMB_LAUNCH_TS
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   if (phases & 2) {

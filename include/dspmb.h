@@ -38,6 +38,7 @@ extern "C" {
 #define DSPMB_ERR_MINING_THRESH -4     /* operator/multibox_target.cc:184 CHECK_GT(negative_mining_thresh)  */
 #define DSPMB_ERR_WORKSPACE -5         /* workspace pointer NULL / too small / misaligned                   */
 #define DSPMB_ERR_CUDA -6              /* CUDA runtime error (message in dspmb_last_error)                  */
+#define DSPMB_ERR_INTERNAL -7          /* an internal invariant failed (never expected; please report)      */
 
 int dspmb_version(void);
 
