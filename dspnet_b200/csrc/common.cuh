@@ -88,6 +88,11 @@ __device__ __forceinline__ float4 ld_stream_f4(const float *p) {
                : "l"(p));
   return v;
 }
+__device__ __forceinline__ float2 ld_stream_f2(const float *p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float ld_stream_f1(const float *p) {
   float v;
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));

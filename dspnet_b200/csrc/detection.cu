@@ -29,6 +29,8 @@
 //                                  test, IEEE division only for overlapping pairs) + a word-serial resolve that only
 //                                  visits rows that suppress something;
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dspmb {
@@ -700,15 +702,28 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
       if (take) sel[p] = ((unsigned long long)kv << 32) | (unsigned)s;
     }
     __syncthreads();
-    if (nkeep <= kRankSortMax && nkeep <= a.sel_cap) {
-      // rank sort: one key per thread, n broadcast reads, no barriers inside
-      const int n = nkeep;
-      const unsigned long long mine = (int)threadIdx.x < n ? ssel[threadIdx.x] : 0ull;  // sel == ssel here
-      int rank = 0;
-#pragma unroll 8
-      for (int j = 0; j < n; ++j) rank += ssel[j] < mine ? 1 : 0;
-      __syncthreads();
-      if ((int)threadIdx.x < n) ssel[rank] = mine;
+    if (npad <= kRankSortMax && npad <= a.sel_cap) {
+      // register bitonic sort, one key per thread: exchanges at distance < 32 are warp shuffles, only the
+      // log2(npad/32) * (log2(npad/32) + 1) / 2 longer ones go through shared memory (sel == ssel here)
+      const int tid = threadIdx.x;
+      const bool in = tid < npad;
+      unsigned long long k = tid < nkeep ? ssel[tid] : ~0ull;
+      for (int K = 2; K <= npad; K <<= 1) {
+        for (int j = K >> 1; j > 0; j >>= 1) {
+          unsigned long long other;
+          if (j >= 32) {
+            if (in) ssel[tid] = k;
+            __syncthreads();
+            other = in ? ssel[tid ^ j] : k;
+            __syncthreads();
+          } else {
+            other = __shfl_xor_sync(kFullMask, k, j);
+          }
+          const bool take_min = ((tid & j) == 0) == ((tid & K) == 0);
+          k = (take_min == (other < k)) ? other : k;
+        }
+      }
+      if (in) ssel[tid] = k;
       __syncthreads();
     } else {
       for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
@@ -802,7 +817,7 @@ struct NmsArgs {
   float *seg_area;
   int A, cls_stride, C;
   float nms_threshold;
-  int force_suppress, mask_rows, smem_rows;
+  int force_suppress, mask_rows, smem_rows, debug;
 };
 
 // IoU >= thr test of multibox_detection.cc:44-51,162 on boxes staged by stage_box().
@@ -828,8 +843,8 @@ __device__ __forceinline__ float4 stage_box(float4 b, float *area) {
   if (!(b.z > b.x && b.w > b.y)) b.x = __int_as_float(0x7f800000);
   return b;
 }
-__device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, NmsThr t) {
-  if (!(a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y)) return false;
+// threshold test for a pair already known to overlap
+__device__ __forceinline__ bool iou_ge(float4 a, float area_a, float4 b, float area_b, NmsThr t) {
   const float w = fsub(fminf(a.z, b.z), fmaxf(a.x, b.x));
   const float h = fsub(fminf(a.w, b.w), fmaxf(a.y, b.y));
   const float i = fmul(w, h);
@@ -840,6 +855,10 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
     if (i < fmul(t.lo, u)) return false;
   }
   return fdiv(i, u) >= t.thr;
+}
+__device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, float area_b, NmsThr t) {
+  if (!(a.z > b.x && b.z > a.x && a.w > b.y && b.w > a.y)) return false;
+  return iou_ge(a, area_a, b, area_b, t);
 }
 
 constexpr int kNmsTab = 512;  // ballot-count table entries: 64 iterations x 8 warps = 131072 rows per sweep
@@ -862,7 +881,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
 
   const int b = blockIdx.y, seg = blockIdx.x;
   const int V = a.nms_rows[b];
-  if (V == 0) return;
+  if (V == 0 || (a.debug & 4)) return;
   float *out = a.out + (size_t)b * a.A * 7;
   const float4 *row_box = a.row_box + (size_t)b * a.A;
   const bool identity = a.force_suppress != 0;  // single segment: row q is list entry q
@@ -962,6 +981,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     return;
   }
 
+  if (a.debug & 2) return;
   if (n <= a.mask_rows) {
     // ---------------- small segment: full bit mask in shared memory + word-serial resolve ----------------
     float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
@@ -974,18 +994,31 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x one
     // 64-column word, dealt round-robin to the warps; the column box is a shared-memory broadcast.
     const int ngroups = (n + 31) >> 5;
+    constexpr int kWarps = kNmsThreads / 32;
     int unit = 0;
     for (int rg = 0; rg < ngroups; ++rg) {
       for (int w = rg >> 1; w < W; ++w, ++unit) {
-        if (unit % (int)nwarps != (int)warp) continue;
+        if ((unit & (kWarps - 1)) != (int)warp) continue;
         const int i = (rg << 5) + lane;
-        unsigned long long bits = 0ull;
-        if (i < n) {
-          const float4 bi = boxes[i];
-          const float ai = areas[i];
-          const int j1 = min(n, (w + 1) << 6);
-          for (int j = max(w << 6, i + 1); j < j1; ++j)
-            if (suppresses(bi, ai, boxes[j], areas[j], thr)) bits |= 1ull << (j & 63);
+        const bool row_ok = i < n && !(a.debug & 1);
+        float4 bi = boxes[row_ok ? i : 0];
+        if (!row_ok) bi.x = __int_as_float(0x7f800000);  // fails every overlap test
+        const float ai = areas[row_ok ? i : 0];
+        const int jb = w << 6;
+        const int cnt = min(64, n - jb);
+        unsigned lo = 0u, hi = 0u;
+        // the column index is warp-uniform: boxes[jb + jj] is one broadcast LDS.128 for the 32 rows of the unit
+#pragma unroll 4
+        for (int jj = 0; jj < cnt; ++jj) {
+          const float4 bj = boxes[jb + jj];
+          if (bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y && jb + jj > i) {
+            if (iou_ge(bi, ai, bj, areas[jb + jj], thr)) {
+              if (jj < 32) lo |= 1u << jj; else hi |= 1u << (jj - 32);
+            }
+          }
+        }
+        if (row_ok) {
+          const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
           mask[i * W + w] = bits;
           if (bits) atomicOr(&rowany[i >> 6], 1ull << (i & 63));
         }
@@ -1322,6 +1355,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.force_suppress = force_suppress;
     na.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
     na.smem_rows = tuning(DSPMB_TUNE_NMS_SMEM_ROWS);
+    na.debug = getenv("DSPMB_NMS_DEBUG") ? atoi(getenv("DSPMB_NMS_DEBUG")) : 0;
     dim3 grid3(force_suppress ? 1 : C - 1, B);
     {
       ProfileScope _p(kSlotDetNms, stream);

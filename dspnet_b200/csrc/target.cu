@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
         if constexpr (VEC == 4) {
           const float4 q = ld_stream_f4(cp + (size_t)c * A);
           xr[c][0] = q.x, xr[c][1] = q.y, xr[c][2] = q.z, xr[c][3] = q.w;
+        } else if constexpr (VEC == 2) {
+          const float2 q = ld_stream_f2(cp + (size_t)c * A);
+          xr[c][0] = q.x, xr[c][1] = q.y;
         } else {
           xr[c][0] = ld_stream_f1(cp + (size_t)c * A);
         }
@@ -311,6 +314,9 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
           if constexpr (VEC == 4) {
             const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
             x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+          } else if constexpr (VEC == 2) {
+            const float2 q = __ldg(reinterpret_cast<const float2 *>(cp + (size_t)c * A));
+            x[0] = q.x, x[1] = q.y;
           } else {
             x[0] = __ldg(cp + (size_t)c * A);
           }
@@ -330,6 +336,9 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
           if constexpr (VEC == 4) {
             const float4 q = __ldg(reinterpret_cast<const float4 *>(cp + (size_t)c * A));
             x[0] = q.x, x[1] = q.y, x[2] = q.z, x[3] = q.w;
+          } else if constexpr (VEC == 2) {
+            const float2 q = __ldg(reinterpret_cast<const float2 *>(cp + (size_t)c * A));
+            x[0] = q.x, x[1] = q.y;
           } else {
             x[0] = __ldg(cp + (size_t)c * A);
           }
@@ -386,6 +395,15 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
       if (a.match_out)
         *reinterpret_cast<int4 *>(a.match_out + row0) =
             make_int4(pos[0] ? best_k[0] : -1, pos[1] ? best_k[1] : -1, pos[2] ? best_k[2] : -1, pos[3] ? best_k[3] : -1);
+    } else if constexpr (VEC == 2) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        reinterpret_cast<float2 *>(plt)[q] = make_float2(lt[2 * q], lt[2 * q + 1]);
+        reinterpret_cast<float2 *>(plm)[q] = make_float2(lm[2 * q], lm[2 * q + 1]);
+      }
+      *reinterpret_cast<float2 *>(a.cls_target + row0) = make_float2(ct[0], ct[1]);
+      *reinterpret_cast<uint2 *>(a.key + row0) = make_uint2(key[0], key[1]);
+      if (a.match_out) *reinterpret_cast<int2 *>(a.match_out + row0) = make_int2(pos[0] ? best_k[0] : -1, pos[1] ? best_k[1] : -1);
     } else {
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
@@ -428,6 +446,7 @@ __device__ __forceinline__ unsigned long long block_max_u64(unsigned long long v
 
 enum { kStateDone = 0, kStateRecompute = 1 };
 
+template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned long long red_smem[kMatchThreads / 32];
@@ -453,6 +472,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   unsigned char *done = reinterpret_cast<unsigned char *>(m_gt + L);
   unsigned *bits = reinterpret_cast<unsigned *>(done + ((L + 15) / 16) * 16);
   const int nwords = (A + 31) / 32;
+  unsigned *skeys = bits + ((nwords + 3) & ~3);  // [A] staged mining keys (kKeysInSmem)
 
   const float *lab = a.labels + (size_t)b * L * W;
   const float4 *anchors = reinterpret_cast<const float4 *>(a.anchors);
@@ -581,7 +601,20 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   }
   if (num_negative <= 0) return;
 
-  const unsigned *keys = a.key + (size_t)b * A;
+  const unsigned *gkeys = a.key + (size_t)b * A;
+  // Stage the keys in shared memory (the fix-up above has already replaced the matched anchors' keys).
+  if (kKeysInSmem) {
+    if ((A & 3) == 0 && (reinterpret_cast<uintptr_t>(gkeys) & 15) == 0) {  // 128-bit loads, all in flight at once
+      const uint4 *g4 = reinterpret_cast<const uint4 *>(gkeys);
+      uint4 *s4 = reinterpret_cast<uint4 *>(skeys);
+#pragma unroll 8
+      for (int j = threadIdx.x; j < (A >> 2); j += blockDim.x) s4[j] = g4[j];
+    } else {
+#pragma unroll 8
+      for (int j = threadIdx.x; j < A; j += blockDim.x) skeys[j] = gkeys[j];
+    }
+  }
+  auto key_at = [&](int j) -> unsigned { return kKeysInSmem ? skeys[j] : gkeys[j]; };
   // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
   // (larger than the bits of any probability), so they are only reached if there are too few candidates.
   if (threadIdx.x == 0) {
@@ -596,7 +629,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     const unsigned prefix = sm_prefix;
     for (int base = 0; base < A; base += blockDim.x) {
       const int j = base + threadIdx.x;
-      const unsigned kv = j < A ? keys[j] : kKeySentinel;
+      const unsigned kv = j < A ? key_at(j) : kKeySentinel;
       const bool hit = j < A && (kv & mask) == prefix;
       // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
       const unsigned digit = (kv >> shift) & 0xffu;
@@ -607,16 +640,30 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
-      unsigned acc = 0;
-      int d = 0;
-      for (; d < 255; ++d) {
-        if ((int)(acc + hist[d]) >= need) break;
-        acc += hist[d];
+    if (warp_id() == 0) {  // digit search: 8 bins per lane + warp scan
+      const unsigned lane = lane_id();
+      unsigned h[8];
+      int tot = 0;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        h[d] = hist[lane * 8 + d];
+        tot += (int)h[d];
       }
-      sm_need = need - (int)acc;
-      sm_prefix = prefix | ((unsigned)d << shift);
+      const int incl = warp_scan_incl(tot);
+      const int excl = incl - tot;
+      const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
+      if (excl < need && incl >= need) {
+        int acc = excl;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          if (acc + (int)h[d] >= need) {
+            sm_need = need - acc;
+            sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
+            break;
+          }
+          acc += (int)h[d];
+        }
+      }
     }
     __syncthreads();
   }
@@ -644,7 +691,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   int n_in_local = 0;
   for (int base = 0; base < A; base += blockDim.x) {
     const int j = base + threadIdx.x;
-    const unsigned kv = j < A ? keys[j] : kKeySentinel;
+    const unsigned kv = j < A ? key_at(j) : kKeySentinel;
     if (kv < klo) {
       ct[j] = 0.0f;
       ++n_in_local;
@@ -729,7 +776,9 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
                              (uintptr_t)cls_target | (uintptr_t)match_out;
   const bool vec4 = (A % 4 == 0) && (align_or & 15) == 0;
-  const int tile = kStreamThreads * (vec4 ? 4 : 1);
+  // register-resident variants: 2 anchors/thread (about 85 registers => 6 CTAs/SM) unless knob 0 says otherwise
+  const int tvec = (vec4 && (C == 21 || C == 9) && tuning(DSPMB_TUNE_DET_STREAM_VARIANT) != 4) ? 2 : 4;
+  const int tile = kStreamThreads * (vec4 ? tvec : 1);
 
   TargetArgs ta;
   ta.anchors = anchors;
@@ -766,12 +815,15 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
 
   const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L;
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
-                       (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((A + 31) / 32);
+                       (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
+  const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 180 * 1024;
+  const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
   DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 28);
   DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
   static bool attr_set = false;
   if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int phases = tuning(DSPMB_TUNE_PHASES);
@@ -786,7 +838,11 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     else                                                                               \
       target_stream_kernel<V, N, false><<<grid1, kStreamThreads, smem1, stream>>>(ta); \
   } while (0)
-    if (vec4 && C == 21)
+    if (vec4 && C == 21 && tvec == 2)
+      DSPMB_LAUNCH_TS(2, 21);
+    else if (vec4 && C == 9 && tvec == 2)
+      DSPMB_LAUNCH_TS(2, 9);
+    else if (vec4 && C == 21)
       DSPMB_LAUNCH_TS(4, 21);
     else if (vec4 && C == 9)
       DSPMB_LAUNCH_TS(4, 9);
@@ -799,7 +855,10 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   DSPMB_CUDA_TRY(cudaGetLastError());
   if (phases & 2) {
     ProfileScope _p(kSlotTargetMatch, stream);
-    target_match_kernel<<<B, kMatchThreads, smem2, stream>>>(ta);
+    if (keys_in_smem)
+      target_match_kernel<true><<<B, kMatchThreads, smem2_total, stream>>>(ta);
+    else
+      target_match_kernel<false><<<B, kMatchThreads, smem2_total, stream>>>(ta);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
