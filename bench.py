@@ -225,8 +225,8 @@ def main():
     out_sets = [plan.new_output() for _ in range(ROTATE)]
     gatherer = None
     if world > 1:
-        from dspnet_b200.dist import DetectionGatherer
-        gatherer = DetectionGatherer(BATCH, A, DET_PARAMS["nms_topk"], dev, world)
+        from dspnet_b200.dist import P2PDetectionGatherer
+        gatherer = P2PDetectionGatherer(BATCH, A, DET_PARAMS["nms_topk"], dev, world, rank)
 
     def step(i):
         s = i % ROTATE
@@ -244,9 +244,10 @@ def main():
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
-    t_end = time.perf_counter() + (0.0 if args.no_soak else 1.5)
+    # the soak is a FIXED number of steps (about 1.5 s), identical on every rank: the exchange step counts arrivals
+    soak_steps = 0 if args.no_soak else 12000
     i = args.warmup
-    while time.perf_counter() < t_end:
+    for _ in range(soak_steps // 50):
         for _ in range(50):
             step(i)
             i += 1
@@ -258,8 +259,8 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for i in range(args.steps):
-        step(i)
+    for k in range(args.steps):
+        step(i + k)
     if gatherer is not None:
         gatherer.drain()
     ev1.record()
@@ -410,6 +411,18 @@ def main():
                                               "per thread; single thread: %.1f images/s" % v1}
         print(json.dumps(line))
     if world > 1:
+        # sanity of the exchange step: every rank holds every rank's compacted detections
+        last_step = i + args.steps - 1
+        rows, counts = gatherer.gathered(last_step)
+        from dspnet_b200.dist import compact_rows
+        mine, mine_n = compact_rows(out_sets[last_step % ROTATE], DET_PARAMS["nms_topk"])
+        ok = torch.equal(rows[rank * BATCH:(rank + 1) * BATCH], mine) and torch.equal(counts[rank * BATCH:(rank + 1) * BATCH], mine_n)
+        ok = ok and bool((counts > 0).all())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0 and int(flag.item()) != 1:
+            print(json.dumps({"error": "gathered detections differ from the local compaction"}))
+        gatherer.close()
         dist.destroy_process_group()
 
 

@@ -30,6 +30,7 @@
 //                                  visits rows that suppress something;
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -1363,5 +1364,185 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     }
     DSPMB_CUDA_TRY(cudaGetLastError());
   }
+  return DSPMB_OK;
+}
+
+// ====================================================================================================
+// Fused compaction + all-gather over NVLink peer memory (the one exchange step of the path).
+//
+// Every rank owns a gather buffer (cudaMalloc'd, shared with its peers through CUDA IPC) with two slots of
+//   [world][B][K*7] float rows | [world][B] int counts | int arrived
+// One CTA per local image compacts the surviving rows (id >= 0, row order, at most K, padded with -1) into shared
+// memory once and then stores the block into section `rank` of EVERY rank's buffer with 128-bit stores -- the
+// remote ones travel over NVLink/NVSwitch while other CTAs are still compacting, no NCCL launch, no host round
+// trip.  After a system-scope fence one thread bumps the `arrived` counter of every peer; a consumer (or the
+// drain at the end of a run) waits until its own counter has reached steps_on_slot * world * B.
+namespace dspmb {
+namespace {
+
+constexpr int kMaxPeers = 16;
+struct GatherArgs {
+  const float *out;
+  const int *valid;
+  unsigned char *peer[kMaxPeers];
+  int B, A, K, rank, world;
+  size_t slot_off, counts_off, arrived_off;  // byte offsets inside a peer buffer for this slot
+};
+
+__global__ void __launch_bounds__(256) det_gather_kernel(const __grid_constant__ GatherArgs g) {
+  extern __shared__ __align__(16) float stage[];  // K * 7 floats
+  __shared__ int scan_smem[256 / 32 + 1];
+  __shared__ int carry_smem;
+  const int b = blockIdx.x;
+  const float *src = g.out + (size_t)b * g.A * 7;
+  const int V = g.valid ? min(g.valid[b], g.A) : g.A;
+  const int K = g.K;
+  if (threadIdx.x == 0) carry_smem = 0;
+  __syncthreads();
+  for (int base = 0; base < V; base += blockDim.x) {
+    const int r = base + threadIdx.x;
+    const int keep = (r < V && src[(size_t)r * 7] >= 0.f) ? 1 : 0;
+    int total;
+    const int ex = block_scan_excl(keep, scan_smem, &total);
+    const int carry = carry_smem;
+    const int pos = carry + ex;
+    if (keep && pos < K) {
+#pragma unroll
+      for (int c = 0; c < 7; ++c) stage[pos * 7 + c] = src[(size_t)r * 7 + c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) carry_smem = carry + total;
+    __syncthreads();
+    if (carry_smem >= K) break;
+  }
+  const int n = min(carry_smem, K);
+  for (int q = n * 7 + threadIdx.x; q < K * 7; q += blockDim.x) stage[q] = -1.f;
+  __syncthreads();
+  const size_t row_off = g.slot_off + ((size_t)g.rank * g.B + b) * K * 7 * sizeof(float);
+  const size_t cnt_off = g.counts_off + ((size_t)g.rank * g.B + b) * sizeof(int);
+  const int nvec = (K * 7) >> 2;  // K * 7 * 4 bytes is a multiple of 16 when K % 4 == 0 (checked on the host)
+  for (int p = 0; p < g.world; ++p) {
+    const int peer = (g.rank + p) % g.world;  // start with the local copy, spread the remote targets
+    float4 *dst = reinterpret_cast<float4 *>(g.peer[peer] + row_off);
+    for (int q = threadIdx.x; q < nvec; q += blockDim.x) dst[q] = reinterpret_cast<const float4 *>(stage)[q];
+    if (threadIdx.x == 0) *reinterpret_cast<int *>(g.peer[peer] + cnt_off) = n;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < g.world)
+    atomicAdd_system(reinterpret_cast<int *>(g.peer[threadIdx.x] + g.arrived_off), 1);
+}
+
+__global__ void det_gather_wait_kernel(int *arrived, int expected) {
+  // bounded spin (a few seconds): a peer that never arrives must not wedge the GPU; the shortfall is visible to
+  // the host in the counter itself (word after it is set to 1)
+  for (long long spins = 0; spins < 20000000ll; ++spins) {
+    if (atomicAdd_system(arrived, 0) >= expected) {
+      __threadfence_system();
+      return;
+    }
+    __nanosleep(200);
+  }
+  arrived[1] = 1;
+}
+
+}  // namespace
+}  // namespace dspmb
+
+extern "C" size_t dspmb_gather_buffer_bytes(int B, int K, int world) {
+  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
+  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
+  return 2 * (rows + counts + 256);
+}
+
+extern "C" int dspmb_p2p_alloc(size_t bytes, void **dev_ptr, unsigned char *handle_out) {
+  DSPMB_REQUIRE(dev_ptr && handle_out && bytes > 0, "p2p_alloc: bad argument");
+  DSPMB_CUDA_TRY(cudaMalloc(dev_ptr, bytes));
+  DSPMB_CUDA_TRY(cudaMemset(*dev_ptr, 0, bytes));
+  cudaIpcMemHandle_t h;
+  DSPMB_CUDA_TRY(cudaIpcGetMemHandle(&h, *dev_ptr));
+  memcpy(handle_out, &h, sizeof(h));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_p2p_open(const unsigned char *handle, void **dev_ptr) {
+  DSPMB_REQUIRE(handle && dev_ptr, "p2p_open: bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  DSPMB_CUDA_TRY(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_p2p_close(void *dev_ptr) {
+  DSPMB_CUDA_TRY(cudaIpcCloseMemHandle(dev_ptr));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_p2p_free(void *dev_ptr) {
+  DSPMB_CUDA_TRY(cudaFree(dev_ptr));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, int B, int A, int K, int rank,
+                                          int world, void *const *peer_bases, int slot, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSPMB_REQUIRE(B > 0 && A > 0 && K > 0 && (K % 4) == 0, "detection_gather: need B, A > 0 and K a positive multiple of 4");
+  DSPMB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "detection_gather: bad rank/world");
+  DSPMB_REQUIRE(out && peer_bases && (slot == 0 || slot == 1), "detection_gather: bad argument");
+  DSPMB_REQUIRE((size_t)K * 7 * sizeof(float) <= 160 * 1024, "detection_gather: K too large");
+  GatherArgs g;
+  g.out = out;
+  g.valid = valid_count;
+  for (int p = 0; p < world; ++p) {
+    DSPMB_REQUIRE(peer_bases[p] != nullptr, "detection_gather: peer %d has no buffer", p);
+    g.peer[p] = (unsigned char *)peer_bases[p];
+  }
+  g.B = B;
+  g.A = A;
+  g.K = K;
+  g.rank = rank;
+  g.world = world;
+  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
+  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
+  const size_t slot_bytes = rows + counts + 256;
+  g.slot_off = (size_t)slot * slot_bytes;
+  g.counts_off = g.slot_off + rows;
+  g.arrived_off = g.counts_off + counts;
+  const size_t smem = (size_t)K * 7 * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_set = true;
+  }
+  {
+    ProfileScope _p(kSlotDetCompact, stream);
+    det_gather_kernel<<<B, 256, smem, stream>>>(g);
+  }
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_detection_gather_wait(const void *local_base, int B, int K, int world, int slot, int expected,
+                                           void *stream_) {
+  DSPMB_REQUIRE(local_base && (slot == 0 || slot == 1), "detection_gather_wait: bad argument");
+  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
+  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
+  const size_t slot_bytes = rows + counts + 256;
+  int *arrived = (int *)((unsigned char *)const_cast<void *>(local_base) + slot * slot_bytes + rows + counts);
+  det_gather_wait_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(arrived, expected);
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_detection_gather_read(const void *local_base, int B, int K, int world, int slot, float *rows_out,
+                                           int32_t *counts_out, void *stream_) {
+  DSPMB_REQUIRE(local_base && rows_out && counts_out && (slot == 0 || slot == 1), "detection_gather_read: bad argument");
+  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
+  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
+  const unsigned char *base = (const unsigned char *)local_base + (size_t)slot * (rows + counts + 256);
+  DSPMB_CUDA_TRY(cudaMemcpyAsync(rows_out, base, (size_t)world * B * K * 7 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream_));
+  DSPMB_CUDA_TRY(cudaMemcpyAsync(counts_out, base + rows, (size_t)world * B * sizeof(int), cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream_));
   return DSPMB_OK;
 }

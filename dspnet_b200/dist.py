@@ -137,3 +137,100 @@ class DetectionGatherer:
 
     def drain(self):
         torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+
+class P2PDetectionGatherer:
+    """The exchange step without NCCL on the critical path: ``dspmb_detection_gather_f32`` compacts this rank's
+    detections and stores them straight into every peer's gather buffer over NVLink (CUDA IPC mapped peer memory).
+    torch.distributed is only used once, at construction, to exchange the 64-byte IPC handles.
+
+    submit(out, step) is one C-ABI call on the current stream; gathered(step) returns views of this rank's copy of
+    the whole batch ((world*B, K, 7) rows and (world*B,) counts) after enqueueing a wait for all peers' data.
+    """
+
+    launches_per_submit = 1  # det_gather_kernel
+
+    def __init__(self, batch, anchors, max_rows, device, world, rank, group=None):
+        assert max_rows % 4 == 0
+        self.B, self.A, self.K, self.device, self.world, self.rank = batch, anchors, max_rows, device, world, rank
+        self.lib = _lib.lib()
+        self.nbytes = self.lib.dspmb_gather_buffer_bytes(batch, max_rows, world)
+        base = ctypes.c_void_p()
+        handle = ctypes.create_string_buffer(64)
+        with torch.cuda.device(device):
+            _lib.check(self.lib.dspmb_p2p_alloc(self.nbytes, ctypes.byref(base), handle))
+        self.local = base.value
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, handle.raw, group=group)
+        else:
+            handles[0] = handle.raw
+        self.peers = (ctypes.c_void_p * world)()
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.peers[r] = self.local
+            else:
+                p = ctypes.c_void_p()
+                with torch.cuda.device(device):
+                    _lib.check(self.lib.dspmb_p2p_open(handles[r], ctypes.byref(p)))
+                self.peers[r] = p.value
+                self._opened.append(p.value)
+        self.uses = [0, 0]
+        self.side = torch.cuda.Stream(device)  # the exchange runs beside the next step's kernels
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        rows = (world * batch * max_rows * 7 * 4 + 255) // 256 * 256
+        counts = (world * batch * 4 + 255) // 256 * 256
+        self._slot_bytes = rows + counts + 256
+        self._rows_bytes = rows
+        if world > 1:
+            dist.barrier(group=group)  # every peer has mapped every buffer before the first store
+
+    def submit(self, out, step, valid_count=None):
+        slot = step & 1
+        compute = torch.cuda.current_stream(self.device)
+        if self.uses[slot]:
+            compute.wait_event(self.done[slot])  # the gather that read from two steps ago has finished
+        self.uses[slot] += 1
+        self.ready[slot].record(compute)
+        self.side.wait_event(self.ready[slot])
+        _lib.check(self.lib.dspmb_detection_gather_f32(
+            out.data_ptr(), valid_count.data_ptr() if valid_count is not None else None, self.B, self.A, self.K,
+            self.rank, self.world, self.peers, slot, ctypes.c_void_p(self.side.cuda_stream)))
+        self.done[slot].record(self.side)
+
+    def wait(self, slot):
+        """Enqueue (on the current stream) a wait until every rank's data of the latest use of `slot` has landed."""
+        _lib.check(self.lib.dspmb_detection_gather_wait(
+            self.local, self.B, self.K, self.world, slot, self.uses[slot] * self.world * self.B,
+            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def gathered(self, step):
+        """(rows (world*B, K, 7) float32, counts (world*B,) int32) copied out of this rank's buffer."""
+        slot = step & 1
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        self.wait(slot)
+        n = self.world * self.B
+        rows = torch.empty((n, self.K, 7), dtype=torch.float32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.dspmb_detection_gather_read(
+            self.local, self.B, self.K, self.world, slot, rows.data_ptr(), counts.data_ptr(),
+            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return rows, counts
+
+    def drain(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.side)
+        for slot in (0, 1):
+            if self.uses[slot]:
+                self.wait(slot)
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for p in self._opened:
+                self.lib.dspmb_p2p_close(p)
+            self._opened = []
+            if self.local:
+                self.lib.dspmb_p2p_free(self.local)
+                self.local = None

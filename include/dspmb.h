@@ -110,6 +110,29 @@ int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const floa
 int dspmb_detection_compact_f32(const float *out, const int32_t *valid_count, int B, int A, int K, float *dst,
                                 int32_t *counts, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Fused compaction + all-gather of the detections over NVLink peer memory (multi-GPU exchange step).
+ * Every rank allocates one gather buffer with dspmb_p2p_alloc(dspmb_gather_buffer_bytes(B, K, world)), publishes
+ * the 64-byte CUDA IPC handle to its peers (any host channel) and maps theirs with dspmb_p2p_open.
+ * dspmb_detection_gather_f32 compacts the surviving rows (id >= 0, row order, at most K -- a multiple of 4 --,
+ * padded with -1) of this rank's B images and stores them into section `rank` of EVERY rank's buffer (HOST array
+ * peer_bases[world] of device pointers, own buffer at index `rank`), slot 0/1, then raises the peers' `arrived`
+ * counters.  Buffer layout per slot: rows (world,B,K,7) float | counts (world,B) int32 | arrived int32
+ * (each part padded to 256 B).  dspmb_detection_gather_wait enqueues a kernel that returns once this rank's
+ * counter for `slot` has reached `expected` (= uses of the slot so far * world * B).
+ * ------------------------------------------------------------------------------------------------- */
+size_t dspmb_gather_buffer_bytes(int B, int K, int world);
+int dspmb_p2p_alloc(size_t bytes, void **dev_ptr, unsigned char *ipc_handle_out /* 64 bytes */);
+int dspmb_p2p_open(const unsigned char *ipc_handle, void **dev_ptr);
+int dspmb_p2p_close(void *dev_ptr);
+int dspmb_p2p_free(void *dev_ptr);
+int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, int B, int A, int K, int rank, int world,
+                               void *const *peer_bases, int slot, void *stream);
+int dspmb_detection_gather_wait(const void *local_base, int B, int K, int world, int slot, int expected, void *stream);
+/* Copies slot `slot` of this rank's buffer into rows_out (world*B, K, 7) and counts_out (world*B) (device, async). */
+int dspmb_detection_gather_read(const void *local_base, int B, int K, int world, int slot, float *rows_out,
+                                int32_t *counts_out, void *stream);
+
 /* Synchronises `stream` and returns the data-dependent status latched by the last target/detection call
  * that used `workspace` (0 or a DSPMB_ERR_* code). */
 int dspmb_status(const void *workspace, void *stream);
