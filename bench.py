@@ -308,23 +308,47 @@ def main():
     pin_loc = torch.from_numpy(inputs["loc"]).pin_memory()
     pin_out = torch.empty((BATCH, A, 7), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
+    # Three streams, double-buffered device tensors: the H2D copy of step i+1, the operator of step i and the D2H
+    # copy of step i-1 overlap (PCIe is full duplex); every step still moves its own inputs in and its result out.
+    s_in, s_run, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_prob = [torch.empty_like(prob_sets[0]) for _ in range(2)]
+    d_loc = [torch.empty_like(loc_sets[0]) for _ in range(2)]
+    d_out = [None, None]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_run = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
+    state = {"n": 0}
 
     def e2e_step():
-        d_prob = pin_prob.to(dev, non_blocking=True)
-        d_loc = pin_loc.to(dev, non_blocking=True)
-        out = MultiBoxDetection(d_prob, d_loc, anchors, **DET_PARAMS)
-        pin_out.copy_(out, non_blocking=True)
+        i = state["n"]
+        k = i & 1
+        with torch.cuda.stream(s_in):
+            if i >= 2:
+                s_in.wait_event(ev_run[k])      # the operator that read this input buffer two steps ago is done
+            d_prob[k].copy_(pin_prob, non_blocking=True)
+            d_loc[k].copy_(pin_loc, non_blocking=True)
+            ev_in[k].record(s_in)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(ev_in[k])
+            if i >= 2:
+                s_run.wait_event(ev_out[k])     # the previous result in this slot has been copied out
+            d_out[k] = MultiBoxDetection(d_prob[k], d_loc[k], anchors, **DET_PARAMS)
+            ev_run[k].record(s_run)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_run[k])
+            pin_out.copy_(d_out[k], non_blocking=True)
+            ev_out[k].record(s_out)
+        state["n"] = i + 1
 
-    for _ in range(3):
+    for _ in range(4):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    ev0.record()
     for _ in range(e2e_steps):
         e2e_step()
-    ev1.record()
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)  # wall clock around fully synchronised work on three streams
     barrier()
-    e2e_ms = max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,7 +417,7 @@ def main():
             "e2e": {"value": BATCH * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": int(pin_prob.numel() * 4 + pin_loc.numel() * 4),
                     "d2h_bytes_per_step": int(pin_out.numel() * 4), "steps": e2e_steps,
-                    "api": "dspnet_b200.MultiBoxDetection on pinned host tensors, result copied back"},
+                    "api": "dspnet_b200.MultiBoxDetection; per step: pinned host -> device copy of cls_prob+loc_pred, operator, full (B,A,7) result copied back to pinned host; copy-in / operator / copy-out of consecutive steps overlap on three streams"},
             "gpu_launches": launches,
             "clocks": clocks,
             "target": tgt,
