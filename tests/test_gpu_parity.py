@@ -315,3 +315,73 @@ def test_detection_forced_code_paths(oracle, cuda, knobs):
     finally:
         for k, v in old.items():
             L.dspmb_set_tuning(k, v)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 256])
+def test_detection_stream_kernel_variants(oracle, cuda, variant):
+    """Generic, TMA-ring and register-resident stream kernels produce identical results."""
+    from dspnet_b200 import _lib
+    L = _lib.lib()
+    old = L.dspmb_set_tuning(_lib.TUNE_DET_STREAM_VARIANT, variant)
+    try:
+        for preset, batch in (("ssd512", 2), ("dspnet_cs", 2)):
+            anchors, prob, lp = util.detection_inputs(oracle, preset, batch, config_id=17)
+            _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=400)
+    finally:
+        L.dspmb_set_tuning(_lib.TUNE_DET_STREAM_VARIANT, old)
+
+
+def test_target_generic_class_count_and_vec4(oracle, cuda):
+    """C outside the register-resident specialisations (21, 9) and the 4-anchors-per-thread variant."""
+    from dspnet_b200 import _lib
+    rng = np.random.default_rng(8)
+    A, C, B, L = 2048, 13, 3, 12
+    xy = rng.uniform(0, 0.8, (A, 2))
+    wh = rng.uniform(0.05, 0.4, (A, 2))
+    anchors = np.concatenate([xy, xy + wh], axis=1).reshape(1, A, 4).astype(np.float32)
+    lab = synth.labels(26, B, L, C, max_gt=9, edge_cases=False)
+    cp = synth.cls_preds(26, B, C, A)
+    _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+    Lb = _lib.lib()
+    old = Lb.dspmb_set_tuning(_lib.TUNE_DET_STREAM_VARIANT, 4)
+    try:
+        anchors, lab, cp = util.target_inputs(oracle, "ssd300", 3, config_id=27)
+        _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+    finally:
+        Lb.dspmb_set_tuning(_lib.TUNE_DET_STREAM_VARIANT, old)
+
+
+def test_target_mining_band_with_massive_ties(oracle, cuda):
+    """Constant logits: every candidate has the same probability, so the whole image sits inside the pivot's error
+    band and the exact re-evaluation + (prob, anchor) ranking decides everything."""
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 2, config_id=28)
+    cp[:] = 0.25
+    _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+    cp2 = np.zeros_like(cp)
+    cp2[:, 0] = -120.0   # background probability in the denormal range -> exact path inside the stream kernel
+    cp2[:, 0, ::3] = -95.0
+    _check_target(oracle, cuda, anchors, lab, cp2, negative_mining_ratio=3)
+
+
+def test_fused_gather_single_rank(oracle, cuda):
+    """The fused compaction + peer all-gather kernel with world = 1 (the multi-rank path is exercised by bench.py
+    under torchrun): gathered rows equal the surviving rows of the operator output in row order."""
+    from dspnet_b200 import MultiBoxDetection
+    from dspnet_b200.dist import P2PDetectionGatherer, compact_rows
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 3, config_id=33)
+    out = MultiBoxDetection(_t(prob, cuda), _t(lp, cuda), _t(anchors, cuda), nms_threshold=0.45, nms_topk=400)
+    g = P2PDetectionGatherer(3, anchors.shape[1], 200, cuda, 1, 0)
+    try:
+        g.submit(out, 0)
+        rows, counts = g.gathered(0)
+        torch.cuda.synchronize()
+        want = oracle.multibox_detection(prob, lp, anchors, nms_threshold=0.45, nms_topk=400)
+        for b in range(3):
+            keep = want[b][want[b, :, 0] >= 0][:200]
+            assert int(counts[b]) == len(keep)
+            util.assert_bit_equal(rows[b, : len(keep)].cpu().numpy(), keep, "gathered rows")
+            assert (rows[b, len(keep):].cpu().numpy() == -1).all()
+        r2, c2 = compact_rows(out, 200)
+        assert torch.equal(r2, rows) and torch.equal(c2, counts)
+    finally:
+        g.close()
