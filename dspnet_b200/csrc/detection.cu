@@ -38,6 +38,7 @@ namespace dspmb {
 namespace {
 
 constexpr int kStreamThreads = 128;
+constexpr int kRegThreads = 128;      // CTA size of the register-resident stream kernel
 constexpr int kSortThreads = 1024;
 constexpr int kNmsThreads = 256;
 constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared memory
@@ -240,12 +241,12 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
 // before the first compare, so a thread has (NFG + 9) x 16 B in flight, the decode has no dependent memory round
 // trip, and the ~150 registers/thread cap residency at 3 CTAs/SM: the grid runs in several waves whose load and
 // store/decode phases overlap instead of all CTAs being resident and in lockstep.
-template <int NFG>
-__global__ void __launch_bounds__(kStreamThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
-  __shared__ int scan_smem[kStreamThreads / 32 + 1];
-  __shared__ __align__(16) unsigned sm_keys[kStreamThreads * 4];
+template <int NFG, int kThreads>
+__global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
+  __shared__ int scan_smem[kThreads / 32 + 1];
+  __shared__ __align__(16) unsigned sm_keys[kThreads * 4];
   const int b = blockIdx.y, t = blockIdx.x;
-  constexpr int kTile = kStreamThreads * 4;
+  constexpr int kTile = kThreads * 4;
   const int tile_begin = t * kTile;
   const int i0 = tile_begin + threadIdx.x * 4;
   const int A = a.A;
@@ -267,7 +268,7 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_reg_kernel(const __
     float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
     const int nfl = min(kTile, A - tile_begin) * 7;
     const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
-    for (int x = threadIdx.x * 4; x < nfl; x += kStreamThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
+    for (int x = threadIdx.x * 4; x < nfl; x += kThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
   }
   float score[4] = {-1.f, -1.f, -1.f, -1.f};
   int id[4] = {0, 0, 0, 0};
@@ -1236,7 +1237,8 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 0;
   }
-  const int tile = stages ? kPipeTile : kStreamThreads * (vec4 ? 4 : 1);
+  const bool reg_variant = vec4 && variant > 1 && (C == 21 || C == 9);
+  const int tile = stages ? kPipeTile : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1));
   const int T = ceil_div(A, tile);
   const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
 
@@ -1281,9 +1283,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     dim3 grid1(T, B);
     ProfileScope _p(kSlotDetStream, stream);
     if (vec4 && variant > 1 && C == 21)
-      det_stream_reg_kernel<20><<<grid1, kStreamThreads, 0, stream>>>(sa);
+      det_stream_reg_kernel<20, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);
     else if (vec4 && variant > 1 && C == 9)
-      det_stream_reg_kernel<8><<<grid1, kStreamThreads, 0, stream>>>(sa);
+      det_stream_reg_kernel<8, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);
     else if (vec4)
       det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
     else
