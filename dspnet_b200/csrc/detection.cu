@@ -31,6 +31,9 @@
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+
+#include <atomic>
 
 #include "common.cuh"
 
@@ -46,17 +49,16 @@ constexpr int kRankSortMax = 1024;    // selections up to this size are rank-sor
 constexpr int kKeySmemMax = 28672;    // slot keys (T * tile) that fit in shared memory next to the sort keys
 constexpr int kNmsMaskRows = 320;     // NMS segments up to this size use the shared-memory bit mask (5 words/row)
 constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in shared memory
-constexpr int kRecFloats = 8;         // score, id, x1, y1, x2, y2, dist, pad
 constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every real key
 
 struct DetWorkspace {
   WsHeader *header;
-  int *tile_count;            // (B, T)
+  unsigned long long *state;  // (B, T) decoupled look-back words of the stream kernel (zeroed per call)
   int *valid;                 // (B) V
   int *nms_rows;              // (B) rows taking part in NMS (0 = skipped)
   int *cursor;                // (B) allocator of seg_list regions for large segments
-  unsigned *keys;             // (B, Apad) order key of every record slot, sentinel where empty
-  float *rec;                 // (B, Apad, 8) decoded records in per-tile slots
+  unsigned *keys;             // (B, Apad) order key of every surviving row, by rank
+  float *stage;               // (B, A, 8) staging of the sorted head rows
   unsigned short *row_cls;    // (B, Apad) class of every output row
   float4 *row_box;            // (B, A) box of every output row
   int *seg_list;              // (B, A) member rows of large segments
@@ -66,6 +68,16 @@ struct DetWorkspace {
   unsigned long long *sort_keys;  // (B, npad) spill for selections larger than the shared-memory budget
   size_t bytes;
 };
+
+// Per-call tag for the look-back words: a process-wide counter on top of a time-derived base, never zero.
+inline unsigned long long next_nonce() {
+  static std::atomic<unsigned long long> counter{(unsigned long long)time(nullptr) * 2654435761ull};
+  unsigned long long n;
+  do {
+    n = counter.fetch_add(1) & ((1ull << 38) - 1);
+  } while (n == 0);
+  return n;
+}
 
 inline int next_pow2(int v) {
   int p = 1;
@@ -86,12 +98,12 @@ DetWorkspace carve(void *base, int B, int A, int C) {
     return (char *)base + o;
   };
   w.header = (WsHeader *)take(sizeof(WsHeader));
-  w.tile_count = (int *)take(sizeof(int) * B * Tmax);
+  w.state = (unsigned long long *)take(sizeof(unsigned long long) * B * Tmax);
   w.valid = (int *)take(sizeof(int) * B);
   w.nms_rows = (int *)take(sizeof(int) * B);
   w.cursor = (int *)take(sizeof(int) * B);
   w.keys = (unsigned *)take(sizeof(unsigned) * B * Apad);
-  w.rec = (float *)take(sizeof(float) * kRecFloats * B * Apad);
+  w.stage = (float *)take(sizeof(float) * 8 * (size_t)B * A);
   w.row_cls = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
   w.row_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
   w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
@@ -106,14 +118,17 @@ DetWorkspace carve(void *base, int B, int A, int C) {
 struct StreamArgs {
   const float *cls_prob, *loc_pred, *anchors;
   float *out;
-  int *tile_count;
-  unsigned *keys;
-  float *rec;
-  int A, C, T, Apad;
+  unsigned long long *state;  // (B, T) decoupled look-back words: flag << 32 | value
+  int *valid;                 // (B) V, written by the last tile of every image
+  unsigned *keys;             // (B, Apad) order keys by RANK
+  unsigned short *row_cls;    // (B, cls_stride)
+  float4 *row_box;            // (B, A)
+  int A, C, T, Apad, cls_stride;
   float threshold;
   int clip;
   float vx, vy, vw, vh;
   int fma_build;
+  unsigned long long nonce;  // per-call tag of the look-back words
 };
 
 __device__ __forceinline__ float clip01(float v) {
@@ -122,21 +137,84 @@ __device__ __forceinline__ float clip01(float v) {
   return 0.f < m ? m : 0.f;
 }
 
-// Decode one surviving anchor (multibox_detection.cc:98-125) into a record.
-__device__ __forceinline__ void decode_record(const StreamArgs &a, const float *loc, int i, int id, float score,
-                                              float *rec) {
-  const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i);
-  const float aw = fsub(an.z, an.x);
-  const float ah = fsub(an.w, an.y);
-  const float ax = fdiv(fadd(an.x, an.z), 2.f);
-  const float ay = fdiv(fadd(an.y, an.w), 2.f);
-  const float *lp = loc + (size_t)i * 5;
-  const float px = __ldg(lp), py = __ldg(lp + 1), pw = __ldg(lp + 2), ph = __ldg(lp + 3), pz = __ldg(lp + 4);
-  const float ox = fadd(fmul(fmul(px, a.vx), aw), ax);
-  const float oy = fadd(fmul(fmul(py, a.vy), ah), ay);
-  const float ow = fdiv(fmul(libm::expf_glibc(fmul(pw, a.vw), a.fma_build), aw), 2.f);
-  const float oh = fdiv(fmul(libm::expf_glibc(fmul(ph, a.vh), a.fma_build), ah), 2.f);
-  const float oz = __double2float_rn(__dmul_rn((double)pz, 0.1));
+// Rank base of a tile = number of surviving anchors in the tiles before it (same image): single-pass chained scan
+// with decoupled look-back.  Tiles of an image are consecutive linear block indices (or, in the persistent
+// kernel, visited in increasing order by co-resident CTAs), so every predecessor is already running or done.
+// Ordering contract: the caller's -1 fill of the tile's output rows precedes this call (block barrier inside the
+// scan that produced `total`); thread 0 fences before publishing, and fences again after reading a predecessor's
+// word, so a tile that has acquired a rank base also sees the fills of all earlier tiles -- which is what makes it
+// safe for it to store its surviving rows (rank <= anchor index) into those tiles' row ranges.
+// Contains one __syncthreads(); returns the base to every thread.
+// State word: nonce (38 bits) | flag (2 bits: 1 aggregate, 2 inclusive prefix) | value (24 bits).  The nonce is
+// unique per call (host counter), so words left in the caller's scratch memory by earlier calls -- or arbitrary
+// scratch contents -- read as "not there yet" and no per-call memset is needed (a random 64-bit pattern passes for a
+// live word with probability 2^-38).
+__device__ __forceinline__ unsigned long long pack_state(unsigned long long nonce, unsigned flag, int value) {
+  return (nonce << 26) | ((unsigned long long)flag << 24) | (unsigned)value;
+}
+
+// Step 1 (one thread, right after the block scan): make this tile's survivor count visible to its successors.
+__device__ __forceinline__ void publish_aggregate(const StreamArgs &a, int b, int t, int total) {
+  volatile unsigned long long *st = a.state + (size_t)b * a.T;
+  __threadfence();
+  st[t] = pack_state(a.nonce, t == 0 ? 2u : 1u, total);
+}
+
+// Step 2 (whole CTA, after the rows have been staged): exclusive rank base of the tile.
+__device__ __forceinline__ int tile_rank_base(const StreamArgs &a, int b, int t, int total, int *sm_base) {
+  if (threadIdx.x < 32) {  // warp 0: one window of 32 predecessors per round trip
+    volatile unsigned long long *st = a.state + (size_t)b * a.T;
+    const int lane = threadIdx.x;
+    int excl = 0;
+    int hi = t - 1;  // nearest predecessor not yet accounted for
+    while (hi >= 0) {
+      const int p = hi - lane;
+      const unsigned long long v = p >= 0 ? st[p] : pack_state(a.nonce, 2u, 0);  // before tile 0: empty prefix
+      const unsigned flag = (v >> 26) == a.nonce ? (unsigned)((v >> 24) & 3ull) : 0u;
+      // the window is usable up to (and including) the first inclusive prefix, if no word before it is missing
+      const unsigned missing = __ballot_sync(kFullMask, flag == 0u);
+      const unsigned prefix = __ballot_sync(kFullMask, flag == 2u);
+      const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
+      const int first_missing = missing ? __ffs(missing) - 1 : 32;
+      if (first_missing < first_prefix) continue;  // a needed predecessor is not there yet
+      const int upto = first_prefix < 32 ? first_prefix : 31;
+      excl += warp_sum_i32(lane <= upto ? (int)(unsigned)(v & 0xffffffull) : 0);
+      if (first_prefix < 32) break;
+      hi -= 32;
+    }
+    if (lane == 0) {
+      __threadfence();
+      if (t > 0) st[t] = pack_state(a.nonce, 2u, excl + total);
+      if (t == a.T - 1) a.valid[b] = excl + total;
+      *sm_base = excl;
+    }
+  }
+  __syncthreads();
+  return *sm_base;
+}
+
+// Shared-memory staging of a tile's surviving rows.  Their ranks are consecutive, so rows, keys, classes and boxes
+// each form ONE contiguous run in global memory: the CTA stages them and writes the runs with coalesced stores
+// (per-row scattered 4-byte stores cost ten times the L2 write traffic).
+template <int kRows>
+struct RowStage {
+  float rows[kRows * 7];
+  float4 box[kRows];
+  unsigned keys[kRows];
+  unsigned short cls[kRows];
+};
+
+// Final pass-1 row of one surviving anchor (multibox_detection.cc:89-127), staged at its index inside the tile.
+template <int kRows>
+__device__ __forceinline__ void stage_row(const StreamArgs &a, RowStage<kRows> &sm, int local, int id, float score,
+                                          float4 an, const float *lp) {
+  const float aw = fsub(an.z, an.x), ah = fsub(an.w, an.y);
+  const float ax = fdiv(fadd(an.x, an.z), 2.f), ay = fdiv(fadd(an.y, an.w), 2.f);
+  const float ox = fadd(fmul(fmul(lp[0], a.vx), aw), ax);
+  const float oy = fadd(fmul(fmul(lp[1], a.vy), ah), ay);
+  const float ow = fdiv(fmul(libm::expf_glibc(fmul(lp[2], a.vw), a.fma_build), aw), 2.f);
+  const float oh = fdiv(fmul(libm::expf_glibc(fmul(lp[3], a.vh), a.fma_build), ah), 2.f);
+  const float oz = __double2float_rn(__dmul_rn((double)lp[4], 0.1));
   float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
   if (a.clip) {
     x1 = clip01(x1);
@@ -145,15 +223,39 @@ __device__ __forceinline__ void decode_record(const StreamArgs &a, const float *
     y2 = clip01(y2);
     z = clip01(z);
   }
-  float4 *r4 = reinterpret_cast<float4 *>(rec);
-  r4[0] = make_float4(score, (float)(id - 1), x1, y1);
-  r4[1] = make_float4(x2, y2, z, 0.f);
+  float *o = sm.rows + local * 7;
+  o[0] = (float)(id - 1);
+  o[1] = score;
+  o[2] = x1;
+  o[3] = y1;
+  o[4] = x2;
+  o[5] = y2;
+  o[6] = z;
+  sm.keys[local] = ~float_order_key(score);  // ascending key == descending score
+  sm.cls[local] = (unsigned short)(id - 1);
+  sm.box[local] = make_float4(x1, y1, x2, y2);
+}
+
+// Coalesced write-out of `total` staged rows whose first rank is `base`.  Call after a block barrier.
+template <int kRows>
+__device__ __forceinline__ void flush_rows(const StreamArgs &a, const RowStage<kRows> &sm, int b, int base, int total) {
+  float *o = a.out + ((size_t)b * a.A + base) * 7;
+  for (int q = threadIdx.x; q < total * 7; q += blockDim.x) o[q] = sm.rows[q];
+  unsigned *gk = a.keys + (size_t)b * a.Apad + base;
+  unsigned short *gc = a.row_cls + (size_t)b * a.cls_stride + base;
+  float4 *gb = a.row_box + (size_t)b * a.A + base;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    gk[q] = sm.keys[q];
+    gc[q] = sm.cls[q];
+    gb[q] = sm.box[q];
+  }
 }
 
 template <int VEC>
 __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kStreamThreads / 32 + 1];
-  __shared__ __align__(16) unsigned sm_keys[kStreamThreads * VEC];
+  __shared__ int sm_base;
+  __shared__ RowStage<kStreamThreads * VEC> sm_rows;
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kStreamThreads * VEC;
   const int tile_begin = t * kTile;
@@ -181,7 +283,6 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
   for (int k = 0; k < VEC; ++k) {
     score[k] = -1.f;
     id[k] = 0;
-    sm_keys[threadIdx.x * VEC + k] = kKeySentinel;
   }
   if (i0 < A) {
 #pragma unroll 5
@@ -211,28 +312,25 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
     nvalid += id[k] > 0;
   }
 
-  // ---- ordered compaction inside the tile ----
+  // ---- ordered compaction: rank = survivors before this anchor in the image ----
   int total;
   int pos = block_scan_excl(nvalid, scan_smem, &total);
-  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
   if (nvalid) {
     const float *loc = a.loc_pred + (size_t)b * A * 5;
-    float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
 #pragma unroll
     for (int k = 0; k < VEC; ++k)
       if (id[k] > 0) {
-        decode_record(a, loc, i0 + k, id[k], score[k], rec + (size_t)pos * kRecFloats);
-        sm_keys[pos] = ~float_order_key(score[k]);  // ascending key == descending score
+        const int i = i0 + k;
+        const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i);
+        const float *lsrc = loc + (size_t)i * 5;
+        const float lp[5] = {__ldg(lsrc), __ldg(lsrc + 1), __ldg(lsrc + 2), __ldg(lsrc + 3), __ldg(lsrc + 4)};
+        stage_row(a, sm_rows, pos, id[k], score[k], an, lp);
         ++pos;
       }
   }
-  __syncthreads();
-  unsigned *gk = a.keys + (size_t)b * a.Apad + tile_begin;
-  if constexpr (VEC == 4) {
-    reinterpret_cast<uint4 *>(gk)[threadIdx.x] = reinterpret_cast<const uint4 *>(sm_keys)[threadIdx.x];
-  } else {
-    gk[threadIdx.x] = sm_keys[threadIdx.x];
-  }
+  const int base = tile_rank_base(a, b, t, total, &sm_base);  // block barrier inside: the staged rows are complete
+  flush_rows(a, sm_rows, b, base, total);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -244,7 +342,8 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
 template <int NFG, int kThreads>
 __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kThreads / 32 + 1];
-  __shared__ __align__(16) unsigned sm_keys[kThreads * 4];
+  __shared__ int sm_base;
+  __shared__ RowStage<kThreads * 4> sm_rows;
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kThreads * 4;
   const int tile_begin = t * kTile;
@@ -272,8 +371,6 @@ __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_c
   }
   float score[4] = {-1.f, -1.f, -1.f, -1.f};
   int id[4] = {0, 0, 0, 0};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) sm_keys[threadIdx.x * 4 + k] = kKeySentinel;
   if (active) {
 #pragma unroll
     for (int j = 0; j < NFG; ++j) {
@@ -294,40 +391,19 @@ __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_c
   }
   int total;
   int pos = block_scan_excl(nvalid, scan_smem, &total);
-  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
   if (nvalid) {
-    float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
     const float lf[20] = {lp[0].x, lp[0].y, lp[0].z, lp[0].w, lp[1].x, lp[1].y, lp[1].z, lp[1].w, lp[2].x, lp[2].y,
                           lp[2].z, lp[2].w, lp[3].x, lp[3].y, lp[3].z, lp[3].w, lp[4].x, lp[4].y, lp[4].z, lp[4].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (id[k] > 0) {
-        // decode, multibox_detection.cc:98-125
-        const float aw = fsub(an[k].z, an[k].x), ah = fsub(an[k].w, an[k].y);
-        const float ax = fdiv(fadd(an[k].x, an[k].z), 2.f), ay = fdiv(fadd(an[k].y, an[k].w), 2.f);
-        const float ox = fadd(fmul(fmul(lf[5 * k], a.vx), aw), ax);
-        const float oy = fadd(fmul(fmul(lf[5 * k + 1], a.vy), ah), ay);
-        const float ow = fdiv(fmul(libm::expf_glibc(fmul(lf[5 * k + 2], a.vw), a.fma_build), aw), 2.f);
-        const float oh = fdiv(fmul(libm::expf_glibc(fmul(lf[5 * k + 3], a.vh), a.fma_build), ah), 2.f);
-        const float oz = __double2float_rn(__dmul_rn((double)lf[5 * k + 4], 0.1));
-        float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
-        if (a.clip) {
-          x1 = clip01(x1);
-          y1 = clip01(y1);
-          x2 = clip01(x2);
-          y2 = clip01(y2);
-          z = clip01(z);
-        }
-        float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)pos * kRecFloats);
-        r4[0] = make_float4(score[k], (float)(id[k] - 1), x1, y1);
-        r4[1] = make_float4(x2, y2, z, 0.f);
-        sm_keys[pos] = ~float_order_key(score[k]);
+        stage_row(a, sm_rows, pos, id[k], score[k], an[k], lf + 5 * k);
         ++pos;
       }
   }
-  __syncthreads();
-  reinterpret_cast<uint4 *>(a.keys + (size_t)b * a.Apad + tile_begin)[threadIdx.x] =
-      reinterpret_cast<const uint4 *>(sm_keys)[threadIdx.x];
+  const int base = tile_rank_base(a, b, t, total, &sm_base);  // block barrier inside: the staged rows are complete
+  flush_rows(a, sm_rows, b, base, total);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -380,7 +456,8 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) unsigned long long full_bar[4];
   __shared__ int scan_smem[kPipeThreads / 32 + 1];
-  __shared__ __align__(16) unsigned sm_keys[kPipeTile];
+  __shared__ int sm_base;
+  __shared__ RowStage<kPipeTile> sm_rows;
   const StreamArgs &a = p.s;
   const int A = a.A, T = a.T, nfg = a.C - 1;
   float *ring = reinterpret_cast<float *>(dyn_smem);
@@ -428,8 +505,6 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
       const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
       for (int q = threadIdx.x * 4; q < nfl; q += kPipeThreads * 4) *reinterpret_cast<float4 *>(ob + q) = m1;
     }
-    sm_keys[l0] = kKeySentinel;
-    sm_keys[l0 + 1] = kKeySentinel;
 
     mbar_wait(&full_bar[stage], (unsigned)((it / p.stages) & 1));
     const float *cls = ring + (size_t)stage * p.stage_floats;
@@ -459,40 +534,19 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
     }
     int total;
     int pos = block_scan_excl(nvalid, scan_smem, &total);
-    if (threadIdx.x == 0) a.tile_count[(size_t)b * T + t] = total;
+    if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
     if (nvalid) {
-      float *rec = a.rec + ((size_t)b * a.Apad + tile_begin) * kRecFloats;
 #pragma unroll
       for (int k = 0; k < kPipeVec; ++k)
         if (id[k] > 0) {
-          // decode (multibox_detection.cc:98-125) from the staged loc_pred row
           const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + tile_begin + l0 + k);
-          const float *lp = locs + (l0 + k) * 5;
-          const float aw = fsub(an.z, an.x), ah = fsub(an.w, an.y);
-          const float ax = fdiv(fadd(an.x, an.z), 2.f), ay = fdiv(fadd(an.y, an.w), 2.f);
-          const float ox = fadd(fmul(fmul(lp[0], a.vx), aw), ax);
-          const float oy = fadd(fmul(fmul(lp[1], a.vy), ah), ay);
-          const float ow = fdiv(fmul(libm::expf_glibc(fmul(lp[2], a.vw), a.fma_build), aw), 2.f);
-          const float oh = fdiv(fmul(libm::expf_glibc(fmul(lp[3], a.vh), a.fma_build), ah), 2.f);
-          const float oz = __double2float_rn(__dmul_rn((double)lp[4], 0.1));
-          float x1 = fsub(ox, ow), y1 = fsub(oy, oh), x2 = fadd(ox, ow), y2 = fadd(oy, oh), z = oz;
-          if (a.clip) {
-            x1 = clip01(x1);
-            y1 = clip01(y1);
-            x2 = clip01(x2);
-            y2 = clip01(y2);
-            z = clip01(z);
-          }
-          float4 *r4 = reinterpret_cast<float4 *>(rec + (size_t)pos * kRecFloats);
-          r4[0] = make_float4(score[k], (float)(id[k] - 1), x1, y1);
-          r4[1] = make_float4(x2, y2, z, 0.f);
-          sm_keys[pos] = ~float_order_key(score[k]);
+          stage_row(a, sm_rows, pos, id[k], score[k], an, locs + (l0 + k) * 5);
           ++pos;
         }
     }
-    __syncthreads();  // keys complete; every thread is done with this stage -> it may be refilled next iteration
-    reinterpret_cast<uint2 *>(a.keys + (size_t)b * a.Apad + tile_begin)[threadIdx.x] =
-        reinterpret_cast<const uint2 *>(sm_keys)[threadIdx.x];
+    const int base = tile_rank_base(a, b, t, total, &sm_base);
+    flush_rows(a, sm_rows, b, base, total);
+    __syncthreads();  // every thread is done with this stage and the row staging -> both may be refilled
   }
 }
 
@@ -539,21 +593,25 @@ __device__ __forceinline__ int warp_append(int *counter, bool pred) {
 
 struct SortArgs {
   float *out;
-  const int *tile_count;
-  const unsigned *keys;
-  const float *rec;
-  int *valid, *nms_rows, *cursor;
+  const unsigned *keys;   // (B, Apad) order keys by rank (written by the stream kernel)
+  const int *valid;       // (B) V
+  int *nms_rows, *cursor;
   unsigned short *row_cls;
   float4 *row_box;
+  float *stage;           // (B, A, 8) staging of the sorted head rows
   unsigned long long *sort_keys;
   int *valid_count_out;
   WsHeader *header;
-  int A, C, T, Apad, cls_stride, tile, npad_max, niter;
-  int keys_in_smem, sel_cap;
+  int A, Apad, cls_stride, npad_max, niter_max;
+  int sel_cap;
   float nms_threshold;
   int force_suppress, nms_topk;
 };
 
+// One CTA per image.  The stream kernel has already written every surviving row at its rank (= the reference's
+// pass-1 output), so rows [nkeep, V) are final.  This kernel only produces the sorted head: radix select of the
+// nkeep best keys over the V rank-ordered keys, sort, and a permuted copy of those rows (through a staging buffer,
+// because head positions are both sources and destinations) into rows [0, nkeep) -- multibox_detection.cc:132-151.
 template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -562,248 +620,177 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;
   __shared__ unsigned sm_prefix;
   const int b = blockIdx.x;
-  const int T = a.T, tile = a.tile, A = a.A;
-  const int Tt = T * tile;
-  // dynamic smem: [sel: sel_cap u64][skeys: Tt u32 (optional)][tile_off: T+1 int][wtab: niter*32 int]
-  unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
-  unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
-  int *tile_off = reinterpret_cast<int *>(skeys + (kKeysInSmem ? Tt : 0));
-  int *wtab = tile_off + (T + 1);
-  const unsigned *gkeys = a.keys + (size_t)b * a.Apad;
-  // explicit address spaces: shared-memory keys must compile to LDS, not to generic loads
-  auto key_at = [&](int s) -> unsigned { return kKeysInSmem ? skeys[s] : gkeys[s]; };
-  const unsigned warp = warp_id(), lane = lane_id();
-  if (b == 0 && threadIdx.x == 0) a.header->status = DSPMB_OK;
-
-  // 0. stage the slot keys (coalesced 128-bit loads; Tt is a multiple of 128)
-  if (kKeysInSmem)
-    for (int i = threadIdx.x; i < (Tt >> 2); i += blockDim.x)
-      reinterpret_cast<uint4 *>(skeys)[i] = __ldg(reinterpret_cast<const uint4 *>(gkeys) + i);
-
-  // 1. exclusive prefix over the tile counts -> rank of every record in anchor order
-  if (threadIdx.x == 0) carry_smem = 0;
-  __syncthreads();
-  const int *cnt = a.tile_count + (size_t)b * T;
-  for (int base = 0; base < T; base += blockDim.x) {
-    const int t = base + threadIdx.x;
-    const int v = t < T ? cnt[t] : 0;
-    int total;
-    const int ex = block_scan_excl(v, scan_smem, &total);
-    const int carry = carry_smem;
-    if (t < T) tile_off[t] = carry + ex;
-    __syncthreads();
-    if (threadIdx.x == 0) carry_smem = carry + total;
-    __syncthreads();
-  }
-  const int V = carry_smem;
+  const int A = a.A;
+  const int V = a.valid[b];
   const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;  // multibox_detection.cc:130
   if (threadIdx.x == 0) {
-    tile_off[T] = V;
-    a.valid[b] = V;
+    if (b == 0) a.header->status = DSPMB_OK;
     if (a.valid_count_out) a.valid_count_out[b] = V;
     a.nms_rows[b] = do_sort ? V : 0;
     a.cursor[b] = 0;
     sm_prefix = 0u;
     sm_count = 0;
     sm_eq_total = 0;
+    carry_smem = 0;
   }
-  if (V == 0) return;
+  if (!do_sort) return;  // pass-1 rows are the final output
+  // dynamic smem: [sel: sel_cap u64][skeys: round4(A) u32 (optional)][wtab: niter_max*32 int]
+  unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
+  unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
+  int *wtab = reinterpret_cast<int *>(skeys + (kKeysInSmem ? ((A + 3) & ~3) : 0));
+  const unsigned *gkeys = a.keys + (size_t)b * a.Apad;
+  auto key_at = [&](int p) -> unsigned { return kKeysInSmem ? skeys[p] : gkeys[p]; };
+  const unsigned warp = warp_id(), lane = lane_id();
+  const int niter = (V + (int)blockDim.x - 1) / (int)blockDim.x;
 
-  // 2. the nkeep best keys (stable_sort + top-k of multibox_detection.cc:132-151), as (key << 32 | slot)
-  int nkeep = 0;
-  unsigned long long *sel = ssel;
-  if (do_sort) {
-    nkeep = V;
-    if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;
-    int npad = 2;
-    while (npad < nkeep) npad <<= 1;
-    if (npad > a.sel_cap) sel = a.sort_keys + (size_t)b * a.npad_max;
-    if (threadIdx.x == 0) sm_need = nkeep;
+  if (kKeysInSmem) {  // coalesced 128-bit loads (rows of `keys` are 16-byte aligned; reads beyond V stay inside Apad)
+    for (int i = threadIdx.x; i < ((V + 3) >> 2); i += blockDim.x)
+      reinterpret_cast<uint4 *>(skeys)[i] = __ldg(reinterpret_cast<const uint4 *>(gkeys) + i);
+  }
+  int nkeep = V;
+  if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;  // multibox_detection.cc:142-145
+  int npad = 2;
+  while (npad < nkeep) npad <<= 1;
+  unsigned long long *sel = npad > a.sel_cap ? a.sort_keys + (size_t)b * a.npad_max : ssel;
+  if (threadIdx.x == 0) sm_need = nkeep;
+  __syncthreads();
+
+  if (nkeep == V) {
+    for (int p = threadIdx.x; p < npad; p += blockDim.x)
+      sel[p] = p < V ? (((unsigned long long)key_at(p) << 32) | (unsigned)p) : ~0ull;
     __syncthreads();
-    unsigned pivot = kKeySentinel - 1u;  // nkeep == V: every real key is selected
-    bool ordered_ties = false;
-    int need_eq = 0;
-    if (nkeep < V) {
-      // MSB-first radix select of the nkeep-th smallest key over the slot keys (empty slots are skipped)
-      for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist256[i] = 0u;
-        __syncthreads();
-        const unsigned prefix = sm_prefix;
-        for (int it = 0; it < a.niter; ++it) {
-          const int s = it * blockDim.x + threadIdx.x;
-          const unsigned kv = s < Tt ? key_at(s) : kKeySentinel;
-          hist_add(hist256, (kv >> shift) & 0xffu, kv != kKeySentinel && (kv & mask) == prefix);
+  } else {
+    // MSB-first radix select of the nkeep-th smallest key
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist256[i] = 0u;
+      __syncthreads();
+      const unsigned prefix = sm_prefix;
+      for (int it = 0; it < niter; ++it) {
+        const int p = it * blockDim.x + threadIdx.x;
+        const unsigned kv = p < V ? key_at(p) : 0u;
+        hist_add(hist256, (kv >> shift) & 0xffu, p < V && (kv & mask) == prefix);
+      }
+      __syncthreads();
+      if (warp == 0) {  // digit search: 8 bins per lane, warp scan
+        unsigned h[8];
+        int tot = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          h[d] = hist256[lane * 8 + d];
+          tot += (int)h[d];
         }
-        __syncthreads();
-        if (warp == 0) {  // digit search: 8 bins per lane, warp scan
-          unsigned h[8];
-          int tot = 0;
+        const int incl = warp_scan_incl(tot);
+        const int excl = incl - tot;
+        const int need = sm_need;
+        if (excl < need && incl >= need) {
+          int acc = excl;
 #pragma unroll
           for (int d = 0; d < 8; ++d) {
-            h[d] = hist256[lane * 8 + d];
-            tot += (int)h[d];
-          }
-          const int incl = warp_scan_incl(tot);
-          const int excl = incl - tot;
-          const int need = sm_need;
-          if (excl < need && incl >= need) {
-            int acc = excl;
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-              if (acc + (int)h[d] >= need) {
-                sm_need = need - acc;
-                sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
-                sm_eq_total = (int)h[d];
-                break;
-              }
-              acc += (int)h[d];
+            if (acc + (int)h[d] >= need) {
+              sm_need = need - acc;
+              sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
+              sm_eq_total = (int)h[d];
+              break;
             }
+            acc += (int)h[d];
           }
         }
-        __syncthreads();
       }
-      pivot = sm_prefix;
-      need_eq = sm_need;
-      ordered_ties = need_eq < sm_eq_total;  // only some of the keys equal to the pivot make it: lowest slots first
+      __syncthreads();
     }
+    const unsigned pivot = sm_prefix;
+    const int need_eq = sm_need;
+    const bool ordered_ties = need_eq < sm_eq_total;  // only the lowest-ranked of the pivot-valued keys make it
     if (ordered_ties) {
-      // ballot counts of the pivot-valued keys per (iteration, warp), scanned in slot order
-      for (int it = 0; it < a.niter; ++it) {
-        const int s = it * blockDim.x + threadIdx.x;
-        const unsigned m = __ballot_sync(kFullMask, s < Tt && key_at(s) == pivot);
+      for (int it = 0; it < niter; ++it) {
+        const int p = it * blockDim.x + threadIdx.x;
+        const unsigned m = __ballot_sync(kFullMask, p < V && key_at(p) == pivot);
         if (lane == 0) wtab[it * 32 + warp] = __popc(m);
       }
       __syncthreads();
-      if (threadIdx.x == 0) carry_smem = 0;
-      __syncthreads();
-      for (int base = 0; base < a.niter * 32; base += blockDim.x) {
+      for (int base = 0; base < niter * 32; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const int v = i < a.niter * 32 ? wtab[i] : 0;
+        const int v = i < niter * 32 ? wtab[i] : 0;
         int total;
         const int ex = block_scan_excl(v, scan_smem, &total);
         const int carry = carry_smem;
-        if (i < a.niter * 32) wtab[i] = carry + ex;
+        if (i < niter * 32) wtab[i] = carry + ex;
         __syncthreads();
         if (threadIdx.x == 0) carry_smem = carry + total;
         __syncthreads();
       }
     }
-    // gather the selection (any order: the 64-bit keys are unique and get sorted next)
-    for (int it = 0; it < a.niter; ++it) {
-      const int s = it * blockDim.x + threadIdx.x;
-      const unsigned kv = s < Tt ? key_at(s) : kKeySentinel;
-      bool take = kv != kKeySentinel && kv <= pivot;
+    for (int it = 0; it < niter; ++it) {  // gather (any order: the 64-bit keys are unique and get sorted next)
+      const int p = it * blockDim.x + threadIdx.x;
+      const unsigned kv = p < V ? key_at(p) : 0xffffffffu;
+      bool take = p < V && kv <= pivot;
       if (ordered_ties) {
-        const bool eq = kv == pivot;
+        const bool eq = p < V && kv == pivot;
         const unsigned m = __ballot_sync(kFullMask, eq);
         if (eq) take = wtab[it * 32 + warp] + __popc(m & ((1u << lane) - 1u)) < need_eq;
       }
-      const int p = warp_append(&sm_count, take);
-      if (take) sel[p] = ((unsigned long long)kv << 32) | (unsigned)s;
+      const int q = warp_append(&sm_count, take);
+      if (take) sel[q] = ((unsigned long long)kv << 32) | (unsigned)p;
     }
-    __syncthreads();
-    if (npad <= kRankSortMax && npad <= a.sel_cap) {
-      // register bitonic sort, one key per thread: exchanges at distance < 32 are warp shuffles, only the
-      // log2(npad/32) * (log2(npad/32) + 1) / 2 longer ones go through shared memory (sel == ssel here)
-      const int tid = threadIdx.x;
-      const bool in = tid < npad;
-      unsigned long long k = tid < nkeep ? ssel[tid] : ~0ull;
-      for (int K = 2; K <= npad; K <<= 1) {
-        for (int j = K >> 1; j > 0; j >>= 1) {
-          unsigned long long other;
-          if (j >= 32) {
-            if (in) ssel[tid] = k;
-            __syncthreads();
-            other = in ? ssel[tid ^ j] : k;
-            __syncthreads();
-          } else {
-            other = __shfl_xor_sync(kFullMask, k, j);
-          }
-          const bool take_min = ((tid & j) == 0) == ((tid & K) == 0);
-          k = (take_min == (other < k)) ? other : k;
-        }
-      }
-      if (in) ssel[tid] = k;
-      __syncthreads();
-    } else {
-      for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
-      __syncthreads();
-      bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
-    }
-  } else {
     __syncthreads();
   }
+  if (npad <= kRankSortMax && npad <= a.sel_cap) {
+    // register bitonic sort, one key per thread: exchanges at distance < 32 are warp shuffles, only the longer
+    // ones go through shared memory (sel == ssel here)
+    const int tid = threadIdx.x;
+    const bool in = tid < npad;
+    unsigned long long k = tid < nkeep ? ssel[tid] : ~0ull;
+    for (int K = 2; K <= npad; K <<= 1) {
+      for (int j = K >> 1; j > 0; j >>= 1) {
+        unsigned long long other;
+        if (j >= 32) {
+          if (in) ssel[tid] = k;
+          __syncthreads();
+          other = in ? ssel[tid ^ j] : k;
+          __syncthreads();
+        } else {
+          other = __shfl_xor_sync(kFullMask, k, j);
+        }
+        const bool take_min = ((tid & j) == 0) == ((tid & K) == 0);
+        k = (take_min == (other < k)) ? other : k;
+      }
+    }
+    if (in) ssel[tid] = k;
+    __syncthreads();
+  } else {
+    for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
+  }
 
-  // 3. emit the V rows: sorted head [0, nkeep), anchor-ordered tail [nkeep, V) (multibox_detection.cc:146-151),
-  //    plus class and box of every row for the NMS launch.  Four rows per thread in flight.
-  const float *rec = a.rec + (size_t)b * a.Apad * kRecFloats;
+  // head rows: gather through the staging buffer, then overwrite rows [0, nkeep)
   float *out = a.out + (size_t)b * A * 7;
   unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
   float4 *row_box = a.row_box + (size_t)b * A;
-  // Rows are staged in shared memory (the key array is dead by now) and written out as one contiguous run of
-  // 128-bit stores per chunk; without a staging area (keys in global memory) each thread stores its 7 floats.
-  float *stage = reinterpret_cast<float *>(skeys);
-  const int stage_rows = kKeysInSmem ? min(4 * (int)blockDim.x, ((Tt * 4) / 28) & ~3) : 0;
-  const int chunk = stage_rows >= 64 ? stage_rows : 4 * (int)blockDim.x;
-  const bool staged = stage_rows >= 64;
-  for (int base = 0; base < V; base += chunk) {
-    const int rows = min(chunk, V - base);
-    float4 s0[4], s1[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = u * blockDim.x + threadIdx.x;
-      const int r = base + q;
-      if (q < rows) {
-        int slot;
-        if (r < nkeep) {
-          slot = (int)(unsigned)(sel[r] & 0xffffffffull);
-        } else {  // rank r -> slot: last tile whose first rank is <= r
-          int lo = 0, hi = T - 1;
-          while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (tile_off[mid] <= r) lo = mid; else hi = mid - 1;
-          }
-          slot = lo * tile + (r - tile_off[lo]);
-        }
-        const float4 *src = reinterpret_cast<const float4 *>(rec + (size_t)slot * kRecFloats);
-        s0[u] = __ldg(src);
-        s1[u] = __ldg(src + 1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = u * blockDim.x + threadIdx.x;
-      const int r = base + q;
-      if (q < rows) {
-        float *o = staged ? stage + q * 7 : out + (size_t)r * 7;
-        o[0] = s0[u].y;  // id
-        o[1] = s0[u].x;  // score
-        o[2] = s0[u].z;
-        o[3] = s0[u].w;
-        o[4] = s1[u].x;
-        o[5] = s1[u].y;
-        o[6] = s1[u].z;
-        if (do_sort) {
-          row_cls[r] = (unsigned short)s0[u].y;
-          row_box[r] = make_float4(s0[u].z, s0[u].w, s1[u].x, s1[u].y);
-        }
-      }
-    }
-    if (staged) {
-      __syncthreads();
-      float *dst = out + (size_t)base * 7;
-      const int nfl = rows * 7;
-      if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-        for (int i = threadIdx.x; i < (nfl >> 2); i += blockDim.x)
-          reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(stage)[i];
-        for (int i = (nfl & ~3) + threadIdx.x; i < nfl; i += blockDim.x) dst[i] = stage[i];
-      } else {
-        for (int i = threadIdx.x; i < nfl; i += blockDim.x) dst[i] = stage[i];
-      }
-      __syncthreads();
-    }
+  float *stage = a.stage + (size_t)b * A * 8;
+  for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {
+    const int p = (int)(unsigned)(sel[r] & 0xffffffffull);
+    const float *src = out + (size_t)p * 7;
+    float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)r * 8);
+    dst[0] = make_float4(src[0], src[1], src[2], src[3]);
+    dst[1] = make_float4(src[4], src[5], src[6], 0.f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {
+    const float4 *src = reinterpret_cast<const float4 *>(stage + (size_t)r * 8);
+    const float4 s0 = src[0], s1 = src[1];
+    float *o = out + (size_t)r * 7;
+    o[0] = s0.x;
+    o[1] = s0.y;
+    o[2] = s0.z;
+    o[3] = s0.w;
+    o[4] = s1.x;
+    o[5] = s1.y;
+    o[6] = s1.z;
+    row_cls[r] = (unsigned short)s0.x;
+    row_box[r] = make_float4(s0.z, s0.w, s1.x, s1.y);
   }
 }
 
@@ -1214,6 +1201,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   DSPMB_REQUIRE(B >= 0 && A > 0 && C > 0, "MultiBoxDetection: bad shape B=%d A=%d C=%d", B, A, C);
   DSPMB_REQUIRE(cls_prob && loc_pred && anchors && out && variances, "MultiBoxDetection: NULL tensor");
   DSPMB_REQUIRE(B <= 65535 && C <= 65535, "MultiBoxDetection: batch / classes > 65535 not supported in one call");
+  DSPMB_REQUIRE(A < (1 << 24), "MultiBoxDetection: more than 2^24 anchors are not supported");
   DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxDetection: anchors must be 16-byte aligned");
   if (B == 0) return DSPMB_OK;
   const size_t need = carve(nullptr, B, A, C).bytes;
@@ -1247,13 +1235,16 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.loc_pred = loc_pred;
   sa.anchors = anchors;
   sa.out = out;
-  sa.tile_count = w.tile_count;
+  sa.state = w.state;
+  sa.valid = w.valid;
+  sa.row_cls = w.row_cls;
+  sa.row_box = w.row_box;
   sa.keys = w.keys;
-  sa.rec = w.rec;
   sa.A = A;
   sa.C = C;
   sa.T = T;
   sa.Apad = Apad;
+  sa.cls_stride = (Apad + 7) & ~7;
   sa.threshold = threshold;
   sa.clip = clip;
   sa.vx = variances[0];
@@ -1261,6 +1252,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.vw = variances[2];
   sa.vh = variances[3];
   sa.fma_build = libm_fma_mode();
+  sa.nonce = next_nonce();
   const int phases = tuning(DSPMB_TUNE_PHASES);
   if (!(phases & 1)) {
     // stream phase skipped (per-phase timing: the workspace still holds the previous call's records)
@@ -1295,35 +1287,31 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
 
   SortArgs so;
   so.out = out;
-  so.tile_count = w.tile_count;
   so.keys = w.keys;
-  so.rec = w.rec;
   so.valid = w.valid;
   so.nms_rows = w.nms_rows;
   so.cursor = w.cursor;
   so.row_cls = w.row_cls;
   so.row_box = w.row_box;
+  so.stage = w.stage;
   so.sort_keys = w.sort_keys;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
   so.A = A;
-  so.C = C;
-  so.T = T;
   so.Apad = Apad;
   so.cls_stride = (Apad + 7) & ~7;
-  so.tile = tile;
   so.npad_max = next_pow2(A);
-  so.niter = ceil_div(T * tile, kSortThreads);
+  so.niter_max = ceil_div(A, kSortThreads);
   so.nms_threshold = nms_threshold;
   so.force_suppress = force_suppress;
   so.nms_topk = nms_topk;
-  so.keys_in_smem = T * tile <= kKeySmemMax ? 1 : 0;
+  const bool keys_in_smem = A <= kKeySmemMax;
   // sort keys in shared memory: enough for the top-k head, or for everything when no top-k limit applies
   const int smem_keys = tuning(DSPMB_TUNE_SORT_SMEM_KEYS) < 2 ? 2 : tuning(DSPMB_TUNE_SORT_SMEM_KEYS);
   const int want = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
   so.sel_cap = want < smem_keys ? (want < 2 ? 2 : want) : smem_keys;
-  const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (so.keys_in_smem ? sizeof(unsigned) * (size_t)T * tile : 0) +
-                       sizeof(int) * ((size_t)T + 1 + 32 * (size_t)so.niter);
+  const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (keys_in_smem ? sizeof(unsigned) * (size_t)((A + 3) & ~3) : 0) +
+                       sizeof(int) * 32 * (size_t)so.niter_max;
   DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
   static bool attr_set = false;
   if (!attr_set) {
@@ -1333,7 +1321,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
-    if (so.keys_in_smem)
+    if (keys_in_smem)
       det_sort_kernel<true><<<B, kSortThreads, smem2, stream>>>(so);
     else
       det_sort_kernel<false><<<B, kSortThreads, smem2, stream>>>(so);
