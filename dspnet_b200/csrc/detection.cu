@@ -15,19 +15,22 @@
 // candidate, and it diverges from the CPU semantics; it is not followed.
 //
 // Structure here (three launches, all images in every grid):
-//   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread,
-//                      fills `out` with -1 (128-bit stores), decodes the survivors and writes records + 32-bit
-//                      order keys in anchor order into per-tile slots (block scan => deterministic order).
-//   det_sort_kernel    one CTA per image: tile prefix; MSB-first radix select of the nms_topk best keys straight on
-//                      the slot keys in shared memory (ties resolved in slot order through ballot-count tables,
-//                      no atomics on the ordering path); rank sort (<= 1024 keys, barrier-free) or bitonic sort of
-//                      the selection; emits the V rows in the reference's order (sorted head + anchor-ordered
-//                      tail) plus a compact class / box array per row for the NMS launch.
+//   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread
+//   (reg / TMA         (register-resident variant: every load of a thread in flight before the first compare),
+//    variants)         fills `out` with -1, decodes the survivors and writes each of them ONCE, at its final
+//                      pass-1 position: rank = survivors before it in the image, obtained with an in-tile block
+//                      scan plus a single-pass decoupled look-back over the tiles of the image (nonce-tagged state
+//                      words, no memset).  Rows, order keys, classes and boxes of a tile are staged in shared memory
+//                      and written as contiguous runs.
+//   det_sort_kernel    one CTA per image: MSB-first radix select of the nms_topk best of the V rank-ordered keys
+//                      (ties resolved in rank order through ballot-count tables), register/shuffle bitonic sort of
+//                      the selection, permuted copy of those rows into the head [0, nkeep); the tail [nkeep, V)
+//                      is already final.
 //   det_nms_kernel     one CTA per (image, class) segment (one per image with force_suppress): ordered member
 //                      list from ballot-count tables, boxes staged in shared memory, then
-//                        n <= 512: full upper-triangular bit mask built by balanced warp units (4-compare overlap
-//                                  test, IEEE division only for overlapping pairs) + a word-serial resolve that only
-//                                  visits rows that suppress something;
+//                        n <= 320: upper-triangular bit mask built by balanced warp units (4-compare overlap test,
+//                                  division-free threshold test with an exact fallback band) + a word-serial resolve
+//                                  that only visits rows that suppress something;
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include <stdlib.h>
 #include <string.h>
