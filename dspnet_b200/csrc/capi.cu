@@ -35,8 +35,8 @@ static int detect_host_libm_mode() {
 #endif
 }
 
-static int g_tuning[5] = {256, 320, 1024, 8192, 7};
-static const int kTuningMax[5] = {256, 320, 1024, 8192, 7};
+static int g_tuning[5] = {256, 320, 1024, 8192, 15};
+static const int kTuningMax[5] = {256, 320, 1024, 8192, 15};
 int tuning(int knob) { return g_tuning[knob]; }
 
 int libm_fma_mode() {
@@ -55,7 +55,7 @@ std::vector<ProfileRecord> g_profile_records;
 const char *const kSlotNames[kNumKernelSlots] = {
     "prior_kernel",        "det_stream_kernel", "det_sort_kernel", "det_nms_kernel",  "target_stream_kernel",
     "target_match_kernel", "nms_sort_kernel",   "nms_gather_kernel", "nms_mask_kernel", "nms_scan_kernel",
-    "det_compact_kernel"};
+    "det_compact_kernel",  "det_rank_kernel"};
 }  // namespace
 
 void profile_mark(int slot, cudaStream_t stream, bool begin) {

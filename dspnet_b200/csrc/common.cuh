@@ -47,6 +47,7 @@ enum KernelSlot {
   kSlotNmsMask,
   kSlotNmsScan,
   kSlotDetCompact,
+  kSlotDetRank,
   kNumKernelSlots
 };
 extern bool g_profile_on;

@@ -14,14 +14,16 @@
 // atomicAdd compaction (non-deterministic order), a global-memory merge sort and one __syncthreads per NMS
 // candidate, and it diverges from the CPU semantics; it is not followed.
 //
-// Structure here (three launches, all images in every grid):
+// Structure here (four launches, all images in every grid):
 //   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread
 //   (reg / TMA         (register-resident variant: every load of a thread in flight before the first compare),
-//    variants)         fills `out` with -1, decodes the survivors and writes each of them ONCE, at its final
-//                      pass-1 position: rank = survivors before it in the image, obtained with an in-tile block
-//                      scan plus a single-pass decoupled look-back over the tiles of the image (nonce-tagged state
-//                      words, no memset).  Rows, order keys, classes and boxes of a tile are staged in shared memory
-//                      and written as contiguous runs.
+//    variants)         fills `out` with -1 (128-bit stores), decodes the survivors and stages their finished pass-1
+//                      rows, order keys, classes and boxes in shared memory (block scan => anchor order), then
+//                      writes them as contiguous runs into the tile's slots together with the tile's count.
+//   det_rank_kernel    one CTA per (tile, image): rank base = survivors in the earlier tiles of the image; copies the
+//                      tile's runs to their final positions, so rows [0, V) hold exactly the reference's pass 1.
+//                      (A single-pass decoupled look-back inside the stream kernel was measured instead: it made
+//                      that kernel 10 us slower because the CTAs idle on the look-back round trips.)
 //   det_sort_kernel    one CTA per image: MSB-first radix select of the nms_topk best of the V rank-ordered keys
 //                      (ties resolved in rank order through ballot-count tables), register/shuffle bitonic sort of
 //                      the selection, permuted copy of those rows into the head [0, nkeep); the tail [nkeep, V)
@@ -34,9 +36,6 @@
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include <stdlib.h>
 #include <string.h>
-#include <time.h>
-
-#include <atomic>
 
 #include "common.cuh"
 
@@ -56,7 +55,11 @@ constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every
 
 struct DetWorkspace {
   WsHeader *header;
-  unsigned long long *state;  // (B, T) decoupled look-back words of the stream kernel (zeroed per call)
+  int *tile_count;            // (B, T) survivors per tile
+  float *slot_rows;           // (B, Apad, 7) per-tile compacted pass-1 rows
+  unsigned *slot_keys;        // (B, Apad)
+  unsigned short *slot_cls;   // (B, cls_stride)
+  float4 *slot_box;           // (B, Apad)
   int *valid;                 // (B) V
   int *nms_rows;              // (B) rows taking part in NMS (0 = skipped)
   int *cursor;                // (B) allocator of seg_list regions for large segments
@@ -71,16 +74,6 @@ struct DetWorkspace {
   unsigned long long *sort_keys;  // (B, npad) spill for selections larger than the shared-memory budget
   size_t bytes;
 };
-
-// Per-call tag for the look-back words: a process-wide counter on top of a time-derived base, never zero.
-inline unsigned long long next_nonce() {
-  static std::atomic<unsigned long long> counter{(unsigned long long)time(nullptr) * 2654435761ull};
-  unsigned long long n;
-  do {
-    n = counter.fetch_add(1) & ((1ull << 38) - 1);
-  } while (n == 0);
-  return n;
-}
 
 inline int next_pow2(int v) {
   int p = 1;
@@ -101,7 +94,11 @@ DetWorkspace carve(void *base, int B, int A, int C) {
     return (char *)base + o;
   };
   w.header = (WsHeader *)take(sizeof(WsHeader));
-  w.state = (unsigned long long *)take(sizeof(unsigned long long) * B * Tmax);
+  w.tile_count = (int *)take(sizeof(int) * B * Tmax);
+  w.slot_rows = (float *)take(sizeof(float) * 7 * B * Apad);
+  w.slot_keys = (unsigned *)take(sizeof(unsigned) * B * Apad);
+  w.slot_cls = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
+  w.slot_box = (float4 *)take(sizeof(float4) * B * Apad);
   w.valid = (int *)take(sizeof(int) * B);
   w.nms_rows = (int *)take(sizeof(int) * B);
   w.cursor = (int *)take(sizeof(int) * B);
@@ -121,79 +118,22 @@ DetWorkspace carve(void *base, int B, int A, int C) {
 struct StreamArgs {
   const float *cls_prob, *loc_pred, *anchors;
   float *out;
-  unsigned long long *state;  // (B, T) decoupled look-back words: flag << 32 | value
-  int *valid;                 // (B) V, written by the last tile of every image
-  unsigned *keys;             // (B, Apad) order keys by RANK
-  unsigned short *row_cls;    // (B, cls_stride)
-  float4 *row_box;            // (B, A)
+  int *tile_count;            // (B, T) survivors per tile
+  float *slot_rows;           // (B, Apad, 7) pass-1 rows of the survivors, compacted per tile (slot = tile_begin + k)
+  unsigned *slot_keys;        // (B, Apad) their order keys
+  unsigned short *slot_cls;   // (B, cls_stride)
+  float4 *slot_box;           // (B, Apad)
   int A, C, T, Apad, cls_stride;
   float threshold;
   int clip;
   float vx, vy, vw, vh;
   int fma_build;
-  unsigned long long nonce;  // per-call tag of the look-back words
 };
 
 __device__ __forceinline__ float clip01(float v) {
   // std::max(0, std::min(1, v)) of multibox_detection.cc:121-125
   const float m = v < 1.f ? v : 1.f;
   return 0.f < m ? m : 0.f;
-}
-
-// Rank base of a tile = number of surviving anchors in the tiles before it (same image): single-pass chained scan
-// with decoupled look-back.  Tiles of an image are consecutive linear block indices (or, in the persistent
-// kernel, visited in increasing order by co-resident CTAs), so every predecessor is already running or done.
-// Ordering contract: the caller's -1 fill of the tile's output rows precedes this call (block barrier inside the
-// scan that produced `total`); thread 0 fences before publishing, and fences again after reading a predecessor's
-// word, so a tile that has acquired a rank base also sees the fills of all earlier tiles -- which is what makes it
-// safe for it to store its surviving rows (rank <= anchor index) into those tiles' row ranges.
-// Contains one __syncthreads(); returns the base to every thread.
-// State word: nonce (38 bits) | flag (2 bits: 1 aggregate, 2 inclusive prefix) | value (24 bits).  The nonce is
-// unique per call (host counter), so words left in the caller's scratch memory by earlier calls -- or arbitrary
-// scratch contents -- read as "not there yet" and no per-call memset is needed (a random 64-bit pattern passes for a
-// live word with probability 2^-38).
-__device__ __forceinline__ unsigned long long pack_state(unsigned long long nonce, unsigned flag, int value) {
-  return (nonce << 26) | ((unsigned long long)flag << 24) | (unsigned)value;
-}
-
-// Step 1 (one thread, right after the block scan): make this tile's survivor count visible to its successors.
-__device__ __forceinline__ void publish_aggregate(const StreamArgs &a, int b, int t, int total) {
-  volatile unsigned long long *st = a.state + (size_t)b * a.T;
-  __threadfence();
-  st[t] = pack_state(a.nonce, t == 0 ? 2u : 1u, total);
-}
-
-// Step 2 (whole CTA, after the rows have been staged): exclusive rank base of the tile.
-__device__ __forceinline__ int tile_rank_base(const StreamArgs &a, int b, int t, int total, int *sm_base) {
-  if (threadIdx.x < 32) {  // warp 0: one window of 32 predecessors per round trip
-    volatile unsigned long long *st = a.state + (size_t)b * a.T;
-    const int lane = threadIdx.x;
-    int excl = 0;
-    int hi = t - 1;  // nearest predecessor not yet accounted for
-    while (hi >= 0) {
-      const int p = hi - lane;
-      const unsigned long long v = p >= 0 ? st[p] : pack_state(a.nonce, 2u, 0);  // before tile 0: empty prefix
-      const unsigned flag = (v >> 26) == a.nonce ? (unsigned)((v >> 24) & 3ull) : 0u;
-      // the window is usable up to (and including) the first inclusive prefix, if no word before it is missing
-      const unsigned missing = __ballot_sync(kFullMask, flag == 0u);
-      const unsigned prefix = __ballot_sync(kFullMask, flag == 2u);
-      const int first_prefix = prefix ? __ffs(prefix) - 1 : 32;
-      const int first_missing = missing ? __ffs(missing) - 1 : 32;
-      if (first_missing < first_prefix) continue;  // a needed predecessor is not there yet
-      const int upto = first_prefix < 32 ? first_prefix : 31;
-      excl += warp_sum_i32(lane <= upto ? (int)(unsigned)(v & 0xffffffull) : 0);
-      if (first_prefix < 32) break;
-      hi -= 32;
-    }
-    if (lane == 0) {
-      __threadfence();
-      if (t > 0) st[t] = pack_state(a.nonce, 2u, excl + total);
-      if (t == a.T - 1) a.valid[b] = excl + total;
-      *sm_base = excl;
-    }
-  }
-  __syncthreads();
-  return *sm_base;
 }
 
 // Shared-memory staging of a tile's surviving rows.  Their ranks are consecutive, so rows, keys, classes and boxes
@@ -239,14 +179,16 @@ __device__ __forceinline__ void stage_row(const StreamArgs &a, RowStage<kRows> &
   sm.box[local] = make_float4(x1, y1, x2, y2);
 }
 
-// Coalesced write-out of `total` staged rows whose first rank is `base`.  Call after a block barrier.
+// Coalesced write-out of the tile's `total` staged rows into the tile's slots (slot = tile_begin + k).  The rank of
+// a row is only known once every earlier tile of the image has been counted; det_rank_kernel moves the runs to
+// their final positions afterwards, so this kernel never waits on another CTA.  Call after a block barrier.
 template <int kRows>
-__device__ __forceinline__ void flush_rows(const StreamArgs &a, const RowStage<kRows> &sm, int b, int base, int total) {
-  float *o = a.out + ((size_t)b * a.A + base) * 7;
+__device__ __forceinline__ void flush_rows(const StreamArgs &a, const RowStage<kRows> &sm, int b, int tile_begin, int total) {
+  float *o = a.slot_rows + ((size_t)b * a.Apad + tile_begin) * 7;
   for (int q = threadIdx.x; q < total * 7; q += blockDim.x) o[q] = sm.rows[q];
-  unsigned *gk = a.keys + (size_t)b * a.Apad + base;
-  unsigned short *gc = a.row_cls + (size_t)b * a.cls_stride + base;
-  float4 *gb = a.row_box + (size_t)b * a.A + base;
+  unsigned *gk = a.slot_keys + (size_t)b * a.Apad + tile_begin;
+  unsigned short *gc = a.slot_cls + (size_t)b * a.cls_stride + tile_begin;
+  float4 *gb = a.slot_box + (size_t)b * a.Apad + tile_begin;
   for (int q = threadIdx.x; q < total; q += blockDim.x) {
     gk[q] = sm.keys[q];
     gc[q] = sm.cls[q];
@@ -257,7 +199,6 @@ __device__ __forceinline__ void flush_rows(const StreamArgs &a, const RowStage<k
 template <int VEC>
 __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kStreamThreads / 32 + 1];
-  __shared__ int sm_base;
   __shared__ RowStage<kStreamThreads * VEC> sm_rows;
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kStreamThreads * VEC;
@@ -318,7 +259,7 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
   // ---- ordered compaction: rank = survivors before this anchor in the image ----
   int total;
   int pos = block_scan_excl(nvalid, scan_smem, &total);
-  if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
   if (nvalid) {
     const float *loc = a.loc_pred + (size_t)b * A * 5;
 #pragma unroll
@@ -332,8 +273,8 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
         ++pos;
       }
   }
-  const int base = tile_rank_base(a, b, t, total, &sm_base);  // block barrier inside: the staged rows are complete
-  flush_rows(a, sm_rows, b, base, total);
+  __syncthreads();  // the staged rows are complete
+  flush_rows(a, sm_rows, b, tile_begin, total);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -345,7 +286,6 @@ __global__ void __launch_bounds__(kStreamThreads) det_stream_kernel(const __grid
 template <int NFG, int kThreads>
 __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kThreads / 32 + 1];
-  __shared__ int sm_base;
   __shared__ RowStage<kThreads * 4> sm_rows;
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kThreads * 4;
@@ -394,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_c
   }
   int total;
   int pos = block_scan_excl(nvalid, scan_smem, &total);
-  if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
   if (nvalid) {
     const float lf[20] = {lp[0].x, lp[0].y, lp[0].z, lp[0].w, lp[1].x, lp[1].y, lp[1].z, lp[1].w, lp[2].x, lp[2].y,
                           lp[2].z, lp[2].w, lp[3].x, lp[3].y, lp[3].z, lp[3].w, lp[4].x, lp[4].y, lp[4].z, lp[4].w};
@@ -405,8 +345,8 @@ __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_c
         ++pos;
       }
   }
-  const int base = tile_rank_base(a, b, t, total, &sm_base);  // block barrier inside: the staged rows are complete
-  flush_rows(a, sm_rows, b, base, total);
+  __syncthreads();  // the staged rows are complete
+  flush_rows(a, sm_rows, b, tile_begin, total);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -459,7 +399,6 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ __align__(8) unsigned long long full_bar[4];
   __shared__ int scan_smem[kPipeThreads / 32 + 1];
-  __shared__ int sm_base;
   __shared__ RowStage<kPipeTile> sm_rows;
   const StreamArgs &a = p.s;
   const int A = a.A, T = a.T, nfg = a.C - 1;
@@ -537,7 +476,7 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
     }
     int total;
     int pos = block_scan_excl(nvalid, scan_smem, &total);
-    if (threadIdx.x == 0) publish_aggregate(a, b, t, total);
+    if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
     if (nvalid) {
 #pragma unroll
       for (int k = 0; k < kPipeVec; ++k)
@@ -547,9 +486,57 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
           ++pos;
         }
     }
-    const int base = tile_rank_base(a, b, t, total, &sm_base);
-    flush_rows(a, sm_rows, b, base, total);
+    __syncthreads();  // the staged rows are complete
+    flush_rows(a, sm_rows, b, tile_begin, total);
     __syncthreads();  // every thread is done with this stage and the row staging -> both may be refilled
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Moves every tile's run of surviving rows from its slots to its final pass-1 position: rank base of tile t =
+// survivors in the tiles before it (all counts are final: the stream kernel has completed), so the reference's
+// anchor-ordered compaction (multibox_detection.cc:93-127) is reproduced without any CTA waiting on another.
+// Both sides of every copy are contiguous runs.
+struct RankArgs {
+  const int *tile_count;
+  const float *slot_rows;
+  const unsigned *slot_keys;
+  const unsigned short *slot_cls;
+  const float4 *slot_box;
+  float *out;
+  unsigned *keys;
+  unsigned short *row_cls;
+  float4 *row_box;
+  int *valid;
+  int A, T, Apad, cls_stride, tile;
+};
+
+__global__ void __launch_bounds__(128) det_rank_kernel(const __grid_constant__ RankArgs a) {
+  __shared__ int red[4];
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int *cnt = a.tile_count + (size_t)b * a.T;
+  int part = 0;
+  for (int u = threadIdx.x; u < t; u += blockDim.x) part += cnt[u];
+  part = warp_sum_i32(part);
+  if (lane_id() == 0) red[warp_id()] = part;
+  __syncthreads();
+  const int base = red[0] + red[1] + red[2] + red[3];
+  const int total = cnt[t];
+  if (t == a.T - 1 && threadIdx.x == 0) a.valid[b] = base + total;
+  const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
+  const float *src = a.slot_rows + slot0 * 7;
+  float *dst = a.out + ((size_t)b * a.A + base) * 7;
+  for (int q = threadIdx.x; q < total * 7; q += blockDim.x) dst[q] = src[q];
+  const unsigned *sk = a.slot_keys + slot0;
+  const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
+  const float4 *sb = a.slot_box + slot0;
+  unsigned *dk = a.keys + (size_t)b * a.Apad + base;
+  unsigned short *dc = a.row_cls + (size_t)b * a.cls_stride + base;
+  float4 *db = a.row_box + (size_t)b * a.A + base;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    dk[q] = sk[q];
+    dc[q] = sc[q];
+    db[q] = sb[q];
   }
 }
 
@@ -1238,11 +1225,11 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.loc_pred = loc_pred;
   sa.anchors = anchors;
   sa.out = out;
-  sa.state = w.state;
-  sa.valid = w.valid;
-  sa.row_cls = w.row_cls;
-  sa.row_box = w.row_box;
-  sa.keys = w.keys;
+  sa.tile_count = w.tile_count;
+  sa.slot_rows = w.slot_rows;
+  sa.slot_keys = w.slot_keys;
+  sa.slot_cls = w.slot_cls;
+  sa.slot_box = w.slot_box;
   sa.A = A;
   sa.C = C;
   sa.T = T;
@@ -1255,7 +1242,6 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.vw = variances[2];
   sa.vh = variances[3];
   sa.fma_build = libm_fma_mode();
-  sa.nonce = next_nonce();
   const int phases = tuning(DSPMB_TUNE_PHASES);
   if (!(phases & 1)) {
     // stream phase skipped (per-phase timing: the workspace still holds the previous call's records)
@@ -1285,6 +1271,28 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
       det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
     else
       det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
+  }
+  DSPMB_CUDA_TRY(cudaGetLastError());
+
+  if (phases & 8) {
+    RankArgs ra;
+    ra.tile_count = w.tile_count;
+    ra.slot_rows = w.slot_rows;
+    ra.slot_keys = w.slot_keys;
+    ra.slot_cls = w.slot_cls;
+    ra.slot_box = w.slot_box;
+    ra.out = out;
+    ra.keys = w.keys;
+    ra.row_cls = w.row_cls;
+    ra.row_box = w.row_box;
+    ra.valid = w.valid;
+    ra.A = A;
+    ra.T = T;
+    ra.Apad = Apad;
+    ra.cls_stride = (Apad + 7) & ~7;
+    ra.tile = tile;
+    ProfileScope _p(kSlotDetRank, stream);
+    det_rank_kernel<<<dim3(T, B), 128, 0, stream>>>(ra);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 

@@ -176,8 +176,8 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_NMS_MASK_ROWS 1      /* largest segment for the shared-memory bit-mask NMS (default/max 320) */
 #define DSPMB_TUNE_NMS_SMEM_ROWS 2      /* largest segment staged in shared memory by the sweep NMS (max 1024) */
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
-#define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 7:
-                                           1 stream, 2 sort/match, 4 nms) -- bench.py times one phase at a time     */
+#define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 15:
+                                           1 stream, 2 sort/match, 4 nms, 8 rank) -- bench.py times one at a time   */
 int dspmb_set_tuning(int knob, int value);
 
 /* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same
