@@ -271,6 +271,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     launches = args.steps * (plan.launches_per_run + (gatherer.launches_per_submit if gatherer else 0))
+    gather_ok = True
+    if world > 1:
+        # sanity of the exchange step: every rank holds every rank's compacted detections
+        last_step = i + args.steps - 1
+        rows, counts = gatherer.gathered(last_step)
+        from dspnet_b200.dist import compact_rows
+        mine, mine_n = compact_rows(out_sets[last_step % ROTATE], DET_PARAMS["nms_topk"])
+        ok = torch.equal(rows[rank * BATCH:(rank + 1) * BATCH], mine) and torch.equal(counts[rank * BATCH:(rank + 1) * BATCH], mine_n)
+        ok = ok and bool((counts > 0).all())
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_ok = int(flag.item()) == 1
 
     # ---- per-kernel durations: after the timed region each launch of the step is timed on its own -- K back-to-back
     #      launches of ONE phase (DSPMB_TUNE_PHASES) between a single cudaEvent pair on the launching stream, so the
@@ -420,6 +432,7 @@ def main():
                     "d2h_bytes_per_step": int(pin_out.numel() * 4), "steps": e2e_steps,
                     "api": "dspnet_b200.MultiBoxDetection; per step: pinned host -> device copy of cls_prob+loc_pred, operator, full (B,A,7) result copied back to pinned host; copy-in / operator / copy-out of consecutive steps overlap on three streams"},
             "gpu_launches": launches,
+            "gather_check": ("ok" if gather_ok else "MISMATCH") if world > 1 else None,
             "clocks": clocks,
             "target": tgt,
         }
@@ -436,17 +449,6 @@ def main():
                                               "per thread; single thread: %.1f images/s" % v1}
         print(json.dumps(line))
     if world > 1:
-        # sanity of the exchange step: every rank holds every rank's compacted detections
-        last_step = i + args.steps - 1
-        rows, counts = gatherer.gathered(last_step)
-        from dspnet_b200.dist import compact_rows
-        mine, mine_n = compact_rows(out_sets[last_step % ROTATE], DET_PARAMS["nms_topk"])
-        ok = torch.equal(rows[rank * BATCH:(rank + 1) * BATCH], mine) and torch.equal(counts[rank * BATCH:(rank + 1) * BATCH], mine_n)
-        ok = ok and bool((counts > 0).all())
-        flag = torch.tensor([1 if ok else 0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if rank == 0 and int(flag.item()) != 1:
-            print(json.dumps({"error": "gathered detections differ from the local compaction"}))
         gatherer.close()
         dist.destroy_process_group()
 
