@@ -986,9 +986,11 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
         const int jb = w << 6;
         const int cnt = min(64, n - jb);
         unsigned lo = 0u, hi = 0u;
-        // the column index is warp-uniform: boxes[jb + jj] is one broadcast LDS.128 for the 32 rows of the unit
+        // the column index is warp-uniform: boxes[jb + jj] is one broadcast LDS.128 for the 32 rows of the unit;
+        // in the diagonal word the columns before the unit's first row can never satisfy j > i
+        const int jj0 = max(0, (rg << 5) + 1 - jb);
 #pragma unroll 4
-        for (int jj = 0; jj < cnt; ++jj) {
+        for (int jj = jj0; jj < cnt; ++jj) {
           const float4 bj = boxes[jb + jj];
           if (bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y && jb + jj > i) {
             if (iou_ge(bi, ai, bj, areas[jb + jj], thr)) {
