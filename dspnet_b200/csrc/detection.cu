@@ -840,6 +840,7 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
   return iou_ge(a, area_a, b, area_b, t);
 }
 
+constexpr int kNmsQueue = 256;  // per-warp candidate queue entries of the small-segment path
 constexpr int kNmsTab = 512;  // ballot-count table entries: 64 iterations x 8 warps = 131072 rows per sweep
 
 __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
@@ -848,9 +849,10 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   //   large:                         boxes[1024] float4 + dead[1024] + 64 words + areas[1024]             (21.5 KB)
   // kept near 22 KB so that 8 CTAs (all 2048 threads) fit on an SM and the usual grid is a single wave.
   constexpr int kOffMask = kNmsMaskRows * 16, kOffList = kOffMask + kNmsMaskRows * 5 * 8, kOffArea = kOffList + kNmsMaskRows * 4;
+  constexpr int kOffQueue = kOffArea + kNmsMaskRows * 4, kSmallBytes = kOffQueue + (kNmsThreads / 32) * kNmsQueue * 2;
   constexpr int kOffDead = kNmsSmemRows * 16, kOffWord = kOffDead + kNmsSmemRows, kOffAreaL = kOffWord + 512;
-  __shared__ __align__(16) unsigned char smem_raw[kOffAreaL + kNmsSmemRows * 4];
-  static_assert(kOffArea + kNmsMaskRows * 4 <= kOffAreaL + kNmsSmemRows * 4, "small-path layout exceeds the union");
+  constexpr int kLargeBytes = kOffAreaL + kNmsSmemRows * 4;
+  __shared__ __align__(16) unsigned char smem_raw[kSmallBytes > kLargeBytes ? kSmallBytes : kLargeBytes];
   __shared__ int wtab[kNmsTab];
   __shared__ unsigned long long rowany[8];
   __shared__ unsigned sm_deadbits[2];
@@ -967,41 +969,69 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kOffMask);
     const int W = (n + 63) >> 6;
     float *areas = reinterpret_cast<float *>(smem_raw + kOffArea);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) boxes[q] = stage_box(__ldg(row_box + (identity ? q : slist[q])), &areas[q]);
+    unsigned short *queue = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue) + warp * kNmsQueue;
+    const int npad = (n + 31) & ~31;
+    for (int q = threadIdx.x; q < npad; q += blockDim.x) {
+      if (q < n) {
+        boxes[q] = stage_box(__ldg(row_box + (identity ? q : slist[q])), &areas[q]);
+      } else {
+        boxes[q] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);  // overlaps nothing
+      }
+    }
+    for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = 0ull;
     if (threadIdx.x < 8) rowany[threadIdx.x] = 0ull;  // W <= 5
     __syncthreads();
-    // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x one
-    // 64-column word, dealt round-robin to the warps; the column box is a shared-memory broadcast.
-    const int ngroups = (n + 31) >> 5;
+    // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x 32
+    // consecutive columns, dealt round-robin to the warps, in two phases so that no lane idles in a divergent branch:
+    //   (A) branch-free overlap test against the 32 column boxes (one broadcast LDS.128 each) -> candidate bits;
+    //   (B) the candidates of the whole unit (a few percent of the pairs) are compacted into a per-warp queue and the
+    //       exact IoU >= thr test runs on dense lanes, hits are OR-ed into the mask with shared-memory atomics.
+    unsigned *mask32 = reinterpret_cast<unsigned *>(mask);
+    const int ngroups = npad >> 5;
     constexpr int kWarps = kNmsThreads / 32;
     int unit = 0;
     for (int rg = 0; rg < ngroups; ++rg) {
-      for (int w = rg >> 1; w < W; ++w, ++unit) {
+      for (int cg = rg; cg < ngroups; ++cg, ++unit) {
         if ((unit & (kWarps - 1)) != (int)warp) continue;
         const int i = (rg << 5) + lane;
         const bool row_ok = i < n && !(a.debug & 1);
-        float4 bi = boxes[row_ok ? i : 0];
+        float4 bi = boxes[i];
         if (!row_ok) bi.x = __int_as_float(0x7f800000);  // fails every overlap test
-        const float ai = areas[row_ok ? i : 0];
-        const int jb = w << 6;
-        const int cnt = min(64, n - jb);
-        unsigned lo = 0u, hi = 0u;
-        // the column index is warp-uniform: boxes[jb + jj] is one broadcast LDS.128 for the 32 rows of the unit;
-        // in the diagonal word the columns before the unit's first row can never satisfy j > i
-        const int jj0 = max(0, (rg << 5) + 1 - jb);
-#pragma unroll 4
-        for (int jj = jj0; jj < cnt; ++jj) {
+        const int jb = cg << 5;
+        unsigned cand = 0u;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
           const float4 bj = boxes[jb + jj];
-          if (bi.z > bj.x && bj.z > bi.x && bi.w > bj.y && bj.w > bi.y && jb + jj > i) {
-            if (iou_ge(bi, ai, bj, areas[jb + jj], thr)) {
-              if (jj < 32) lo |= 1u << jj; else hi |= 1u << (jj - 32);
+          // four chained FSETP + one predicated OR (the compiler's own lowering spends 8-9 instructions on selects)
+          asm("{\n\t.reg .pred p;\n\t"
+              "setp.gt.f32 p, %1, %2;\n\t"
+              "setp.gt.and.f32 p, %3, %4, p;\n\t"
+              "setp.gt.and.f32 p, %5, %6, p;\n\t"
+              "setp.gt.and.f32 p, %7, %8, p;\n\t"
+              "@p or.b32 %0, %0, %9;\n\t}"
+              : "+r"(cand)
+              : "f"(bi.z), "f"(bj.x), "f"(bj.z), "f"(bi.x), "f"(bi.w), "f"(bj.y), "f"(bj.w), "f"(bi.y), "r"(1u << jj));
+        }
+        if (cg == rg) cand &= lane == 31 ? 0u : ~0u << (lane + 1);  // j > i
+        const int c = __popc(cand);
+        const int incl = warp_scan_incl(c);
+        const int total = __shfl_sync(kFullMask, incl, 31);
+        for (int base = 0; base < total; base += kNmsQueue) {
+          int pos = incl - c - base;
+          for (unsigned m = cand; m; m &= m - 1, ++pos) {
+            if (pos >= 0 && pos < kNmsQueue) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+          }
+          __syncwarp();
+          const int cnt = min(kNmsQueue, total - base);
+          for (int q = lane; q < cnt; q += 32) {
+            const unsigned e = queue[q];
+            const int r = (rg << 5) + (int)(e >> 5), jj = (int)(e & 31u);
+            if (iou_ge(boxes[r], areas[r], boxes[jb + jj], areas[jb + jj], thr)) {
+              atomicOr(&mask32[r * 2 * W + cg], 1u << jj);
+              atomicOr(&rowany[r >> 6], 1ull << (r & 63));
             }
           }
-        }
-        if (row_ok) {
-          const unsigned long long bits = ((unsigned long long)hi << 32) | lo;
-          mask[i * W + w] = bits;
-          if (bits) atomicOr(&rowany[i >> 6], 1ull << (i & 63));
+          __syncwarp();
         }
       }
     }
