@@ -50,6 +50,7 @@ constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared mem
 constexpr int kRankSortMax = 1024;    // selections up to this size are rank-sorted (one key per thread)
 constexpr int kKeySmemMax = 28672;    // slot keys (T * tile) that fit in shared memory next to the sort keys
 constexpr int kNmsMaskRows = 320;     // NMS segments up to this size use the shared-memory bit mask (5 words/row)
+static_assert(kNmsMaskRows <= 320, "unit_tab holds (row group, column group) in 4 bits each, 55 units");
 constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in shared memory
 constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every real key
 
@@ -855,6 +856,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   __shared__ __align__(16) unsigned char smem_raw[kSmallBytes > kLargeBytes ? kSmallBytes : kLargeBytes];
   __shared__ int wtab[kNmsTab];
   __shared__ unsigned long long rowany[8];
+  __shared__ unsigned char unit_tab[64];
   __shared__ unsigned sm_deadbits[2];
   __shared__ unsigned long long sm_alive, sm_deadmask;
   __shared__ int scan_smem[kNmsThreads / 32 + 1];
@@ -878,20 +880,27 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
   if (!identity) {
     const uint4 *cls8 = reinterpret_cast<const uint4 *>(a.row_cls + (size_t)b * a.cls_stride);
     const unsigned short want = (unsigned short)seg;
-    auto hits_of = [&](int it) -> unsigned {  // 8-bit mask of the rows 8*(it*blockDim + tid) .. +7 in this class
+    const unsigned want2 = (unsigned)want * 0x10001u;
+    auto hits_raw = [&](int it) -> unsigned {  // 8-bit mask of the rows 8*(it*blockDim + tid) .. +7 in this class
       const int g = it * blockDim.x + threadIdx.x;
       const int r0 = g * 8;
       if (r0 >= V) return 0u;
       const uint4 q = __ldg(cls8 + g);
-      const unsigned w[4] = {q.x, q.y, q.z, q.w};
+      const unsigned w[4] = {q.x ^ want2, q.y ^ want2, q.z ^ want2, q.w ^ want2};
       unsigned h = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const unsigned short c = (unsigned short)(w[k >> 1] >> ((k & 1) * 16));
-        if (r0 + k < V && c == want) h |= 1u << k;
+      for (int k = 0; k < 4; ++k) {
+        if ((w[k] & 0xffffu) == 0u) h |= 1u << (2 * k);
+        if ((w[k] >> 16) == 0u) h |= 2u << (2 * k);
       }
-      return h;
+      return V - r0 >= 8 ? h : h & ((1u << (V - r0)) - 1u);
     };
+    // the first four iterations (8192 rows) are remembered between the two sweeps, 8 bits each
+    unsigned hcache = 0u;
+    auto hits_of = [&](int it) -> unsigned { return it < 4 ? (hcache >> (8 * it)) & 0xffu : hits_raw(it); };
+#pragma unroll
+    for (int it = 0; it < 4; ++it)
+      if (it < niter) hcache |= hits_raw(it) << (8 * it);
     // sweep 1: counts per (iteration, warp)
     int total_n = 0;
     for (int it0 = 0; it0 < niter; it0 += kNmsTab / 8) {
@@ -980,6 +989,16 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     }
     for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = 0ull;
     if (threadIdx.x < 8) rowany[threadIdx.x] = 0ull;  // W <= 5
+    const int ngroups = npad >> 5;
+    const int nunits = ngroups * (ngroups + 1) / 2;  // <= 55
+    if ((int)threadIdx.x < nunits) {  // unit u -> (row group, column group >= row group), row-major over the triangle
+      int rg = 0, rem = threadIdx.x;
+      while (rem >= ngroups - rg) {
+        rem -= ngroups - rg;
+        ++rg;
+      }
+      unit_tab[threadIdx.x] = (unsigned char)((rg << 4) | (rg + rem));
+    }
     __syncthreads();
     // mask[i * W + w] bit j: row i suppresses row 64 w + j (> i).  A unit = 32 consecutive rows (one per lane) x 32
     // consecutive columns, dealt round-robin to the warps, in two phases so that no lane idles in a divergent branch:
@@ -987,12 +1006,11 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
     //   (B) the candidates of the whole unit (a few percent of the pairs) are compacted into a per-warp queue and the
     //       exact IoU >= thr test runs on dense lanes, hits are OR-ed into the mask with shared-memory atomics.
     unsigned *mask32 = reinterpret_cast<unsigned *>(mask);
-    const int ngroups = npad >> 5;
     constexpr int kWarps = kNmsThreads / 32;
-    int unit = 0;
-    for (int rg = 0; rg < ngroups; ++rg) {
-      for (int cg = rg; cg < ngroups; ++cg, ++unit) {
-        if ((unit & (kWarps - 1)) != (int)warp) continue;
+    {
+      for (int u = warp; u < nunits; u += kWarps) {
+        const unsigned rc = unit_tab[u];
+        const int rg = (int)(rc >> 4), cg = (int)(rc & 15u);
         const int i = (rg << 5) + lane;
         const bool row_ok = i < n && !(a.debug & 1);
         float4 bi = boxes[i];
@@ -1018,8 +1036,12 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
         const int total = __shfl_sync(kFullMask, incl, 31);
         for (int base = 0; base < total; base += kNmsQueue) {
           int pos = incl - c - base;
-          for (unsigned m = cand; m; m &= m - 1, ++pos) {
-            if (pos >= 0 && pos < kNmsQueue) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+          if (total <= kNmsQueue) {
+            for (unsigned m = cand; m; m &= m - 1, ++pos) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+          } else {
+            for (unsigned m = cand; m; m &= m - 1, ++pos) {
+              if (pos >= 0 && pos < kNmsQueue) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+            }
           }
           __syncwarp();
           const int cnt = min(kNmsQueue, total - base);
