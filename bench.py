@@ -292,6 +292,8 @@ def main():
 
     def time_phases(run, names):
         res = {}
+        # plain launches here: a single-kernel CUDA graph would add its own launch overhead to every sample
+        cache_was = lib.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
         for bit, name in names:
             lib.dspmb_set_tuning(_lib.TUNE_PHASES, bit)
             for i in range(3):
@@ -304,6 +306,7 @@ def main():
             torch.cuda.synchronize()
             res[name] = ev0.elapsed_time(ev1) / args.steps
         lib.dspmb_set_tuning(_lib.TUNE_PHASES, 15)
+        lib.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, cache_was)
         return res
 
     def det_run(i):

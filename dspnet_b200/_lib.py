@@ -17,7 +17,7 @@ ERR_MINING_CANDIDATES = -3
 ERR_MINING_THRESH = -4
 ERR_WORKSPACE = -5
 ERR_CUDA = -6
-TUNE_DET_STREAM_VARIANT, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS, TUNE_PHASES = range(5)
+TUNE_DET_STREAM_VARIANT, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS, TUNE_PHASES, TUNE_GRAPH_CACHE = range(6)
 
 # every symbol include/dspmb.h declares (tests check that the built library exports all of them)
 EXPORTS = (

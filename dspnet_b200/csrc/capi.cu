@@ -35,8 +35,9 @@ static int detect_host_libm_mode() {
 #endif
 }
 
-static int g_tuning[5] = {256, 320, 1024, 8192, 15};
-static const int kTuningMax[5] = {256, 320, 1024, 8192, 15};
+constexpr int kNumTuning = 6;
+static int g_tuning[kNumTuning] = {256, 320, 1024, 8192, 15, 1};
+static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 15, 1};
 int tuning(int knob) { return g_tuning[knob]; }
 
 int libm_fma_mode() {
@@ -77,6 +78,97 @@ void profile_mark(int slot, cudaStream_t stream, bool begin) {
 }
 
 namespace {
+struct GraphEntry {
+  std::vector<unsigned char> key;
+  cudaGraphExec_t exec = nullptr;
+  bool uncacheable = false;
+  unsigned long long last_use = 0;
+};
+constexpr size_t kGraphCacheEntries = 32;
+std::mutex g_graph_mutex;
+std::vector<GraphEntry> g_graph_cache;
+unsigned long long g_graph_clock = 0;
+cudaStream_t g_capture_stream[64] = {};
+}  // namespace
+
+int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
+                        const std::function<int(cudaStream_t)> &launch) {
+  if (!tuning(DSPMB_TUNE_GRAPH_CACHE) || g_profile_on) return launch(stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return launch(stream);
+  }
+  int dev = 0;
+  DSPMB_CUDA_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return launch(stream);
+  // the key also pins the device and every path-selection knob
+  std::vector<unsigned char> key(key_len + sizeof(int) * (kNumTuning + 2));
+  memcpy(key.data(), key_, key_len);
+  int extra[kNumTuning + 2];
+  for (int k = 0; k < kNumTuning; ++k) extra[k] = g_tuning[k];
+  extra[kNumTuning] = dev;
+  extra[kNumTuning + 1] = libm_fma_mode();
+  memcpy(key.data() + key_len, extra, sizeof(extra));
+
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  GraphEntry *hit = nullptr;
+  for (auto &e : g_graph_cache)
+    if (e.key == key) {
+      hit = &e;
+      break;
+    }
+  if (!hit) {  // first sighting: remember the key, run directly
+    if (g_graph_cache.size() >= kGraphCacheEntries) {
+      size_t lru = 0;
+      for (size_t i = 1; i < g_graph_cache.size(); ++i)
+        if (g_graph_cache[i].last_use < g_graph_cache[lru].last_use) lru = i;
+      if (g_graph_cache[lru].exec) {
+        cudaDeviceSynchronize();  // rare; the evicted graph may still be in flight
+        cudaGraphExecDestroy(g_graph_cache[lru].exec);
+      }
+      g_graph_cache.erase(g_graph_cache.begin() + lru);
+    }
+    GraphEntry e;
+    e.key = std::move(key);
+    e.last_use = ++g_graph_clock;
+    g_graph_cache.push_back(std::move(e));
+    return launch(stream);
+  }
+  hit->last_use = ++g_graph_clock;
+  if (hit->uncacheable) return launch(stream);
+  if (!hit->exec) {  // second sighting: capture on the private stream of this device
+    if (!g_capture_stream[dev]) DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking));
+    cudaStream_t cs = g_capture_stream[dev];
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      hit->uncacheable = true;
+      return launch(stream);
+    }
+    const int rc = launch(cs);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    if (rc != DSPMB_OK || ce != cudaSuccess || !graph) {
+      cudaGetLastError();
+      if (graph) cudaGraphDestroy(graph);
+      hit->uncacheable = true;
+      return rc != DSPMB_OK ? rc : launch(stream);
+    }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess || !exec) {
+      cudaGetLastError();
+      hit->uncacheable = true;
+      return launch(stream);
+    }
+    hit->exec = exec;
+  }
+  DSPMB_CUDA_TRY(cudaGraphLaunch(hit->exec, stream));
+  return DSPMB_OK;
+}
+
+namespace {
 __global__ void test_expf_kernel(const float *x, float *y, long n, int fma_build) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     y[i] = libm::expf_glibc(x[i], fma_build != 0);
@@ -100,7 +192,7 @@ extern "C" int dspmb_set_libm_mode(int mode) {
 }
 
 extern "C" int dspmb_set_tuning(int knob, int value) {
-  if (knob < 0 || knob >= 5) return -1;
+  if (knob < 0 || knob >= kNumTuning) return -1;
   const int old = g_tuning[knob];
   g_tuning[knob] = value < 0 ? 0 : (value > kTuningMax[knob] ? kTuningMax[knob] : value);
   return old;

@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <functional>
+
 #include "../../include/dspmb.h"
 #include "libm_compat.h"
 
@@ -62,6 +64,14 @@ struct ProfileScope {  // brackets one kernel launch when profiling is enabled
     if (g_profile_on) profile_mark(slot, stream, false);
   }
 };
+
+// ---- CUDA-graph cache for the multi-launch operators (capi.cu) ------------------------------------------
+// `launch(s)` enqueues an operator's kernels on stream s.  A call whose key (every pointer, shape and parameter
+// that reaches a kernel argument) is seen for the second time is captured once on a private stream and replayed
+// with one cudaGraphLaunch from then on, which removes the per-launch gaps of a 4-kernel step.  Bypassed while
+// per-kernel profiling is on, while `stream` is itself being captured, or with DSPMB_TUNE_GRAPH_CACHE = 0.
+int graph_cached_launch(const void *key, size_t key_len, cudaStream_t stream,
+                        const std::function<int(cudaStream_t)> &launch);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

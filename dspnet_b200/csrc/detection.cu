@@ -1240,7 +1240,6 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
                                    int B, int A, int C, float threshold, int clip, const float *variances,
                                    float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out,
                                    void *workspace, size_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
   // Shape CHECKs of MultiBoxDetectionProp::InferShape (multibox_detection-inl.h:149-171).
   DSPMB_REQUIRE(B >= 0 && A > 0 && C > 0, "MultiBoxDetection: bad shape B=%d A=%d C=%d", B, A, C);
   DSPMB_REQUIRE(cls_prob && loc_pred && anchors && out && variances, "MultiBoxDetection: NULL tensor");
@@ -1254,7 +1253,20 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     return DSPMB_ERR_WORKSPACE;
   }
   DetWorkspace w = carve(workspace, B, A, C);
+  const int nms_debug = getenv("DSPMB_NMS_DEBUG") ? atoi(getenv("DSPMB_NMS_DEBUG")) : 0;
 
+  struct {
+    const void *p[6];
+    int i[7];
+    float f[6];
+  } key;
+  memset(&key, 0, sizeof(key));
+  key.p[0] = cls_prob, key.p[1] = loc_pred, key.p[2] = anchors, key.p[3] = out, key.p[4] = valid_count_out, key.p[5] = workspace;
+  key.i[0] = B, key.i[1] = A, key.i[2] = C, key.i[3] = clip, key.i[4] = force_suppress, key.i[5] = nms_topk, key.i[6] = nms_debug;
+  key.f[0] = threshold, key.f[1] = nms_threshold;
+  for (int k = 0; k < 4; ++k) key.f[2 + k] = variances[k];
+
+  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](cudaStream_t stream) -> int {
   const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out | (uintptr_t)loc_pred) & 15) == 0;
   // TMA-fed persistent kernel whenever the ring fits (2..4 stages); plain kernels otherwise
   const size_t stage_bytes = ((size_t)(C - 1) * kPipeTile + (size_t)kPipeTile * 5) * sizeof(float);
@@ -1411,7 +1423,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.force_suppress = force_suppress;
     na.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
     na.smem_rows = tuning(DSPMB_TUNE_NMS_SMEM_ROWS);
-    na.debug = getenv("DSPMB_NMS_DEBUG") ? atoi(getenv("DSPMB_NMS_DEBUG")) : 0;
+    na.debug = nms_debug;
     dim3 grid3(force_suppress ? 1 : C - 1, B);
     {
       ProfileScope _p(kSlotDetNms, stream);
@@ -1420,6 +1432,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     DSPMB_CUDA_TRY(cudaGetLastError());
   }
   return DSPMB_OK;
+  });
 }
 
 // ====================================================================================================

@@ -750,7 +750,6 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
                                 float negative_mining_ratio, float negative_mining_thresh,
                                 int minimum_negative_samples, const float *variances, int32_t *match_out,
                                 int32_t *stats_out, void *workspace, size_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
   (void)minimum_negative_samples;  // declared but never read by the CPU operator (multibox_target.cc:182-241)
   // Shape CHECKs of MultiBoxTargetProp::InferShape (multibox_target-inl.h:213-238).
   DSPMB_REQUIRE(B >= 0 && A > 0 && L > 0 && C > 0, "MultiBoxTarget: bad shape B=%d A=%d L=%d C=%d", B, A, L, C);
@@ -770,6 +769,20 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     return DSPMB_ERR_WORKSPACE;
   }
   TargetWorkspace w = carve(workspace, B, A, L);
+
+  struct {
+    const void *p[9];
+    int i[5];
+    float f[8];
+  } key;
+  memset(&key, 0, sizeof(key));
+  key.p[0] = anchors, key.p[1] = labels, key.p[2] = cls_preds, key.p[3] = loc_target, key.p[4] = loc_mask;
+  key.p[5] = cls_target, key.p[6] = match_out, key.p[7] = stats_out, key.p[8] = workspace;
+  key.i[0] = B, key.i[1] = A, key.i[2] = L, key.i[3] = label_width, key.i[4] = C;
+  key.f[0] = overlap_threshold, key.f[1] = ignore_label, key.f[2] = negative_mining_ratio, key.f[3] = negative_mining_thresh;
+  for (int k = 0; k < 4; ++k) key.f[4 + k] = variances[k];
+
+  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](cudaStream_t stream) -> int {
   if (tuning(DSPMB_TUNE_PHASES) & 1)
     DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
 
@@ -862,4 +875,5 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
+  });
 }

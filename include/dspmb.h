@@ -178,6 +178,9 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
 #define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 15:
                                            1 stream, 2 sort/match, 4 nms, 8 rank) -- bench.py times one at a time   */
+#define DSPMB_TUNE_GRAPH_CACHE 5        /* 1 (default): a detection/target call repeated with identical arguments is
+                                           captured into a CUDA graph on its second sighting and replayed from then
+                                           on (one cudaGraphLaunch instead of 3-4 kernel launches); 0: always launch */
 int dspmb_set_tuning(int knob, int value);
 
 /* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same

@@ -385,3 +385,69 @@ def test_fused_gather_single_rank(oracle, cuda):
         assert torch.equal(r2, rows) and torch.equal(c2, counts)
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("side_stream", [False, True])
+def test_graph_cache_replays_are_identical(oracle, cuda, side_stream):
+    """A call repeated with identical arguments is captured into a CUDA graph on its second sighting
+    (DSPMB_TUNE_GRAPH_CACHE); direct launches, the capturing call and the replays must all equal the oracle, the
+    replay must read the CURRENT contents of the input buffers, and switching the knob off must not change results."""
+    from dspnet_b200 import _lib
+    from dspnet_b200.plan import DetectionPlan, TargetPlan
+    L = _lib.lib()
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 3, config_id=41)
+    A, C = anchors.shape[1], prob.shape[1]
+    kw = dict(nms_threshold=0.45, nms_topk=400)
+    want = [oracle.multibox_detection(prob, lp, anchors, **kw),
+            oracle.multibox_detection(np.ascontiguousarray(prob[::-1]), np.ascontiguousarray(lp[::-1]), anchors, **kw)]
+    stream = torch.cuda.Stream(cuda) if side_stream else torch.cuda.current_stream(cuda)
+    with torch.cuda.stream(stream):
+        plan = DetectionPlan(3, A, C, cuda, **kw)
+        a, p, l, out = _t(anchors, cuda), _t(prob, cuda), _t(lp, cuda), plan.new_output()
+        for i in range(5):
+            which = i & 1
+            p.copy_(_t(prob[::-1] if which else prob, cuda))
+            l.copy_(_t(lp[::-1] if which else lp, cuda))
+            out.fill_(123.0)
+            plan.run(p, l, a, out)
+            util.assert_bit_equal(out.cpu().numpy(), want[which], "detection call %d" % i)
+        old = L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
+        try:
+            plan.run(p, l, a, out)
+            util.assert_bit_equal(out.cpu().numpy(), want[0], "detection, cache off")
+        finally:
+            L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, old)
+
+        anchors, lab, cp = util.target_inputs(oracle, "ssd300", 3, config_id=42)
+        tkw = dict(negative_mining_ratio=3.0, negative_mining_thresh=0.5)
+        twant = oracle.multibox_target(anchors, lab, cp, **tkw)
+        tplan = TargetPlan(3, anchors.shape[1], lab.shape[1], cp.shape[1], cuda, **tkw)
+        ta, tl, tc, outs = _t(anchors, cuda), _t(lab, cuda), _t(cp, cuda), tplan.new_outputs()
+        for i in range(4):
+            for o in outs:
+                o.fill_(55.0)
+            tplan.run(ta, tl, tc, outs)
+            tplan.status()
+            for got, w, name in zip(outs, twant, ("loc_target", "loc_mask", "cls_target")):
+                util.assert_bit_equal(got.cpu().numpy().reshape(w.shape), w, "target call %d %s" % (i, name))
+
+
+def test_graph_cache_inside_user_capture(oracle, cuda):
+    """When the caller's stream is itself being captured the operator launches its kernels into that capture."""
+    from dspnet_b200.plan import DetectionPlan
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=43)
+    kw = dict(nms_threshold=0.45, nms_topk=400)
+    want = oracle.multibox_detection(prob, lp, anchors, **kw)
+    plan = DetectionPlan(2, anchors.shape[1], prob.shape[1], cuda, **kw)
+    a, p, l, out = _t(anchors, cuda), _t(prob, cuda), _t(lp, cuda), plan.new_output()
+    plan.run(p, l, a, out)
+    plan.run(p, l, a, out)  # now cached
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream(cuda)
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            plan.run(p, l, a, out)
+    out.fill_(7.0)
+    g.replay()
+    torch.cuda.synchronize()
+    util.assert_bit_equal(out.cpu().numpy(), want, "replay of a user capture")
