@@ -314,8 +314,7 @@ def main():
         plan.run(prob_sets[s], loc_sets[s], anchors, out_sets[s])
     for s in range(ROTATE):  # every workspace-dependent phase input exists for every rotating set
         det_run(s)
-    kernels = time_phases(det_run, [(1, "det_stream_kernel"), (8, "det_rank_kernel"), (2, "det_sort_kernel"),
-                                    (4, "det_nms_kernel")])
+    kernels = time_phases(det_run, [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_nms_kernel")])
     nslots = 16
 
     # ---- end to end through the public operator with HOST buffers (pinned in, result read back) ----

@@ -56,7 +56,7 @@ std::vector<ProfileRecord> g_profile_records;
 const char *const kSlotNames[kNumKernelSlots] = {
     "prior_kernel",        "det_stream_kernel", "det_sort_kernel", "det_nms_kernel",  "target_stream_kernel",
     "target_match_kernel", "nms_sort_kernel",   "nms_gather_kernel", "nms_mask_kernel", "nms_scan_kernel",
-    "det_compact_kernel",  "det_rank_kernel"};
+    "det_compact_kernel"};
 }  // namespace
 
 void profile_mark(int slot, cudaStream_t stream, bool begin) {

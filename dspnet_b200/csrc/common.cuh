@@ -49,7 +49,6 @@ enum KernelSlot {
   kSlotNmsMask,
   kSlotNmsScan,
   kSlotDetCompact,
-  kSlotDetRank,
   kNumKernelSlots
 };
 extern bool g_profile_on;

@@ -14,25 +14,27 @@
 // atomicAdd compaction (non-deterministic order), a global-memory merge sort and one __syncthreads per NMS
 // candidate, and it diverges from the CPU semantics; it is not followed.
 //
-// Structure here (four launches, all images in every grid):
+// Structure here (three launches, all images in every grid; a repeated call replays them as one CUDA graph):
 //   det_stream_kernel  HBM-bound: streams cls_prob (B,C,A) with 128-bit no-allocate loads, 4 anchors/thread
 //   (reg / TMA         (register-resident variant: every load of a thread in flight before the first compare),
 //    variants)         fills `out` with -1 (128-bit stores), decodes the survivors and stages their finished pass-1
 //                      rows, order keys, classes and boxes in shared memory (block scan => anchor order), then
 //                      writes them as contiguous runs into the tile's slots together with the tile's count.
-//   det_rank_kernel    one CTA per (tile, image): rank base = survivors in the earlier tiles of the image; copies the
-//                      tile's runs to their final positions, so rows [0, V) hold exactly the reference's pass 1.
-//                      (A single-pass decoupled look-back inside the stream kernel was measured instead: it made
-//                      that kernel 10 us slower because the CTAs idle on the look-back round trips.)
-//   det_sort_kernel    one CTA per image: MSB-first radix select of the nms_topk best of the V rank-ordered keys
-//                      (ties resolved in rank order through ballot-count tables), register/shuffle bitonic sort of
-//                      the selection, permuted copy of those rows into the head [0, nkeep); the tail [nkeep, V)
-//                      is already final.
+//   det_sort_kernel    grid (1 + parts, B), two roles that write disjoint rows:
+//                      sort role (one CTA per image): rank base of every tile = prefix of the tile counts; keys of the
+//                      V survivors staged in rank order; MSB-first radix select of the nms_topk best (ties resolved
+//                      in rank order through ballot-count tables); register/shuffle bitonic sort of the selection;
+//                      those rows gathered straight from the slots into the head [0, nkeep).
+//                      rank role (the other CTAs): copy the tiles' runs to their pass-1 positions [nkeep, V).
+//                      (Ranking inside the stream kernel with a decoupled look-back was measured instead: it made
+//                      that kernel 10 us slower because the CTAs idle on the look-back round trips; a separate rank
+//                      launch cost 8 us.)
 //   det_nms_kernel     one CTA per (image, class) segment (one per image with force_suppress): ordered member
 //                      list from ballot-count tables, boxes staged in shared memory, then
-//                        n <= 320: upper-triangular bit mask built by balanced warp units (4-compare overlap test,
-//                                  division-free threshold test with an exact fallback band) + a word-serial resolve
-//                                  that only visits rows that suppress something;
+//                        n <= 320: upper-triangular bit mask built by 32x32 warp units in two phases (branch-free
+//                                  4-compare overlap bits; the few overlapping pairs are queued and take the
+//                                  division-free threshold test with its exact fallback band on dense lanes) + a
+//                                  word-serial resolve that only visits rows that suppress something;
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
 #include <stdlib.h>
 #include <string.h>
@@ -64,8 +66,8 @@ struct DetWorkspace {
   int *valid;                 // (B) V
   int *nms_rows;              // (B) rows taking part in NMS (0 = skipped)
   int *cursor;                // (B) allocator of seg_list regions for large segments
-  unsigned *keys;             // (B, Apad) order key of every surviving row, by rank
-  float *stage;               // (B, A, 8) staging of the sorted head rows
+  unsigned *keys;             // (B, Apad) order key of every surviving row, by rank (large A only)
+  int *tile_base;             // (B, T) rank base of every tile (large T only)
   unsigned short *row_cls;    // (B, Apad) class of every output row
   float4 *row_box;            // (B, A) box of every output row
   int *seg_list;              // (B, A) member rows of large segments
@@ -104,7 +106,7 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.nms_rows = (int *)take(sizeof(int) * B);
   w.cursor = (int *)take(sizeof(int) * B);
   w.keys = (unsigned *)take(sizeof(unsigned) * B * Apad);
-  w.stage = (float *)take(sizeof(float) * 8 * (size_t)B * A);
+  w.tile_base = (int *)take(sizeof(int) * B * Tmax);
   w.row_cls = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
   w.row_box = (float4 *)take(sizeof(float4) * (size_t)B * A);
   w.seg_list = (int *)take(sizeof(int) * (size_t)B * A);
@@ -181,7 +183,7 @@ __device__ __forceinline__ void stage_row(const StreamArgs &a, RowStage<kRows> &
 }
 
 // Coalesced write-out of the tile's `total` staged rows into the tile's slots (slot = tile_begin + k).  The rank of
-// a row is only known once every earlier tile of the image has been counted; det_rank_kernel moves the runs to
+// a row is only known once every earlier tile of the image has been counted; det_sort_kernel moves the runs to
 // their final positions afterwards, so this kernel never waits on another CTA.  Call after a block barrier.
 template <int kRows>
 __device__ __forceinline__ void flush_rows(const StreamArgs &a, const RowStage<kRows> &sm, int b, int tile_begin, int total) {
@@ -494,54 +496,6 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
 }
 
 // ----------------------------------------------------------------------------------------------------
-// Moves every tile's run of surviving rows from its slots to its final pass-1 position: rank base of tile t =
-// survivors in the tiles before it (all counts are final: the stream kernel has completed), so the reference's
-// anchor-ordered compaction (multibox_detection.cc:93-127) is reproduced without any CTA waiting on another.
-// Both sides of every copy are contiguous runs.
-struct RankArgs {
-  const int *tile_count;
-  const float *slot_rows;
-  const unsigned *slot_keys;
-  const unsigned short *slot_cls;
-  const float4 *slot_box;
-  float *out;
-  unsigned *keys;
-  unsigned short *row_cls;
-  float4 *row_box;
-  int *valid;
-  int A, T, Apad, cls_stride, tile;
-};
-
-__global__ void __launch_bounds__(128) det_rank_kernel(const __grid_constant__ RankArgs a) {
-  __shared__ int red[4];
-  const int b = blockIdx.y, t = blockIdx.x;
-  const int *cnt = a.tile_count + (size_t)b * a.T;
-  int part = 0;
-  for (int u = threadIdx.x; u < t; u += blockDim.x) part += cnt[u];
-  part = warp_sum_i32(part);
-  if (lane_id() == 0) red[warp_id()] = part;
-  __syncthreads();
-  const int base = red[0] + red[1] + red[2] + red[3];
-  const int total = cnt[t];
-  if (t == a.T - 1 && threadIdx.x == 0) a.valid[b] = base + total;
-  const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
-  const float *src = a.slot_rows + slot0 * 7;
-  float *dst = a.out + ((size_t)b * a.A + base) * 7;
-  for (int q = threadIdx.x; q < total * 7; q += blockDim.x) dst[q] = src[q];
-  const unsigned *sk = a.slot_keys + slot0;
-  const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
-  const float4 *sb = a.slot_box + slot0;
-  unsigned *dk = a.keys + (size_t)b * a.Apad + base;
-  unsigned short *dc = a.row_cls + (size_t)b * a.cls_stride + base;
-  float4 *db = a.row_box + (size_t)b * a.A + base;
-  for (int q = threadIdx.x; q < total; q += blockDim.x) {
-    dk[q] = sk[q];
-    dc[q] = sc[q];
-    db[q] = sb[q];
-  }
-}
-
-// ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
 // global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used above kRankSortMax keys.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
@@ -584,25 +538,105 @@ __device__ __forceinline__ int warp_append(int *counter, bool pred) {
 
 struct SortArgs {
   float *out;
-  const unsigned *keys;   // (B, Apad) order keys by rank (written by the stream kernel)
-  const int *valid;       // (B) V
+  const int *tile_count;            // (B, T) survivors per tile (stream kernel)
+  const float *slot_rows;           // per-tile slots written by the stream kernel
+  const unsigned *slot_keys;
+  const unsigned short *slot_cls;
+  const float4 *slot_box;
+  unsigned *keys;                   // (B, Apad) rank-ordered keys, only when they do not fit in shared memory
+  int *tile_base;                   // (B, T) exclusive prefix of tile_count, only when T > kSortSmemTiles
+  int *valid;                       // (B) V
   int *nms_rows, *cursor;
   unsigned short *row_cls;
   float4 *row_box;
-  float *stage;           // (B, A, 8) staging of the sorted head rows
   unsigned long long *sort_keys;
   int *valid_count_out;
   WsHeader *header;
-  int A, Apad, cls_stride, npad_max, niter_max;
-  int sel_cap;
+  int A, T, tile, Apad, cls_stride, npad_max, niter_max;
+  int sel_cap, rank_parts;
   float nms_threshold;
   int force_suppress, nms_topk;
 };
 
-// One CTA per image.  The stream kernel has already written every surviving row at its rank (= the reference's
-// pass-1 output), so rows [nkeep, V) are final.  This kernel only produces the sorted head: radix select of the
-// nkeep best keys over the V rank-ordered keys, sort, and a permuted copy of those rows (through a staging buffer,
-// because head positions are both sources and destinations) into rows [0, nkeep) -- multibox_detection.cc:132-151.
+constexpr int kSortSmemTiles = 1024;  // tile bases kept in shared memory up to this many tiles per image
+
+// Rank role of det_sort_kernel (blockIdx.x >= 1): moves the runs of a slice of the image's tiles from their slots to
+// their final pass-1 positions -- rank base of tile t = survivors in the tiles before it, so the reference's
+// anchor-ordered compaction (multibox_detection.cc:93-127) is reproduced without any CTA waiting on another.
+// Rows below nkeep are skipped: the sort role of the same launch writes the sorted head there.
+__device__ void det_rank_role(const SortArgs &a, int b, int part, int *red) {
+  const int T = a.T;
+  const int *cnt = a.tile_count + (size_t)b * T;
+  const int per = (T + a.rank_parts - 1) / a.rank_parts;
+  const int t0 = part * per, t1 = min(T, t0 + per);
+  if (t0 >= t1) return;
+  int s_all = 0, s_before = 0;
+  for (int u = threadIdx.x; u < T; u += blockDim.x) {
+    const int c = cnt[u];
+    s_all += c;
+    if (u < t0) s_before += c;
+  }
+  s_all = warp_sum_i32(s_all);
+  s_before = warp_sum_i32(s_before);
+  const unsigned warp = warp_id(), lane = lane_id(), nwarps = blockDim.x >> 5;
+  if (lane == 0) {
+    red[warp] = s_all;
+    red[32 + warp] = s_before;
+  }
+  __syncthreads();
+  const int V = warp_sum_i32(lane < nwarps ? red[lane] : 0);
+  const int base0 = warp_sum_i32(lane < nwarps ? red[32 + lane] : 0);
+  const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;
+  int nkeep = 0;
+  if (do_sort) nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
+  if (nkeep >= V) return;
+  // wpt warps per tile (as many as the CTA has to spare), loads batched four deep: the copies are latency bound
+  const int ntiles = t1 - t0;
+  int wpt = (int)nwarps / ntiles;
+  wpt = wpt < 1 ? 1 : (wpt > 8 ? 8 : wpt);
+  const int sub = (int)warp % wpt, step = wpt * 32;
+  for (int t = t0 + (int)warp / wpt; t < t1; t += (int)nwarps / wpt) {
+    int sb = 0;
+    for (int u = t0 + (int)lane; u < t; u += 32) sb += cnt[u];
+    const int base = base0 + warp_sum_i32(sb);
+    const int n = cnt[t];
+    const int skip = min(n, max(0, nkeep - base));
+    if (skip >= n) continue;
+    const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
+    const float *src = a.slot_rows + slot0 * 7;
+    float *dst = a.out + ((size_t)b * a.A + base) * 7;
+    const int end = n * 7;
+    for (int q = skip * 7 + sub * 32 + (int)lane; q < end; q += 4 * step) {
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = q + k * step < end ? src[q + k * step] : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (q + k * step < end) dst[q + k * step] = v[k];
+    }
+    const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
+    const float4 *sbx = a.slot_box + slot0;
+    unsigned short *dc = a.row_cls + (size_t)b * a.cls_stride + base;
+    float4 *db = a.row_box + (size_t)b * a.A + base;
+    for (int q = skip + sub * 32 + (int)lane; q < n; q += 2 * step) {
+      const bool two = q + step < n;
+      const unsigned short c0 = sc[q], c1 = two ? sc[q + step] : (unsigned short)0;
+      const float4 b0 = sbx[q], b1 = two ? sbx[q + step] : b0;
+      dc[q] = c0;
+      db[q] = b0;
+      if (two) {
+        dc[q + step] = c1;
+        db[q + step] = b1;
+      }
+    }
+  }
+}
+
+// grid (1 + rank_parts, B).  blockIdx.x == 0 is the sort role, one CTA per image: it ranks the image's tiles
+// (prefix of the tile counts), stages the keys of the V survivors in rank order, radix-selects the nkeep best, sorts
+// them and writes those rows -- gathered straight from the slots -- to rows [0, nkeep) of the output
+// (multibox_detection.cc:132-151).  The other CTAs of the image move rows [nkeep, V) (det_rank_role); the two roles
+// write disjoint rows, so they need no ordering between them.
 template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
@@ -610,13 +644,36 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ unsigned hist256[256];
   __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;
   __shared__ unsigned sm_prefix;
-  const int b = blockIdx.x;
-  const int A = a.A;
-  const int V = a.valid[b];
+  __shared__ int sm_tbase[kSortSmemTiles];
+  const int b = blockIdx.y;
+  if (blockIdx.x != 0) {
+    det_rank_role(a, b, (int)blockIdx.x - 1, reinterpret_cast<int *>(hist256));
+    return;
+  }
+  const int A = a.A, T = a.T;
+  // rank base of every tile (block scan over the tile counts) and V
+  const int *cnt = a.tile_count + (size_t)b * T;
+  int *tbase = T <= kSortSmemTiles ? sm_tbase : a.tile_base + (size_t)b * T;
+  if (threadIdx.x == 0) carry_smem = 0;
+  __syncthreads();
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = i < T ? cnt[i] : 0;
+    int total;
+    const int ex = block_scan_excl(v, scan_smem, &total);
+    const int carry = carry_smem;
+    if (i < T) tbase[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry_smem = carry + total;
+    __syncthreads();
+  }
+  const int V = carry_smem;
   const bool do_sort = V >= 1 && a.nms_threshold > 0.f && a.nms_threshold <= 1.f;  // multibox_detection.cc:130
+  __syncthreads();
   if (threadIdx.x == 0) {
     if (b == 0) a.header->status = DSPMB_OK;
     if (a.valid_count_out) a.valid_count_out[b] = V;
+    a.valid[b] = V;
     a.nms_rows[b] = do_sort ? V : 0;
     a.cursor[b] = 0;
     sm_prefix = 0u;
@@ -629,14 +686,18 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
   unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
   int *wtab = reinterpret_cast<int *>(skeys + (kKeysInSmem ? ((A + 3) & ~3) : 0));
-  const unsigned *gkeys = a.keys + (size_t)b * a.Apad;
+  unsigned *gkeys = a.keys + (size_t)b * a.Apad;
   auto key_at = [&](int p) -> unsigned { return kKeysInSmem ? skeys[p] : gkeys[p]; };
   const unsigned warp = warp_id(), lane = lane_id();
   const int niter = (V + (int)blockDim.x - 1) / (int)blockDim.x;
 
-  if (kKeysInSmem) {  // coalesced 128-bit loads (rows of `keys` are 16-byte aligned; reads beyond V stay inside Apad)
-    for (int i = threadIdx.x; i < ((V + 3) >> 2); i += blockDim.x)
-      reinterpret_cast<uint4 *>(skeys)[i] = __ldg(reinterpret_cast<const uint4 *>(gkeys) + i);
+  {  // keys of the survivors in rank order: one warp per tile, contiguous on both sides
+    unsigned *dstk = kKeysInSmem ? skeys : gkeys;
+    for (int t = (int)warp; t < T; t += (int)(blockDim.x >> 5)) {
+      const int n = cnt[t], tb = tbase[t];
+      const unsigned *src = a.slot_keys + (size_t)b * a.Apad + (size_t)t * a.tile;
+      for (int k = (int)lane; k < n; k += 32) dstk[tb + k] = src[k];
+    }
   }
   int nkeep = V;
   if (a.nms_topk > 0 && a.nms_topk < nkeep) nkeep = a.nms_topk;  // multibox_detection.cc:142-145
@@ -756,32 +817,29 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
   }
 
-  // head rows: gather through the staging buffer, then overwrite rows [0, nkeep)
+  // head rows: rank p lives in tile t = last tile with tbase[t] <= p, slot p - tbase[t] of that tile
   float *out = a.out + (size_t)b * A * 7;
   unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
   float4 *row_box = a.row_box + (size_t)b * A;
-  float *stage = a.stage + (size_t)b * A * 8;
   for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {
     const int p = (int)(unsigned)(sel[r] & 0xffffffffull);
-    const float *src = out + (size_t)p * 7;
-    float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)r * 8);
-    dst[0] = make_float4(src[0], src[1], src[2], src[3]);
-    dst[1] = make_float4(src[4], src[5], src[6], 0.f);
-  }
-  __syncthreads();
-  for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {
-    const float4 *src = reinterpret_cast<const float4 *>(stage + (size_t)r * 8);
-    const float4 s0 = src[0], s1 = src[1];
+    int lo = 0, hi = T - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tbase[mid] <= p) lo = mid; else hi = mid - 1;
+    }
+    const float *src = a.slot_rows + ((size_t)b * a.Apad + (size_t)lo * a.tile + (size_t)(p - tbase[lo])) * 7;
+    const float s0 = src[0], s1 = src[1], s2 = src[2], s3 = src[3], s4 = src[4], s5 = src[5], s6 = src[6];
     float *o = out + (size_t)r * 7;
-    o[0] = s0.x;
-    o[1] = s0.y;
-    o[2] = s0.z;
-    o[3] = s0.w;
-    o[4] = s1.x;
-    o[5] = s1.y;
-    o[6] = s1.z;
-    row_cls[r] = (unsigned short)s0.x;
-    row_box[r] = make_float4(s0.z, s0.w, s1.x, s1.y);
+    o[0] = s0;
+    o[1] = s1;
+    o[2] = s2;
+    o[3] = s3;
+    o[4] = s4;
+    o[5] = s5;
+    o[6] = s6;
+    row_cls[r] = (unsigned short)s0;
+    row_box[r] = make_float4(s2, s3, s4, s5);
   }
 }
 
@@ -1340,40 +1398,26 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 
-  if (phases & 8) {
-    RankArgs ra;
-    ra.tile_count = w.tile_count;
-    ra.slot_rows = w.slot_rows;
-    ra.slot_keys = w.slot_keys;
-    ra.slot_cls = w.slot_cls;
-    ra.slot_box = w.slot_box;
-    ra.out = out;
-    ra.keys = w.keys;
-    ra.row_cls = w.row_cls;
-    ra.row_box = w.row_box;
-    ra.valid = w.valid;
-    ra.A = A;
-    ra.T = T;
-    ra.Apad = Apad;
-    ra.cls_stride = (Apad + 7) & ~7;
-    ra.tile = tile;
-    ProfileScope _p(kSlotDetRank, stream);
-    det_rank_kernel<<<dim3(T, B), 128, 0, stream>>>(ra);
-  }
-  DSPMB_CUDA_TRY(cudaGetLastError());
-
   SortArgs so;
   so.out = out;
+  so.tile_count = w.tile_count;
+  so.slot_rows = w.slot_rows;
+  so.slot_keys = w.slot_keys;
+  so.slot_cls = w.slot_cls;
+  so.slot_box = w.slot_box;
   so.keys = w.keys;
+  so.tile_base = w.tile_base;
   so.valid = w.valid;
   so.nms_rows = w.nms_rows;
   so.cursor = w.cursor;
   so.row_cls = w.row_cls;
   so.row_box = w.row_box;
-  so.stage = w.stage;
   so.sort_keys = w.sort_keys;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
+  so.T = T;
+  so.tile = tile;
+  so.rank_parts = ceil_div(T, 8) < 8 ? ceil_div(T, 8) : 8;
   so.A = A;
   so.Apad = Apad;
   so.cls_stride = (Apad + 7) & ~7;
@@ -1399,9 +1443,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
     if (keys_in_smem)
-      det_sort_kernel<true><<<B, kSortThreads, smem2, stream>>>(so);
+      det_sort_kernel<true><<<dim3(1 + so.rank_parts, B), kSortThreads, smem2, stream>>>(so);
     else
-      det_sort_kernel<false><<<B, kSortThreads, smem2, stream>>>(so);
+      det_sort_kernel<false><<<dim3(1 + so.rank_parts, B), kSortThreads, smem2, stream>>>(so);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 

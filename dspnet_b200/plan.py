@@ -30,7 +30,7 @@ class DetectionPlan:
         self._var = _lib.float_array(variances)
         self._tail = (B, A, C, float(threshold), int(bool(clip)), self._var, float(nms_threshold),
                       int(bool(force_suppress)), int(nms_topk), _ptr(self.valid), _ptr(self.ws), self.ws.numel())
-        self.launches_per_run = 4 if 0 < nms_threshold <= 1 else 3  # stream, rank, sort(, nms)
+        self.launches_per_run = 3 if 0 < nms_threshold <= 1 else 2  # stream, rank+sort(, nms)
 
     def new_output(self):
         return torch.empty((self.B, self.A, 7), dtype=torch.float32, device=self.device)

@@ -177,7 +177,7 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_NMS_SMEM_ROWS 2      /* largest segment staged in shared memory by the sweep NMS (max 1024) */
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
 #define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 15:
-                                           1 stream, 2 sort/match, 4 nms, 8 rank) -- bench.py times one at a time   */
+                                           1 stream, 2 rank+sort / match, 4 nms) -- bench.py times one at a time     */
 #define DSPMB_TUNE_GRAPH_CACHE 5        /* 1 (default): a detection/target call repeated with identical arguments is
                                            captured into a CUDA graph on its second sighting and replayed from then
                                            on (one cudaGraphLaunch instead of 3-4 kernel launches); 0: always launch */
