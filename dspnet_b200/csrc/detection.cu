@@ -150,6 +150,15 @@ struct RowStage {
   unsigned short cls[kRows];
 };
 
+// Decode inputs of a tile's survivors in rank order (register-resident stream kernel).
+template <int kRows>
+struct DecodeStage {
+  float4 an[kRows];
+  float lp[5][kRows];
+  float score[kRows];
+  unsigned short id[kRows];
+};
+
 // Final pass-1 row of one surviving anchor (multibox_detection.cc:89-127), staged at its index inside the tile.
 template <int kRows>
 __device__ __forceinline__ void stage_row(const StreamArgs &a, RowStage<kRows> &sm, int local, int id, float score,
@@ -290,6 +299,7 @@ template <int NFG, int kThreads>
 __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_constant__ StreamArgs a) {
   __shared__ int scan_smem[kThreads / 32 + 1];
   __shared__ RowStage<kThreads * 4> sm_rows;
+  __shared__ DecodeStage<kThreads * 4> sm_in;
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kThreads * 4;
   const int tile_begin = t * kTile;
@@ -338,15 +348,27 @@ __global__ void __launch_bounds__(kThreads) det_stream_reg_kernel(const __grid_c
   int total;
   int pos = block_scan_excl(nvalid, scan_smem, &total);
   if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  // Survivors are ~1 in 5 anchors, so decoding them where they sit would run the fp64-expf decode four times per
+  // warp with a fifth of the lanes busy.  Their inputs are parked in shared memory in rank order instead (a few
+  // predicated stores), and the decode runs once on dense lanes.
   if (nvalid) {
     const float lf[20] = {lp[0].x, lp[0].y, lp[0].z, lp[0].w, lp[1].x, lp[1].y, lp[1].z, lp[1].w, lp[2].x, lp[2].y,
                           lp[2].z, lp[2].w, lp[3].x, lp[3].y, lp[3].z, lp[3].w, lp[4].x, lp[4].y, lp[4].z, lp[4].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (id[k] > 0) {
-        stage_row(a, sm_rows, pos, id[k], score[k], an[k], lf + 5 * k);
+        sm_in.an[pos] = an[k];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) sm_in.lp[c][pos] = lf[5 * k + c];
+        sm_in.score[pos] = score[k];
+        sm_in.id[pos] = (unsigned short)id[k];
         ++pos;
       }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < total; j += kThreads) {
+    const float l5[5] = {sm_in.lp[0][j], sm_in.lp[1][j], sm_in.lp[2][j], sm_in.lp[3][j], sm_in.lp[4][j]};
+    stage_row(a, sm_rows, j, (int)sm_in.id[j], sm_in.score[j], sm_in.an[j], l5);
   }
   __syncthreads();  // the staged rows are complete
   flush_rows(a, sm_rows, b, tile_begin, total);
