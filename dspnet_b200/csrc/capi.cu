@@ -36,7 +36,7 @@ static int detect_host_libm_mode() {
 }
 
 constexpr int kNumTuning = 6;
-static int g_tuning[kNumTuning] = {256, 320, 1024, 8192, 15, 1};
+static int g_tuning[kNumTuning] = {2, 320, 1024, 8192, 15, 1};
 static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 15, 1};
 int tuning(int knob) { return g_tuning[knob]; }
 

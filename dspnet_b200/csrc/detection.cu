@@ -20,7 +20,7 @@
 //    variants)         fills `out` with -1 (128-bit stores), decodes the survivors and stages their finished pass-1
 //                      rows, order keys, classes and boxes in shared memory (block scan => anchor order), then
 //                      writes them as contiguous runs into the tile's slots together with the tile's count.
-//   det_sort_kernel    grid (1 + parts, B), two roles that write disjoint rows:
+//   det_sort_kernel    grid (B, 1 + parts), two roles that write disjoint rows:
 //                      sort role (one CTA per image): rank base of every tile = prefix of the tile counts; keys of the
 //                      V survivors staged in rank order; MSB-first radix select of the nms_topk best (ties resolved
 //                      in rank order through ballot-count tables); register/shuffle bitonic sort of the selection;
@@ -518,6 +518,102 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
 }
 
 // ----------------------------------------------------------------------------------------------------
+// One-tile-per-CTA variant fed by the TMA engine.  The register-resident kernel spends its load phase throttled by
+// the load/store unit (29 LDG.128 per thread queue up behind each other) and holds ~140 registers per thread.
+// Here one thread issues the tile's NFG class rows, its loc_pred rows and its anchors as 1-D bulk async copies
+// (cp.async.bulk ... mbarrier::complete_tx) into shared memory; the CTA fills its `out = -1` rows while the bytes
+// are in flight, then consumes the tile from shared memory.  ~40 registers and ~32 KB of shared memory per CTA
+// give 7 CTAs/SM whose load and compute phases interleave freely (the hardware CTA scheduler replaces a software
+// pipeline).  The row staging aliases the class rows, which are dead once the arg-max is done.
+constexpr int kBulkThreads = 128;
+constexpr int kBulkTile = 256;  // anchors per CTA, 2 per thread
+
+template <int NFG>
+struct BulkSmem {
+  union {
+    float cls[NFG][kBulkTile];       // class rows of the tile (bulk copies)
+    RowStage<kBulkTile> rows;        // finished rows of the survivors (after the arg-max)
+  } u;
+  float loc[kBulkTile * 5];
+  float4 anc[kBulkTile];
+  float score[kBulkTile];            // survivors in rank order
+  unsigned short idx[kBulkTile], id[kBulkTile];
+};
+
+template <int NFG>
+__global__ void __launch_bounds__(kBulkThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
+  __shared__ __align__(128) BulkSmem<NFG> sm;
+  __shared__ __align__(8) unsigned long long full_bar;
+  __shared__ int scan_smem[kBulkThreads / 32 + 1];
+  const int b = blockIdx.y, t = blockIdx.x;
+  const int A = a.A;
+  const int tile_begin = t * kBulkTile;
+  const int rows = min(kBulkTile, A - tile_begin);  // multiple of 4 (A % 4 == 0)
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&full_bar, (unsigned)(rows * 4 * NFG + rows * 20 + rows * 16));
+    const float *cp = a.cls_prob + ((size_t)b * a.C + 1) * A + tile_begin;
+#pragma unroll 4
+    for (int j = 0; j < NFG; ++j) bulk_g2s(&sm.u.cls[j][0], cp + (size_t)j * A, rows * 4, &full_bar);
+    bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
+    bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
+  }
+  {  // `out = -1` for this tile's rows (multibox_detection-inl.h:103) while the copies are in flight
+    float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
+    const int nfl = rows * 7;
+    const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+    for (int x = threadIdx.x * 4; x < nfl; x += kBulkThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
+  }
+  __syncthreads();  // the barrier initialisation is visible to every waiter
+  mbar_wait(&full_bar, 0u);
+
+  const int l0 = threadIdx.x * 2;
+  float score[2] = {-1.f, -1.f};
+  int id[2] = {0, 0};
+  if (l0 < rows) {
+#pragma unroll
+    for (int j = 0; j < NFG; ++j) {
+      const float2 v = *reinterpret_cast<const float2 *>(&sm.u.cls[j][l0]);
+      if (v.x > score[0]) {
+        score[0] = v.x;
+        id[0] = j + 1;
+      }
+      if (v.y > score[1]) {
+        score[1] = v.y;
+        id[1] = j + 1;
+      }
+    }
+  }
+  int nvalid = 0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (id[k] > 0 && score[k] < a.threshold) id[k] = 0;
+    nvalid += id[k] > 0;
+  }
+  int total;
+  int pos = block_scan_excl(nvalid, scan_smem, &total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+#pragma unroll
+  for (int k = 0; k < 2; ++k)
+    if (id[k] > 0) {
+      sm.score[pos] = score[k];
+      sm.idx[pos] = (unsigned short)(l0 + k);
+      sm.id[pos] = (unsigned short)id[k];
+      ++pos;
+    }
+  __syncthreads();  // survivor list complete; the class rows are dead from here on
+  for (int j = threadIdx.x; j < total; j += kBulkThreads) {
+    const int l = sm.idx[j];
+    const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
+    stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
+  }
+  __syncthreads();  // the staged rows are complete
+  flush_rows(a, sm.u.rows, b, tile_begin, total);
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
 // global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used above kRankSortMax keys.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
@@ -582,7 +678,7 @@ struct SortArgs {
 
 constexpr int kSortSmemTiles = 1024;  // tile bases kept in shared memory up to this many tiles per image
 
-// Rank role of det_sort_kernel (blockIdx.x >= 1): moves the runs of a slice of the image's tiles from their slots to
+// Rank role of det_sort_kernel (blockIdx.y >= 1): moves the runs of a slice of the image's tiles from their slots to
 // their final pass-1 positions -- rank base of tile t = survivors in the tiles before it, so the reference's
 // anchor-ordered compaction (multibox_detection.cc:93-127) is reproduced without any CTA waiting on another.
 // Rows below nkeep are skipped: the sort role of the same launch writes the sorted head there.
@@ -654,7 +750,7 @@ __device__ void det_rank_role(const SortArgs &a, int b, int part, int *red) {
   }
 }
 
-// grid (1 + rank_parts, B).  blockIdx.x == 0 is the sort role, one CTA per image: it ranks the image's tiles
+// grid (B, 1 + rank_parts).  blockIdx.y == 0 is the sort role, one CTA per image: it ranks the image's tiles
 // (prefix of the tile counts), stages the keys of the V survivors in rank order, radix-selects the nkeep best, sorts
 // them and writes those rows -- gathered straight from the slots -- to rows [0, nkeep) of the output
 // (multibox_detection.cc:132-151).  The other CTAs of the image move rows [nkeep, V) (det_rank_role); the two roles
@@ -667,9 +763,9 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;
   __shared__ unsigned sm_prefix;
   __shared__ int sm_tbase[kSortSmemTiles];
-  const int b = blockIdx.y;
-  if (blockIdx.x != 0) {
-    det_rank_role(a, b, (int)blockIdx.x - 1, reinterpret_cast<int *>(hist256));
+  const int b = blockIdx.x;  // image in x: the sort-role CTAs (y == 0) of all images are scheduled first
+  if (blockIdx.y != 0) {
+    det_rank_role(a, b, (int)blockIdx.y - 1, reinterpret_cast<int *>(hist256));
     return;
   }
   const int A = a.A, T = a.T;
@@ -713,12 +809,17 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   const unsigned warp = warp_id(), lane = lane_id();
   const int niter = (V + (int)blockDim.x - 1) / (int)blockDim.x;
 
-  {  // keys of the survivors in rank order: one warp per tile, contiguous on both sides
+  {  // keys of the survivors in rank order: rank p lives in the last tile with tbase[t] <= p; every load is
+     // independent, so the whole staging costs one memory round trip whatever the number of tiles
     unsigned *dstk = kKeysInSmem ? skeys : gkeys;
-    for (int t = (int)warp; t < T; t += (int)(blockDim.x >> 5)) {
-      const int n = cnt[t], tb = tbase[t];
-      const unsigned *src = a.slot_keys + (size_t)b * a.Apad + (size_t)t * a.tile;
-      for (int k = (int)lane; k < n; k += 32) dstk[tb + k] = src[k];
+    const unsigned *srck = a.slot_keys + (size_t)b * a.Apad;
+    for (int p = threadIdx.x; p < V; p += blockDim.x) {
+      int lo = 0, hi = T - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (tbase[mid] <= p) lo = mid; else hi = mid - 1;
+      }
+      dstk[p] = srck[(size_t)lo * a.tile + (size_t)(p - tbase[lo])];
     }
   }
   int nkeep = V;
@@ -1372,8 +1473,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 0;
   }
-  const bool reg_variant = vec4 && variant > 1 && (C == 21 || C == 9);
-  const int tile = stages ? kPipeTile : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1));
+  const bool bulk_variant = vec4 && variant == 2 && (C == 21 || C == 9) && ((uintptr_t)cls_prob & 15) == 0;
+  const bool reg_variant = vec4 && variant > 2 && (C == 21 || C == 9);
+  const int tile = stages ? kPipeTile : (bulk_variant ? kBulkTile : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1)));
   const int T = ceil_div(A, tile);
   const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
 
@@ -1420,9 +1522,13 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   } else {
     dim3 grid1(T, B);
     ProfileScope _p(kSlotDetStream, stream);
-    if (vec4 && variant > 1 && C == 21)
+    if (bulk_variant && C == 21)
+      det_stream_bulk_kernel<20><<<grid1, kBulkThreads, 0, stream>>>(sa);
+    else if (bulk_variant && C == 9)
+      det_stream_bulk_kernel<8><<<grid1, kBulkThreads, 0, stream>>>(sa);
+    else if (reg_variant && C == 21)
       det_stream_reg_kernel<20, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);
-    else if (vec4 && variant > 1 && C == 9)
+    else if (reg_variant && C == 9)
       det_stream_reg_kernel<8, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);
     else if (vec4)
       det_stream_kernel<4><<<grid1, kStreamThreads, 0, stream>>>(sa);
@@ -1450,7 +1556,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.header = w.header;
   so.T = T;
   so.tile = tile;
-  so.rank_parts = ceil_div(T, 8) < 8 ? ceil_div(T, 8) : 8;
+  so.rank_parts = ceil_div(T, 6) < 16 ? ceil_div(T, 6) : 16;
   so.A = A;
   so.Apad = Apad;
   so.cls_stride = (Apad + 7) & ~7;
@@ -1476,9 +1582,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
     if (keys_in_smem)
-      det_sort_kernel<true><<<dim3(1 + so.rank_parts, B), kSortThreads, smem2, stream>>>(so);
+      det_sort_kernel<true><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
     else
-      det_sort_kernel<false><<<dim3(1 + so.rank_parts, B), kSortThreads, smem2, stream>>>(so);
+      det_sort_kernel<false><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
 

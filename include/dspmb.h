@@ -172,7 +172,8 @@ const char *dspmb_profile_kernel_name(int slot);
 /* Path-selection knobs.  The detection pipeline picks between equivalent code paths by problem size (class
  * bucketing in the sort kernel vs. in the NMS kernel, bit-mask vs. chunk-sweep NMS, shared vs. global staging);
  * the tests use these to force every path on small inputs.  Returns the previous value, or -1 for a bad knob. */
-#define DSPMB_TUNE_DET_STREAM_VARIANT 0 /* detection stream kernel: 0 generic, 1 TMA ring, >1 register-resident    */
+#define DSPMB_TUNE_DET_STREAM_VARIANT 0 /* detection stream kernel: 0 generic, 1 persistent TMA ring, 2 (default) one
+                                           TMA-fed tile per CTA, >2 register-resident (4: + 4-anchor target variant) */
 #define DSPMB_TUNE_NMS_MASK_ROWS 1      /* largest segment for the shared-memory bit-mask NMS (default/max 320) */
 #define DSPMB_TUNE_NMS_SMEM_ROWS 2      /* largest segment staged in shared memory by the sweep NMS (max 1024) */
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
