@@ -525,30 +525,29 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
 // are in flight, then consumes the tile from shared memory.  ~40 registers and ~32 KB of shared memory per CTA
 // give 7 CTAs/SM whose load and compute phases interleave freely (the hardware CTA scheduler replaces a software
 // pipeline).  The row staging aliases the class rows, which are dead once the arg-max is done.
-constexpr int kBulkThreads = 128;
-constexpr int kBulkTile = 256;  // anchors per CTA, 2 per thread
-
-template <int NFG>
+template <int NFG, int kTile>
 struct BulkSmem {
   union {
-    float cls[NFG][kBulkTile];       // class rows of the tile (bulk copies)
-    RowStage<kBulkTile> rows;        // finished rows of the survivors (after the arg-max)
+    float cls[NFG][kTile];       // class rows of the tile (bulk copies)
+    RowStage<kTile> rows;        // finished rows of the survivors (after the arg-max)
   } u;
-  float loc[kBulkTile * 5];
-  float4 anc[kBulkTile];
-  float score[kBulkTile];            // survivors in rank order
-  unsigned short idx[kBulkTile], id[kBulkTile];
+  float loc[kTile * 5];
+  float4 anc[kTile];
+  float score[kTile];            // survivors in rank order
+  unsigned short idx[kTile], id[kTile];
 };
 
-template <int NFG>
-__global__ void __launch_bounds__(kBulkThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
-  __shared__ __align__(128) BulkSmem<NFG> sm;
+template <int NFG, int kThreads, int kVec>
+__global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
+  constexpr int kTile = kThreads * kVec;
+  extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
+  BulkSmem<NFG, kTile> &sm = *reinterpret_cast<BulkSmem<NFG, kTile> *>(bulk_smem_raw);
   __shared__ __align__(8) unsigned long long full_bar;
-  __shared__ int scan_smem[kBulkThreads / 32 + 1];
+  __shared__ int scan_smem[kThreads / 32 + 1];
   const int b = blockIdx.y, t = blockIdx.x;
   const int A = a.A;
-  const int tile_begin = t * kBulkTile;
-  const int rows = min(kBulkTile, A - tile_begin);  // multiple of 4 (A % 4 == 0)
+  const int tile_begin = t * kTile;
+  const int rows = min(kTile, A - tile_begin);  // multiple of 4 (A % 4 == 0)
 
   if (threadIdx.x == 0) {
     mbar_init(&full_bar, 1);
@@ -564,31 +563,41 @@ __global__ void __launch_bounds__(kBulkThreads) det_stream_bulk_kernel(const __g
     float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
     const int nfl = rows * 7;
     const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
-    for (int x = threadIdx.x * 4; x < nfl; x += kBulkThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
+    for (int x = threadIdx.x * 4; x < nfl; x += kThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
   }
   __syncthreads();  // the barrier initialisation is visible to every waiter
   mbar_wait(&full_bar, 0u);
 
-  const int l0 = threadIdx.x * 2;
-  float score[2] = {-1.f, -1.f};
-  int id[2] = {0, 0};
+  const int l0 = threadIdx.x * kVec;
+  float score[kVec];
+  int id[kVec];
+#pragma unroll
+  for (int k = 0; k < kVec; ++k) {
+    score[k] = -1.f;
+    id[k] = 0;
+  }
   if (l0 < rows) {
 #pragma unroll
     for (int j = 0; j < NFG; ++j) {
-      const float2 v = *reinterpret_cast<const float2 *>(&sm.u.cls[j][l0]);
-      if (v.x > score[0]) {
-        score[0] = v.x;
-        id[0] = j + 1;
+      float v[kVec];
+      if constexpr (kVec == 4) {
+        const float4 q = *reinterpret_cast<const float4 *>(&sm.u.cls[j][l0]);
+        v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+      } else {
+        const float2 q = *reinterpret_cast<const float2 *>(&sm.u.cls[j][l0]);
+        v[0] = q.x, v[1] = q.y;
       }
-      if (v.y > score[1]) {
-        score[1] = v.y;
-        id[1] = j + 1;
-      }
+#pragma unroll
+      for (int k = 0; k < kVec; ++k)
+        if (v[k] > score[k]) {
+          score[k] = v[k];
+          id[k] = j + 1;
+        }
     }
   }
   int nvalid = 0;
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < kVec; ++k) {
     if (id[k] > 0 && score[k] < a.threshold) id[k] = 0;
     nvalid += id[k] > 0;
   }
@@ -596,7 +605,7 @@ __global__ void __launch_bounds__(kBulkThreads) det_stream_bulk_kernel(const __g
   int pos = block_scan_excl(nvalid, scan_smem, &total);
   if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < kVec; ++k)
     if (id[k] > 0) {
       sm.score[pos] = score[k];
       sm.idx[pos] = (unsigned short)(l0 + k);
@@ -604,7 +613,7 @@ __global__ void __launch_bounds__(kBulkThreads) det_stream_bulk_kernel(const __g
       ++pos;
     }
   __syncthreads();  // survivor list complete; the class rows are dead from here on
-  for (int j = threadIdx.x; j < total; j += kBulkThreads) {
+  for (int j = threadIdx.x; j < total; j += kThreads) {
     const int l = sm.idx[j];
     const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
     stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
@@ -632,6 +641,73 @@ __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
       __syncthreads();
     }
   }
+}
+
+// Bitonic sort of 128 * KPT 64-bit keys (ascending; entries >= nkeep are padding) held in the registers of the
+// first four warps.  Element index = lane | reg << 5 | warp << (5 + log2 KPT): exchanges at distance < 32 are warp
+// shuffles, distances 32 .. 16 KPT are register-to-register inside a thread, and only the two highest index bits
+// (three steps of the whole sort) go through shared memory behind a 128-thread named barrier.  Every step runs KPT
+// independent compare-exchanges per thread, so the shuffle latency is pipelined instead of exposed.
+constexpr int kRegSortThreads = 128;
+template <int KPT>
+__device__ __forceinline__ void bitonic_sort_regs(unsigned long long *ssel, int nkeep) {
+  constexpr int LR = KPT == 1 ? 0 : (KPT == 2 ? 1 : (KPT == 4 ? 2 : 3));
+  constexpr int S = kRegSortThreads * KPT;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int idx0 = lane | (w << (5 + LR));
+  unsigned long long k[KPT];
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) {
+    const int idx = idx0 | (q << 5);
+    k[q] = idx < nkeep ? ssel[idx] : ~0ull;
+  }
+#pragma unroll 1
+  for (int K = 2; K <= S; K <<= 1) {
+#pragma unroll 1
+    for (int j = K >> 1; j > 0; j >>= 1) {
+      if (j < 32) {
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+          const int idx = idx0 | (q << 5);
+          const unsigned long long other = __shfl_xor_sync(kFullMask, k[q], j);
+          const bool take_min = ((idx & j) == 0) == ((idx & K) == 0);
+          k[q] = (take_min == (other < k[q])) ? other : k[q];
+        }
+      } else if (j < 32 * KPT) {
+#pragma unroll
+        for (int r = 0; r < LR; ++r) {
+          if (j == (32 << r)) {
+#pragma unroll
+            for (int q = 0; q < KPT; ++q) {
+              if (q & (1 << r)) continue;
+              const int idx = idx0 | (q << 5);
+              const bool up = (idx & K) == 0;
+              const unsigned long long x = k[q], y = k[q | (1 << r)];
+              const bool swap = (x > y) == up;
+              k[q] = swap ? y : x;
+              k[q | (1 << r)] = swap ? x : y;
+            }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) ssel[idx0 | (q << 5)] = k[q];
+        asm volatile("bar.sync 1, %0;" ::"n"(kRegSortThreads) : "memory");
+        unsigned long long other[KPT];
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) other[q] = ssel[(idx0 | (q << 5)) ^ j];
+        asm volatile("bar.sync 1, %0;" ::"n"(kRegSortThreads) : "memory");
+#pragma unroll
+        for (int q = 0; q < KPT; ++q) {
+          const int idx = idx0 | (q << 5);
+          const bool take_min = ((idx & j) == 0) == ((idx & K) == 0);
+          k[q] = (take_min == (other[q] < k[q])) ? other[q] : k[q];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < KPT; ++q) ssel[idx0 | (q << 5)] = k[q];
 }
 
 // Warp-aggregated shared-memory histogram increment: lanes with the same bin elect one leader.
@@ -671,7 +747,7 @@ struct SortArgs {
   int *valid_count_out;
   WsHeader *header;
   int A, T, tile, Apad, cls_stride, npad_max, niter_max;
-  int sel_cap, rank_parts;
+  int sel_cap, rank_parts, debug;
   float nms_threshold;
   int force_suppress, nms_topk;
 };
@@ -765,6 +841,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ int sm_tbase[kSortSmemTiles];
   const int b = blockIdx.x;  // image in x: the sort-role CTAs (y == 0) of all images are scheduled first
   if (blockIdx.y != 0) {
+    if (a.debug & 8) return;  // timing experiments only
     det_rank_role(a, b, (int)blockIdx.y - 1, reinterpret_cast<int *>(hist256));
     return;
   }
@@ -809,17 +886,35 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   const unsigned warp = warp_id(), lane = lane_id();
   const int niter = (V + (int)blockDim.x - 1) / (int)blockDim.x;
 
-  {  // keys of the survivors in rank order: rank p lives in the last tile with tbase[t] <= p; every load is
-     // independent, so the whole staging costs one memory round trip whatever the number of tiles
+  {  // keys of the survivors in rank order: one warp per tile, four tiles and two 32-key chunks per tile in flight
+     // (the staging is one memory round trip for the usual tile occupancy); n = tbase[t + 1] - tbase[t]
     unsigned *dstk = kKeysInSmem ? skeys : gkeys;
     const unsigned *srck = a.slot_keys + (size_t)b * a.Apad;
-    for (int p = threadIdx.x; p < V; p += blockDim.x) {
-      int lo = 0, hi = T - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (tbase[mid] <= p) lo = mid; else hi = mid - 1;
+    const int nwarps = (int)(blockDim.x >> 5);
+    for (int tb4 = (int)warp; tb4 < T; tb4 += nwarps * 4) {
+      int n[4], tb[4];
+      unsigned v[4][2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int t = tb4 + i * nwarps;
+        tb[i] = t < T ? tbase[t] : 0;
+        n[i] = t < T ? (t + 1 < T ? tbase[t + 1] : V) - tb[i] : 0;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int k = (int)lane + 32 * c;
+          v[i][c] = k < n[i] ? srck[(size_t)t * a.tile + k] : 0u;
+        }
       }
-      dstk[p] = srck[(size_t)lo * a.tile + (size_t)(p - tbase[lo])];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int k = (int)lane + 32 * c;
+          if (k < n[i]) dstk[tb[i] + k] = v[i][c];
+        }
+        const int t = tb4 + i * nwarps;
+        for (int k = (int)lane + 64; k < n[i]; k += 32) dstk[tb[i] + k] = srck[(size_t)t * a.tile + k];
+      }
     }
   }
   int nkeep = V;
@@ -875,7 +970,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
       }
       __syncthreads();
     }
-    const unsigned pivot = sm_prefix;
+      const unsigned pivot = sm_prefix;
     const int need_eq = sm_need;
     const bool ordered_ties = need_eq < sm_eq_total;  // only the lowest-ranked of the pivot-valued keys make it
     if (ordered_ties) {
@@ -911,28 +1006,16 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     }
     __syncthreads();
   }
-  if (npad <= kRankSortMax && npad <= a.sel_cap) {
-    // register bitonic sort, one key per thread: exchanges at distance < 32 are warp shuffles, only the longer
-    // ones go through shared memory (sel == ssel here)
-    const int tid = threadIdx.x;
-    const bool in = tid < npad;
-    unsigned long long k = tid < nkeep ? ssel[tid] : ~0ull;
-    for (int K = 2; K <= npad; K <<= 1) {
-      for (int j = K >> 1; j > 0; j >>= 1) {
-        unsigned long long other;
-        if (j >= 32) {
-          if (in) ssel[tid] = k;
-          __syncthreads();
-          other = in ? ssel[tid ^ j] : k;
-          __syncthreads();
-        } else {
-          other = __shfl_xor_sync(kFullMask, k, j);
-        }
-        const bool take_min = ((tid & j) == 0) == ((tid & K) == 0);
-        k = (take_min == (other < k)) ? other : k;
+  const int ssort = npad < kRegSortThreads ? kRegSortThreads : npad;
+  if (ssort <= 4 * kRegSortThreads && ssort <= a.sel_cap) {
+    // bitonic sort in the registers of four warps, ssort / 128 keys per thread (sel == ssel here)
+    if (threadIdx.x < kRegSortThreads) {
+      switch (ssort / kRegSortThreads) {
+        case 1: bitonic_sort_regs<1>(ssel, nkeep); break;
+        case 2: bitonic_sort_regs<2>(ssel, nkeep); break;
+        default: bitonic_sort_regs<4>(ssel, nkeep); break;
       }
     }
-    if (in) ssel[tid] = k;
     __syncthreads();
   } else {
     for (int p = nkeep + threadIdx.x; p < npad; p += blockDim.x) sel[p] = ~0ull;
@@ -1473,9 +1556,11 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 0;
   }
-  const bool bulk_variant = vec4 && variant == 2 && (C == 21 || C == 9) && ((uintptr_t)cls_prob & 15) == 0;
-  const bool reg_variant = vec4 && variant > 2 && (C == 21 || C == 9);
-  const int tile = stages ? kPipeTile : (bulk_variant ? kBulkTile : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1)));
+  const bool bulk_ok = vec4 && (C == 21 || C == 9) && ((uintptr_t)cls_prob & 15) == 0;
+  const int bulk_threads = variant == 3 ? 256 : 128, bulk_vec = variant == 5 ? 4 : 2;
+  const bool bulk_variant = bulk_ok && (variant == 2 || variant == 3 || variant == 5);
+  const bool reg_variant = vec4 && !bulk_variant && variant > 2 && (C == 21 || C == 9);
+  const int tile = stages ? kPipeTile : (bulk_variant ? bulk_threads * bulk_vec : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1)));
   const int T = ceil_div(A, tile);
   const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
 
@@ -1522,10 +1607,26 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   } else {
     dim3 grid1(T, B);
     ProfileScope _p(kSlotDetStream, stream);
-    if (bulk_variant && C == 21)
-      det_stream_bulk_kernel<20><<<grid1, kBulkThreads, 0, stream>>>(sa);
-    else if (bulk_variant && C == 9)
-      det_stream_bulk_kernel<8><<<grid1, kBulkThreads, 0, stream>>>(sa);
+    if (bulk_variant) {
+#define DSPMB_LAUNCH_BULK(NFG, TH, VEC)                                                                           \
+  do {                                                                                                            \
+    constexpr size_t kBytes = sizeof(BulkSmem<NFG, TH * VEC>);                                                    \
+    static bool attr_done = false;                                                                                \
+    if (!attr_done) {                                                                                             \
+      DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_stream_bulk_kernel<NFG, TH, VEC>,                                   \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));             \
+      attr_done = true;                                                                                           \
+    }                                                                                                             \
+    det_stream_bulk_kernel<NFG, TH, VEC><<<grid1, TH, kBytes, stream>>>(sa);                                      \
+  } while (0)
+      if (C == 21 && variant == 2) DSPMB_LAUNCH_BULK(20, 128, 2);
+      else if (C == 21 && variant == 3) DSPMB_LAUNCH_BULK(20, 256, 2);
+      else if (C == 21) DSPMB_LAUNCH_BULK(20, 128, 4);
+      else if (variant == 2) DSPMB_LAUNCH_BULK(8, 128, 2);
+      else if (variant == 3) DSPMB_LAUNCH_BULK(8, 256, 2);
+      else DSPMB_LAUNCH_BULK(8, 128, 4);
+#undef DSPMB_LAUNCH_BULK
+    }
     else if (reg_variant && C == 21)
       det_stream_reg_kernel<20, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);
     else if (reg_variant && C == 9)
@@ -1557,6 +1658,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.T = T;
   so.tile = tile;
   so.rank_parts = ceil_div(T, 6) < 16 ? ceil_div(T, 6) : 16;
+  so.debug = nms_debug;
   so.A = A;
   so.Apad = Apad;
   so.cls_stride = (Apad + 7) & ~7;
@@ -1568,8 +1670,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const bool keys_in_smem = A <= kKeySmemMax;
   // sort keys in shared memory: enough for the top-k head, or for everything when no top-k limit applies
   const int smem_keys = tuning(DSPMB_TUNE_SORT_SMEM_KEYS) < 2 ? 2 : tuning(DSPMB_TUNE_SORT_SMEM_KEYS);
-  const int want = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
-  so.sel_cap = want < smem_keys ? (want < 2 ? 2 : want) : smem_keys;
+  const int want0 = (nms_topk > 0 && nms_topk < A) ? next_pow2(nms_topk) : so.npad_max;
+  const int want = want0 < kRegSortThreads ? kRegSortThreads : want0;  // the register sort pads to 128 keys
+  so.sel_cap = want < smem_keys ? want : smem_keys;
   const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (keys_in_smem ? sizeof(unsigned) * (size_t)((A + 3) & ~3) : 0) +
                        sizeof(int) * 32 * (size_t)so.niter_max;
   DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);

@@ -317,7 +317,7 @@ def test_detection_forced_code_paths(oracle, cuda, knobs):
             L.dspmb_set_tuning(k, v)
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 256])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 5, 256])
 def test_detection_stream_kernel_variants(oracle, cuda, variant):
     """Generic, TMA-ring and register-resident stream kernels produce identical results."""
     from dspnet_b200 import _lib
