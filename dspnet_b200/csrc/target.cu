@@ -143,6 +143,34 @@ __device__ __noinline__ float exact_bg_prob(const float *p_cls, int j, int A, in
   return fdiv(libm::expf_glibc_t<kFma>(fsub(__ldg(p_cls + j), mx), libm::GlobalExpTab()), sum);
 }
 
+// The same value computed by a whole warp for ONE anchor (every lane passes the same j and receives the result): the
+// C logits are loaded and exponentiated in parallel, only the fp32 sum keeps the reference's class order (one
+// shuffle + add per class).  Used when only a handful of anchors need the exact value, where the serial routine's
+// 2 C dependent loads and expf calls would sit on the critical path of the match kernel.
+template <bool kFma>
+__device__ __forceinline__ float exact_bg_prob_warp(const float *p_cls, int j, int A, int C) {
+  const int lane = (int)lane_id();
+  float mx = __int_as_float(0xff800000);
+  for (int k = lane; k < C; k += 32) {
+    const float t = __ldg(p_cls + j + (size_t)A * k);
+    if (t > mx) mx = t;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const float o = __shfl_xor_sync(kFullMask, mx, m);
+    if (o > mx) mx = o;
+  }
+  float sum = 0.f, e0 = 0.f;
+  for (int k0 = 0; k0 < C; k0 += 32) {
+    const int k = k0 + lane;
+    const float e = k < C ? libm::expf_glibc_t<kFma>(fsub(__ldg(p_cls + j + (size_t)A * k), mx), libm::GlobalExpTab()) : 0.f;
+    if (k0 == 0) e0 = __shfl_sync(kFullMask, e, 0);
+    const int n = min(32, C - k0);
+    for (int i = 0; i < n; ++i) sum = fadd(sum, __shfl_sync(kFullMask, e, i));
+  }
+  return fdiv(e0, sum);
+}
+
 struct SmemExpTab {
   const unsigned long long *t;
   __device__ __forceinline__ uint64_t operator()(unsigned i) const { return t[i]; }
@@ -548,7 +576,10 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     unsigned long long tkey = 0ull;
     for (int j = threadIdx.x; j < A; j += blockDim.x) {
       if ((bits[j >> 5] >> (j & 31)) & 1u) continue;
-      const float iou = iou_target(__ldg(anchors + j), g);
+      const float4 an = __ldg(anchors + j);
+      // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
+      if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
+      const float iou = iou_target(an, g);
       if (iou > 1e-6f) {
         const unsigned long long ck = col_key(iou, j);
         tkey = ck > tkey ? ck : tkey;
@@ -561,14 +592,21 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   const int nmatch = sm_nmatch;
 
   // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
-  for (int q = threadIdx.x; q < nmatch; q += blockDim.x) {
+  // one warp per matched anchor: the G IoUs of its row are spread over the lanes
+  for (int q = (int)warp_id(); q < nmatch; q += (int)(blockDim.x >> 5)) {
     const int j = m_anchor[q], k = m_gt[q];
     const float4 an = __ldg(anchors + j);
     float max_iou = -1.0f;
-    for (int kk = 0; kk < G; ++kk) {
+    for (int kk = (int)lane_id(); kk < G; kk += 32) {
       const float iou = iou_target(an, sm_gt[kk]);
       if (iou > max_iou) max_iou = iou;
     }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      const float o = __shfl_xor_sync(kFullMask, max_iou, m);
+      if (o > max_iou) max_iou = o;
+    }
+    if (lane_id() != 0) continue;
     if (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) atomicAdd(&sm_dup, 1);  // counted by the stream kernel
     const size_t row = (size_t)b * A + j;
     const float *lrow = lab + (size_t)k * W;
@@ -627,16 +665,38 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
     const unsigned prefix = sm_prefix;
-    for (int base = 0; base < A; base += blockDim.x) {
-      const int j = base + threadIdx.x;
-      const unsigned kv = j < A ? key_at(j) : kKeySentinel;
-      const bool hit = j < A && (kv & mask) == prefix;
-      // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
-      const unsigned digit = (kv >> shift) & 0xffu;
+    // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise); a warp whose hits
+    // all share one digit -- the usual case in the first pass -- takes one ballot, one shuffle and one atomic
+    auto hist_add = [&](unsigned kv, bool in_range) {
+      const bool hit = in_range && (kv & mask) == prefix;
       const unsigned active = __ballot_sync(kFullMask, hit);
-      if (hit) {
+      if (active == 0u) return;
+      const unsigned digit = (kv >> shift) & 0xffu;
+      const int leader = __ffs(active) - 1;
+      const unsigned d0 = __shfl_sync(kFullMask, digit, leader);
+      if (__ballot_sync(kFullMask, hit && digit == d0) == active) {
+        if ((int)lane_id() == leader) atomicAdd(&hist[d0], (unsigned)__popc(active));
+      } else if (hit) {
         const unsigned peers = __match_any_sync(active, digit);
         if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
+      }
+    };
+    if (kKeysInSmem && (A & 3) == 0) {  // four keys per thread and iteration: one LDS.128, four independent updates
+      const uint4 *s4 = reinterpret_cast<const uint4 *>(skeys);
+      const int n4 = A >> 2;
+      for (int base = 0; base < n4; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        const bool in = j < n4;
+        const uint4 kv = in ? s4[j] : make_uint4(0u, 0u, 0u, 0u);
+        hist_add(kv.x, in);
+        hist_add(kv.y, in);
+        hist_add(kv.z, in);
+        hist_add(kv.w, in);
+      }
+    } else {
+      for (int base = 0; base < A; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        hist_add(j < A ? key_at(j) : kKeySentinel, j < A);
       }
     }
     __syncthreads();
@@ -715,10 +775,18 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     return;
   }
   const float *p_cls = a.cls_preds + (size_t)b * a.C * A;
-  for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
-    const int j = amb_list[q];
-    const float pe = a.fma_build ? exact_bg_prob<true>(p_cls, j, A, a.C) : exact_bg_prob<false>(p_cls, j, A, a.C);
-    amb_key[q] = __float_as_uint(pe);
+  if (n_amb <= 4 * (int)(blockDim.x >> 5)) {  // a handful: one warp each (latency); many: one thread each (throughput)
+    for (int q = (int)warp_id(); q < n_amb; q += (int)(blockDim.x >> 5)) {
+      const int j = amb_list[q];
+      const float pe = a.fma_build ? exact_bg_prob_warp<true>(p_cls, j, A, a.C) : exact_bg_prob_warp<false>(p_cls, j, A, a.C);
+      if (lane_id() == 0) amb_key[q] = __float_as_uint(pe);
+    }
+  } else {
+    for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+      const int j = amb_list[q];
+      const float pe = a.fma_build ? exact_bg_prob<true>(p_cls, j, A, a.C) : exact_bg_prob<false>(p_cls, j, A, a.C);
+      amb_key[q] = __float_as_uint(pe);
+    }
   }
   __syncthreads();
   for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
