@@ -519,6 +519,37 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   __syncthreads();
 
   // ---- bipartite stage (multibox_target.cc:113-149) ----
+  // Fast path: if the cached best anchors of the gts are pairwise distinct, the greedy loop never meets a stale
+  // maximum -- it visits the gts in descending key order and takes each one's cached anchor -- so all gts with a
+  // candidate (key != 0) are assigned at once.  Otherwise the sequential lazy-greedy loop below runs.
+  {
+    int clash = 0;
+    for (int k = threadIdx.x; k < G; k += blockDim.x) {
+      const unsigned long long ck = sm_col[k];
+      if (ck == 0ull) continue;
+      const unsigned mine = (unsigned)(ck & 0xffffffffull);
+      for (int kk = 0; kk < G; ++kk)
+        if (kk != k && sm_col[kk] != 0ull && (unsigned)(sm_col[kk] & 0xffffffffull) == mine) clash = 1;
+    }
+    if (clash) sm_dup = 1;
+    __syncthreads();
+    const bool distinct = sm_dup == 0;
+    __syncthreads();
+    if (distinct) {
+      for (int k = threadIdx.x; k < G; k += blockDim.x) {
+        const unsigned long long ck = sm_col[k];
+        if (ck == 0ull) continue;
+        const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
+        const int n = atomicAdd(&sm_nmatch, 1);
+        m_anchor[n] = j;
+        m_gt[n] = k;
+        atomicOr(&bits[j >> 5], 1u << (j & 31));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) sm_dup = 0;
+    __syncthreads();
+    if (!distinct)
   while (true) {
     if (warp_id() == 0) {
       const unsigned lane = lane_id();
@@ -589,24 +620,27 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (threadIdx.x == 0) sm_col[k] = bm;
     __syncthreads();
   }
+  }
   const int nmatch = sm_nmatch;
 
   // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
-  // one warp per matched anchor: the G IoUs of its row are spread over the lanes
-  for (int q = (int)warp_id(); q < nmatch; q += (int)(blockDim.x >> 5)) {
+  // sixteen lanes per matched anchor: the G IoUs of its row are spread over them
+  for (int q = (int)(threadIdx.x >> 4); q < nmatch; q += (int)(blockDim.x >> 4)) {
+    const int sub = threadIdx.x & 15;
     const int j = m_anchor[q], k = m_gt[q];
     const float4 an = __ldg(anchors + j);
     float max_iou = -1.0f;
-    for (int kk = (int)lane_id(); kk < G; kk += 32) {
+    for (int kk = sub; kk < G; kk += 16) {
       const float iou = iou_target(an, sm_gt[kk]);
       if (iou > max_iou) max_iou = iou;
     }
+    const unsigned gmask = 0xffffu << (lane_id() & 16);  // the half-warp of this anchor (may be alone in the loop)
 #pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      const float o = __shfl_xor_sync(kFullMask, max_iou, m);
+    for (int m = 8; m > 0; m >>= 1) {
+      const float o = __shfl_xor_sync(gmask, max_iou, m);
       if (o > max_iou) max_iou = o;
     }
-    if (lane_id() != 0) continue;
+    if (sub != 0) continue;
     if (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) atomicAdd(&sm_dup, 1);  // counted by the stream kernel
     const size_t row = (size_t)b * A + j;
     const float *lrow = lab + (size_t)k * W;
@@ -665,21 +699,19 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
     __syncthreads();
     const unsigned prefix = sm_prefix;
-    // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise); a warp whose hits
-    // all share one digit -- the usual case in the first pass -- takes one ballot, one shuffle and one atomic
+    // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
     auto hist_add = [&](unsigned kv, bool in_range) {
       const bool hit = in_range && (kv & mask) == prefix;
       const unsigned active = __ballot_sync(kFullMask, hit);
       if (active == 0u) return;
+      // the digit of the first hit lane is counted for the whole warp with one ballot (probabilities cluster: in the
+      // first pass that is nearly every lane); the other lanes add themselves, and their digits rarely coincide
       const unsigned digit = (kv >> shift) & 0xffu;
       const int leader = __ffs(active) - 1;
       const unsigned d0 = __shfl_sync(kFullMask, digit, leader);
-      if (__ballot_sync(kFullMask, hit && digit == d0) == active) {
-        if ((int)lane_id() == leader) atomicAdd(&hist[d0], (unsigned)__popc(active));
-      } else if (hit) {
-        const unsigned peers = __match_any_sync(active, digit);
-        if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[digit], (unsigned)__popc(peers));
-      }
+      const unsigned same = __ballot_sync(kFullMask, hit && digit == d0);
+      if ((int)lane_id() == leader) atomicAdd(&hist[d0], (unsigned)__popc(same));
+      else if (hit && digit != d0) atomicAdd(&hist[digit], 1u);
     };
     if (kKeysInSmem && (A & 3) == 0) {  // four keys per thread and iteration: one LDS.128, four independent updates
       const uint4 *s4 = reinterpret_cast<const uint4 *>(skeys);
