@@ -269,9 +269,41 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     area[v] = fmul(fsub(an[v].z, an[v].x), fsub(an[v].w, an[v].y));
   }
 
+  // Bounding box of the warp's anchors (consecutive anchors are neighbouring cells of one feature map): a gt that
+  // does not reach into it has IoU 0 with every anchor of the warp, which only matters for gt 0 (the row's first
+  // maximum starts at iou 0, gt 0) -- three quarters of the (warp, gt) pairs leave the loop after four compares.
+  float4 bb = make_float4(__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0xff800000),
+                          __int_as_float(0xff800000));
+  if (active) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      bb.x = fminf(bb.x, an[v].x);
+      bb.y = fminf(bb.y, an[v].y);
+      bb.z = fmaxf(bb.z, an[v].z);
+      bb.w = fmaxf(bb.w, an[v].w);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    bb.x = fminf(bb.x, __shfl_xor_sync(kFullMask, bb.x, m));
+    bb.y = fminf(bb.y, __shfl_xor_sync(kFullMask, bb.y, m));
+    bb.z = fmaxf(bb.z, __shfl_xor_sync(kFullMask, bb.z, m));
+    bb.w = fmaxf(bb.w, __shfl_xor_sync(kFullMask, bb.w, m));
+  }
+
   // ---- fused IoU + row first-max + column max (multibox_target-inl.h:137-161, .cc:113-134,158-166) ----
   for (int k = 0; k < G; ++k) {
     const float4 g = sm_gt[k];
+    if (!(bb.z > g.x && g.z > bb.x && bb.w > g.y && g.w > bb.y)) {  // warp-uniform
+      if (k == 0) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          best_iou[v] = 0.0f;
+          best_k[v] = 0;
+        }
+      }
+      continue;
+    }
     const float ga = sm_garea[k];
     unsigned long long tkey = 0ull;
     if (active) {
@@ -330,7 +362,7 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
         for (int c = 1; c < NC; ++c)
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
-            if (xr[c][v] > mx[v]) mx[v] = xr[c][v];
+            mx[v] = fmaxf(mx[v], xr[c][v]);
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
