@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs ON THE GPU BOX under `gpurun --gpus 8`: the driver's scaling sequence N = 1, 2, 4, 8.
 mkdir -p gpurun_out
-for n in 1 2 4 8; do
+for n in ${SCALE_NS:-1 2 4 8}; do
   if [ "$n" = "1" ]; then
     timeout 200 python bench.py --gpus 1 --steps 200 --warmup 20 2>/dev/null | tail -1 > gpurun_out/scale_$n.json
   else
