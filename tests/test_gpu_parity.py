@@ -451,3 +451,35 @@ def test_graph_cache_inside_user_capture(oracle, cuda):
     g.replay()
     torch.cuda.synchronize()
     util.assert_bit_equal(out.cpu().numpy(), want, "replay of a user capture")
+
+
+def test_autograd_backward_is_zero_like_the_reference(oracle, cuda):
+    """The operators' Backward methods only write zeros (multibox_prior-inl.h:131-143, multibox_target-inl.h:173-185,
+    multibox_detection-inl.h:109-125); the autograd wrappers reproduce forward values and those gradients."""
+    from dspnet_b200 import autograd as ag
+    anchors, lab, cp = util.target_inputs(oracle, "ssd300", 2, config_id=51)
+    a, l = _t(anchors, cuda), _t(lab, cuda)
+    c = _t(cp, cuda).requires_grad_(True)
+    lt, lm, ct = ag.multibox_target(a, l, c, negative_mining_ratio=3.0)
+    want = oracle.multibox_target(anchors, lab, cp, negative_mining_ratio=3.0)
+    util.assert_bit_equal(ct.detach().cpu().numpy(), want[2], "cls_target through autograd")
+    (lt.sum() + ct.sum() + lm.sum()).backward()
+    assert c.grad is not None and c.grad.shape == c.shape and not c.grad.any()
+
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 2, config_id=52)
+    p = _t(prob, cuda).requires_grad_(True)
+    q = _t(lp, cuda).requires_grad_(True)
+    an = _t(anchors, cuda).requires_grad_(True)
+    out = ag.multibox_detection(p, q, an, nms_threshold=0.45, nms_topk=400)
+    util.assert_bit_equal(out.detach().cpu().numpy(),
+                          oracle.multibox_detection(prob, lp, anchors, nms_threshold=0.45, nms_topk=400), "detection")
+    out.sum().backward()
+    for g, t in ((p.grad, p), (q.grad, q), (an.grad, an)):
+        assert g is not None and g.shape == t.shape and not g.any()
+
+    data = torch.zeros(1, 4, 6, 5, device=cuda, requires_grad=True)
+    pr = ag.multibox_prior(data, sizes=(0.3, 0.5), ratios=(1.0, 2.0))
+    util.assert_bit_equal(pr.detach().cpu().numpy(), oracle.multibox_prior(6, 5, (0.3, 0.5), (1.0, 2.0), False, (-1.0, -1.0)),
+                          "prior through autograd")
+    pr.sum().backward()
+    assert data.grad is not None and not data.grad.any()
