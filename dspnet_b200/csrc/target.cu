@@ -610,7 +610,9 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
           state = kStateDone;  // no remaining pair above 1e-6 (:136-138) or every gt matched
         } else {
           const int j = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
-          if ((bits[j >> 5] >> (j & 31)) & 1u) {
+          const bool taken = (bits[j >> 5] >> (j & 31)) & 1u;
+          __syncwarp();  // (bk is warp-uniform) every lane has read `bits` and `done` before lane 0 updates them
+          if (taken) {
             state = kStateRecompute;  // cached maximum points at an anchor that has been taken since
           } else if (lane == 0) {
             const int n = sm_nmatch;
@@ -776,6 +778,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       const int incl = warp_scan_incl(tot);
       const int excl = incl - tot;
       const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
+      __syncwarp();  // every lane has read sm_need before one lane overwrites it
       if (excl < need && incl >= need) {
         int acc = excl;
 #pragma unroll
