@@ -1113,7 +1113,7 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
 constexpr int kNmsQueue = 256;  // per-warp candidate queue entries of the small-segment path
 constexpr int kNmsTab = 512;  // ballot-count table entries: 64 iterations x 8 warps = 131072 rows per sweep
 
-__global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_constant__ NmsArgs a) {
+__global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_constant__ NmsArgs a) {
   // shared memory is a union of the two paths:
   //   small (n <= mask_rows <= 320): boxes[320] float4 + mask[320 * 5] u64 + list[320] int + areas[320]  (20 KB)
   //   large:                         boxes[1024] float4 + dead[1024] + 64 words + areas[1024]             (21.5 KB)
@@ -1170,6 +1170,58 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
 #pragma unroll
     for (int it = 0; it < 4; ++it)
       if (it < niter) hcache |= hits_raw(it) << (8 * it);
+    if (niter <= kNmsTab / 8) {
+      // usual case (V <= 131072 rows): one sweep -- the scan of the per-(iteration, warp) counts yields both the
+      // segment size and every warp's write offset
+      const int entries = niter * (int)nwarps;
+      for (int it = 0; it < niter; ++it) {
+        const int c = warp_sum_i32(__popc(hits_of(it)));
+        if (lane == 0) wtab[it * nwarps + warp] = c;
+      }
+      __syncthreads();
+      if (entries <= 32) {
+        if (warp == 0) {
+          const int v = (int)lane < entries ? wtab[lane] : 0;
+          const int incl = warp_scan_incl(v);
+          if ((int)lane < entries) wtab[lane] = incl - v;
+          if (lane == 31) carry_smem = incl;
+        }
+        __syncthreads();
+      } else {
+        if (threadIdx.x == 0) carry_smem = 0;
+        __syncthreads();
+        for (int base = 0; base < entries; base += blockDim.x) {
+          const int i = base + threadIdx.x;
+          const int v = i < entries ? wtab[i] : 0;
+          int total;
+          const int ex = block_scan_excl(v, scan_smem, &total);
+          const int carry = carry_smem;
+          if (i < entries) wtab[i] = carry + ex;
+          __syncthreads();
+          if (threadIdx.x == 0) carry_smem = carry + total;
+          __syncthreads();
+        }
+      }
+      n = carry_smem;
+      if (n < 2) return;
+      if (n > a.mask_rows) {  // large segment: claim a region of the per-image list buffer
+        if (threadIdx.x == 0) sm_base = atomicAdd(&a.cursor[b], n);
+        __syncthreads();
+        glist = a.seg_list + (size_t)b * a.A + sm_base;
+      }
+      for (int it = 0; it < niter; ++it) {
+        const unsigned h = hits_of(it);
+        const int c = __popc(h);
+        int pos = wtab[it * nwarps + warp] + warp_scan_incl(c) - c;
+        const int r0 = (it * blockDim.x + threadIdx.x) * 8;
+        for (unsigned m = h; m; m &= m - 1) {
+          const int r = r0 + __ffs(m) - 1;
+          if (glist) glist[pos] = r; else slist[pos] = r;
+          ++pos;
+        }
+      }
+      __syncthreads();
+    } else {
     // sweep 1: counts per (iteration, warp)
     int total_n = 0;
     for (int it0 = 0; it0 < niter; it0 += kNmsTab / 8) {
@@ -1235,6 +1287,7 @@ __global__ void __launch_bounds__(kNmsThreads) det_nms_kernel(const __grid_const
       }
       running = carry_smem;
       __syncthreads();
+    }
     }
   } else if (n < 2) {
     return;
