@@ -877,9 +877,6 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     carry_smem = 0;
   }
   if (!do_sort) return;  // pass-1 rows are the final output
-  // the NMS kernel reads row_cls eight entries at a time: define the entries between V and the next multiple of 8
-  if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7))
-    a.row_cls[(size_t)b * a.cls_stride + V + threadIdx.x] = (unsigned short)0xffffu;
   // dynamic smem: [sel: sel_cap u64][skeys: round4(A) u32 (optional)][wtab: niter_max*32 int]
   unsigned long long *ssel = reinterpret_cast<unsigned long long *>(dyn_smem);
   unsigned *skeys = reinterpret_cast<unsigned *>(ssel + a.sel_cap);
@@ -1051,6 +1048,8 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     row_cls[r] = (unsigned short)s0;
     row_box[r] = make_float4(s2, s3, s4, s5);
   }
+  // the NMS kernel reads row_cls eight entries at a time: define the entries between V and the next multiple of 8
+  if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7)) row_cls[V + threadIdx.x] = (unsigned short)0xffffu;
 }
 
 struct NmsArgs {
