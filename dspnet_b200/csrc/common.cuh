@@ -122,12 +122,11 @@ __device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v,
   return __shfl_xor_sync(kFullMask, v, m);
 }
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) {
-    unsigned long long o = shfl_xor_u64(v, m);
-    v = o > v ? o : v;
-  }
-  return v;
+  // two REDUX instructions: maximum of the high words, then of the low words among the lanes that hold it
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_max_sync(kFullMask, hi);
+  const unsigned mlo = __reduce_max_sync(kFullMask, hi == mhi ? lo : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
 }
 __device__ __forceinline__ int warp_sum_i32(int v) {
 #pragma unroll
