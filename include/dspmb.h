@@ -159,6 +159,14 @@ int dspmb_nms_host(int *keep_out, int *num_out, const float *boxes_host, int box
                    float nms_overlap_thresh, int device_id);
 
 /* ---------------------------------------------------------------------------------------------------
+ * bbox_overlaps_cython -- cython/bbox.pyx:15-55.
+ * boxes (N,4), query_boxes (K,4) float64 [x1,y1,x2,y2] -> overlaps (N,K) float64, row-major; "+1" pixel convention,
+ * 0 unless the intersection has positive width and height.  Device pointers, asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------------- */
+int dspmb_bbox_overlaps_f64(const double *boxes, int N, const double *query_boxes, int K, double *overlaps,
+                            void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Per-kernel timing (used by bench.py for the roofline line).  While enabled, every kernel the library launches
  * is bracketed by a cudaEvent pair recorded on the launching stream.  dspmb_profile_read synchronises those
  * events, adds the elapsed milliseconds and launch counts per kernel slot into ms[] / launches[] (up to

@@ -7,7 +7,8 @@
                        Forward() glue from the -inl.h headers is restated in oracle/shim/ref_*.cc);
   cpu_nms_ref*.so      cython/cpu_nms.pyx with the 3-token numpy-2 / Cython-3 patch of SURVEY.md section 8c
                        (np.int_t -> np.intp_t, dtype=np.int -> np.intp, `np.float thresh` -> `double thresh`),
-                       applied on the fly to a scratch copy under oracle/_ref/.
+                       applied on the fly to a scratch copy under oracle/_ref/;
+  bbox_ref*.so         cython/bbox.pyx (bbox_overlaps_cython) with `np.float` -> `np.float64`.
 
 The reference's own build (MXNet's make/cmake with the operators dropped into src/operator/contrib) cannot be run:
 MXNet is neither vendored nor installable here.
@@ -55,6 +56,25 @@ def build_cpu_nms():
     os.unlink(pyx)
 
 
+def build_bbox():
+    """cython/bbox.pyx with the numpy-2 patch `np.float` -> `np.float64` (the alias was removed from numpy)."""
+    import numpy
+    src = open(os.path.join(REF, "cython", "bbox.pyx")).read()
+    patched = src.replace("DTYPE = np.float\n", "DTYPE = np.float64\n").replace("ctypedef np.float_t DTYPE_t", "ctypedef np.float64_t DTYPE_t")
+    assert patched != src
+    pyx = os.path.join(OUT, "bbox_ref.pyx")
+    with open(pyx, "w") as f:
+        f.write(patched)
+    subprocess.check_call([sys.executable, "-m", "cython", "-3", "--fast-fail", pyx, "-o", os.path.join(OUT, "bbox_ref.c")])
+    ext = sysconfig.get_config_var("EXT_SUFFIX")
+    subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-w",
+                           "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION", "-I", sysconfig.get_paths()["include"],
+                           "-I", numpy.get_include(), os.path.join(OUT, "bbox_ref.c"), "-o",
+                           os.path.join(OUT, "bbox_ref" + ext)])
+    os.unlink(os.path.join(OUT, "bbox_ref.c"))
+    os.unlink(pyx)
+
+
 def main():
     if not os.path.isdir(os.path.join(REF, "operator")):
         print("build_ref: %s not present, keeping the prebuilt oracle/_ref/ (if any)" % REF)
@@ -65,6 +85,10 @@ def main():
         build_cpu_nms()
     except Exception as e:  # Cython missing etc.: the operators are the important part
         print("build_ref: cpu_nms not built (%r)" % (e,))
+    try:
+        build_bbox()
+    except Exception as e:
+        print("build_ref: bbox not built (%r)" % (e,))
     print("build_ref: ok ->", sorted(os.listdir(OUT)))
     return 0
 

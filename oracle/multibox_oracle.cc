@@ -530,4 +530,24 @@ void oracle_logf_array(const float *x, float *y, long n) {
   for (long i = 0; i < n; ++i) y[i] = logf(x[i]);
 }
 
+// cython/bbox.pyx:15-55 (bbox_overlaps_cython): float64, "+1" pixel convention, zero unless both extents > 0.
+void oracle_bbox_overlaps(const double *boxes, int N, const double *query, int K, double *overlaps) {
+  for (size_t i = 0; i < (size_t)N * K; ++i) overlaps[i] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double *q = query + (size_t)k * 4;
+    const double box_area = (q[2] - q[0] + 1) * (q[3] - q[1] + 1);
+    for (int n = 0; n < N; ++n) {
+      const double *b = boxes + (size_t)n * 4;
+      const double iw = (b[2] < q[2] ? b[2] : q[2]) - (b[0] > q[0] ? b[0] : q[0]) + 1;
+      if (iw > 0) {
+        const double ih = (b[3] < q[3] ? b[3] : q[3]) - (b[1] > q[1] ? b[1] : q[1]) + 1;
+        if (ih > 0) {
+          const double ua = (b[2] - b[0] + 1) * (b[3] - b[1] + 1) + box_area - iw * ih;
+          overlaps[(size_t)n * K + k] = iw * ih / ua;
+        }
+      }
+    }
+  }
+}
+
 }  // extern "C"

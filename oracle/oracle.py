@@ -63,6 +63,9 @@ def lib():
         L.oracle_cpu_nms.argtypes = [fp, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
                                      ctypes.c_double, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)]
         L.oracle_cpu_nms.restype = ctypes.c_int
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.oracle_bbox_overlaps.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, dp]
+        L.oracle_bbox_overlaps.restype = None
         L.oracle_expf_array.argtypes = [fp, fp, ctypes.c_long]
         L.oracle_logf_array.argtypes = [fp, fp, ctypes.c_long]
         _lib = L
@@ -167,6 +170,16 @@ def cpu_nms(dets, thresh, mode="cpu"):
     k = lib().oracle_cpu_nms(_p(dets), n, dim, _p(order, ctypes.c_int64), float(thresh),
                              0 if mode == "cpu" else 1, _p(keep, ctypes.c_int64))
     return [int(i) for i in keep[:k]]
+
+
+def bbox_overlaps(boxes, query_boxes):
+    """cython/bbox.pyx:15-55 (bbox_overlaps_cython): (N, 4) x (K, 4) float64 -> (N, K) float64."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+    query_boxes = np.ascontiguousarray(query_boxes, dtype=np.float64)
+    out = np.empty((boxes.shape[0], query_boxes.shape[0]), np.float64)
+    lib().oracle_bbox_overlaps(_p(boxes, ctypes.c_double), boxes.shape[0], _p(query_boxes, ctypes.c_double),
+                               query_boxes.shape[0], _p(out, ctypes.c_double))
+    return out
 
 
 def py_nms(dets, thresh):

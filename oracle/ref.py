@@ -97,3 +97,22 @@ def cpu_nms(dets, thresh):
         _nms = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(_nms)
     return [int(i) for i in _nms.cpu_nms(np.ascontiguousarray(dets, dtype=np.float32), float(thresh))]
+
+
+_bbox = None
+
+
+def bbox_available():
+    return bool(glob.glob(os.path.join(_DIR, "bbox_ref*.so")))
+
+
+def bbox_overlaps_cython(boxes, query_boxes):
+    """The reference's Cython bbox_overlaps_cython (cython/bbox.pyx:15-55) itself."""
+    global _bbox
+    if _bbox is None:
+        path = glob.glob(os.path.join(_DIR, "bbox_ref*.so"))[0]
+        spec = importlib.util.spec_from_file_location("bbox_ref", path)
+        _bbox = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_bbox)
+    return _bbox.bbox_overlaps_cython(np.ascontiguousarray(boxes, dtype=np.float64),
+                                      np.ascontiguousarray(query_boxes, dtype=np.float64))
