@@ -524,12 +524,13 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     return;
   }
-  // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
+  // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][ord: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + L);
   int *m_anchor = reinterpret_cast<int *>(sm_col + L);
   int *m_gt = m_anchor + L;
-  unsigned char *done = reinterpret_cast<unsigned char *>(m_gt + L);
+  int *ord = m_gt + L;  // gts with a candidate, sorted by cached key (sequential bipartite path)
+  unsigned char *done = reinterpret_cast<unsigned char *>(ord + ((L + 3) & ~3));  // keeps `skeys` 16-byte aligned
   unsigned *bits = reinterpret_cast<unsigned *>(done + ((L + 15) / 16) * 16);
   const int nwords = (A + 31) / 32;
   unsigned *skeys = bits + ((nwords + 3) & ~3);  // [A] staged mining keys (kKeysInSmem)
@@ -581,79 +582,91 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
     if (threadIdx.x == 0) sm_dup = 0;
     __syncthreads();
-    if (!distinct)
-  while (true) {
-    if (warp_id() == 0) {
-      const unsigned lane = lane_id();
+    if (!distinct) {
+      // Sequential lazy greedy on a SORTED list: the gts with a candidate, ordered by cached key (descending; equal
+      // keys -> lower gt index first, the reference's scan order).  The head of the list is the global maximum of
+      // the cached keys.  If its anchor is still free the pair is final (cached keys are upper bounds of the true
+      // column maxima over the unmatched anchors); otherwise the column is recomputed by the whole CTA and the gt is
+      // re-inserted further down.  One thread walks the list, so a step without a recompute costs a few shared
+      // memory accesses instead of a warp-wide arg-max over all gts.
+      if (threadIdx.x == 0) sm_arg = 0;
+      __syncthreads();
+      for (int k = threadIdx.x; k < G; k += blockDim.x) {
+        const unsigned long long ck = sm_col[k];
+        if (ck == 0ull) continue;
+        int r = 0;
+        for (int kk = 0; kk < G; ++kk) {
+          const unsigned long long o = sm_col[kk];
+          r += (o > ck || (o == ck && kk < k)) ? 1 : 0;
+        }
+        ord[r] = k;
+        atomicAdd(&sm_arg, 1);
+      }
+      __syncthreads();
+      int n_ord = sm_arg;  // keys that are 0 rank behind every candidate and are not listed
+      int head = 0;        // both are kept identical in every thread
       while (true) {
-        // best cached (iou, anchor) over the unmatched gts; ties on both go to the lower gt index
-        unsigned long long best = 0ull;
-        int bk = -1;
-        for (int k = lane; k < G; k += 32) {
-          const unsigned long long ck = sm_col[k];
-          if (!done[k] && ck > best) {
-            best = ck;
-            bk = k;
-          }
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-          const unsigned long long ob = shfl_xor_u64(best, m);
-          const int ok = __shfl_xor_sync(kFullMask, bk, m);
-          if (ob > best || (ob == best && ob != 0ull && ok < bk)) {
-            best = ob;
-            bk = ok;
-          }
-        }
-        int state = -1;
-        if (bk < 0) {
-          state = kStateDone;  // no remaining pair above 1e-6 (:136-138) or every gt matched
-        } else {
-          const int j = (int)(0xffffffffu - (unsigned)(best & 0xffffffffull));
-          const bool taken = (bits[j >> 5] >> (j & 31)) & 1u;
-          __syncwarp();  // (bk is warp-uniform) every lane has read `bits` and `done` before lane 0 updates them
-          if (taken) {
-            state = kStateRecompute;  // cached maximum points at an anchor that has been taken since
-          } else if (lane == 0) {
+        if (threadIdx.x == 0) {
+          int state = kStateDone;
+          while (head < n_ord) {
+            const int k = ord[head];
+            const unsigned long long ck = sm_col[k];
+            const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
+            if ((bits[j >> 5] >> (j & 31)) & 1u) {
+              state = kStateRecompute;  // cached maximum points at an anchor that has been taken since
+              break;
+            }
             const int n = sm_nmatch;
             m_anchor[n] = j;
-            m_gt[n] = bk;
+            m_gt[n] = k;
             sm_nmatch = n + 1;
-            done[bk] = 1;
             bits[j >> 5] |= 1u << (j & 31);
+            ++head;
+          }
+          sm_state = state;
+          sm_arg = head;
+        }
+        __syncthreads();
+        if (sm_state == kStateDone) break;
+        head = sm_arg;
+        // recompute the column maximum of the head gt over the anchors that are still unmatched
+        const int k = ord[head];
+        const float4 g = sm_gt[k];
+        unsigned long long tkey = 0ull;
+        for (int j = threadIdx.x; j < A; j += blockDim.x) {
+          if ((bits[j >> 5] >> (j & 31)) & 1u) continue;
+          const float4 an = __ldg(anchors + j);
+          // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
+          if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
+          const float iou = iou_target(an, g);
+          if (iou > 1e-6f) {
+            const unsigned long long ck = col_key(iou, j);
+            tkey = ck > tkey ? ck : tkey;
           }
         }
-        __syncwarp();
-        if (state >= 0) {
-          if (lane == 0) {
-            sm_state = state;
-            sm_arg = bk;
+        const unsigned long long bm = block_max_u64(tkey, red_smem);
+        __syncthreads();  // every thread has read ord[head] and the old list
+        if (threadIdx.x == 0) {
+          sm_col[k] = bm;
+          // move gt k from the head to its place among the remaining entries (bm <= its old key); a gt without
+          // any remaining candidate (bm == 0) leaves the list
+          int pos = head + 1;
+          while (pos < n_ord) {
+            const int e = ord[pos];
+            const unsigned long long ek = sm_col[e];
+            if (bm == 0ull || ek > bm || (ek == bm && e < k)) {
+              ord[pos - 1] = e;
+              ++pos;
+            } else {
+              break;
+            }
           }
-          break;
+          ord[pos - 1] = k;
         }
+        if (bm == 0ull) --n_ord;  // bm is the same in every thread
+        __syncthreads();
       }
     }
-    __syncthreads();
-    if (sm_state == kStateDone) break;
-    // recompute the column maximum of gt sm_arg over the anchors that are still unmatched
-    const int k = sm_arg;
-    const float4 g = sm_gt[k];
-    unsigned long long tkey = 0ull;
-    for (int j = threadIdx.x; j < A; j += blockDim.x) {
-      if ((bits[j >> 5] >> (j & 31)) & 1u) continue;
-      const float4 an = __ldg(anchors + j);
-      // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
-      if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
-      const float iou = iou_target(an, g);
-      if (iou > 1e-6f) {
-        const unsigned long long ck = col_key(iou, j);
-        tkey = ck > tkey ? ck : tkey;
-      }
-    }
-    const unsigned long long bm = block_max_u64(tkey, red_smem);
-    if (threadIdx.x == 0) sm_col[k] = bm;
-    __syncthreads();
-  }
   }
   const int nmatch = sm_nmatch;
 
@@ -963,6 +976,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
 
   const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L;
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
+                       sizeof(int) * (size_t)((L + 3) & ~3) +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
   const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 180 * 1024;
   const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
