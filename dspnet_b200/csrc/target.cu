@@ -645,23 +645,27 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
           }
         }
         const unsigned long long bm = block_max_u64(tkey, red_smem);
-        __syncthreads();  // every thread has read ord[head] and the old list
-        if (threadIdx.x == 0) {
-          sm_col[k] = bm;
-          // move gt k from the head to its place among the remaining entries (bm <= its old key); a gt without
-          // any remaining candidate (bm == 0) leaves the list
-          int pos = head + 1;
-          while (pos < n_ord) {
-            const int e = ord[pos];
+        // move gt k from the head to its place among the remaining entries (bm <= its old key): the entries that
+        // still rank before it form a prefix of the rest of the list and shift up by one, a chunk of blockDim at a
+        // time; a gt without any remaining candidate (bm == 0) ends up behind the list and leaves it
+        int base = head + 1;
+        while (true) {
+          const int pos = base + (int)threadIdx.x;
+          int e = -1;
+          bool before = false;
+          if (pos < n_ord) {
+            e = ord[pos];
             const unsigned long long ek = sm_col[e];
-            if (bm == 0ull || ek > bm || (ek == bm && e < k)) {
-              ord[pos - 1] = e;
-              ++pos;
-            } else {
-              break;
-            }
+            before = bm == 0ull || ek > bm || (ek == bm && e < k);
           }
-          ord[pos - 1] = k;
+          const int moved = __syncthreads_count(before);  // also orders the reads above before the writes below
+          if (before) ord[pos - 1] = e;
+          base += moved;
+          if (moved < (int)blockDim.x) break;
+        }
+        if (threadIdx.x == 0) {
+          ord[base - 1] = k;
+          sm_col[k] = bm;
         }
         if (bm == 0ull) --n_ord;  // bm is the same in every thread
         __syncthreads();
@@ -678,7 +682,10 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     const float4 an = __ldg(anchors + j);
     float max_iou = -1.0f;
     for (int kk = sub; kk < G; kk += 16) {
-      const float iou = iou_target(an, sm_gt[kk]);
+      const float4 g = sm_gt[kk];
+      // a disjoint gt has IoU 0 (G > 0, so the row maximum is at least that): no arithmetic, no division
+      const bool reach = an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y;
+      const float iou = reach ? iou_target(an, g) : 0.0f;
       if (iou > max_iou) max_iou = iou;
     }
     const unsigned gmask = 0xffffu << (lane_id() & 16);  // the half-warp of this anchor (may be alone in the loop)
