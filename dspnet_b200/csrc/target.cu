@@ -633,15 +633,27 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
         const int k = ord[head];
         const float4 g = sm_gt[k];
         unsigned long long tkey = 0ull;
-        for (int j = threadIdx.x; j < A; j += blockDim.x) {
-          if ((bits[j >> 5] >> (j & 31)) & 1u) continue;
-          const float4 an = __ldg(anchors + j);
-          // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
-          if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
-          const float iou = iou_target(an, g);
-          if (iou > 1e-6f) {
-            const unsigned long long ck = col_key(iou, j);
-            tkey = ck > tkey ? ck : tkey;
+        // four anchors per thread in flight: the anchor table lives in L2, one dependent load per iteration would
+        // put its latency on this loop twelve to twenty-four times
+        for (int j0 = threadIdx.x; j0 < A; j0 += 4 * blockDim.x) {
+          float4 an4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * (int)blockDim.x;
+            an4[u] = j < A ? __ldg(anchors + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * (int)blockDim.x;
+            if (j >= A || ((bits[j >> 5] >> (j & 31)) & 1u)) continue;
+            const float4 an = an4[u];
+            // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
+            if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
+            const float iou = iou_target(an, g);
+            if (iou > 1e-6f) {
+              const unsigned long long ck = col_key(iou, j);
+              tkey = ck > tkey ? ck : tkey;
+            }
           }
         }
         const unsigned long long bm = block_max_u64(tkey, red_smem);
@@ -675,22 +687,23 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   const int nmatch = sm_nmatch;
 
   // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
-  // sixteen lanes per matched anchor: the G IoUs of its row are spread over them
-  for (int q = (int)(threadIdx.x >> 4); q < nmatch; q += (int)(blockDim.x >> 4)) {
-    const int sub = threadIdx.x & 15;
+  // a group of lanes per matched anchor (16, or 4 when there are more than 64 matches so that one round covers
+  // them): the G IoUs of its row are spread over the group
+  const int gs = nmatch > (int)(blockDim.x >> 4) ? 4 : 16;
+  for (int q = (int)threadIdx.x / gs; q < nmatch; q += (int)blockDim.x / gs) {
+    const int sub = threadIdx.x & (gs - 1);
     const int j = m_anchor[q], k = m_gt[q];
     const float4 an = __ldg(anchors + j);
     float max_iou = -1.0f;
-    for (int kk = sub; kk < G; kk += 16) {
+    for (int kk = sub; kk < G; kk += gs) {
       const float4 g = sm_gt[kk];
       // a disjoint gt has IoU 0 (G > 0, so the row maximum is at least that): no arithmetic, no division
       const bool reach = an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y;
       const float iou = reach ? iou_target(an, g) : 0.0f;
       if (iou > max_iou) max_iou = iou;
     }
-    const unsigned gmask = 0xffffu << (lane_id() & 16);  // the half-warp of this anchor (may be alone in the loop)
-#pragma unroll
-    for (int m = 8; m > 0; m >>= 1) {
+    const unsigned gmask = (gs == 16 ? 0xffffu : 0xfu) << (lane_id() & ~(unsigned)(gs - 1));  // this anchor's group
+    for (int m = gs >> 1; m > 0; m >>= 1) {
       const float o = __shfl_xor_sync(gmask, max_iou, m);
       if (o > max_iou) max_iou = o;
     }
