@@ -605,6 +605,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       __syncthreads();
       int n_ord = sm_arg;  // keys that are 0 rank behind every candidate and are not listed
       int head = 0;        // both are kept identical in every thread
+      __syncthreads();     // everyone has read sm_arg before thread 0 reuses it below
       while (true) {
         if (threadIdx.x == 0) {
           int state = kStateDone;
