@@ -48,13 +48,10 @@ constexpr int kStreamThreads = 128;
 constexpr int kRegThreads = 128;      // CTA size of the register-resident stream kernel
 constexpr int kSortThreads = 1024;
 constexpr int kNmsThreads = 256;
-constexpr int kSortSmemKeys = 8192;   // 64 KB of 64-bit sort keys in shared memory
-constexpr int kRankSortMax = 1024;    // selections up to this size are rank-sorted (one key per thread)
 constexpr int kKeySmemMax = 28672;    // slot keys (T * tile) that fit in shared memory next to the sort keys
 constexpr int kNmsMaskRows = 320;     // NMS segments up to this size use the shared-memory bit mask (5 words/row)
 static_assert(kNmsMaskRows <= 320, "unit_tab holds (row group, column group) in 4 bits each, 55 units");
 constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in shared memory
-constexpr unsigned kKeySentinel = 0xffffffffu;  // empty slot: sorts after every real key
 
 struct DetWorkspace {
   WsHeader *header;
@@ -624,7 +621,7 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
 
 // ----------------------------------------------------------------------------------------------------
 // Bitonic sort of n (power of two) 64-bit keys, ascending, by the whole CTA.  `keys` may point to shared or
-// global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used above kRankSortMax keys.
+// global memory.  Shared-memory bandwidth bound (32 B per compare-exchange): only used for selections of more than 512 keys.
 __device__ void bitonic_sort_u64(unsigned long long *keys, int n) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -710,14 +707,17 @@ __device__ __forceinline__ void bitonic_sort_regs(unsigned long long *ssel, int 
   for (int q = 0; q < KPT; ++q) ssel[idx0 | (q << 5)] = k[q];
 }
 
-// Warp-aggregated shared-memory histogram increment: lanes with the same bin elect one leader.
+// Warp-aggregated shared-memory histogram increment: the bin of the first participating lane is counted for the
+// whole warp with one ballot (scores cluster: in the first pass that is nearly every lane), the other lanes add
+// themselves -- their bins rarely coincide.  (__match_any_sync costs more than both once the bins are spread.)
 __device__ __forceinline__ void hist_add(unsigned *hist, unsigned bin, bool pred) {
   const unsigned active = __ballot_sync(kFullMask, pred);
   if (active == 0u) return;
-  if (pred) {
-    const unsigned peers = __match_any_sync(active, bin);
-    if ((int)lane_id() == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
-  }
+  const int leader = __ffs(active) - 1;
+  const unsigned b0 = __shfl_sync(kFullMask, bin, leader);
+  const unsigned same = __ballot_sync(kFullMask, pred && bin == b0);
+  if ((int)lane_id() == leader) atomicAdd(&hist[b0], (unsigned)__popc(same));
+  else if (pred && bin != b0) atomicAdd(&hist[bin], 1u);
 }
 
 // Unordered append of the lanes with `pred` to a shared list through one atomic per warp.
@@ -833,7 +833,7 @@ __device__ void det_rank_role(const SortArgs &a, int b, int part, int *red) {
 // write disjoint rows, so they need no ordering between them.
 template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_constant__ SortArgs a) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ int scan_smem[kSortThreads / 32 + 1];
   __shared__ unsigned hist256[256];
   __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;

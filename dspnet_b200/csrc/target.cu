@@ -171,11 +171,6 @@ __device__ __forceinline__ float exact_bg_prob_warp(const float *p_cls, int j, i
   return fdiv(e0, sum);
 }
 
-struct SmemExpTab {
-  const unsigned long long *t;
-  __device__ __forceinline__ uint64_t operator()(unsigned i) const { return t[i]; }
-};
-
 // IoU of the target operator with the division skipped for disjoint boxes: inter == 0 gives iou == 0 both through
 // safe_divide's union == 0 branch and through 0 / union (multibox_target-inl.h:44-50,153-161).
 __device__ __forceinline__ float iou_target_fast(float4 a, float area_a, float4 g, float area_g) {
@@ -510,7 +505,6 @@ template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned long long red_smem[kMatchThreads / 32];
-  __shared__ int scan_smem[kMatchThreads / 32 + 1];
   __shared__ unsigned hist[256];
   __shared__ int sm_state, sm_arg, sm_nmatch, sm_dup, sm_carry;
   __shared__ unsigned sm_prefix;
