@@ -26,7 +26,7 @@ EXPORTS = (
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
     "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32", "dspmb_set_tuning", "dspmb_gather_buffer_bytes", "dspmb_p2p_alloc",
     "dspmb_p2p_open", "dspmb_p2p_close", "dspmb_p2p_free", "dspmb_detection_gather_f32", "dspmb_detection_gather_wait", "dspmb_detection_gather_read",
-    "dspmb_bbox_overlaps_f64",
+    "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32",
 )
 
 
@@ -87,6 +87,8 @@ def lib():
                                 c_size_t, c_void_p]
     L.dspmb_nms_host.argtypes = [ip, ip, fp, c_int, c_int, c_float, c_int]
     L.dspmb_bbox_overlaps_f64.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]
+    L.dspmb_detection_postfilter_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
+    L.dspmb_map_match_f32.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]
     L.dspmb_profile_enable.argtypes = [c_int]
     L.dspmb_profile_read.argtypes = [fp, ip, c_int]
     L.dspmb_profile_kernel_name.argtypes = [c_int]

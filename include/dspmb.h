@@ -167,6 +167,23 @@ int dspmb_bbox_overlaps_f64(const double *boxes, int N, const double *query_boxe
                             void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Evaluation consumers of the detection output.
+ *
+ * dspmb_detection_postfilter_f32 -- multi_solver.py:419-432: per image the rows of `out` (B,A,7) with id >= 0 and
+ *   score > score_thresh (0.25 there), in row order, at most K (200 there; the reference raises beyond, here the rest
+ *   is cut), into rows (B,K,7) padded with -1; counts (B) int32.  valid_count (B) may bound the scan or be NULL.
+ * dspmb_map_match_f32 -- the per-image TP/FP matching of MApMetric.update (evaluate/eval_metric.py:113-160):
+ *   labels (B,L,label_width>=5) [cls,xmin,ymin,xmax,ymax,(difficult)], preds (B,M,pred_width>=6)
+ *   [id,score,xmin,ymin,xmax,ymax,...] -> flags (B,M) int32: 0 not recorded (id < 0, or the best gt is difficult and
+ *   use_difficult == 0), 1 true positive, 2 false positive.  Record accumulation and AP stay on the host
+ *   (dspnet_b200.evalmap).  Device pointers, asynchronous on `stream`.
+ * ------------------------------------------------------------------------------------------------- */
+int dspmb_detection_postfilter_f32(const float *out, const int32_t *valid_count, int B, int A, int K,
+                                   float score_thresh, float *rows, int32_t *counts, void *stream);
+int dspmb_map_match_f32(const float *labels, int B, int L, int label_width, const float *preds, int M, int pred_width,
+                        float ovp_thresh, int use_difficult, int32_t *flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
  * Per-kernel timing (used by bench.py for the roofline line).  While enabled, every kernel the library launches
  * is bracketed by a cudaEvent pair recorded on the launching stream.  dspmb_profile_read synchronises those
  * events, adds the elapsed milliseconds and launch counts per kernel slot into ms[] / launches[] (up to
