@@ -61,126 +61,103 @@ def match_flags(labels, preds, ovp_thresh=0.5, use_difficult=False):
     return flags
 
 
+def _pr_curve(record, gt_count):
+    """Cumulative recall / precision of one class from its (score, flag) records (eval_metric.py:196-207): records
+    with flag 0 are dropped, the rest ordered by descending score."""
+    flags = record[:, 1].astype(int)
+    kept = record[flags != 0]
+    kept_flags = kept[kept[:, 0].argsort()[::-1], 1].astype(int)
+    tp, fp = np.cumsum(kept_flags == 1), np.cumsum(kept_flags == 2)
+    recall = tp / float(gt_count) if gt_count > 0 else tp * 0.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        precision = tp.astype(float) / (tp + fp)
+    return recall, precision
+
+
+def _ap_area(recall, precision):
+    """Area under the monotone precision envelope (eval_metric.py:209-231)."""
+    r = np.concatenate(([0.0], recall, [1.0]))
+    p = np.concatenate(([0.0], precision, [0.0]))
+    p = np.maximum.accumulate(p[::-1])[::-1]            # envelope from the right
+    steps = np.flatnonzero(r[1:] != r[:-1])
+    return np.sum((r[steps + 1] - r[steps]) * p[steps + 1])
+
+
+def _ap_voc07(recall, precision):
+    """PASCAL VOC 07 eleven-point AP (eval_metric.py:254-277)."""
+    ap = 0.0
+    for t in np.arange(0.0, 1.1, 0.1):
+        reached = recall >= t
+        ap += (np.max(precision[reached]) if np.sum(reached) != 0 else 0) / 11.0
+    return ap
+
+
 class MApMetric(object):
-    """Mean AP for detection -- evaluate/eval_metric.py:4-247 with the matching on the GPU."""
+    """Mean AP for detection with the interface of evaluate/eval_metric.py:4-247 (constructor arguments, ``update``,
+    ``get``, ``reset``, the ``records`` / ``counts`` dictionaries); the IoU matching of ``update`` runs on the GPU."""
+
+    _ap = staticmethod(_ap_area)
 
     def __init__(self, ovp_thresh=0.5, use_difficult=False, class_names=None, pred_idx=0):
-        if class_names is None:
-            self.num = None
-            self.name = "mAP"
-        else:
-            assert isinstance(class_names, (list, tuple))
-            for name in class_names:
-                assert isinstance(name, str), "must provide names as str"
-            self.name = list(class_names) + ["mAP"]
-            self.num = len(class_names) + 1
-        self.ovp_thresh = ovp_thresh
-        self.use_difficult = use_difficult
+        if class_names is not None:
+            if not isinstance(class_names, (list, tuple)) or not all(isinstance(n, str) for n in class_names):
+                raise AssertionError("must provide names as str")
         self.class_names = class_names
-        self.pred_idx = int(pred_idx)
+        self.name = "mAP" if class_names is None else list(class_names) + ["mAP"]
+        self.num = None if class_names is None else len(class_names) + 1
+        self.ovp_thresh, self.use_difficult, self.pred_idx = ovp_thresh, use_difficult, int(pred_idx)
         self.reset()
 
     def reset(self):
-        if self.num is None:
-            self.num_inst = 0
-            self.sum_metric = 0.0
+        self.records, self.counts = dict(), dict()
+        self.num_inst = 0 if self.num is None else [0] * self.num
+        self.sum_metric = 0.0 if self.num is None else [0.0] * self.num
+
+    def _push(self, cid, rows, gt_count):
+        if cid in self.records:
+            self.records[cid] = np.vstack((self.records[cid], rows))
+            self.counts[cid] += gt_count
         else:
-            self.num_inst = [0] * self.num
-            self.sum_metric = [0.0] * self.num
-        self.records = dict()
-        self.counts = dict()
+            self.records[cid], self.counts[cid] = rows, gt_count
 
     def update(self, labels, preds):
         """labels: [ (B, L, 5 or 6) ], preds: list whose entry ``pred_idx`` is (B, M, >=6) -- like the reference."""
         lab_t, pred_t = _dev(labels[0]), _dev(preds[self.pred_idx])
         flags = match_flags(lab_t, pred_t, self.ovp_thresh, self.use_difficult).cpu().numpy()
         lab, pred = lab_t.cpu().numpy(), pred_t.cpu().numpy()
-        for b in range(pred.shape[0]):
-            pcls = pred[b, :, 0].astype(int)
-            lcls = lab[b, :, 0].astype(int)
-            seen = []
-            for c in pcls:  # the reference takes the classes in order of first appearance (:118-124)
-                if c >= 0 and c not in seen:
-                    seen.append(int(c))
-            for cid in seen:
-                rows = np.where(pcls == cid)[0]
-                records = np.hstack((pred[b, rows, 1][:, np.newaxis].astype(np.float64),
-                                     flags[b, rows][:, np.newaxis].astype(np.float64)))
-                gts = lab[b][lcls == cid]
-                if (not self.use_difficult) and gts.shape[1] >= 6:  # :156-159
-                    gt_count = int(np.sum(gts[:, 5] < 1))
-                else:
-                    gt_count = gts.shape[0]
-                records = records[np.where(records[:, -1] > 0)[0], :]
-                if records.size > 0:
-                    self._insert(cid, records, gt_count)
-            rest = []
-            for c in lcls:  # classes that occur only in the labels (:168-176)
-                if c not in seen and c not in rest:
-                    rest.append(int(c))
-            for cid in rest:
-                if cid >= 0:
-                    self._insert(cid, np.array([[0, 0]], dtype=np.float64), int(np.sum(lcls == cid)))
+        count_easy_only = (not self.use_difficult) and lab.shape[2] >= 6          # eval_metric.py:156-159
+        for image_labels, image_preds, image_flags in zip(lab, pred, flags):
+            pcls, lcls = image_preds[:, 0].astype(int), image_labels[:, 0].astype(int)
+            # predicted classes in order of first appearance (:118-124), then the classes that only occur in the
+            # labels (:168-176); ids < 0 are padding on both sides
+            pred_order = [int(c) for c in pcls[np.sort(np.unique(pcls, return_index=True)[1])] if c >= 0]
+            for cid in pred_order:
+                mine = pcls == cid
+                rows = np.column_stack((image_preds[mine, 1].astype(np.float64), image_flags[mine].astype(np.float64)))
+                rows = rows[rows[:, 1] > 0]
+                gts = image_labels[lcls == cid]
+                if rows.size > 0:
+                    self._push(cid, rows, int(np.sum(gts[:, 5] < 1)) if count_easy_only else gts.shape[0])
+            label_order = [int(c) for c in lcls[np.sort(np.unique(lcls, return_index=True)[1])]]
+            for cid in label_order:
+                if cid >= 0 and cid not in pred_order:
+                    self._push(cid, np.zeros((1, 2), dtype=np.float64), int(np.sum(lcls == cid)))
 
     def get(self):
-        self._update()
+        aps = {k: self._ap(*_pr_curve(v, self.counts[k])) for k, v in self.records.items()}
+        mean_ap = np.mean(list(aps.values()))
         if self.num is None:
-            if self.num_inst == 0:
-                return (self.name, float("nan"))
+            self.num_inst, self.sum_metric = 1, mean_ap
             return (self.name, self.sum_metric / self.num_inst)
-        names = ["%s" % (self.name[i]) for i in range(self.num)]
+        for k, ap in aps.items():
+            if k < self.num - 1:
+                self.sum_metric[k], self.num_inst[k] = ap, 1
+        self.sum_metric[-1], self.num_inst[-1] = mean_ap, 1
         values = [x / y if y != 0 else float("nan") for x, y in zip(self.sum_metric, self.num_inst)]
-        return (names, values)
-
-    def _update(self):
-        aps = []
-        for k, v in self.records.items():
-            recall, prec = self._recall_prec(v, self.counts[k])
-            ap = self._average_precision(recall, prec)
-            aps.append(ap)
-            if self.num is not None and k < (self.num - 1):
-                self.sum_metric[k] = ap
-                self.num_inst[k] = 1
-        if self.num is None:
-            self.num_inst = 1
-            self.sum_metric = np.mean(aps)
-        else:
-            self.num_inst[-1] = 1
-            self.sum_metric[-1] = np.mean(aps)
-
-    def _recall_prec(self, record, count):
-        record = np.delete(record, np.where(record[:, 1].astype(int) == 0)[0], axis=0)
-        sorted_records = record[record[:, 0].argsort()[::-1]]
-        tp = np.cumsum(sorted_records[:, 1].astype(int) == 1)
-        fp = np.cumsum(sorted_records[:, 1].astype(int) == 2)
-        recall = tp * 0.0 if count <= 0 else tp / float(count)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            prec = tp.astype(float) / (tp + fp)
-        return recall, prec
-
-    def _average_precision(self, rec, prec):
-        mrec = np.concatenate(([0.0], rec, [1.0]))
-        mpre = np.concatenate(([0.0], prec, [0.0]))
-        for i in range(mpre.size - 1, 0, -1):
-            mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
-        i = np.where(mrec[1:] != mrec[:-1])[0]
-        return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
-
-    def _insert(self, key, records, count):
-        if key not in self.records:
-            self.records[key] = records
-            self.counts[key] = count
-        else:
-            self.records[key] = np.vstack((self.records[key], records))
-            self.counts[key] += count
+        return (["%s" % n for n in self.name], values)
 
 
 class VOC07MApMetric(MApMetric):
     """11-point PASCAL VOC 07 AP -- evaluate/eval_metric.py:249-277."""
 
-    def _average_precision(self, rec, prec):
-        ap = 0.0
-        for t in np.arange(0.0, 1.1, 0.1):
-            p = 0 if np.sum(rec >= t) == 0 else np.max(prec[rec >= t])
-            ap += p / 11.0
-        return ap
+    _ap = staticmethod(_ap_voc07)

@@ -83,13 +83,12 @@ class MApAccumulator(object):
         self.records = {}
         self.counts = {}
 
-    def _insert(self, key, records, count):
-        if key not in self.records:
-            self.records[key] = records
-            self.counts[key] = count
+    def _push(self, cid, rows, gt_count):
+        if cid in self.records:
+            self.records[cid] = np.vstack((self.records[cid], rows))
+            self.counts[cid] += gt_count
         else:
-            self.records[key] = np.vstack((self.records[key], records))
-            self.counts[key] += count
+            self.records[cid], self.counts[cid] = rows, gt_count
 
     def update(self, labels, preds, flags):
         labels = np.asarray(labels, dtype=F32)
@@ -104,49 +103,44 @@ class MApAccumulator(object):
                     seen.append(int(c))
             for cid in seen:
                 rows = np.where(pcls == cid)[0]
-                rec = np.hstack((pred[rows, 1][:, None].astype(np.float64), fl[rows][:, None].astype(np.float64)))
+                rec = np.stack((pred[rows, 1].astype(np.float64), fl[rows].astype(np.float64)), axis=1)
+                rec = rec[rec[:, 1] > 0]
                 gts = lab[lcls == cid]
-                if (not self.use_difficult) and gts.shape[1] >= 6:
-                    gt_count = int(np.sum(gts[:, 5] < 1))
-                else:
-                    gt_count = gts.shape[0]
-                rec = rec[rec[:, -1] > 0]
+                easy_only = (not self.use_difficult) and gts.shape[1] >= 6
                 if rec.size > 0:
-                    self._insert(cid, rec, gt_count)
+                    self._push(cid, rec, int(np.sum(gts[:, 5] < 1)) if easy_only else gts.shape[0])
             rest = []
             for c in lcls:  # classes that only occur in the labels, in order of first appearance
-                if c not in seen and c not in rest:
+                if c >= 0 and c not in seen and c not in rest:
                     rest.append(int(c))
             for cid in rest:
-                if cid < 0:
-                    continue
-                self._insert(cid, np.array([[0, 0]], dtype=np.float64), int(np.sum(lcls == cid)))
+                self._push(cid, np.zeros((1, 2)), int(np.sum(lcls == cid)))
 
     @staticmethod
-    def _recall_prec(record, count):
-        record = np.delete(record, np.where(record[:, 1].astype(int) == 0)[0], axis=0)
-        sorted_records = record[record[:, 0].argsort()[::-1]]
-        tp = np.cumsum(sorted_records[:, 1].astype(int) == 1)
-        fp = np.cumsum(sorted_records[:, 1].astype(int) == 2)
-        recall = tp * 0.0 if count <= 0 else tp / float(count)
+    def pr_curve(record, count):
+        """:196-207 -- flag-0 rows dropped, descending score, cumulative TP / FP."""
+        kept = record[record[:, 1].astype(int) != 0]
+        fl = kept[np.argsort(kept[:, 0])[::-1], 1].astype(int)
+        tp, fp = np.cumsum(fl == 1), np.cumsum(fl == 2)
         with np.errstate(divide="ignore", invalid="ignore"):
-            prec = tp.astype(float) / (tp + fp)
-        return recall, prec
+            return (tp / float(count) if count > 0 else tp * 0.0), tp.astype(float) / (tp + fp)
 
-    def _average_precision(self, rec, prec):
-        if self.voc07:
-            ap = 0.0
+    def average_precision(self, rec, prec):
+        if self.voc07:  # :254-277, eleven recall levels
+            total = 0.0
             for t in np.arange(0.0, 1.1, 0.1):
-                p = 0 if np.sum(rec >= t) == 0 else np.max(prec[rec >= t])
-                ap += p / 11.0
-            return ap
-        mrec = np.concatenate(([0.0], rec, [1.0]))
-        mpre = np.concatenate(([0.0], prec, [0.0]))
-        for i in range(mpre.size - 1, 0, -1):
-            mpre[i - 1] = np.maximum(mpre[i - 1], mpre[i])
-        i = np.where(mrec[1:] != mrec[:-1])[0]
-        return np.sum((mrec[i + 1] - mrec[i]) * mpre[i + 1])
+                hit = rec >= t
+                total += (prec[hit].max() if hit.any() else 0) / 11.0
+            return total
+        # :209-231, area under the right-to-left running maximum of the precision
+        r = np.concatenate(([0.0], rec, [1.0]))
+        p = np.concatenate(([0.0], prec, [0.0]))
+        for k in range(p.size - 2, -1, -1):
+            if p[k + 1] > p[k]:
+                p[k] = p[k + 1]
+        idx = np.nonzero(r[1:] != r[:-1])[0]
+        return np.sum((r[idx + 1] - r[idx]) * p[idx + 1])
 
     def get(self):
-        aps = [self._average_precision(*self._recall_prec(v, self.counts[k])) for k, v in self.records.items()]
+        aps = [self.average_precision(*self.pr_curve(v, self.counts[k])) for k, v in self.records.items()]
         return "mAP", float(np.mean(aps)) if aps else float("nan")
