@@ -483,3 +483,22 @@ def test_autograd_backward_is_zero_like_the_reference(oracle, cuda):
                           "prior through autograd")
     pr.sum().backward()
     assert data.grad is not None and not data.grad.any()
+
+
+def test_graph_cache_eviction(oracle, cuda):
+    """More distinct argument sets than the cache holds (32): the least recently used graphs are evicted and destroyed
+    while others keep replaying; every call still returns the oracle's result."""
+    from dspnet_b200.plan import DetectionPlan
+    anchors, prob, lp = util.detection_inputs(oracle, "ssd300", 1, config_id=71)
+    kw = dict(nms_threshold=0.45, nms_topk=400)
+    want = oracle.multibox_detection(prob, lp, anchors, **kw)
+    plan = DetectionPlan(1, anchors.shape[1], prob.shape[1], cuda, **kw)
+    a, p, l = _t(anchors, cuda), _t(prob, cuda), _t(lp, cuda)
+    outs = [plan.new_output() for _ in range(40)]       # 40 distinct `out` pointers = 40 keys
+    for rnd in range(3):
+        for o in outs:
+            o.fill_(3.0)
+            plan.run(p, l, a, o)
+        torch.cuda.synchronize()
+        for i in (0, 17, 39):
+            util.assert_bit_equal(outs[i].cpu().numpy(), want, "round %d buffer %d" % (rnd, i))
