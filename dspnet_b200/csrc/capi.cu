@@ -91,6 +91,17 @@ unsigned long long g_graph_clock = 0;
 cudaStream_t g_capture_stream[64] = {};
 }  // namespace
 
+int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long long> &done) {
+  int dev = 0;
+  DSPMB_CUDA_TRY(cudaGetDevice(&dev));
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    DSPMB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return DSPMB_OK;
+}
+
 int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
                         const std::function<int(cudaStream_t)> &launch) {
   if (!tuning(DSPMB_TUNE_GRAPH_CACHE) || g_profile_on) return launch(stream);

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <functional>
 
 #include "../../include/dspmb.h"
@@ -63,6 +64,18 @@ struct ProfileScope {  // brackets one kernel launch when profiling is enabled
     if (g_profile_on) profile_mark(slot, stream, false);
   }
 };
+
+// ---- opt-in to more than 48 KB of dynamic shared memory (capi.cu) ----------------------------------------
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of a kernel ON ONE DEVICE: it is set once per (kernel,
+// device) -- `done` is the call site's bit mask of devices that have it -- and setting it twice is harmless, so the
+// check needs no lock.
+int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long long> &done);
+#define DSPMB_ENSURE_DYN_SMEM(kernel, bytes)                                             \
+  do {                                                                                   \
+    static std::atomic<unsigned long long> dyn_smem_done_{0ull};                         \
+    const int rc_ = ensure_dyn_smem((const void *)(kernel), (int)(bytes), dyn_smem_done_); \
+    if (rc_ != DSPMB_OK) return rc_;                                                     \
+  } while (0)
 
 // ---- CUDA-graph cache for the multi-launch operators (capi.cu) ------------------------------------------
 // `launch(s)` enqueues an operator's kernels on stream s.  A call whose key (every pointer, shape and parameter

@@ -1651,11 +1651,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     pa.num_tiles = B * T;
     pa.stages = stages;
     pa.stage_floats = (int)(stage_bytes / sizeof(float));
-    static bool pipe_attr_set = false;
-    if (!pipe_attr_set) {
-      DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_stream_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      pipe_attr_set = true;
-    }
+    DSPMB_ENSURE_DYN_SMEM(det_stream_tma_kernel, 200 * 1024);
     int grid = kNumSMs * ctas_per_sm;
     if (grid > pa.num_tiles) grid = pa.num_tiles;
     ProfileScope _p(kSlotDetStream, stream);
@@ -1667,12 +1663,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
 #define DSPMB_LAUNCH_BULK(NFG, TH, VEC)                                                                           \
   do {                                                                                                            \
     constexpr size_t kBytes = sizeof(BulkSmem<NFG, TH * VEC>);                                                    \
-    static bool attr_done = false;                                                                                \
-    if (!attr_done) {                                                                                             \
-      DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_stream_bulk_kernel<NFG, TH, VEC>,                                   \
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBytes));             \
-      attr_done = true;                                                                                           \
-    }                                                                                                             \
+    DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, TH, VEC>), kBytes);                                        \
     det_stream_bulk_kernel<NFG, TH, VEC><<<grid1, TH, kBytes, stream>>>(sa);                                      \
   } while (0)
       if (C == 21 && variant == 2) DSPMB_LAUNCH_BULK(20, 128, 2);
@@ -1732,12 +1723,8 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (keys_in_smem ? sizeof(unsigned) * (size_t)((A + 3) & ~3) : 0) +
                        sizeof(int) * 32 * (size_t)so.niter_max;
   DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_sort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<true>, 220 * 1024);
+  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<false>, 220 * 1024);
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
     if (keys_in_smem)
@@ -1919,11 +1906,7 @@ extern "C" int dspmb_detection_gather_f32(const float *out, const int32_t *valid
   g.counts_off = g.slot_off + rows;
   g.arrived_off = g.counts_off + counts;
   const size_t smem = (size_t)K * 7 * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(det_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    attr_set = true;
-  }
+  DSPMB_ENSURE_DYN_SMEM(det_gather_kernel, 160 * 1024);
   {
     ProfileScope _p(kSlotDetCompact, stream);
     det_gather_kernel<<<B, 256, smem, stream>>>(g);

@@ -224,12 +224,8 @@ extern "C" int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, i
   NmsWorkspace w = carve(workspace, N);
   const int W = ceil_div(N, 64);
   DSPMB_REQUIRE((size_t)W * 8 <= 200 * 1024, "nms: more than %d boxes are not supported", 200 * 1024 / 8 * 64);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(nms_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortSmemKeys * 8));
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  DSPMB_ENSURE_DYN_SMEM(nms_sort_kernel, kSortSmemKeys * 8);
+  DSPMB_ENSURE_DYN_SMEM(nms_scan_kernel, 200 * 1024);
   const int *order = nullptr;
   if (!presorted) {
     const int npad = next_pow2(N < 2 ? 2 : N);

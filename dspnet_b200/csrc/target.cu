@@ -997,12 +997,8 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
   DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 28);
   DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    DSPMB_CUDA_TRY(cudaFuncSetAttribute(target_match_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 200 * 1024);
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 200 * 1024);
   const int phases = tuning(DSPMB_TUNE_PHASES);
   dim3 grid1(ta.T, B);
   if (phases & 1) {
