@@ -305,7 +305,7 @@ def main():
             ev1.record()
             torch.cuda.synchronize()
             res[name] = ev0.elapsed_time(ev1) / args.steps
-        lib.dspmb_set_tuning(_lib.TUNE_PHASES, 15)
+        lib.dspmb_set_tuning(_lib.TUNE_PHASES, _lib.PHASES_ALL)
         lib.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, cache_was)
         return res
 
@@ -314,7 +314,8 @@ def main():
         plan.run(prob_sets[s], loc_sets[s], anchors, out_sets[s])
     for s in range(ROTATE):  # every workspace-dependent phase input exists for every rotating set
         det_run(s)
-    kernels = time_phases(det_run, [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_nms_kernel")])
+    kernels = time_phases(det_run, [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_pair_kernel"),
+                                    (8, "det_resolve_kernel")])
     nslots = 16
 
     # ---- end to end through the public operator with HOST buffers (pinned in, result read back) ----

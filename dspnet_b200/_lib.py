@@ -17,7 +17,9 @@ ERR_MINING_CANDIDATES = -3
 ERR_MINING_THRESH = -4
 ERR_WORKSPACE = -5
 ERR_CUDA = -6
-TUNE_DET_STREAM_VARIANT, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS, TUNE_PHASES, TUNE_GRAPH_CACHE = range(6)
+(TUNE_DET_STREAM_VARIANT, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS, TUNE_PHASES, TUNE_GRAPH_CACHE,
+ TUNE_DET_PIPELINE, TUNE_TARGET_PIPELINE, TUNE_NMS_PIPELINE) = range(9)
+PHASES_ALL = 31
 
 # every symbol include/dspmb.h declares (tests check that the built library exports all of them)
 EXPORTS = (
@@ -26,7 +28,7 @@ EXPORTS = (
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
     "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32", "dspmb_set_tuning", "dspmb_gather_buffer_bytes", "dspmb_p2p_alloc",
     "dspmb_p2p_open", "dspmb_p2p_close", "dspmb_p2p_free", "dspmb_detection_gather_f32", "dspmb_detection_gather_wait", "dspmb_detection_gather_read",
-    "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32",
+    "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32", "dspmb_last_launch_count",
 )
 
 
@@ -55,6 +57,7 @@ def lib():
     fp = ctypes.POINTER(c_float)
     ip = ctypes.POINTER(c_int)
     L.dspmb_version.restype = c_int
+    L.dspmb_last_launch_count.restype = c_int
     L.dspmb_last_error.restype = ctypes.c_char_p
     L.dspmb_set_libm_mode.argtypes = [c_int]
     L.dspmb_set_libm_mode.restype = c_int

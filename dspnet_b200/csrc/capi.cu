@@ -10,7 +10,8 @@
 namespace dspmb {
 
 static thread_local char g_error[512] = "";
-static int g_libm_mode = -1;
+static thread_local int g_last_launches = 0;
+static std::atomic<int> g_libm_mode{-1};
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -35,17 +36,22 @@ static int detect_host_libm_mode() {
 #endif
 }
 
-constexpr int kNumTuning = 6;
-static int g_tuning[kNumTuning] = {2, 320, 1024, 8192, 15, 1};
-static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 15, 1};
-int tuning(int knob) { return g_tuning[knob]; }
+constexpr int kNumTuning = DSPMB_NUM_TUNING;
+// knobs may be set from one thread while another launches: relaxed atomics (each call reads a knob once)
+static std::atomic<int> g_tuning[kNumTuning] = {{2}, {320}, {1024}, {8192}, {31}, {1}, {1}, {1}, {1}};
+static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 31, 1, 1, 1, 1};
+int tuning(int knob) { return g_tuning[knob].load(std::memory_order_relaxed); }
 
 int libm_fma_mode() {
-  if (g_libm_mode < 0) g_libm_mode = detect_host_libm_mode();
-  return g_libm_mode;
+  int m = g_libm_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    m = detect_host_libm_mode();
+    g_libm_mode.store(m, std::memory_order_relaxed);
+  }
+  return m;
 }
 
-bool g_profile_on = false;
+std::atomic<bool> g_profile_on{false};
 namespace {
 struct ProfileRecord {
   int slot;
@@ -56,7 +62,8 @@ std::vector<ProfileRecord> g_profile_records;
 const char *const kSlotNames[kNumKernelSlots] = {
     "prior_kernel",        "det_stream_kernel", "det_sort_kernel", "det_nms_kernel",  "target_stream_kernel",
     "target_match_kernel", "nms_sort_kernel",   "nms_gather_kernel", "nms_mask_kernel", "nms_scan_kernel",
-    "det_compact_kernel"};
+    "det_compact_kernel",  "det_pair_kernel",   "det_resolve_kernel", "target_fixup_kernel", "nms_tile_kernel",
+    "nms_reduce_kernel",   "softmax_det_kernel", "multibox_loss_kernel"};
 }  // namespace
 
 void profile_mark(int slot, cudaStream_t stream, bool begin) {
@@ -82,19 +89,43 @@ struct GraphEntry {
   std::vector<unsigned char> key;
   cudaGraphExec_t exec = nullptr;
   bool uncacheable = false;
+  int device = 0;
+  int launches = 0;
   unsigned long long last_use = 0;
 };
 constexpr size_t kGraphCacheEntries = 32;
+constexpr int kMaxDevices = 64;
 std::mutex g_graph_mutex;
 std::vector<GraphEntry> g_graph_cache;
 unsigned long long g_graph_clock = 0;
-cudaStream_t g_capture_stream[64] = {};
+struct CaptureSet {  // private streams / events of one device, used only under g_graph_mutex
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+CaptureSet g_capture[kMaxDevices];
 }  // namespace
+
+int LaunchCtx::fork() const {
+  if (!side) return DSPMB_OK;
+  DSPMB_CUDA_TRY(cudaEventRecord(ev_fork, stream));
+  DSPMB_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+  return DSPMB_OK;
+}
+int LaunchCtx::join() const {
+  if (!side) return DSPMB_OK;
+  DSPMB_CUDA_TRY(cudaEventRecord(ev_join, side));
+  DSPMB_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+  return DSPMB_OK;
+}
 
 int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long long> &done) {
   int dev = 0;
   DSPMB_CUDA_TRY(cudaGetDevice(&dev));
-  const unsigned long long bit = 1ull << (dev & 63);
+  if (dev < 0 || dev >= 64) {
+    set_error("device ordinal %d is outside the supported range [0, 64)", dev);
+    return DSPMB_ERR_BAD_ARG;
+  }
+  const unsigned long long bit = 1ull << dev;
   if (!(done.load(std::memory_order_acquire) & bit)) {
     DSPMB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     done.fetch_or(bit, std::memory_order_release);
@@ -103,21 +134,27 @@ int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long lon
 }
 
 int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
-                        const std::function<int(cudaStream_t)> &launch) {
-  if (!tuning(DSPMB_TUNE_GRAPH_CACHE) || g_profile_on) return launch(stream);
+                        const std::function<int(const LaunchCtx &)> &launch) {
+  LaunchCtx direct;
+  direct.stream = stream;
+  struct Publish {  // whichever context ran last tells this thread how many kernels the call enqueued
+    const LaunchCtx &c;
+    ~Publish() { g_last_launches = c.launches; }
+  } publish{direct};
+  if (!tuning(DSPMB_TUNE_GRAPH_CACHE) || g_profile_on) return launch(direct);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
     cudaGetLastError();
-    return launch(stream);
+    return launch(direct);
   }
   int dev = 0;
   DSPMB_CUDA_TRY(cudaGetDevice(&dev));
-  if (dev < 0 || dev >= 64) return launch(stream);
+  if (dev < 0 || dev >= kMaxDevices) return launch(direct);
   // the key also pins the device and every path-selection knob
   std::vector<unsigned char> key(key_len + sizeof(int) * (kNumTuning + 2));
   memcpy(key.data(), key_, key_len);
   int extra[kNumTuning + 2];
-  for (int k = 0; k < kNumTuning; ++k) extra[k] = g_tuning[k];
+  for (int k = 0; k < kNumTuning; ++k) extra[k] = tuning(k);
   extra[kNumTuning] = dev;
   extra[kNumTuning + 1] = libm_fma_mode();
   memcpy(key.data() + key_len, extra, sizeof(extra));
@@ -135,35 +172,50 @@ int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
       for (size_t i = 1; i < g_graph_cache.size(); ++i)
         if (g_graph_cache[i].last_use < g_graph_cache[lru].last_use) lru = i;
       if (g_graph_cache[lru].exec) {
-        cudaDeviceSynchronize();  // rare; the evicted graph may still be in flight
+        // rare; the evicted graph may still be in flight on ITS device (not necessarily the current one)
+        if (g_graph_cache[lru].device != dev) cudaSetDevice(g_graph_cache[lru].device);
+        cudaDeviceSynchronize();
         cudaGraphExecDestroy(g_graph_cache[lru].exec);
+        if (g_graph_cache[lru].device != dev) cudaSetDevice(dev);
       }
       g_graph_cache.erase(g_graph_cache.begin() + lru);
     }
     GraphEntry e;
     e.key = std::move(key);
+    e.device = dev;
     e.last_use = ++g_graph_clock;
     g_graph_cache.push_back(std::move(e));
-    return launch(stream);
+    return launch(direct);
   }
   hit->last_use = ++g_graph_clock;
-  if (hit->uncacheable) return launch(stream);
-  if (!hit->exec) {  // second sighting: capture on the private stream of this device
-    if (!g_capture_stream[dev]) DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&g_capture_stream[dev], cudaStreamNonBlocking));
-    cudaStream_t cs = g_capture_stream[dev];
-    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+  if (hit->uncacheable) return launch(direct);
+  if (!hit->exec) {  // second sighting: capture on the private streams of this device
+    CaptureSet &cs = g_capture[dev];
+    if (!cs.main) {
+      DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.main, cudaStreamNonBlocking));
+      DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.side, cudaStreamNonBlocking));
+      DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_fork, cudaEventDisableTiming));
+      DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_join, cudaEventDisableTiming));
+    }
+    if (cudaStreamBeginCapture(cs.main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
       hit->uncacheable = true;
-      return launch(stream);
+      return launch(direct);
     }
-    const int rc = launch(cs);
+    LaunchCtx ctx;
+    ctx.stream = cs.main;
+    ctx.side = cs.side;
+    ctx.ev_fork = cs.ev_fork;
+    ctx.ev_join = cs.ev_join;
+    const int rc = launch(ctx);
+    hit->launches = ctx.launches;
     cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    const cudaError_t ce = cudaStreamEndCapture(cs.main, &graph);
     if (rc != DSPMB_OK || ce != cudaSuccess || !graph) {
       cudaGetLastError();
       if (graph) cudaGraphDestroy(graph);
       hit->uncacheable = true;
-      return rc != DSPMB_OK ? rc : launch(stream);
+      return rc != DSPMB_OK ? rc : launch(direct);
     }
     cudaGraphExec_t exec = nullptr;
     const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
@@ -171,11 +223,12 @@ int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
     if (ie != cudaSuccess || !exec) {
       cudaGetLastError();
       hit->uncacheable = true;
-      return launch(stream);
+      return launch(direct);
     }
     hit->exec = exec;
   }
   DSPMB_CUDA_TRY(cudaGraphLaunch(hit->exec, stream));
+  direct.launches = hit->launches;
   return DSPMB_OK;
 }
 
@@ -195,18 +248,20 @@ using namespace dspmb;
 
 extern "C" int dspmb_version(void) { return DSPMB_VERSION; }
 
+extern "C" int dspmb_last_launch_count(void) { return g_last_launches; }
+
 extern "C" const char *dspmb_last_error(void) { return g_error; }
 
 extern "C" int dspmb_set_libm_mode(int mode) {
-  g_libm_mode = mode < 0 ? detect_host_libm_mode() : (mode ? 1 : 0);
-  return g_libm_mode;
+  const int m = mode < 0 ? detect_host_libm_mode() : (mode ? 1 : 0);
+  g_libm_mode.store(m, std::memory_order_relaxed);
+  return m;
 }
 
 extern "C" int dspmb_set_tuning(int knob, int value) {
   if (knob < 0 || knob >= kNumTuning) return -1;
-  const int old = g_tuning[knob];
-  g_tuning[knob] = value < 0 ? 0 : (value > kTuningMax[knob] ? kTuningMax[knob] : value);
-  return old;
+  const int v = value < 0 ? 0 : (value > kTuningMax[knob] ? kTuningMax[knob] : value);
+  return g_tuning[knob].exchange(v, std::memory_order_relaxed);
 }
 
 extern "C" int dspmb_status(const void *workspace, void *stream) {
@@ -234,7 +289,7 @@ extern "C" int dspmb_status(const void *workspace, void *stream) {
 
 extern "C" int dspmb_profile_enable(int on) {
   g_profile_on = on != 0;
-  return g_profile_on ? 1 : 0;
+  return on != 0 ? 1 : 0;
 }
 
 extern "C" int dspmb_profile_read(float *ms, int *launches, int max_slots) {

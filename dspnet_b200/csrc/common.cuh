@@ -50,9 +50,16 @@ enum KernelSlot {
   kSlotNmsMask,
   kSlotNmsScan,
   kSlotDetCompact,
+  kSlotDetPair,
+  kSlotDetResolve,
+  kSlotTargetFixup,
+  kSlotNmsTile,
+  kSlotNmsReduce,
+  kSlotSoftmaxDet,
+  kSlotLoss,
   kNumKernelSlots
 };
-extern bool g_profile_on;
+extern std::atomic<bool> g_profile_on;
 void profile_mark(int slot, cudaStream_t stream, bool begin);
 struct ProfileScope {  // brackets one kernel launch when profiling is enabled
   int slot;
@@ -82,8 +89,22 @@ int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long lon
 // that reaches a kernel argument) is seen for the second time is captured once on a private stream and replayed
 // with one cudaGraphLaunch from then on, which removes the per-launch gaps of a 4-kernel step.  Bypassed while
 // per-kernel profiling is on, while `stream` is itself being captured, or with DSPMB_TUNE_GRAPH_CACHE = 0.
+// An operator whose launches form a fork/join (detection v2: the sort kernel and the pair-test kernel both depend
+// only on the stream kernel) receives a side stream and two events while it is being captured by the cache: work
+// enqueued on `side` between fork() and join() becomes a parallel branch of the graph.  Outside our own capture
+// (first sighting, profiling, a caller's capture) `side` is null and fork()/join() are no-ops: everything runs in
+// order on `stream`.
+struct LaunchCtx {
+  cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  mutable int launches = 0;  // kernels (and memset nodes) the operator enqueued; read back by dspmb_last_launch_count
+  cudaStream_t branch() const { return side ? side : stream; }
+  int fork() const;
+  int join() const;
+};
 int graph_cached_launch(const void *key, size_t key_len, cudaStream_t stream,
-                        const std::function<int(cudaStream_t)> &launch);
+                        const std::function<int(const LaunchCtx &)> &launch);
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

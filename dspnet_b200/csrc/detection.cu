@@ -72,8 +72,21 @@ struct DetWorkspace {
   unsigned char *seg_dead;    // (B, A)
   float *seg_area;            // (B, A) areas of large segments
   unsigned long long *sort_keys;  // (B, npad) spill for selections larger than the shared-memory budget
+  // fork/join pipeline (det_pair_kernel / det_resolve_kernel)
+  float4 *cbox;               // (B, Apad) boxes of a tile's survivors grouped by class (rank order inside a class)
+  unsigned short *crank;      // (B, cls_stride) their index inside the tile's run
+  unsigned *tile_cls;         // (B, kV2ClsPad, Tmax) per (class, tile): offset | count << 16 inside the tile's run
+  int *head_rank;             // (B, Apad) pass-1 rank of the row sorted to head position q
+  unsigned char *seg;         // (B, kV2ClsPad) segment records: member ranks + symmetric suppression mask
   size_t bytes;
 };
+
+constexpr int kV2ClsPad = 32;    // foreground classes the fork/join pipeline supports
+constexpr int kV2MaxTiles = 512; // tiles per image whose bases fit its shared-memory tables
+// segment record: [0] n | [64] rowany u64[8] | [128] selfadj u64[8] | [192] ranks int[320] | [1472] mask u64[320*W]
+constexpr int kSegRowanyOff = 64, kSegSelfOff = 128, kSegRankOff = 192;
+constexpr int kSegMaskOff = kSegRankOff + kNmsMaskRows * 4;
+constexpr int kSegBytes = (kSegMaskOff + kNmsMaskRows * 5 * 8 + 255) / 256 * 256;
 
 inline int next_pow2(int v) {
   int p = 1;
@@ -83,7 +96,6 @@ inline int next_pow2(int v) {
 
 // Layout is a pure function of (B, A, C); T and Apad are bounded with the smallest tile (128 anchors).
 DetWorkspace carve(void *base, int B, int A, int C) {
-  (void)C;
   DetWorkspace w;
   const size_t Tmax = (size_t)ceil_div(A, kStreamThreads);
   const size_t Apad = (((size_t)A + 3) & ~(size_t)3) + 4 * kStreamThreads;  // multiple of 4: 128-bit key loads
@@ -111,6 +123,11 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.seg_dead = (unsigned char *)take((size_t)B * A);
   w.seg_area = (float *)take(sizeof(float) * (size_t)B * A);
   w.sort_keys = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * next_pow2(A));
+  w.cbox = (float4 *)take(sizeof(float4) * B * Apad);
+  w.crank = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
+  w.tile_cls = (unsigned *)take(sizeof(unsigned) * (size_t)B * kV2ClsPad * Tmax);
+  w.head_rank = (int *)take(sizeof(int) * B * Apad);
+  w.seg = (unsigned char *)take((size_t)B * (C - 1 <= kV2ClsPad && C > 1 ? C - 1 : 0) * kSegBytes);
   w.bytes = off;
   return w;
 }
@@ -123,6 +140,9 @@ struct StreamArgs {
   unsigned *slot_keys;        // (B, Apad) their order keys
   unsigned short *slot_cls;   // (B, cls_stride)
   float4 *slot_box;           // (B, Apad)
+  float4 *cbox;               // class-grouped copies for the pair-test kernel (fork/join pipeline only)
+  unsigned short *crank;
+  unsigned *tile_cls;
   int A, C, T, Apad, cls_stride;
   float threshold;
   int clip;
@@ -534,7 +554,7 @@ struct BulkSmem {
   unsigned short idx[kTile], id[kTile];
 };
 
-template <int NFG, int kThreads, int kVec>
+template <int NFG, int kThreads, int kVec, bool kV2>
 __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
   constexpr int kTile = kThreads * kVec;
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
@@ -617,6 +637,58 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
   }
   __syncthreads();  // the staged rows are complete
   flush_rows(a, sm.u.rows, b, tile_begin, total);
+  if constexpr (kV2) {
+    // Class-grouped copy of the tile's boxes for the pair-test kernel: a stable counting sort of the <= kTile
+    // survivors by class.  Lanes of a warp that hold the same class find each other with MATCH.ANY; the lowest of
+    // them records the group's size per (round, warp); a 32-lane pass turns the table into offsets.  The table
+    // aliases the loc_pred stage, which is dead once the rows are staged.
+    static_assert(NFG <= kV2ClsPad, "tile_cls holds kV2ClsPad classes");
+    constexpr int kWarps = kThreads / 32, kParts = kVec * kWarps;
+    static_assert(sizeof(float) * kTile * 5 >= (kParts * 32 + 33) * sizeof(unsigned short) + kParts * sizeof(unsigned),
+                  "class table does not fit in the loc stage");
+    unsigned short(*cnt)[32] = reinterpret_cast<unsigned short(*)[32]>(sm.loc);
+    unsigned short *coff = reinterpret_cast<unsigned short *>(sm.loc) + kParts * 32;  // [33]
+    unsigned *present = reinterpret_cast<unsigned *>(coff + 34);                      // [kParts], 4-byte aligned
+    const unsigned lane = lane_id(), warp = warp_id();
+    int within[kVec], cc[kVec];
+#pragma unroll
+    for (int r = 0; r < kVec; ++r) {
+      const int j = r * kThreads + (int)threadIdx.x;
+      const bool valid = j < total;
+      cc[r] = valid ? (int)sm.u.rows.cls[j] : 0xffff;
+      const unsigned m = __match_any_sync(kFullMask, cc[r]);
+      within[r] = __popc(m & ((1u << lane) - 1u));
+      const bool leader = valid && within[r] == 0;
+      if (leader) cnt[r * kWarps + warp][cc[r]] = (unsigned short)__popc(m);
+      const unsigned pres = __reduce_or_sync(kFullMask, leader ? 1u << cc[r] : 0u);
+      if (lane == 0) present[r * kWarps + warp] = pres;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int run = 0;
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) {
+        const int v = (present[q] >> lane) & 1u ? (int)cnt[q][lane] : 0;
+        cnt[q][lane] = (unsigned short)run;
+        run += v;
+      }
+      const int off = warp_scan_incl(run) - run;
+      coff[lane] = (unsigned short)off;
+      if ((int)lane < NFG) a.tile_cls[((size_t)b * kV2ClsPad + lane) * a.T + t] = (unsigned)off | ((unsigned)run << 16);
+    }
+    __syncthreads();
+    float4 *gb = a.cbox + (size_t)b * a.Apad + tile_begin;
+    unsigned short *gr = a.crank + (size_t)b * a.cls_stride + tile_begin;
+#pragma unroll
+    for (int r = 0; r < kVec; ++r) {
+      const int j = r * kThreads + (int)threadIdx.x;
+      if (j < total) {
+        const int pos = (int)coff[cc[r]] + (int)cnt[r * kWarps + warp][cc[r]] + within[r];
+        gb[pos] = sm.u.rows.box[j];
+        gr[pos] = (unsigned short)j;
+      }
+    }
+  }
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -744,6 +816,7 @@ struct SortArgs {
   unsigned short *row_cls;
   float4 *row_box;
   unsigned long long *sort_keys;
+  int *head_rank;                   // (B, Apad) pass-1 rank of every head row (fork/join pipeline), or null
   int *valid_count_out;
   WsHeader *header;
   int A, T, tile, Apad, cls_stride, npad_max, niter_max;
@@ -1047,6 +1120,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     o[6] = s6;
     row_cls[r] = (unsigned short)s0;
     row_box[r] = make_float4(s2, s3, s4, s5);
+    if (a.head_rank) a.head_rank[(size_t)b * a.Apad + r] = p;
   }
   // the NMS kernel reads row_cls eight entries at a time: define the entries between V and the next multiple of 8
   if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7)) row_cls[V + threadIdx.x] = (unsigned short)0xffffu;
@@ -1112,7 +1186,9 @@ __device__ __forceinline__ bool suppresses(float4 a, float area_a, float4 b, flo
 constexpr int kNmsQueue = 256;  // per-warp candidate queue entries of the small-segment path
 constexpr int kNmsTab = 512;  // ballot-count table entries: 64 iterations x 8 warps = 131072 rows per sweep
 
-__global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_constant__ NmsArgs a) {
+// NMS of one (image, class) segment -- or of the whole image with force_suppress -- on rows in FINAL order
+// (row_cls / row_box).  Body of det_nms_kernel; det_resolve_kernel calls it for segments too large for its mask.
+__device__ __forceinline__ void nms_final_order_body(const NmsArgs &a, const int b, const int seg) {
   // shared memory is a union of the two paths:
   //   small (n <= mask_rows <= 320): boxes[320] float4 + mask[320 * 5] u64 + list[320] int + areas[320]  (20 KB)
   //   large:                         boxes[1024] float4 + dead[1024] + 64 words + areas[1024]             (21.5 KB)
@@ -1130,7 +1206,6 @@ __global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_co
   __shared__ int scan_smem[kNmsThreads / 32 + 1];
   __shared__ int carry_smem, sm_base;
 
-  const int b = blockIdx.y, seg = blockIdx.x;
   const int V = a.nms_rows[b];
   if (V == 0 || (a.debug & 4)) return;
   float *out = a.out + (size_t)b * a.A * 7;
@@ -1508,6 +1583,397 @@ __global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_co
     if (dead[q]) out[(size_t)(identity ? q : glist[q]) * 7] = -1.f;
 }
 
+__global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_constant__ NmsArgs a) {
+  nms_final_order_body(a, (int)blockIdx.y, (int)blockIdx.x);
+}
+
+// ====================================================================================================
+// Fork/join pipeline (the default for the VOC / Cityscapes heads):
+//
+//   det_stream_bulk_kernel<.., kV2>  as above + a class-grouped copy of every tile's boxes (cbox / crank / tile_cls)
+//   det_sort_kernel    (grid B)      ||   det_pair_kernel (grid (C-1, B))      -- both depend only on the stream kernel
+//   det_resolve_kernel (grid (C-1, B))
+//
+// Which pairs of a class overlap by IoU >= thr does not depend on the row order -- only the greedy resolve does
+// (multibox_detection.cc:153-167 walks the rows in final order).  det_pair_kernel therefore builds, per (image,
+// class), the member list in pass-1 RANK order straight from the tiles' class-grouped runs (no pass over all V rows)
+// and the SYMMETRIC suppression mask of the segment while the sort kernel is still selecting and sorting the
+// nms_topk head; it also moves the tail rows [nkeep, V) to their final positions (the old rank role).  The final
+// order of a class is  [its head rows in sorted order] ++ [its members of rank >= nkeep in rank order]; a row can
+// appear in both parts (the tail quirk) or in neither (rank < nkeep but not among the nms_topk best).
+// det_resolve_kernel replays the greedy loop on that sequence with the precomputed mask:
+//   * an alive row ORs its mask row into the removed sets; with a symmetric mask that also marks EARLIER adjacent
+//     rows, which is harmless: an earlier adjacent row that was still alive would have removed this one;
+//   * head nodes and tail nodes of the same member are distinct nodes: removed-head and removed-tail bit sets, and
+//     a self bit (IoU(box, box) >= thr, i.e. the box is not degenerate) lets an alive head row remove its own
+//     duplicate in the tail, as the reference does.
+// Segments with more than mask_rows members are left to nms_final_order_body inside the resolve kernel.
+struct PairArgs {
+  float *out;
+  const int *tile_count;
+  const unsigned *tile_cls;
+  const float *slot_rows;
+  const unsigned short *slot_cls;
+  const float4 *slot_box;
+  const float4 *cbox;
+  const unsigned short *crank;
+  unsigned short *row_cls;
+  float4 *row_box;
+  unsigned char *seg;
+  const int *nms_rows;   // resolve kernel only
+  const int *head_rank;  // resolve kernel only
+  int A, T, tile, Apad, cls_stride, nfg;
+  float nms_threshold;
+  int nms_topk, mask_rows;
+};
+
+// Exclusive block scan of one 64-bit value per thread (two packed 32-bit counters); `smem`: blockDim.x/32 + 1 words.
+__device__ __forceinline__ unsigned long long block_scan_excl_u64(unsigned long long v, unsigned long long *smem,
+                                                                  unsigned long long *total) {
+  unsigned long long incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long o = __shfl_up_sync(kFullMask, incl, d);
+    if ((int)lane_id() >= d) incl += o;
+  }
+  const unsigned w = warp_id(), l = lane_id(), nw = (blockDim.x + 31) >> 5;
+  if (l == 31) smem[w] = incl;
+  __syncthreads();
+  if (w == 0) {
+    const unsigned long long s = l < nw ? smem[l] : 0ull;
+    unsigned long long si = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long o = __shfl_up_sync(kFullMask, si, d);
+      if ((int)l >= d) si += o;
+    }
+    if (l < nw) smem[l] = si - s;
+    if (l == 31) smem[nw] = si;
+  }
+  __syncthreads();
+  *total = smem[nw];
+  return smem[w] + incl - v;
+}
+
+__device__ __forceinline__ int lower_bound_i32(const int *v, int n, int x) {  // first index with v[i] >= x
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (v[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_constant__ PairArgs a) {
+  constexpr int kOffMask = kNmsMaskRows * 16, kOffArea = kOffMask + kNmsMaskRows * 5 * 8;
+  constexpr int kOffRank = kOffArea + kNmsMaskRows * 4, kOffQueue = kOffRank + kNmsMaskRows * 4;
+  constexpr int kBytes = kOffQueue + (kNmsThreads / 32) * kNmsQueue * 2;
+  constexpr int kWarps = kNmsThreads / 32;
+  __shared__ __align__(16) unsigned char smem_raw[kBytes];
+  __shared__ int sm_tbase[kV2MaxTiles], sm_mbase[kV2MaxTiles];
+  __shared__ unsigned long long scan_smem[kWarps + 1];
+  __shared__ unsigned long long sm_carry;
+  __shared__ unsigned long long rowany[8], selfadj[8];
+  __shared__ float4 gbb[kNmsMaskRows / 32];
+  __shared__ unsigned char unit_tab[64];
+  __shared__ int sm_nunits;
+
+  const int b = blockIdx.y, c = blockIdx.x, T = a.T;
+  const unsigned lane = lane_id(), warp = warp_id();
+  const int *cnt = a.tile_count + (size_t)b * T;
+  const unsigned *tcls = a.tile_cls + ((size_t)b * kV2ClsPad + c) * T;
+  if (threadIdx.x == 0) {
+    sm_carry = 0ull;
+    sm_nunits = 0;
+  }
+  if (threadIdx.x < 8) {
+    rowany[threadIdx.x] = 0ull;
+    selfadj[threadIdx.x] = 0ull;
+  }
+  __syncthreads();
+  // rank base of every tile (low word) and member base of this class in every tile (high word), one packed scan
+  for (int base = 0; base < T; base += blockDim.x) {
+    const int t = base + threadIdx.x;
+    const unsigned long long v =
+        t < T ? ((unsigned long long)(unsigned)cnt[t] | ((unsigned long long)(tcls[t] >> 16) << 32)) : 0ull;
+    unsigned long long total;
+    const unsigned long long ex = block_scan_excl_u64(v, scan_smem, &total);
+    const unsigned long long carry = sm_carry;
+    if (t < T) {
+      sm_tbase[t] = (int)(unsigned)(carry + ex);
+      sm_mbase[t] = (int)((carry + ex) >> 32);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm_carry = carry + total;
+    __syncthreads();
+  }
+  const int V = (int)(unsigned)sm_carry, n = (int)(sm_carry >> 32);
+  unsigned char *seg = a.seg + ((size_t)b * a.nfg + c) * kSegBytes;
+  if (threadIdx.x == 0) *reinterpret_cast<int *>(seg) = n;
+  if (V < 1) return;
+  const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;  // multibox_detection.cc:142-145
+
+  // ---- tail rows [nkeep, V): the runs of tiles c, c + nfg, ... move to their pass-1 positions (one warp per tile) ----
+  if (nkeep < V) {
+    for (int t = c + (int)warp * a.nfg; t < T; t += kWarps * a.nfg) {
+      const int base = sm_tbase[t];
+      const int nt = (t + 1 < T ? sm_tbase[t + 1] : V) - base;
+      const int skip = min(nt, max(0, nkeep - base));
+      if (skip >= nt) continue;
+      const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
+      const float *src = a.slot_rows + slot0 * 7;
+      float *dst = a.out + ((size_t)b * a.A + base) * 7;
+      const int end = nt * 7;
+      for (int q = skip * 7 + (int)lane; q < end; q += 128) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = q + 32 * k < end ? src[q + 32 * k] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (q + 32 * k < end) dst[q + 32 * k] = v[k];
+      }
+      const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
+      const float4 *sbx = a.slot_box + slot0;
+      unsigned short *dc = a.row_cls + (size_t)b * a.cls_stride + base;
+      float4 *db = a.row_box + (size_t)b * a.A + base;
+      for (int q = skip + (int)lane; q < nt; q += 32) {
+        dc[q] = sc[q];
+        db[q] = sbx[q];
+      }
+    }
+  }
+  if (n < 1 || n > a.mask_rows) return;  // empty, or left to the final-order path of the resolve kernel
+
+  // ---- members of class c in rank order: every tile's run of this class is contiguous in cbox / crank ----
+  float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
+  unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kOffMask);
+  float *areas = reinterpret_cast<float *>(smem_raw + kOffArea);
+  int *ranks = reinterpret_cast<int *>(smem_raw + kOffRank);
+  unsigned short *queue = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue) + warp * kNmsQueue;
+  const NmsThr thr = make_thr(a.nms_threshold);
+  const int W = (n + 63) >> 6, npad = (n + 31) & ~31;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const unsigned cw = tcls[t];
+    const int mc = (int)(cw >> 16);
+    if (mc == 0) continue;
+    const int mb = sm_mbase[t], tb = sm_tbase[t];
+    const size_t s0 = (size_t)t * a.tile + (cw & 0xffffu);
+    const unsigned short *cr = a.crank + (size_t)b * a.cls_stride + s0;
+    const float4 *cb = a.cbox + (size_t)b * a.Apad + s0;
+    for (int i = 0; i < mc; ++i) {
+      ranks[mb + i] = tb + (int)cr[i];
+      boxes[mb + i] = stage_box(__ldg(cb + i), &areas[mb + i]);
+    }
+  }
+  for (int q = n + threadIdx.x; q < npad; q += blockDim.x)
+    boxes[q] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);  // overlaps nothing
+  for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = 0ull;
+  __syncthreads();
+
+  // ---- bounding box of every 32-row group (unit culling) and the self bits ----
+  const int ngroups = npad >> 5;
+  for (int g = warp; g < ngroups; g += kWarps) {
+    const int q = (g << 5) + lane;
+    const float4 bx = boxes[q];
+    const bool ok = bx.x < __int_as_float(0x7f800000);  // padded / degenerate rows never pass the candidate test
+    float x1 = ok ? bx.x : __int_as_float(0x7f800000), y1 = ok ? bx.y : __int_as_float(0x7f800000);
+    float x2 = ok ? bx.z : __int_as_float(0xff800000), y2 = ok ? bx.w : __int_as_float(0xff800000);
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      x1 = fminf(x1, __shfl_xor_sync(kFullMask, x1, m));
+      y1 = fminf(y1, __shfl_xor_sync(kFullMask, y1, m));
+      x2 = fmaxf(x2, __shfl_xor_sync(kFullMask, x2, m));
+      y2 = fmaxf(y2, __shfl_xor_sync(kFullMask, y2, m));
+    }
+    if (lane == 0) gbb[g] = make_float4(x1, y1, x2, y2);
+    // a row appearing both in the sorted head and in the tail suppresses its own copy iff IoU(box, box) >= thr
+    const bool self = q < n && suppresses(bx, areas[q], bx, areas[q], thr);
+    const unsigned bal = __ballot_sync(kFullMask, self);
+    if (lane == 0) reinterpret_cast<unsigned *>(selfadj)[g] = bal;
+  }
+  __syncthreads();
+  {  // units (row group <= column group) whose group boxes touch; any order, dealt round-robin to the warps
+    const int nall = ngroups * (ngroups + 1) / 2;  // <= 55
+    if ((int)threadIdx.x < nall) {
+      int rg = 0, rem = threadIdx.x;
+      while (rem >= ngroups - rg) {
+        rem -= ngroups - rg;
+        ++rg;
+      }
+      const int cg = rg + rem;
+      const float4 p = gbb[rg], q = gbb[cg];
+      if (p.z > q.x && q.z > p.x && p.w > q.y && q.w > p.y) unit_tab[atomicAdd(&sm_nunits, 1)] = (unsigned char)((rg << 4) | cg);
+    }
+  }
+  __syncthreads();
+  const int nunits = sm_nunits;
+  unsigned *mask32 = reinterpret_cast<unsigned *>(mask);
+  unsigned *rowany32 = reinterpret_cast<unsigned *>(rowany);
+  for (int u = warp; u < nunits; u += kWarps) {
+    const unsigned rc = unit_tab[u];
+    const int rg = (int)(rc >> 4), cg = (int)(rc & 15u);
+    const int i = (rg << 5) + lane;
+    float4 bi = boxes[i];
+    // Necessary condition for IoU >= thr (see nms_final_order_body): box j must reach into box i shrunk by
+    // thr x (w_i, h_i) on every side, rounded outwards.
+    const float wi = __fsub_rd(bi.z, bi.x), hi = __fsub_rd(bi.w, bi.y);
+    const bool shrink_ok = wi >= 0x1p-40f && hi >= 0x1p-40f;
+    const float tw = shrink_ok ? __fmul_rd(thr.shrink, wi) : 0.f, th = shrink_ok ? __fmul_rd(thr.shrink, hi) : 0.f;
+    const float sl = __fadd_rd(bi.x, tw), sr = __fsub_ru(bi.z, tw), st = __fadd_rd(bi.y, th), sb = __fsub_ru(bi.w, th);
+    const int jb = cg << 5;
+    unsigned cand = 0u;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const float4 bj = boxes[jb + jj];
+      asm("{\n\t.reg .pred p;\n\t"
+          "setp.gt.f32 p, %1, %2;\n\t"
+          "setp.gt.and.f32 p, %3, %4, p;\n\t"
+          "setp.gt.and.f32 p, %5, %6, p;\n\t"
+          "setp.gt.and.f32 p, %7, %8, p;\n\t"
+          "@p or.b32 %0, %0, %9;\n\t}"
+          : "+r"(cand)
+          : "f"(sr), "f"(bj.x), "f"(bj.z), "f"(sl), "f"(sb), "f"(bj.y), "f"(bj.w), "f"(st), "r"(1u << jj));
+    }
+    if (cg == rg) cand &= lane == 31 ? 0u : ~0u << (lane + 1);  // each unordered pair once
+    const int cnum = __popc(cand);
+    const int incl = warp_scan_incl(cnum);
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    for (int base = 0; base < total; base += kNmsQueue) {
+      int pos = incl - cnum - base;
+      if (total <= kNmsQueue) {
+        for (unsigned m = cand; m; m &= m - 1, ++pos) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+      } else {
+        for (unsigned m = cand; m; m &= m - 1, ++pos)
+          if (pos >= 0 && pos < kNmsQueue) queue[pos] = (unsigned short)((lane << 5) | (__ffs(m) - 1));
+      }
+      __syncwarp();
+      const int qn = min(kNmsQueue, total - base);
+      for (int q = lane; q < qn; q += 32) {
+        const unsigned e = queue[q];
+        const int r = (rg << 5) + (int)(e >> 5), jj = (int)(e & 31u), j = jb + jj;
+        if (iou_ge(boxes[r], areas[r], boxes[j], areas[j], thr)) {
+          atomicOr(&mask32[r * 2 * W + cg], 1u << jj);        // row r, column j  (j >> 5 == cg)
+          atomicOr(&mask32[j * 2 * W + rg], 1u << (r & 31));  // and the transpose
+          atomicOr(&rowany32[rg], 1u << (r & 31));
+          atomicOr(&rowany32[cg], 1u << jj);
+        }
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // ---- segment record for the resolve kernel ----
+  int *g_rank = reinterpret_cast<int *>(seg + kSegRankOff);
+  unsigned long long *g_mask = reinterpret_cast<unsigned long long *>(seg + kSegMaskOff);
+  for (int q = threadIdx.x; q < n; q += blockDim.x) g_rank[q] = ranks[q];
+  for (int q = threadIdx.x; q < n * W; q += blockDim.x) g_mask[q] = mask[q];
+  if (threadIdx.x < 8) {
+    reinterpret_cast<unsigned long long *>(seg + kSegRowanyOff)[threadIdx.x] = rowany[threadIdx.x];
+    reinterpret_cast<unsigned long long *>(seg + kSegSelfOff)[threadIdx.x] = selfadj[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(kNmsThreads, 5) det_resolve_kernel(const __grid_constant__ PairArgs a,
+                                                                     const __grid_constant__ NmsArgs na) {
+  __shared__ unsigned long long mask[kNmsMaskRows * 5];
+  __shared__ int ranks[kNmsMaskRows], hq[kNmsMaskRows], tmpq[kNmsMaskRows];
+  __shared__ unsigned short hm[kNmsMaskRows], hp[kNmsMaskRows];
+  __shared__ unsigned char status[2 * kNmsMaskRows];
+  __shared__ unsigned long long rowany[8], selfadj[8];
+  __shared__ int sm_nh;
+  const int b = blockIdx.y, c = blockIdx.x;
+  const unsigned char *seg = a.seg + ((size_t)b * a.nfg + c) * kSegBytes;
+  const int n = *reinterpret_cast<const int *>(seg);
+  if (n < 1) return;
+  if (n > a.mask_rows) {  // rows are in their final places by now: the chunk-sweep path on final order
+    nms_final_order_body(na, b, c);
+    return;
+  }
+  const int V = a.nms_rows[b];
+  if (V == 0) return;
+  const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
+  const int W = (n + 63) >> 6;
+  {
+    const int *g_rank = reinterpret_cast<const int *>(seg + kSegRankOff);
+    const unsigned long long *g_mask = reinterpret_cast<const unsigned long long *>(seg + kSegMaskOff);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+      ranks[q] = g_rank[q];
+      hp[q] = (unsigned short)0xffffu;
+    }
+    for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = g_mask[q];
+    if (threadIdx.x < 8) {
+      rowany[threadIdx.x] = reinterpret_cast<const unsigned long long *>(seg + kSegRowanyOff)[threadIdx.x];
+      selfadj[threadIdx.x] = reinterpret_cast<const unsigned long long *>(seg + kSegSelfOff)[threadIdx.x];
+    }
+    if (threadIdx.x == 0) sm_nh = 0;
+  }
+  __syncthreads();
+  // head rows of this class (their positions q in the sorted head; every one of them is a member, so <= n)
+  const unsigned short *rcls = a.row_cls + (size_t)b * a.cls_stride;
+  for (int q = threadIdx.x; q < nkeep; q += blockDim.x)
+    if (rcls[q] == (unsigned short)c) tmpq[atomicAdd(&sm_nh, 1)] = q;
+  __syncthreads();
+  const int nh = sm_nh;
+  const int *hrank = a.head_rank + (size_t)b * a.Apad;
+  for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+    const int myq = tmpq[k];
+    int ord = 0;
+    for (int i = 0; i < nh; ++i) ord += tmpq[i] < myq ? 1 : 0;
+    const int m = lower_bound_i32(ranks, n, hrank[myq]);
+    hq[ord] = myq;
+    hm[ord] = (unsigned short)m;
+    hp[m] = (unsigned short)ord;
+  }
+  const int m0 = lower_bound_i32(ranks, n, nkeep);  // members m0 .. n-1 are the tail rows of the class
+  // Nodes in final order: s < nh is head row hm[s]; s >= nh is tail member m0 + (s - nh).  The greedy loop of
+  // multibox_detection.cc:153-167 keeps a node iff no EARLIER adjacent node is kept.  Evaluated as a fixed point over
+  // all nodes in parallel: a node dies as soon as one earlier neighbour is known alive and lives once all of them are
+  // known dead; the earliest undecided node always decides, and real overlap graphs settle in a handful of rounds.
+  const int ns = nh + (n - m0);
+  for (int s = threadIdx.x; s < ns; s += blockDim.x) status[s] = 0;  // 0 undecided, 1 alive, 2 dead
+  __syncthreads();
+  while (true) {
+    int undecided = 0;
+    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
+      if (status[s]) continue;
+      const bool tail = s >= nh;
+      const int m = tail ? m0 + (s - nh) : (int)hm[s];
+      bool any_alive = false, any_open = false;
+      if ((rowany[m >> 6] >> (m & 63)) & 1ull) {
+        for (int w = 0; w < W; ++w) {
+          for (unsigned long long bits = mask[m * W + w]; bits; bits &= bits - 1) {
+            const int j = (w << 6) + __ffsll((long long)bits) - 1;
+            const int hj = hp[j];
+            if (hj != 0xffff && (tail || hj < s)) {  // the head copy of member j precedes this node
+              const int st = status[hj];
+              any_alive |= st == 1;
+              any_open |= st == 0;
+            }
+            if (tail && j >= m0 && j < m) {  // the tail copy of member j precedes this tail node
+              const int st = status[nh + j - m0];
+              any_alive |= st == 1;
+              any_open |= st == 0;
+            }
+          }
+        }
+      }
+      if (tail && hp[m] != 0xffff && ((selfadj[m >> 6] >> (m & 63)) & 1ull)) {  // its own copy in the sorted head
+        const int st = status[hp[m]];
+        any_alive |= st == 1;
+        any_open |= st == 0;
+      }
+      if (any_alive) status[s] = 2;
+      else if (!any_open) status[s] = 1;
+      else undecided = 1;
+    }
+    if (!__syncthreads_or(undecided)) break;
+  }
+  // suppressed rows: only the id field is overwritten (multibox_detection.cc:163)
+  float *out = a.out + (size_t)b * a.A * 7;
+  for (int s = threadIdx.x; s < ns; s += blockDim.x)
+    if (status[s] == 2) out[(size_t)(s < nh ? hq[s] : ranks[m0 + (s - nh)]) * 7] = -1.f;
+}
+
 // Ordered compaction of the surviving rows (id >= 0) of every image into (B, K, 7), padded with -1, plus the
 // per-image count: the `det[:, 0] >= 0` filter every consumer of the op applies on the host
 // (detect/multitask_detector.py:268-271, multi_solver.py:419-432), done on the device so that only K rows per
@@ -1597,7 +2063,8 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   key.f[0] = threshold, key.f[1] = nms_threshold;
   for (int k = 0; k < 4; ++k) key.f[2 + k] = variances[k];
 
-  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](cudaStream_t stream) -> int {
+  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](const LaunchCtx &ctx) -> int {
+  cudaStream_t stream = ctx.stream;
   const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out | (uintptr_t)loc_pred) & 15) == 0;
   // TMA-fed persistent kernel whenever the ring fits (2..4 stages); plain kernels otherwise
   const size_t stage_bytes = ((size_t)(C - 1) * kPipeTile + (size_t)kPipeTile * 5) * sizeof(float);
@@ -1619,6 +2086,10 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const int tile = stages ? kPipeTile : (bulk_variant ? bulk_threads * bulk_vec : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1)));
   const int T = ceil_div(A, tile);
   const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
+  const bool nms_on = nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress);
+  // fork/join pipeline: per-class segments, the default stream kernel, tile tables that fit in shared memory
+  const bool v2 = tuning(DSPMB_TUNE_DET_PIPELINE) != 0 && bulk_variant && variant == 2 && !stages && !force_suppress &&
+                  nms_on && T <= kV2MaxTiles && C - 1 <= kV2ClsPad;
 
   StreamArgs sa;
   sa.cls_prob = cls_prob;
@@ -1630,6 +2101,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.slot_keys = w.slot_keys;
   sa.slot_cls = w.slot_cls;
   sa.slot_box = w.slot_box;
+  sa.cbox = w.cbox;
+  sa.crank = w.crank;
+  sa.tile_cls = w.tile_cls;
   sa.A = A;
   sa.C = C;
   sa.T = T;
@@ -1660,18 +2134,20 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     dim3 grid1(T, B);
     ProfileScope _p(kSlotDetStream, stream);
     if (bulk_variant) {
-#define DSPMB_LAUNCH_BULK(NFG, TH, VEC)                                                                           \
+#define DSPMB_LAUNCH_BULK(NFG, TH, VEC, V2)                                                                       \
   do {                                                                                                            \
     constexpr size_t kBytes = sizeof(BulkSmem<NFG, TH * VEC>);                                                    \
-    DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, TH, VEC>), kBytes);                                        \
-    det_stream_bulk_kernel<NFG, TH, VEC><<<grid1, TH, kBytes, stream>>>(sa);                                      \
+    DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, TH, VEC, V2>), kBytes);                                    \
+    det_stream_bulk_kernel<NFG, TH, VEC, V2><<<grid1, TH, kBytes, stream>>>(sa);                                  \
   } while (0)
-      if (C == 21 && variant == 2) DSPMB_LAUNCH_BULK(20, 128, 2);
-      else if (C == 21 && variant == 3) DSPMB_LAUNCH_BULK(20, 256, 2);
-      else if (C == 21) DSPMB_LAUNCH_BULK(20, 128, 4);
-      else if (variant == 2) DSPMB_LAUNCH_BULK(8, 128, 2);
-      else if (variant == 3) DSPMB_LAUNCH_BULK(8, 256, 2);
-      else DSPMB_LAUNCH_BULK(8, 128, 4);
+      if (C == 21 && v2) DSPMB_LAUNCH_BULK(20, 128, 2, true);
+      else if (v2) DSPMB_LAUNCH_BULK(8, 128, 2, true);
+      else if (C == 21 && variant == 2) DSPMB_LAUNCH_BULK(20, 128, 2, false);
+      else if (C == 21 && variant == 3) DSPMB_LAUNCH_BULK(20, 256, 2, false);
+      else if (C == 21) DSPMB_LAUNCH_BULK(20, 128, 4, false);
+      else if (variant == 2) DSPMB_LAUNCH_BULK(8, 128, 2, false);
+      else if (variant == 3) DSPMB_LAUNCH_BULK(8, 256, 2, false);
+      else DSPMB_LAUNCH_BULK(8, 128, 4, false);
 #undef DSPMB_LAUNCH_BULK
     }
     else if (reg_variant && C == 21)
@@ -1683,6 +2159,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     else
       det_stream_kernel<1><<<grid1, kStreamThreads, 0, stream>>>(sa);
   }
+  if (phases & 1) ++ctx.launches;
   DSPMB_CUDA_TRY(cudaGetLastError());
 
   SortArgs so;
@@ -1700,11 +2177,12 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.row_cls = w.row_cls;
   so.row_box = w.row_box;
   so.sort_keys = w.sort_keys;
+  so.head_rank = v2 ? w.head_rank : nullptr;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
   so.T = T;
   so.tile = tile;
-  so.rank_parts = ceil_div(T, 6) < 16 ? ceil_div(T, 6) : 16;
+  so.rank_parts = v2 ? 0 : (ceil_div(T, 6) < 16 ? ceil_div(T, 6) : 16);  // v2: the pair kernel moves the tail rows
   so.debug = nms_debug;
   so.A = A;
   so.Apad = Apad;
@@ -1725,17 +2203,57 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
   DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<true>, 220 * 1024);
   DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<false>, 220 * 1024);
+  if (v2) {
+    int rc = ctx.fork();
+    if (rc != DSPMB_OK) return rc;
+  }
+  NmsArgs na;
+  PairArgs pa;
+  if (v2) {
+    pa.out = out;
+    pa.tile_count = w.tile_count;
+    pa.tile_cls = w.tile_cls;
+    pa.slot_rows = w.slot_rows;
+    pa.slot_cls = w.slot_cls;
+    pa.slot_box = w.slot_box;
+    pa.cbox = w.cbox;
+    pa.crank = w.crank;
+    pa.row_cls = w.row_cls;
+    pa.row_box = w.row_box;
+    pa.seg = w.seg;
+    pa.nms_rows = w.nms_rows;
+    pa.head_rank = w.head_rank;
+    pa.A = A;
+    pa.T = T;
+    pa.tile = tile;
+    pa.Apad = Apad;
+    pa.cls_stride = (Apad + 7) & ~7;
+    pa.nfg = C - 1;
+    pa.nms_threshold = nms_threshold;
+    pa.nms_topk = nms_topk;
+    pa.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
+  }
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
     if (keys_in_smem)
       det_sort_kernel<true><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
     else
       det_sort_kernel<false><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
+    ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
+  if (v2) {  // enqueued after the sort kernel so that its 32 large CTAs are placed first; the segments fill the rest
+    if (phases & 4) {
+      ProfileScope _p(kSlotDetPair, ctx.branch());
+      det_pair_kernel<<<dim3(C - 1, B), kNmsThreads, 0, ctx.branch()>>>(pa);
+      ++ctx.launches;
+    }
+    DSPMB_CUDA_TRY(cudaGetLastError());
+    int rc = ctx.join();
+    if (rc != DSPMB_OK) return rc;
+  }
 
-  if ((phases & 4) && nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress)) {
-    NmsArgs na;
+  if ((v2 ? (phases & 8) : (phases & 4)) && nms_on) {
     na.out = out;
     na.nms_rows = w.nms_rows;
     na.cursor = w.cursor;
@@ -1754,10 +2272,14 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     na.smem_rows = tuning(DSPMB_TUNE_NMS_SMEM_ROWS);
     na.debug = nms_debug;
     dim3 grid3(force_suppress ? 1 : C - 1, B);
-    {
+    if (v2) {
+      ProfileScope _p(kSlotDetResolve, stream);
+      det_resolve_kernel<<<grid3, kNmsThreads, 0, stream>>>(pa, na);
+    } else {
       ProfileScope _p(kSlotDetNms, stream);
       det_nms_kernel<<<grid3, kNmsThreads, 0, stream>>>(na);
     }
+    ++ctx.launches;
     DSPMB_CUDA_TRY(cudaGetLastError());
   }
   return DSPMB_OK;

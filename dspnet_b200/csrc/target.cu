@@ -945,9 +945,12 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   key.f[0] = overlap_threshold, key.f[1] = ignore_label, key.f[2] = negative_mining_ratio, key.f[3] = negative_mining_thresh;
   for (int k = 0; k < 4; ++k) key.f[4 + k] = variances[k];
 
-  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](cudaStream_t stream) -> int {
-  if (tuning(DSPMB_TUNE_PHASES) & 1)
+  return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](const LaunchCtx &ctx) -> int {
+  cudaStream_t stream = ctx.stream;
+  if (tuning(DSPMB_TUNE_PHASES) & 1) {
     DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
+    ++ctx.launches;
+  }
 
   const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
                              (uintptr_t)cls_target | (uintptr_t)match_out;
@@ -1024,6 +1027,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     else
       DSPMB_LAUNCH_TS(1, 0);
 #undef DSPMB_LAUNCH_TS
+    ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   if (phases & 2) {
@@ -1032,6 +1036,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
       target_match_kernel<true><<<B, kMatchThreads, smem2_total, stream>>>(ta);
     else
       target_match_kernel<false><<<B, kMatchThreads, smem2_total, stream>>>(ta);
+    ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;

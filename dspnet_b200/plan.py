@@ -21,7 +21,8 @@ class DetectionPlan:
 
     def __init__(self, B, A, C, device, clip=True, threshold=0.01, nms_threshold=0.5, force_suppress=False,
                  variances=(0.1, 0.1, 0.2, 0.2), nms_topk=-1, want_valid_count=False):
-        self.B, self.A, self.C, self.device = B, A, C, device
+        self.B, self.A, self.C, self.device = B, A, C, torch.device(device)
+        self._index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.lib = _lib.lib()
         with torch.cuda.device(device):
             self.ws = torch.empty(max(self.lib.dspmb_detection_workspace_bytes(B, A, C), 256), dtype=torch.uint8,
@@ -30,17 +31,22 @@ class DetectionPlan:
         self._var = _lib.float_array(variances)
         self._tail = (B, A, C, float(threshold), int(bool(clip)), self._var, float(nms_threshold),
                       int(bool(force_suppress)), int(nms_topk), _ptr(self.valid), _ptr(self.ws), self.ws.numel())
-        self.launches_per_run = 3 if 0 < nms_threshold <= 1 else 2  # stream, rank+sort(, nms)
+        self.launches_per_run = None  # set by the first run() from the library's own count
 
     def new_output(self):
         return torch.empty((self.B, self.A, 7), dtype=torch.float32, device=self.device)
 
     def run(self, cls_prob, loc_pred, anchor, out, stream=None):
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if torch.cuda.current_device() != self._index:  # the library keys graphs / streams on the CURRENT device
+            with torch.cuda.device(self.device):
+                return self.run(cls_prob, loc_pred, anchor, out, s)
         rc = self.lib.dspmb_detection_f32(cls_prob.data_ptr(), loc_pred.data_ptr(), anchor.data_ptr(), out.data_ptr(),
                                           *self._tail, s)
         if rc:
             _lib.check(rc)
+        if self.launches_per_run is None:
+            self.launches_per_run = self.lib.dspmb_last_launch_count()
         return out
 
 
@@ -50,7 +56,8 @@ class TargetPlan:
     def __init__(self, B, A, L, C, device, overlap_threshold=0.5, ignore_label=-1.0, negative_mining_ratio=-1.0,
                  negative_mining_thresh=0.5, minimum_negative_samples=0, variances=(0.1, 0.1, 0.2, 0.2),
                  label_width=6, want_stats=True):
-        self.B, self.A, self.L, self.C, self.device = B, A, L, C, device
+        self.B, self.A, self.L, self.C, self.device = B, A, L, C, torch.device(device)
+        self._index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self.lib = _lib.lib()
         with torch.cuda.device(device):
             self.ws = torch.empty(max(self.lib.dspmb_target_workspace_bytes(B, A, L, C), 256), dtype=torch.uint8,
@@ -60,7 +67,7 @@ class TargetPlan:
         self._tail = (B, A, L, int(label_width), C, float(overlap_threshold), float(ignore_label),
                       float(negative_mining_ratio), float(negative_mining_thresh), int(minimum_negative_samples),
                       self._var, None, _ptr(self.stats), _ptr(self.ws), self.ws.numel())
-        self.launches_per_run = 2  # + one memset node
+        self.launches_per_run = None  # set by the first run() from the library's own count
 
     def new_outputs(self):
         d = self.device
@@ -70,11 +77,20 @@ class TargetPlan:
 
     def run(self, anchor, label, cls_pred, outs, stream=None):
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if torch.cuda.current_device() != self._index:
+            with torch.cuda.device(self.device):
+                return self.run(anchor, label, cls_pred, outs, s)
         rc = self.lib.dspmb_target_f32(anchor.data_ptr(), label.data_ptr(), cls_pred.data_ptr(), outs[0].data_ptr(),
                                        outs[1].data_ptr(), outs[2].data_ptr(), *self._tail, s)
         if rc:
             _lib.check(rc)
+        if self.launches_per_run is None:
+            self.launches_per_run = self.lib.dspmb_last_launch_count()
         return outs
 
     def status(self):
+        with torch.cuda.device(self.device):
+            self._status()
+
+    def _status(self):
         _lib.check(self.lib.dspmb_status(_ptr(self.ws), ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))

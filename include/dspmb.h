@@ -191,6 +191,9 @@ int dspmb_map_match_f32(const float *labels, int B, int L, int label_width, cons
  * dspmb_profile_kernel_name.  Not for use inside CUDA graph capture.
  * ------------------------------------------------------------------------------------------------- */
 int dspmb_profile_enable(int on);
+/* Kernels (and memset nodes) the last dspmb_detection_f32 / dspmb_target_f32 call of this thread put on the GPU,
+ * whether launched directly or replayed from the graph cache (bench.py's gpu_launches). */
+int dspmb_last_launch_count(void);
 int dspmb_profile_read(float *ms, int *launches, int max_slots);
 const char *dspmb_profile_kernel_name(int slot);
 
@@ -202,11 +205,18 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_NMS_MASK_ROWS 1      /* largest segment for the shared-memory bit-mask NMS (default/max 320) */
 #define DSPMB_TUNE_NMS_SMEM_ROWS 2      /* largest segment staged in shared memory by the sweep NMS (max 1024) */
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
-#define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 15:
-                                           1 stream, 2 rank+sort / match, 4 nms) -- bench.py times one at a time     */
+#define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 31:
+                                           1 stream, 2 sort (+rank) / match, 4 nms or pair tests, 8 resolve) --
+                                           bench.py times one at a time                                             */
 #define DSPMB_TUNE_GRAPH_CACHE 5        /* 1 (default): a detection/target call repeated with identical arguments is
                                            captured into a CUDA graph on its second sighting and replayed from then
                                            on (one cudaGraphLaunch instead of 3-4 kernel launches); 0: always launch */
+#define DSPMB_TUNE_DET_PIPELINE 6       /* 1 (default): detection runs stream -> {sort || class pair tests} -> resolve
+                                           (fork/join inside the cached graph) where its preconditions hold;
+                                           0: stream -> sort+rank -> nms in final row order                         */
+#define DSPMB_TUNE_TARGET_PIPELINE 7    /* 1 (default): multi-CTA target matcher; 0: one CTA per image              */
+#define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
+#define DSPMB_NUM_TUNING 9
 int dspmb_set_tuning(int knob, int value);
 
 /* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same

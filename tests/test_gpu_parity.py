@@ -301,10 +301,12 @@ def test_golden_vectors_from_the_reference(cuda):
         assert gen.digest(*res) == meta["digests"][name]["outputs"], name
 
 
-@pytest.mark.parametrize("knobs", [{0: 0}, {1: 0}, {1: 0, 2: 0}, {0: 0, 1: 0}, {3: 2}, {1: 64}])
+@pytest.mark.parametrize("knobs", [{0: 0}, {1: 0}, {1: 0, 2: 0}, {0: 0, 1: 0}, {3: 2}, {1: 64}, {6: 0}, {6: 0, 1: 0},
+                                   {6: 0, 1: 0, 2: 0}, {6: 0, 3: 2}, {6: 0, 1: 64}, {1: 32}, {1: 150}])
 def test_detection_forced_code_paths(oracle, cuda, knobs):
-    """Every size-dependent path of the detection pipeline on the same inputs: class lists built by the NMS kernel
-    (knob 0), chunk-sweep NMS with shared / global staging (knobs 1, 2), sort keys spilled to global memory (3)."""
+    """Every size-dependent path of the detection pipeline on the same inputs: generic stream kernel (knob 0),
+    chunk-sweep NMS with shared / global staging (knobs 1, 2), sort keys spilled to global memory (3), the
+    stream -> sort+rank -> nms pipeline instead of the fork/join one (knob 6) and mixes of both NMS paths."""
     from dspnet_b200 import _lib
     L = _lib.lib()
     old = {k: L.dspmb_set_tuning(k, v) for k, v in knobs.items()}
