@@ -28,7 +28,9 @@ EXPORTS = (
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
     "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32", "dspmb_set_tuning", "dspmb_gather_buffer_bytes", "dspmb_p2p_alloc",
     "dspmb_p2p_open", "dspmb_p2p_close", "dspmb_p2p_free", "dspmb_detection_gather_f32", "dspmb_detection_gather_wait", "dspmb_detection_gather_read",
+    "dspmb_detection_gather_ack", "dspmb_gather_error",
     "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32", "dspmb_last_launch_count",
+    "dspmb_debug_trace",
 )
 
 
@@ -74,15 +76,20 @@ def lib():
                                                                      c_void_p, c_void_p, c_size_t, c_void_p]
     L.dspmb_detection_compact_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.dspmb_set_tuning.argtypes = [c_int, c_int]
-    L.dspmb_gather_buffer_bytes.argtypes = [c_int, c_int, c_int]
+    c_ll = ctypes.c_longlong
+    L.dspmb_gather_buffer_bytes.argtypes = [c_int, c_int, c_int, c_int]
     L.dspmb_gather_buffer_bytes.restype = c_size_t
     L.dspmb_p2p_alloc.argtypes = [c_size_t, ctypes.POINTER(c_void_p), ctypes.c_char_p]
     L.dspmb_p2p_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(c_void_p)]
     L.dspmb_p2p_close.argtypes = [c_void_p]
     L.dspmb_p2p_free.argtypes = [c_void_p]
-    L.dspmb_detection_gather_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_int, c_void_p]
-    L.dspmb_detection_gather_wait.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
-    L.dspmb_detection_gather_read.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    L.dspmb_detection_gather_f32.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                             ctypes.POINTER(c_void_p), c_int, c_ll, c_void_p]
+    L.dspmb_detection_gather_wait.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p]
+    L.dspmb_detection_gather_ack.argtypes = [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_int, c_ll, c_void_p]
+    L.dspmb_detection_gather_read.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.dspmb_debug_trace.argtypes = [c_void_p]
+    L.dspmb_gather_error.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
     L.dspmb_status.argtypes = [c_void_p, c_void_p]
     L.dspmb_nms_workspace_bytes.argtypes = [c_int]
     L.dspmb_nms_workspace_bytes.restype = c_size_t

@@ -99,22 +99,24 @@ std::mutex g_graph_mutex;
 std::vector<GraphEntry> g_graph_cache;
 unsigned long long g_graph_clock = 0;
 struct CaptureSet {  // private streams / events of one device, used only under g_graph_mutex
-  cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t main = nullptr, side[LaunchCtx::kSides] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[LaunchCtx::kSides] = {nullptr, nullptr};
 };
 CaptureSet g_capture[kMaxDevices];
 }  // namespace
 
 int LaunchCtx::fork() const {
-  if (!side) return DSPMB_OK;
+  if (!forked()) return DSPMB_OK;
   DSPMB_CUDA_TRY(cudaEventRecord(ev_fork, stream));
-  DSPMB_CUDA_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
+  for (int i = 0; i < kSides; ++i) DSPMB_CUDA_TRY(cudaStreamWaitEvent(side[i], ev_fork, 0));
   return DSPMB_OK;
 }
 int LaunchCtx::join() const {
-  if (!side) return DSPMB_OK;
-  DSPMB_CUDA_TRY(cudaEventRecord(ev_join, side));
-  DSPMB_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
+  if (!forked()) return DSPMB_OK;
+  for (int i = 0; i < kSides; ++i) {
+    DSPMB_CUDA_TRY(cudaEventRecord(ev_join[i], side[i]));
+    DSPMB_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join[i], 0));
+  }
   return DSPMB_OK;
 }
 
@@ -193,9 +195,11 @@ int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
     CaptureSet &cs = g_capture[dev];
     if (!cs.main) {
       DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.main, cudaStreamNonBlocking));
-      DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.side, cudaStreamNonBlocking));
       DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_fork, cudaEventDisableTiming));
-      DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_join, cudaEventDisableTiming));
+      for (int i = 0; i < LaunchCtx::kSides; ++i) {
+        DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.side[i], cudaStreamNonBlocking));
+        DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_join[i], cudaEventDisableTiming));
+      }
     }
     if (cudaStreamBeginCapture(cs.main, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
       cudaGetLastError();
@@ -204,9 +208,11 @@ int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
     }
     LaunchCtx ctx;
     ctx.stream = cs.main;
-    ctx.side = cs.side;
     ctx.ev_fork = cs.ev_fork;
-    ctx.ev_join = cs.ev_join;
+    for (int i = 0; i < LaunchCtx::kSides; ++i) {
+      ctx.side[i] = cs.side[i];
+      ctx.ev_join[i] = cs.ev_join[i];
+    }
     const int rc = launch(ctx);
     hit->launches = ctx.launches;
     cudaGraph_t graph = nullptr;

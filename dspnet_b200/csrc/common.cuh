@@ -92,16 +92,18 @@ int ensure_dyn_smem(const void *kernel, int bytes, std::atomic<unsigned long lon
 // An operator whose launches form a fork/join (detection v2: the sort kernel and the pair-test kernel both depend
 // only on the stream kernel) receives a side stream and two events while it is being captured by the cache: work
 // enqueued on `side` between fork() and join() becomes a parallel branch of the graph.  Outside our own capture
-// (first sighting, profiling, a caller's capture) `side` is null and fork()/join() are no-ops: everything runs in
-// order on `stream`.
+// (first sighting, profiling, a caller's capture) the side streams are null and fork()/join() are no-ops: everything
+// runs in order on `stream`.
 struct LaunchCtx {
+  static constexpr int kSides = 2;
   cudaStream_t stream = nullptr;
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side[kSides] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {nullptr, nullptr};
   mutable int launches = 0;  // kernels (and memset nodes) the operator enqueued; read back by dspmb_last_launch_count
-  cudaStream_t branch() const { return side ? side : stream; }
-  int fork() const;
-  int join() const;
+  bool forked() const { return side[0] != nullptr; }
+  cudaStream_t branch(int i) const { return side[i] ? side[i] : stream; }
+  int fork() const;  // both side streams wait for everything enqueued on `stream` so far
+  int join() const;  // `stream` waits for both side streams
 };
 int graph_cached_launch(const void *key, size_t key_len, cudaStream_t stream,
                         const std::function<int(const LaunchCtx &)> &launch);

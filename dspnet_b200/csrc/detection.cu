@@ -53,6 +53,36 @@ constexpr int kNmsMaskRows = 320;     // NMS segments up to this size use the sh
 static_assert(kNmsMaskRows <= 320, "unit_tab holds (row group, column group) in 4 bits each, 55 units");
 constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in shared memory
 
+// Optional device-side timeline (dspmb_debug_trace): per kernel the earliest CTA start and the latest CTA end in
+// %globaltimer nanoseconds, so that the overlap of the graph's branches can be read off without a profiler.
+__device__ unsigned long long *g_trace = nullptr;
+struct TraceScope {
+  int slot;
+  __device__ __forceinline__ explicit TraceScope(int s) : slot(s) {
+    if (g_trace && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMin(g_trace + 2 * slot, t);
+    }
+  }
+  __device__ __forceinline__ ~TraceScope() {
+    if (g_trace && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      atomicMax(g_trace + 2 * slot + 1, t);
+    }
+  }
+};
+
+__device__ __forceinline__ void trace_point(int slot) {  // latest time any CTA passed this point
+  if (g_trace && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    atomicMax(g_trace + 2 * slot + 1, t);
+    atomicMin(g_trace + 2 * slot, t);
+  }
+}
+
 struct DetWorkspace {
   WsHeader *header;
   int *tile_count;            // (B, T) survivors per tile
@@ -77,16 +107,13 @@ struct DetWorkspace {
   unsigned short *crank;      // (B, cls_stride) their index inside the tile's run
   unsigned *tile_cls;         // (B, kV2ClsPad, Tmax) per (class, tile): offset | count << 16 inside the tile's run
   int *head_rank;             // (B, Apad) pass-1 rank of the row sorted to head position q
-  unsigned char *seg;         // (B, kV2ClsPad) segment records: member ranks + symmetric suppression mask
+  int *seg;                   // (B, C-1) members of every class segment as counted by the pair kernel
   size_t bytes;
 };
 
 constexpr int kV2ClsPad = 32;    // foreground classes the fork/join pipeline supports
 constexpr int kV2MaxTiles = 512; // tiles per image whose bases fit its shared-memory tables
-// segment record: [0] n | [64] rowany u64[8] | [128] selfadj u64[8] | [192] ranks int[320] | [1472] mask u64[320*W]
-constexpr int kSegRowanyOff = 64, kSegSelfOff = 128, kSegRankOff = 192;
-constexpr int kSegMaskOff = kSegRankOff + kNmsMaskRows * 4;
-constexpr int kSegBytes = (kSegMaskOff + kNmsMaskRows * 5 * 8 + 255) / 256 * 256;
+
 
 inline int next_pow2(int v) {
   int p = 1;
@@ -127,7 +154,7 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.crank = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
   w.tile_cls = (unsigned *)take(sizeof(unsigned) * (size_t)B * kV2ClsPad * Tmax);
   w.head_rank = (int *)take(sizeof(int) * B * Apad);
-  w.seg = (unsigned char *)take((size_t)B * (C - 1 <= kV2ClsPad && C > 1 ? C - 1 : 0) * kSegBytes);
+  w.seg = (int *)take(sizeof(int) * (size_t)B * (C - 1 <= kV2ClsPad && C > 1 ? C - 1 : 0));
   w.bytes = off;
   return w;
 }
@@ -557,6 +584,7 @@ struct BulkSmem {
 template <int NFG, int kThreads, int kVec, bool kV2>
 __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
   constexpr int kTile = kThreads * kVec;
+  TraceScope trace_(0);
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
   BulkSmem<NFG, kTile> &sm = *reinterpret_cast<BulkSmem<NFG, kTile> *>(bulk_smem_raw);
   __shared__ __align__(8) unsigned long long full_bar;
@@ -820,7 +848,7 @@ struct SortArgs {
   int *valid_count_out;
   WsHeader *header;
   int A, T, tile, Apad, cls_stride, npad_max, niter_max;
-  int sel_cap, rank_parts, debug;
+  int sel_cap, rank_parts, debug, tail_copy;
   float nms_threshold;
   int force_suppress, nms_topk;
 };
@@ -912,7 +940,16 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ int carry_smem, sm_need, sm_count, sm_eq_total;
   __shared__ unsigned sm_prefix;
   __shared__ int sm_tbase[kSortSmemTiles];
+  constexpr int kBuckets = 2 * kSortThreads, kBucketCap = 1024;
+  __shared__ unsigned bucket[kBuckets];
+  __shared__ unsigned long long stage_a[kBucketCap];
+  __shared__ unsigned sm_kmin, sm_kmax;
+  __shared__ int sm_pivot;
   const int b = blockIdx.x;  // image in x: the sort-role CTAs (y == 0) of all images are scheduled first
+  // Programmatic dependent launch: the pair-test kernel enqueued behind this one may start once every CTA of this
+  // grid is resident and has passed this point -- it runs beside the sort and only waits for it before its resolve.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  TraceScope trace_(1);
   if (blockIdx.y != 0) {
     if (a.debug & 8) return;  // timing experiments only
     det_rank_role(a, b, (int)blockIdx.y - 1, reinterpret_cast<int *>(hist256));
@@ -948,6 +985,9 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     sm_count = 0;
     sm_eq_total = 0;
     carry_smem = 0;
+    sm_kmin = 0xffffffffu;
+    sm_kmax = 0u;
+    sm_pivot = 0;
   }
   if (!do_sort) return;  // pass-1 rows are the final output
   // dynamic smem: [sel: sel_cap u64][skeys: round4(A) u32 (optional)][wtab: niter_max*32 int]
@@ -998,7 +1038,76 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   if (threadIdx.x == 0) sm_need = nkeep;
   __syncthreads();
 
-  if (nkeep == V) {
+  trace_point(9);
+  // ---- bucket sort of the head (the usual case: keys in shared memory, a head of at most kBucketCap rows) ----
+  // One 2048-bin histogram over the image's key range replaces the four 8-bit radix-select passes AND the bitonic
+  // sort: the exclusive prefix of the histogram is both the selection (bins below the pivot bin are in, the pivot
+  // bin is cut by rank) and the sorted position of every bin; the keys of bins <= pivot are scattered to their bins
+  // (any order inside a bin) and every key then finds its place by counting the smaller keys of ITS bin -- all keys
+  // in parallel, so a crowded bin (scores piling up near 1.0) costs its size, not its square.  A pivot bin that
+  // would overflow the staging buffers falls back to the radix select + bitonic path below.
+  bool sorted_done = false;
+  if (kKeysInSmem && npad <= a.sel_cap && nkeep <= kBucketCap && !(a.debug & 16)) {
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    for (int p = threadIdx.x; p < V; p += blockDim.x) {
+      const unsigned kv = skeys[p];
+      kmin = min(kmin, kv);
+      kmax = max(kmax, kv);
+    }
+    kmin = __reduce_min_sync(kFullMask, kmin);
+    kmax = __reduce_max_sync(kFullMask, kmax);
+    if (lane == 0) {
+      atomicMin(&sm_kmin, kmin);
+      atomicMax(&sm_kmax, kmax);
+    }
+    for (int i = threadIdx.x; i < kBuckets; i += blockDim.x) bucket[i] = 0u;
+    __syncthreads();
+    kmin = sm_kmin;
+    int shift = 0;
+    while (((sm_kmax - kmin) >> shift) >= (unsigned)kBuckets) ++shift;
+    for (int p = threadIdx.x; p < V; p += blockDim.x) atomicAdd(&bucket[(skeys[p] - kmin) >> shift], 1u);
+    __syncthreads();
+    // exclusive prefix over the buckets (two per thread); pivot bucket P: start < nkeep <= start + count
+    const unsigned c0 = bucket[2 * threadIdx.x], c1 = bucket[2 * threadIdx.x + 1];
+    int total;
+    const int ex = block_scan_excl((int)(c0 + c1), scan_smem, &total);
+    if (ex < nkeep && ex + (int)c0 >= nkeep) {
+      sm_pivot = 2 * threadIdx.x;
+      sm_count = ex + (int)c0;
+    } else if (ex + (int)c0 < nkeep && ex + (int)(c0 + c1) >= nkeep) {
+      sm_pivot = 2 * threadIdx.x + 1;
+      sm_count = ex + (int)(c0 + c1);
+    }
+    __syncthreads();
+    const int P = sm_pivot, nsc = sm_count;  // nsc = keys in buckets <= P (>= nkeep)
+    if (nsc <= kBucketCap) {  // CTA-uniform
+      bucket[2 * threadIdx.x] = (unsigned)ex;  // running write cursors: after the scatter bucket[b] = end of bucket b
+      bucket[2 * threadIdx.x + 1] = (unsigned)ex + c0;
+      __syncthreads();
+      for (int p = threadIdx.x; p < V; p += blockDim.x) {
+        const unsigned kv = skeys[p];
+        const unsigned bk = (kv - kmin) >> shift;
+        if ((int)bk <= P) stage_a[atomicAdd(&bucket[bk], 1u)] = ((unsigned long long)kv << 32) | (unsigned)p;
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nsc; i += blockDim.x) {
+        const unsigned long long x = stage_a[i];
+        const unsigned bk = ((unsigned)(x >> 32) - kmin) >> shift;
+        const int lo = bk ? (int)bucket[bk - 1] : 0, hi = (int)bucket[bk];
+        int cnt = 0;
+        for (int j = lo; j < hi; ++j) cnt += stage_a[j] < x ? 1 : 0;
+        if (lo + cnt < nkeep) ssel[lo + cnt] = x;
+      }
+      __syncthreads();
+      sorted_done = true;
+    }
+    if (threadIdx.x == 0) sm_count = 0;  // the radix path below counts with it
+    __syncthreads();
+  }
+
+  if (sorted_done) {
+    // head = ssel[0, nkeep) in ascending (key, rank) order
+  } else if (nkeep == V) {
     for (int p = threadIdx.x; p < npad; p += blockDim.x)
       sel[p] = p < V ? (((unsigned long long)key_at(p) << 32) | (unsigned)p) : ~0ull;
     __syncthreads();
@@ -1081,7 +1190,8 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     __syncthreads();
   }
   const int ssort = npad < kRegSortThreads ? kRegSortThreads : npad;
-  if (ssort <= 4 * kRegSortThreads && ssort <= a.sel_cap) {
+  if (sorted_done) {
+  } else if (ssort <= 4 * kRegSortThreads && ssort <= a.sel_cap) {
     // bitonic sort in the registers of four warps, ssort / 128 keys per thread (sel == ssel here)
     if (threadIdx.x < kRegSortThreads) {
       switch (ssort / kRegSortThreads) {
@@ -1097,6 +1207,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     bitonic_sort_u64(sel, npad);  // ends with __syncthreads()
   }
 
+  trace_point(sorted_done ? 10 : 11);
   // head rows: rank p lives in tile t = last tile with tbase[t] <= p, slot p - tbase[t] of that tile
   float *out = a.out + (size_t)b * A * 7;
   unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
@@ -1124,6 +1235,36 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   }
   // the NMS kernel reads row_cls eight entries at a time: define the entries between V and the next multiple of 8
   if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7)) row_cls[V + threadIdx.x] = (unsigned short)0xffffu;
+  if (a.tail_copy && nkeep < V) {
+    // Fork/join pipeline: this CTA also moves the image's tail rows [nkeep, V) from the tiles' slots to their pass-1
+    // positions (one warp per tile) -- the pair-test kernel runs far longer than the sort, so the copy is hidden.  The
+    // id column is left out: the resolve owns it for every tail row of its class.
+    const int nwarps = (int)(blockDim.x >> 5);
+    for (int t = (int)warp; t < T; t += nwarps) {
+      const int base = tbase[t];
+      const int nt = (t + 1 < T ? tbase[t + 1] : V) - base;
+      const int skip = min(nt, max(0, nkeep - base));
+      if (skip >= nt) continue;
+      const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
+      const float *src = a.slot_rows + slot0 * 7;
+      float *dst = out + (size_t)base * 7;
+      const int end = nt * 7;
+      for (int q = skip * 7 + (int)lane; q < end; q += 128) {
+        float v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = q + 32 * k < end ? src[q + 32 * k] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (q + 32 * k < end && (q + 32 * k) % 7 != 0) dst[q + 32 * k] = v[k];
+      }
+      const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
+      const float4 *sbx = a.slot_box + slot0;
+      for (int q = skip + (int)lane; q < nt; q += 32) {
+        row_cls[base + q] = sc[q];
+        row_box[base + q] = sbx[q];
+      }
+    }
+  }
 }
 
 struct NmsArgs {
@@ -1591,23 +1732,27 @@ __global__ void __launch_bounds__(kNmsThreads, 5) det_nms_kernel(const __grid_co
 // Fork/join pipeline (the default for the VOC / Cityscapes heads):
 //
 //   det_stream_bulk_kernel<.., kV2>  as above + a class-grouped copy of every tile's boxes (cbox / crank / tile_cls)
-//   det_sort_kernel    (grid B)      ||   det_pair_kernel (grid (C-1, B))      -- both depend only on the stream kernel
+//   det_sort_kernel (grid B)  ||  det_pair_kernel (grid (C-1, B))      -- both depend only on the stream kernel
 //   det_resolve_kernel (grid (C-1, B))
 //
 // Which pairs of a class overlap by IoU >= thr does not depend on the row order -- only the greedy resolve does
 // (multibox_detection.cc:153-167 walks the rows in final order).  det_pair_kernel therefore builds, per (image,
 // class), the member list in pass-1 RANK order straight from the tiles' class-grouped runs (no pass over all V rows)
 // and the SYMMETRIC suppression mask of the segment while the sort kernel is still selecting and sorting the
-// nms_topk head; it also moves the tail rows [nkeep, V) to their final positions (the old rank role).  The final
-// order of a class is  [its head rows in sorted order] ++ [its members of rank >= nkeep in rank order]; a row can
-// appear in both parts (the tail quirk) or in neither (rank < nkeep but not among the nms_topk best).
-// det_resolve_kernel replays the greedy loop on that sequence with the precomputed mask:
-//   * an alive row ORs its mask row into the removed sets; with a symmetric mask that also marks EARLIER adjacent
-//     rows, which is harmless: an earlier adjacent row that was still alive would have removed this one;
-//   * head nodes and tail nodes of the same member are distinct nodes: removed-head and removed-tail bit sets, and
-//     a self bit (IoU(box, box) >= thr, i.e. the box is not degenerate) lets an alive head row remove its own
-//     duplicate in the tail, as the reference does.
-// Segments with more than mask_rows members are left to nms_final_order_body inside the resolve kernel.
+// nms_topk head and moving the tail rows [nkeep, V) to their final positions (all columns but the id, which the
+// resolve owns).  The final order of a class is  [its head rows in sorted order] ++ [its members
+// of rank >= nkeep in rank order]; a row can appear in both parts (the tail quirk) or in neither (rank < nkeep but
+// not among the nms_topk best).  The resolve replays the greedy loop on that sequence with the precomputed mask:
+//   * a node (row of the final order) is kept iff no EARLIER adjacent node is kept; evaluated as a fixed point over
+//     all nodes in parallel (a node dies as soon as one earlier neighbour is known alive and lives once all of them
+//     are known dead; the earliest undecided node always decides; real overlap graphs settle in a few rounds);
+//   * head nodes and tail nodes of the same member are distinct nodes, and a self bit (IoU(box, box) >= thr, i.e. the
+//     box is not degenerate) lets a kept head row remove its own duplicate in the tail, as the reference does.
+// The pair kernel is launched as a PROGRAMMATIC DEPENDENT of the sort kernel (whose CTAs trigger
+// griddepcontrol.launch_dependents on entry): it starts once all 32 sort CTAs are resident -- so the big sort CTAs are
+// never locked out by 640 small ones -- runs its pair tests beside the sort, executes griddepcontrol.wait (the sort
+// grid has completed and its writes are visible) and resolves its segment right there from shared memory.  Only
+// segments with more than mask_rows members are left to det_resolve_kernel (nms_final_order_body on final order).
 struct PairArgs {
   float *out;
   const int *tile_count;
@@ -1619,13 +1764,14 @@ struct PairArgs {
   const unsigned short *crank;
   unsigned short *row_cls;
   float4 *row_box;
-  unsigned char *seg;
   const int *nms_rows;   // resolve kernel only
-  const int *head_rank;  // resolve kernel only
+  const int *head_rank;
+  int *seg;              // (B, nfg) member count of every class segment (the resolve kernel takes those > mask_rows)
   int A, T, tile, Apad, cls_stride, nfg;
   float nms_threshold;
   int nms_topk, mask_rows;
 };
+
 
 // Exclusive block scan of one 64-bit value per thread (two packed 32-bit counters); `smem`: blockDim.x/32 + 1 words.
 __device__ __forceinline__ unsigned long long block_scan_excl_u64(unsigned long long v, unsigned long long *smem,
@@ -1664,19 +1810,111 @@ __device__ __forceinline__ int lower_bound_i32(const int *v, int n, int x) {  //
   return lo;
 }
 
+struct ResolveScratch {
+  int *hq, *tmpq;             // [kNmsMaskRows] head positions of the class, ordered / as found
+  unsigned short *hm, *hp;    // [kNmsMaskRows] member of head node k / head node of member m (0xffff: none)
+  unsigned char *status;      // [2 * kNmsMaskRows] 0 undecided, 1 kept, 2 suppressed
+  int *counter;
+};
+
+// Greedy resolve of one segment (n <= kNmsMaskRows members in rank order, symmetric mask with row stride W) in the
+// image's final row order.  Whole CTA; the caller's arrays must be complete (barrier) and stay untouched.
+__device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, const int c, const int n, const int V,
+                                                const unsigned long long *mask, const int *ranks,
+                                                const unsigned long long *rowany, const unsigned long long *selfadj,
+                                                const ResolveScratch s) {
+  const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
+  const int W = (n + 63) >> 6;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) s.hp[q] = (unsigned short)0xffffu;
+  if (threadIdx.x == 0) *s.counter = 0;
+  __syncthreads();
+  // head rows of this class (their positions q in the sorted head; every one of them is a member, so <= n)
+  const unsigned short *rcls = a.row_cls + (size_t)b * a.cls_stride;
+  for (int q = threadIdx.x; q < nkeep; q += blockDim.x)
+    if (__ldcg(rcls + q) == (unsigned short)c) s.tmpq[atomicAdd(s.counter, 1)] = q;  // L2: written by another SM
+  __syncthreads();
+  const int nh = *s.counter;
+  const int *hrank = a.head_rank + (size_t)b * a.Apad;
+  for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+    const int myq = s.tmpq[k];
+    const int r = __ldcg(hrank + myq);
+    int ord = 0;
+    for (int i = 0; i < nh; ++i) ord += s.tmpq[i] < myq ? 1 : 0;
+    const int m = lower_bound_i32(ranks, n, r);
+    s.hq[ord] = myq;
+    s.hm[ord] = (unsigned short)m;
+    s.hp[m] = (unsigned short)ord;
+  }
+  const int m0 = lower_bound_i32(ranks, n, nkeep);  // members m0 .. n-1 are the tail rows of the class
+  // nodes in final order: s < nh is head row hm[s]; s >= nh is tail member m0 + (s - nh)
+  const int ns = nh + (n - m0);
+  for (int q = threadIdx.x; q < ns; q += blockDim.x) s.status[q] = 0;
+  __syncthreads();
+  while (true) {
+    int undecided = 0;
+    for (int q = threadIdx.x; q < ns; q += blockDim.x) {
+      if (s.status[q]) continue;
+      const bool tail = q >= nh;
+      const int m = tail ? m0 + (q - nh) : (int)s.hm[q];
+      bool any_alive = false, any_open = false;
+      if ((rowany[m >> 6] >> (m & 63)) & 1ull) {
+        for (int w = 0; w < W; ++w) {
+          for (unsigned long long bits = mask[m * W + w]; bits; bits &= bits - 1) {
+            const int j = (w << 6) + __ffsll((long long)bits) - 1;
+            const int hj = s.hp[j];
+            if (hj != 0xffff && (tail || hj < q)) {  // the head copy of member j precedes this node
+              const int st = s.status[hj];
+              any_alive |= st == 1;
+              any_open |= st == 0;
+            }
+            if (tail && j >= m0 && j < m) {  // the tail copy of member j precedes this tail node
+              const int st = s.status[nh + j - m0];
+              any_alive |= st == 1;
+              any_open |= st == 0;
+            }
+          }
+        }
+      }
+      if (tail && s.hp[m] != 0xffff && ((selfadj[m >> 6] >> (m & 63)) & 1ull)) {  // its own copy in the sorted head
+        const int st = s.status[s.hp[m]];
+        any_alive |= st == 1;
+        any_open |= st == 0;
+      }
+      if (any_alive) s.status[q] = 2;
+      else if (!any_open) s.status[q] = 1;
+      else undecided = 1;
+    }
+    if (!__syncthreads_or(undecided)) break;
+  }
+  // ids: a suppressed row gets -1 and keeps everything else (multibox_detection.cc:163); the tail rows receive their
+  // id here in either case (the sort kernel copies the other six columns)
+  float *out = a.out + (size_t)b * a.A * 7;
+  for (int q = threadIdx.x; q < ns; q += blockDim.x) {
+    if (q < nh) {
+      if (s.status[q] == 2) out[(size_t)s.hq[q] * 7] = -1.f;
+    } else {
+      out[(size_t)ranks[m0 + (q - nh)] * 7] = s.status[q] == 2 ? -1.f : (float)c;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_constant__ PairArgs a) {
   constexpr int kOffMask = kNmsMaskRows * 16, kOffArea = kOffMask + kNmsMaskRows * 5 * 8;
   constexpr int kOffRank = kOffArea + kNmsMaskRows * 4, kOffQueue = kOffRank + kNmsMaskRows * 4;
   constexpr int kBytes = kOffQueue + (kNmsThreads / 32) * kNmsQueue * 2;
   constexpr int kWarps = kNmsThreads / 32;
+  static_assert(kNmsMaskRows * 16 >= 2 * kNmsMaskRows * 4, "hq / tmpq alias the box stage");
+  static_assert(kWarps * kNmsQueue * 2 >= 2 * kNmsMaskRows * 2 + 2 * kNmsMaskRows, "hm / hp / status alias the queues");
   __shared__ __align__(16) unsigned char smem_raw[kBytes];
   __shared__ int sm_tbase[kV2MaxTiles], sm_mbase[kV2MaxTiles];
+  __shared__ unsigned short sm_coff[kV2MaxTiles];
   __shared__ unsigned long long scan_smem[kWarps + 1];
   __shared__ unsigned long long sm_carry;
   __shared__ unsigned long long rowany[8], selfadj[8];
   __shared__ float4 gbb[kNmsMaskRows / 32];
   __shared__ unsigned char unit_tab[64];
-  __shared__ int sm_nunits;
+  __shared__ int sm_nunits, sm_next;
+  TraceScope trace_(2);
 
   const int b = blockIdx.y, c = blockIdx.x, T = a.T;
   const unsigned lane = lane_id(), warp = warp_id();
@@ -1685,6 +1923,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   if (threadIdx.x == 0) {
     sm_carry = 0ull;
     sm_nunits = 0;
+    sm_next = 0;
   }
   if (threadIdx.x < 8) {
     rowany[threadIdx.x] = 0ull;
@@ -1694,57 +1933,30 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   // rank base of every tile (low word) and member base of this class in every tile (high word), one packed scan
   for (int base = 0; base < T; base += blockDim.x) {
     const int t = base + threadIdx.x;
-    const unsigned long long v =
-        t < T ? ((unsigned long long)(unsigned)cnt[t] | ((unsigned long long)(tcls[t] >> 16) << 32)) : 0ull;
+    const unsigned cw = t < T ? tcls[t] : 0u;
+    const unsigned long long v = t < T ? ((unsigned long long)(unsigned)cnt[t] | ((unsigned long long)(cw >> 16) << 32)) : 0ull;
     unsigned long long total;
     const unsigned long long ex = block_scan_excl_u64(v, scan_smem, &total);
     const unsigned long long carry = sm_carry;
     if (t < T) {
       sm_tbase[t] = (int)(unsigned)(carry + ex);
       sm_mbase[t] = (int)((carry + ex) >> 32);
+      sm_coff[t] = (unsigned short)(cw & 0xffffu);
     }
     __syncthreads();
     if (threadIdx.x == 0) sm_carry = carry + total;
     __syncthreads();
   }
   const int V = (int)(unsigned)sm_carry, n = (int)(sm_carry >> 32);
-  unsigned char *seg = a.seg + ((size_t)b * a.nfg + c) * kSegBytes;
-  if (threadIdx.x == 0) *reinterpret_cast<int *>(seg) = n;
-  if (V < 1) return;
-  const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;  // multibox_detection.cc:142-145
-
-  // ---- tail rows [nkeep, V): the runs of tiles c, c + nfg, ... move to their pass-1 positions (one warp per tile) ----
-  if (nkeep < V) {
-    for (int t = c + (int)warp * a.nfg; t < T; t += kWarps * a.nfg) {
-      const int base = sm_tbase[t];
-      const int nt = (t + 1 < T ? sm_tbase[t + 1] : V) - base;
-      const int skip = min(nt, max(0, nkeep - base));
-      if (skip >= nt) continue;
-      const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
-      const float *src = a.slot_rows + slot0 * 7;
-      float *dst = a.out + ((size_t)b * a.A + base) * 7;
-      const int end = nt * 7;
-      for (int q = skip * 7 + (int)lane; q < end; q += 128) {
-        float v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = q + 32 * k < end ? src[q + 32 * k] : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (q + 32 * k < end) dst[q + 32 * k] = v[k];
-      }
-      const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
-      const float4 *sbx = a.slot_box + slot0;
-      unsigned short *dc = a.row_cls + (size_t)b * a.cls_stride + base;
-      float4 *db = a.row_box + (size_t)b * a.A + base;
-      for (int q = skip + (int)lane; q < nt; q += 32) {
-        dc[q] = sc[q];
-        db[q] = sbx[q];
-      }
-    }
+  if (threadIdx.x == 0) a.seg[(size_t)b * a.nfg + c] = n;
+  trace_point(5);
+  if (V < 1 || n < 1 || n > a.mask_rows) {  // empty, or left to the final-order path of the resolve kernel
+    // every CTA waits for the sort grid before it exits, so that the completion of THIS grid implies the sort's
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    return;
   }
-  if (n < 1 || n > a.mask_rows) return;  // empty, or left to the final-order path of the resolve kernel
 
-  // ---- members of class c in rank order: every tile's run of this class is contiguous in cbox / crank ----
+  // ---- members of class c in rank order: member m lives in the tile whose member base is the last one <= m ----
   float4 *boxes = reinterpret_cast<float4 *>(smem_raw);
   unsigned long long *mask = reinterpret_cast<unsigned long long *>(smem_raw + kOffMask);
   float *areas = reinterpret_cast<float *>(smem_raw + kOffArea);
@@ -1752,23 +1964,24 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   unsigned short *queue = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue) + warp * kNmsQueue;
   const NmsThr thr = make_thr(a.nms_threshold);
   const int W = (n + 63) >> 6, npad = (n + 31) & ~31;
-  for (int t = threadIdx.x; t < T; t += blockDim.x) {
-    const unsigned cw = tcls[t];
-    const int mc = (int)(cw >> 16);
-    if (mc == 0) continue;
-    const int mb = sm_mbase[t], tb = sm_tbase[t];
-    const size_t s0 = (size_t)t * a.tile + (cw & 0xffffu);
-    const unsigned short *cr = a.crank + (size_t)b * a.cls_stride + s0;
-    const float4 *cb = a.cbox + (size_t)b * a.Apad + s0;
-    for (int i = 0; i < mc; ++i) {
-      ranks[mb + i] = tb + (int)cr[i];
-      boxes[mb + i] = stage_box(__ldg(cb + i), &areas[mb + i]);
+  for (int m = threadIdx.x; m < npad; m += blockDim.x) {
+    if (m < n) {
+      int lo = 0, hi = T;  // first tile whose member base exceeds m
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sm_mbase[mid] <= m) lo = mid + 1; else hi = mid;
+      }
+      const int t = lo - 1;
+      const size_t s0 = (size_t)t * a.tile + sm_coff[t] + (m - sm_mbase[t]);
+      ranks[m] = sm_tbase[t] + (int)a.crank[(size_t)b * a.cls_stride + s0];
+      boxes[m] = stage_box(__ldg(a.cbox + (size_t)b * a.Apad + s0), &areas[m]);
+    } else {
+      boxes[m] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);  // overlaps nothing
     }
   }
-  for (int q = n + threadIdx.x; q < npad; q += blockDim.x)
-    boxes[q] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);  // overlaps nothing
   for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = 0ull;
   __syncthreads();
+  trace_point(6);
 
   // ---- bounding box of every 32-row group (unit culling) and the self bits ----
   const int ngroups = npad >> 5;
@@ -1792,7 +2005,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
     if (lane == 0) reinterpret_cast<unsigned *>(selfadj)[g] = bal;
   }
   __syncthreads();
-  {  // units (row group <= column group) whose group boxes touch; any order, dealt round-robin to the warps
+  {  // units (row group <= column group) whose group boxes touch, in any order
     const int nall = ngroups * (ngroups + 1) / 2;  // <= 55
     if ((int)threadIdx.x < nall) {
       int rg = 0, rem = threadIdx.x;
@@ -1809,11 +2022,15 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   const int nunits = sm_nunits;
   unsigned *mask32 = reinterpret_cast<unsigned *>(mask);
   unsigned *rowany32 = reinterpret_cast<unsigned *>(rowany);
-  for (int u = warp; u < nunits; u += kWarps) {
+  while (true) {  // the warps draw units from a shared counter (diagonal units and culled neighbourhoods differ in cost)
+    int u = 0;
+    if (lane == 0) u = atomicAdd(&sm_next, 1);
+    u = __shfl_sync(kFullMask, u, 0);
+    if (u >= nunits) break;
     const unsigned rc = unit_tab[u];
     const int rg = (int)(rc >> 4), cg = (int)(rc & 15u);
     const int i = (rg << 5) + lane;
-    float4 bi = boxes[i];
+    const float4 bi = boxes[i];
     // Necessary condition for IoU >= thr (see nms_final_order_body): box j must reach into box i shrunk by
     // thr x (w_i, h_i) on every side, rounded outwards.
     const float wi = __fsub_rd(bi.z, bi.x), hi = __fsub_rd(bi.w, bi.y);
@@ -1862,116 +2079,36 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
     }
   }
   __syncthreads();
-  // ---- segment record for the resolve kernel ----
-  int *g_rank = reinterpret_cast<int *>(seg + kSegRankOff);
-  unsigned long long *g_mask = reinterpret_cast<unsigned long long *>(seg + kSegMaskOff);
-  for (int q = threadIdx.x; q < n; q += blockDim.x) g_rank[q] = ranks[q];
-  for (int q = threadIdx.x; q < n * W; q += blockDim.x) g_mask[q] = mask[q];
-  if (threadIdx.x < 8) {
-    reinterpret_cast<unsigned long long *>(seg + kSegRowanyOff)[threadIdx.x] = rowany[threadIdx.x];
-    reinterpret_cast<unsigned long long *>(seg + kSegSelfOff)[threadIdx.x] = selfadj[threadIdx.x];
-  }
+  trace_point(7);
+  // the sort grid has completed and flushed: row_cls / head_rank / the head rows of `out` are final
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  trace_point(8);
+  ResolveScratch rs;
+  rs.hq = reinterpret_cast<int *>(smem_raw);  // the box stage and the queues are dead now
+  rs.tmpq = rs.hq + kNmsMaskRows;
+  rs.hm = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue);
+  rs.hp = rs.hm + kNmsMaskRows;
+  rs.status = reinterpret_cast<unsigned char *>(rs.hp + kNmsMaskRows);
+  rs.counter = &sm_nunits;
+  resolve_segment(a, b, c, n, V, mask, ranks, rowany, selfadj, rs);
 }
 
+// Segments too large for the pair kernel's shared-memory mask: the chunk-sweep NMS on rows in final order.
 __global__ void __launch_bounds__(kNmsThreads, 5) det_resolve_kernel(const __grid_constant__ PairArgs a,
                                                                      const __grid_constant__ NmsArgs na) {
-  __shared__ unsigned long long mask[kNmsMaskRows * 5];
-  __shared__ int ranks[kNmsMaskRows], hq[kNmsMaskRows], tmpq[kNmsMaskRows];
-  __shared__ unsigned short hm[kNmsMaskRows], hp[kNmsMaskRows];
-  __shared__ unsigned char status[2 * kNmsMaskRows];
-  __shared__ unsigned long long rowany[8], selfadj[8];
-  __shared__ int sm_nh;
+  TraceScope trace_(4);
   const int b = blockIdx.y, c = blockIdx.x;
-  const unsigned char *seg = a.seg + ((size_t)b * a.nfg + c) * kSegBytes;
-  const int n = *reinterpret_cast<const int *>(seg);
-  if (n < 1) return;
-  if (n > a.mask_rows) {  // rows are in their final places by now: the chunk-sweep path on final order
-    nms_final_order_body(na, b, c);
-    return;
-  }
+  const int n = a.seg[(size_t)b * a.nfg + c];
+  if (n <= a.mask_rows) return;  // resolved by the pair kernel
   const int V = a.nms_rows[b];
   if (V == 0) return;
   const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
-  const int W = (n + 63) >> 6;
-  {
-    const int *g_rank = reinterpret_cast<const int *>(seg + kSegRankOff);
-    const unsigned long long *g_mask = reinterpret_cast<const unsigned long long *>(seg + kSegMaskOff);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-      ranks[q] = g_rank[q];
-      hp[q] = (unsigned short)0xffffu;
-    }
-    for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = g_mask[q];
-    if (threadIdx.x < 8) {
-      rowany[threadIdx.x] = reinterpret_cast<const unsigned long long *>(seg + kSegRowanyOff)[threadIdx.x];
-      selfadj[threadIdx.x] = reinterpret_cast<const unsigned long long *>(seg + kSegSelfOff)[threadIdx.x];
-    }
-    if (threadIdx.x == 0) sm_nh = 0;
-  }
-  __syncthreads();
-  // head rows of this class (their positions q in the sorted head; every one of them is a member, so <= n)
   const unsigned short *rcls = a.row_cls + (size_t)b * a.cls_stride;
-  for (int q = threadIdx.x; q < nkeep; q += blockDim.x)
-    if (rcls[q] == (unsigned short)c) tmpq[atomicAdd(&sm_nh, 1)] = q;
-  __syncthreads();
-  const int nh = sm_nh;
-  const int *hrank = a.head_rank + (size_t)b * a.Apad;
-  for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-    const int myq = tmpq[k];
-    int ord = 0;
-    for (int i = 0; i < nh; ++i) ord += tmpq[i] < myq ? 1 : 0;
-    const int m = lower_bound_i32(ranks, n, hrank[myq]);
-    hq[ord] = myq;
-    hm[ord] = (unsigned short)m;
-    hp[m] = (unsigned short)ord;
-  }
-  const int m0 = lower_bound_i32(ranks, n, nkeep);  // members m0 .. n-1 are the tail rows of the class
-  // Nodes in final order: s < nh is head row hm[s]; s >= nh is tail member m0 + (s - nh).  The greedy loop of
-  // multibox_detection.cc:153-167 keeps a node iff no EARLIER adjacent node is kept.  Evaluated as a fixed point over
-  // all nodes in parallel: a node dies as soon as one earlier neighbour is known alive and lives once all of them are
-  // known dead; the earliest undecided node always decides, and real overlap graphs settle in a handful of rounds.
-  const int ns = nh + (n - m0);
-  for (int s = threadIdx.x; s < ns; s += blockDim.x) status[s] = 0;  // 0 undecided, 1 alive, 2 dead
-  __syncthreads();
-  while (true) {
-    int undecided = 0;
-    for (int s = threadIdx.x; s < ns; s += blockDim.x) {
-      if (status[s]) continue;
-      const bool tail = s >= nh;
-      const int m = tail ? m0 + (s - nh) : (int)hm[s];
-      bool any_alive = false, any_open = false;
-      if ((rowany[m >> 6] >> (m & 63)) & 1ull) {
-        for (int w = 0; w < W; ++w) {
-          for (unsigned long long bits = mask[m * W + w]; bits; bits &= bits - 1) {
-            const int j = (w << 6) + __ffsll((long long)bits) - 1;
-            const int hj = hp[j];
-            if (hj != 0xffff && (tail || hj < s)) {  // the head copy of member j precedes this node
-              const int st = status[hj];
-              any_alive |= st == 1;
-              any_open |= st == 0;
-            }
-            if (tail && j >= m0 && j < m) {  // the tail copy of member j precedes this tail node
-              const int st = status[nh + j - m0];
-              any_alive |= st == 1;
-              any_open |= st == 0;
-            }
-          }
-        }
-      }
-      if (tail && hp[m] != 0xffff && ((selfadj[m >> 6] >> (m & 63)) & 1ull)) {  // its own copy in the sorted head
-        const int st = status[hp[m]];
-        any_alive |= st == 1;
-        any_open |= st == 0;
-      }
-      if (any_alive) status[s] = 2;
-      else if (!any_open) status[s] = 1;
-      else undecided = 1;
-    }
-    if (!__syncthreads_or(undecided)) break;
-  }
-  // suppressed rows: only the id field is overwritten (multibox_detection.cc:163)
   float *out = a.out + (size_t)b * a.A * 7;
-  for (int s = threadIdx.x; s < ns; s += blockDim.x)
-    if (status[s] == 2) out[(size_t)(s < nh ? hq[s] : ranks[m0 + (s - nh)]) * 7] = -1.f;
+  for (int r = nkeep + threadIdx.x; r < V; r += blockDim.x)  // the sort kernel leaves the tail's id column to the resolve
+    if (rcls[r] == (unsigned short)c) out[(size_t)r * 7] = (float)c;
+  __syncthreads();
+  nms_final_order_body(na, b, c);
 }
 
 // Ordered compaction of the surviving rows (id >= 0) of every image into (B, K, 7), padded with -1, plus the
@@ -2025,6 +2162,11 @@ extern "C" int dspmb_detection_compact_f32(const float *out, const int32_t *vali
     det_compact_kernel<<<B, 256, 0, stream>>>(out, valid_count, A, K, dst, counts);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_debug_trace(unsigned long long *device_buffer) {
+  DSPMB_CUDA_TRY(cudaMemcpyToSymbol(g_trace, &device_buffer, sizeof(device_buffer)));
   return DSPMB_OK;
 }
 
@@ -2178,6 +2320,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.row_box = w.row_box;
   so.sort_keys = w.sort_keys;
   so.head_rank = v2 ? w.head_rank : nullptr;
+  so.tail_copy = v2 ? 1 : 0;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
   so.T = T;
@@ -2200,13 +2343,9 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.sel_cap = want < smem_keys ? want : smem_keys;
   const size_t smem2 = sizeof(unsigned long long) * so.sel_cap + (keys_in_smem ? sizeof(unsigned) * (size_t)((A + 3) & ~3) : 0) +
                        sizeof(int) * 32 * (size_t)so.niter_max;
-  DSPMB_REQUIRE(smem2 <= 220 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
-  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<true>, 220 * 1024);
-  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<false>, 220 * 1024);
-  if (v2) {
-    int rc = ctx.fork();
-    if (rc != DSPMB_OK) return rc;
-  }
+  DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxDetection: too many anchors for the sort kernel (A=%d)", A);
+  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<true>, 200 * 1024);  // + 21.3 KB static <= 227 KB per CTA
+  DSPMB_ENSURE_DYN_SMEM(det_sort_kernel<false>, 200 * 1024);
   NmsArgs na;
   PairArgs pa;
   if (v2) {
@@ -2242,15 +2381,25 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
-  if (v2) {  // enqueued after the sort kernel so that its 32 large CTAs are placed first; the segments fill the rest
+  if (v2) {
     if (phases & 4) {
-      ProfileScope _p(kSlotDetPair, ctx.branch());
-      det_pair_kernel<<<dim3(C - 1, B), kNmsThreads, 0, ctx.branch()>>>(pa);
-      ++ctx.launches;
+      {  // programmatic dependent of the sort kernel, same stream: starts when the sort CTAs are resident
+        ProfileScope _p(kSlotDetPair, stream);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C - 1, B);
+        cfg.blockDim = dim3(kNmsThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        DSPMB_CUDA_TRY(cudaLaunchKernelEx(&cfg, det_pair_kernel, pa));
+        ++ctx.launches;
+      }
     }
     DSPMB_CUDA_TRY(cudaGetLastError());
-    int rc = ctx.join();
-    if (rc != DSPMB_OK) return rc;
   }
 
   if ((v2 ? (phases & 8) : (phases & 4)) && nms_on) {
@@ -2289,89 +2438,181 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
 // ====================================================================================================
 // Fused compaction + all-gather over NVLink peer memory (the one exchange step of the path).
 //
-// Every rank owns a gather buffer (cudaMalloc'd, shared with its peers through CUDA IPC) with two slots of
-//   [world][B][K*7] float rows | [world][B] int counts | int arrived
-// One CTA per local image compacts the surviving rows (id >= 0, row order, at most K, padded with -1) into shared
-// memory once and then stores the block into section `rank` of EVERY rank's buffer with 128-bit stores -- the
-// remote ones travel over NVLink/NVSwitch while other CTAs are still compacting, no NCCL launch, no host round
-// trip.  After a system-scope fence one thread bumps the `arrived` counter of every peer; a consumer (or the
-// drain at the end of a run) waits until its own counter has reached steps_on_slot * world * B.
+// Every rank owns a gather buffer (cudaMalloc'd, shared with its peers through CUDA IPC):
+//   2 slots of  [world][B][K*7] float rows | [world][B] int counts | [world][B][SW] int stats | [world] u64 flags
+//   then        [2][world] u64 acks | 2 int CTA counters | int error
+// submit(step):  one CTA per local image compacts the surviving rows (id >= 0, row order, at most K, padded with -1)
+//   into shared memory once and stores the block -- and the image's SW target statistics -- into section `rank` of
+//   EVERY rank's buffer with 128-bit stores; the remote ones travel over NVLink/NVSwitch while other CTAs are still
+//   compacting, no NCCL launch, no host round trip.  The last CTA to finish (system-scope fences around a counter)
+//   stores the sequence number step + 1 into flag[rank] of every peer.
+// Flow control: slot = step & 1 is reused every two steps.  A reader that has finished with generation g of a slot
+//   (dspmb_detection_gather_ack) stores g + 1 into ack[slot][reader] of every WRITER; the gather kernel of
+//   generation g + 2 does not touch a peer's slot before its own copy of all acks has reached g + 1.  Sequence
+//   numbers (not cumulative counters) make both waits exact, so a rank that runs ahead can neither overwrite an
+//   unread slot nor satisfy a wait with newer data.  Waits are bounded; a timeout latches the error word, which
+//   dspmb_gather_error reads back.
 namespace dspmb {
 namespace {
 
 constexpr int kMaxPeers = 16;
+constexpr long long kGatherSpins = 20000000ll;  // x 200 ns: a few seconds, then the error word is set
+
+struct GatherLayout {
+  size_t rows, counts, stats, flags, slot_bytes, ack_off, done_off, err_off, total;
+};
+inline GatherLayout gather_layout(int B, int K, int SW, int world) {
+  GatherLayout g;
+  g.rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
+  g.counts = align_up((size_t)world * B * sizeof(int), 256);
+  g.stats = align_up((size_t)world * B * SW * sizeof(int), 256);
+  g.flags = align_up((size_t)world * sizeof(unsigned long long), 256);
+  g.slot_bytes = g.rows + g.counts + g.stats + g.flags;
+  g.ack_off = 2 * g.slot_bytes;
+  g.done_off = g.ack_off + align_up((size_t)2 * world * sizeof(unsigned long long), 256);
+  g.err_off = g.done_off + 256;
+  g.total = g.err_off + 256;
+  return g;
+}
+
 struct GatherArgs {
   const float *out;
   const int *valid;
+  const int *stats;
   unsigned char *peer[kMaxPeers];
-  int B, A, K, rank, world;
-  size_t slot_off, counts_off, arrived_off;  // byte offsets inside a peer buffer for this slot
+  int B, A, K, SW, rank, world, slot;
+  unsigned long long seq;
+  size_t slot_off, counts_off, stats_off, flags_off, ack_off, done_off, err_off;  // byte offsets inside a buffer
 };
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Bounded wait until *p >= want; returns false (and latches the error word) on a timeout.
+__device__ __forceinline__ bool spin_until_ge(const unsigned long long *p, unsigned long long want, int *err) {
+  for (long long spins = 0; spins < kGatherSpins; ++spins) {
+    if (ld_acquire_sys_u64(p) >= want) return true;
+    __nanosleep(200);
+  }
+  atomicExch(err, 1);
+  return false;
+}
 
 __global__ void __launch_bounds__(256) det_gather_kernel(const __grid_constant__ GatherArgs g) {
   extern __shared__ __align__(16) float stage[];  // K * 7 floats
   __shared__ int scan_smem[256 / 32 + 1];
-  __shared__ int carry_smem;
+  __shared__ int carry_smem, sm_last;
   const int b = blockIdx.x;
-  const float *src = g.out + (size_t)b * g.A * 7;
-  const int V = g.valid ? min(g.valid[b], g.A) : g.A;
-  const int K = g.K;
+  unsigned char *local = g.peer[g.rank];
+  // every reader has released the generation that used this slot two steps ago
+  if (g.seq >= 3ull && (int)threadIdx.x < g.world)
+    spin_until_ge(reinterpret_cast<const unsigned long long *>(local + g.ack_off) + (size_t)g.slot * g.world + threadIdx.x,
+                  g.seq - 2ull, reinterpret_cast<int *>(local + g.err_off));
   if (threadIdx.x == 0) carry_smem = 0;
   __syncthreads();
-  for (int base = 0; base < V; base += blockDim.x) {
-    const int r = base + threadIdx.x;
-    const int keep = (r < V && src[(size_t)r * 7] >= 0.f) ? 1 : 0;
-    int total;
-    const int ex = block_scan_excl(keep, scan_smem, &total);
-    const int carry = carry_smem;
-    const int pos = carry + ex;
-    if (keep && pos < K) {
+  const int K = g.K;
+  int n = 0;
+  if (K > 0) {
+    const float *src = g.out + (size_t)b * g.A * 7;
+    const int V = g.valid ? min(g.valid[b], g.A) : g.A;
+    for (int base = 0; base < V; base += blockDim.x) {
+      const int r = base + threadIdx.x;
+      const int keep = (r < V && src[(size_t)r * 7] >= 0.f) ? 1 : 0;
+      int total;
+      const int ex = block_scan_excl(keep, scan_smem, &total);
+      const int carry = carry_smem;
+      const int pos = carry + ex;
+      if (keep && pos < K) {
 #pragma unroll
-      for (int c = 0; c < 7; ++c) stage[pos * 7 + c] = src[(size_t)r * 7 + c];
+        for (int c = 0; c < 7; ++c) stage[pos * 7 + c] = src[(size_t)r * 7 + c];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) carry_smem = carry + total;
+      __syncthreads();
+      if (carry_smem >= K) break;
     }
+    n = min(carry_smem, K);
+    for (int q = n * 7 + threadIdx.x; q < K * 7; q += blockDim.x) stage[q] = -1.f;
     __syncthreads();
-    if (threadIdx.x == 0) carry_smem = carry + total;
-    __syncthreads();
-    if (carry_smem >= K) break;
   }
-  const int n = min(carry_smem, K);
-  for (int q = n * 7 + threadIdx.x; q < K * 7; q += blockDim.x) stage[q] = -1.f;
-  __syncthreads();
   const size_t row_off = g.slot_off + ((size_t)g.rank * g.B + b) * K * 7 * sizeof(float);
   const size_t cnt_off = g.counts_off + ((size_t)g.rank * g.B + b) * sizeof(int);
+  const size_t st_off = g.stats_off + ((size_t)g.rank * g.B + b) * g.SW * sizeof(int);
   const int nvec = (K * 7) >> 2;  // K * 7 * 4 bytes is a multiple of 16 when K % 4 == 0 (checked on the host)
   for (int p = 0; p < g.world; ++p) {
     const int peer = (g.rank + p) % g.world;  // start with the local copy, spread the remote targets
     float4 *dst = reinterpret_cast<float4 *>(g.peer[peer] + row_off);
     for (int q = threadIdx.x; q < nvec; q += blockDim.x) dst[q] = reinterpret_cast<const float4 *>(stage)[q];
-    if (threadIdx.x == 0) *reinterpret_cast<int *>(g.peer[peer] + cnt_off) = n;
+    if (threadIdx.x == 0 && K > 0) *reinterpret_cast<int *>(g.peer[peer] + cnt_off) = n;
+    if (g.stats && (int)threadIdx.x < g.SW)
+      reinterpret_cast<int *>(g.peer[peer] + st_off)[threadIdx.x] = g.stats[(size_t)b * g.SW + threadIdx.x];
   }
   __threadfence_system();
   __syncthreads();
-  if ((int)threadIdx.x < g.world)
-    atomicAdd_system(reinterpret_cast<int *>(g.peer[threadIdx.x] + g.arrived_off), 1);
+  if (threadIdx.x == 0) {  // the last CTA of this launch publishes the sequence number (threadFenceReduction pattern)
+    int *done = reinterpret_cast<int *>(local + g.done_off) + g.slot;
+    const int prev = atomicAdd(done, 1);
+    sm_last = prev == (int)gridDim.x - 1;
+    if (sm_last) *done = 0;
+  }
+  __syncthreads();
+  if (sm_last && (int)threadIdx.x < g.world) {
+    __threadfence_system();
+    st_release_sys_u64(reinterpret_cast<unsigned long long *>(g.peer[threadIdx.x] + g.flags_off) + g.rank, g.seq);
+  }
 }
 
-__global__ void det_gather_wait_kernel(int *arrived, int expected) {
-  // bounded spin (a few seconds): a peer that never arrives must not wedge the GPU; the shortfall is visible to
-  // the host in the counter itself (word after it is set to 1)
-  for (long long spins = 0; spins < 20000000ll; ++spins) {
-    if (atomicAdd_system(arrived, 0) >= expected) {
-      __threadfence_system();
-      return;
-    }
-    __nanosleep(200);
+// Returns once flag[r] >= seq for every writer r of this rank's slot (bounded).
+__global__ void det_gather_wait_kernel(const unsigned long long *flags, int world, unsigned long long seq, int *err) {
+  if ((int)threadIdx.x < world) spin_until_ge(flags + threadIdx.x, seq, err);
+}
+
+// Tells every writer that this rank has finished reading generation `seq` of the slot.
+__global__ void det_gather_ack_kernel(const __grid_constant__ GatherArgs g) {
+  if ((int)threadIdx.x < g.world)
+    st_release_sys_u64(reinterpret_cast<unsigned long long *>(g.peer[threadIdx.x] + g.ack_off) + (size_t)g.slot * g.world + g.rank,
+                       g.seq);
+}
+
+int fill_gather_args(GatherArgs &g, int B, int A, int K, int SW, int rank, int world, void *const *peer_bases, int slot,
+                     long long seq) {
+  DSPMB_REQUIRE(B > 0 && K >= 0 && (K % 4) == 0 && SW >= 0 && SW <= 32,
+                "detection_gather: need B > 0, K a multiple of 4, 0 <= stats_width <= 32");
+  DSPMB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "detection_gather: bad rank/world");
+  DSPMB_REQUIRE(peer_bases && (slot == 0 || slot == 1) && seq >= 1, "detection_gather: bad argument");
+  for (int p = 0; p < world; ++p) {
+    DSPMB_REQUIRE(peer_bases[p] != nullptr, "detection_gather: peer %d has no buffer", p);
+    g.peer[p] = (unsigned char *)peer_bases[p];
   }
-  arrived[1] = 1;
+  const GatherLayout l = gather_layout(B, K, SW, world);
+  g.B = B;
+  g.A = A;
+  g.K = K;
+  g.SW = SW;
+  g.rank = rank;
+  g.world = world;
+  g.slot = slot;
+  g.seq = (unsigned long long)seq;
+  g.slot_off = (size_t)slot * l.slot_bytes;
+  g.counts_off = g.slot_off + l.rows;
+  g.stats_off = g.counts_off + l.counts;
+  g.flags_off = g.stats_off + l.stats;
+  g.ack_off = l.ack_off;
+  g.done_off = l.done_off;
+  g.err_off = l.err_off;
+  return DSPMB_OK;
 }
 
 }  // namespace
 }  // namespace dspmb
 
-extern "C" size_t dspmb_gather_buffer_bytes(int B, int K, int world) {
-  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
-  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
-  return 2 * (rows + counts + 256);
+extern "C" size_t dspmb_gather_buffer_bytes(int B, int K, int stats_width, int world) {
+  return gather_layout(B, K, stats_width, world).total;
 }
 
 extern "C" int dspmb_p2p_alloc(size_t bytes, void **dev_ptr, unsigned char *handle_out) {
@@ -2402,31 +2643,19 @@ extern "C" int dspmb_p2p_free(void *dev_ptr) {
   return DSPMB_OK;
 }
 
-extern "C" int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, int B, int A, int K, int rank,
-                                          int world, void *const *peer_bases, int slot, void *stream_) {
+extern "C" int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, const int32_t *stats, int B, int A,
+                                          int K, int stats_width, int rank, int world, void *const *peer_bases, int slot,
+                                          long long seq, void *stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DSPMB_REQUIRE(B > 0 && A > 0 && K > 0 && (K % 4) == 0, "detection_gather: need B, A > 0 and K a positive multiple of 4");
-  DSPMB_REQUIRE(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "detection_gather: bad rank/world");
-  DSPMB_REQUIRE(out && peer_bases && (slot == 0 || slot == 1), "detection_gather: bad argument");
-  DSPMB_REQUIRE((size_t)K * 7 * sizeof(float) <= 160 * 1024, "detection_gather: K too large");
   GatherArgs g;
+  const int rc = fill_gather_args(g, B, A, K, stats_width, rank, world, peer_bases, slot, seq);
+  if (rc != DSPMB_OK) return rc;
+  DSPMB_REQUIRE(K == 0 || (out && A > 0), "detection_gather: rows requested without an output tensor");
+  DSPMB_REQUIRE(stats_width == 0 || stats, "detection_gather: stats_width > 0 without a statistics tensor");
+  DSPMB_REQUIRE((size_t)K * 7 * sizeof(float) <= 160 * 1024, "detection_gather: K too large");
   g.out = out;
   g.valid = valid_count;
-  for (int p = 0; p < world; ++p) {
-    DSPMB_REQUIRE(peer_bases[p] != nullptr, "detection_gather: peer %d has no buffer", p);
-    g.peer[p] = (unsigned char *)peer_bases[p];
-  }
-  g.B = B;
-  g.A = A;
-  g.K = K;
-  g.rank = rank;
-  g.world = world;
-  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
-  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
-  const size_t slot_bytes = rows + counts + 256;
-  g.slot_off = (size_t)slot * slot_bytes;
-  g.counts_off = g.slot_off + rows;
-  g.arrived_off = g.counts_off + counts;
+  g.stats = stats_width ? stats : nullptr;
   const size_t smem = (size_t)K * 7 * sizeof(float);
   DSPMB_ENSURE_DYN_SMEM(det_gather_kernel, 160 * 1024);
   {
@@ -2437,27 +2666,53 @@ extern "C" int dspmb_detection_gather_f32(const float *out, const int32_t *valid
   return DSPMB_OK;
 }
 
-extern "C" int dspmb_detection_gather_wait(const void *local_base, int B, int K, int world, int slot, int expected,
-                                           void *stream_) {
-  DSPMB_REQUIRE(local_base && (slot == 0 || slot == 1), "detection_gather_wait: bad argument");
-  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
-  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
-  const size_t slot_bytes = rows + counts + 256;
-  int *arrived = (int *)((unsigned char *)const_cast<void *>(local_base) + slot * slot_bytes + rows + counts);
-  det_gather_wait_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(arrived, expected);
+extern "C" int dspmb_detection_gather_wait(void *local_base, int B, int K, int stats_width, int world, int slot,
+                                           long long seq, void *stream_) {
+  DSPMB_REQUIRE(local_base && (slot == 0 || slot == 1) && seq >= 1 && world >= 1 && world <= kMaxPeers,
+                "detection_gather_wait: bad argument");
+  const GatherLayout l = gather_layout(B, K, stats_width, world);
+  unsigned char *base = (unsigned char *)local_base;
+  const unsigned long long *flags =
+      (const unsigned long long *)(base + (size_t)slot * l.slot_bytes + l.rows + l.counts + l.stats);
+  det_gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(flags, world, (unsigned long long)seq, (int *)(base + l.err_off));
   DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
 }
 
-extern "C" int dspmb_detection_gather_read(const void *local_base, int B, int K, int world, int slot, float *rows_out,
-                                           int32_t *counts_out, void *stream_) {
-  DSPMB_REQUIRE(local_base && rows_out && counts_out && (slot == 0 || slot == 1), "detection_gather_read: bad argument");
-  const size_t rows = align_up((size_t)world * B * K * 7 * sizeof(float), 256);
-  const size_t counts = align_up((size_t)world * B * sizeof(int), 256);
-  const unsigned char *base = (const unsigned char *)local_base + (size_t)slot * (rows + counts + 256);
-  DSPMB_CUDA_TRY(cudaMemcpyAsync(rows_out, base, (size_t)world * B * K * 7 * sizeof(float), cudaMemcpyDeviceToDevice,
-                                 (cudaStream_t)stream_));
-  DSPMB_CUDA_TRY(cudaMemcpyAsync(counts_out, base + rows, (size_t)world * B * sizeof(int), cudaMemcpyDeviceToDevice,
-                                 (cudaStream_t)stream_));
+extern "C" int dspmb_detection_gather_ack(int B, int K, int stats_width, int rank, int world, void *const *peer_bases,
+                                          int slot, long long seq, void *stream_) {
+  GatherArgs g;
+  const int rc = fill_gather_args(g, B, 1, K, stats_width, rank, world, peer_bases, slot, seq);
+  if (rc != DSPMB_OK) return rc;
+  g.out = nullptr;
+  g.valid = nullptr;
+  g.stats = nullptr;
+  det_gather_ack_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(g);
+  DSPMB_CUDA_TRY(cudaGetLastError());
   return DSPMB_OK;
+}
+
+extern "C" int dspmb_detection_gather_read(const void *local_base, int B, int K, int stats_width, int world, int slot,
+                                           float *rows_out, int32_t *counts_out, int32_t *stats_out, void *stream_) {
+  DSPMB_REQUIRE(local_base && (slot == 0 || slot == 1), "detection_gather_read: bad argument");
+  const GatherLayout l = gather_layout(B, K, stats_width, world);
+  const unsigned char *base = (const unsigned char *)local_base + (size_t)slot * l.slot_bytes;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows_out && K > 0)
+    DSPMB_CUDA_TRY(cudaMemcpyAsync(rows_out, base, (size_t)world * B * K * 7 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (counts_out && K > 0)
+    DSPMB_CUDA_TRY(cudaMemcpyAsync(counts_out, base + l.rows, (size_t)world * B * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+  if (stats_out && stats_width > 0)
+    DSPMB_CUDA_TRY(cudaMemcpyAsync(stats_out, base + l.rows + l.counts, (size_t)world * B * stats_width * sizeof(int),
+                                   cudaMemcpyDeviceToDevice, stream));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_gather_error(const void *local_base, int B, int K, int stats_width, int world) {
+  DSPMB_REQUIRE(local_base, "gather_error: bad argument");
+  const GatherLayout l = gather_layout(B, K, stats_width, world);
+  int err = 0;
+  DSPMB_CUDA_TRY(cudaMemcpy(&err, (const unsigned char *)local_base + l.err_off, sizeof(int), cudaMemcpyDeviceToHost));
+  if (err) set_error("detection_gather: a peer did not arrive / acknowledge within the spin bound");
+  return err;
 }

@@ -8,9 +8,10 @@ the surviving detection rows (``det[:, 0] >= 0``, detect/multitask_detector.py:2
 statistics (what train/metric.py:35-46 reduces).  Training targets themselves stay on the GPU that owns the image.
 
 ``shard_slice`` / ``ShardedMultiBox`` are backend-agnostic host logic (tested on CPU with gloo, world_size 2, with
-the oracle injected as the compute provider); ``DetectionGatherer`` is the CUDA/NCCL pipeline bench.py uses:
-compaction kernel on the compute stream -> all_gather_into_tensor on a side stream, double buffered, so the
-collective of step i overlaps the kernels of step i+1.
+the oracle injected as the compute provider); ``DetectionGatherer`` is the plain CUDA/NCCL pipeline (compaction
+kernel on the compute stream -> all_gather_into_tensor on a side stream, double buffered); ``P2PDetectionGatherer``
+is what bench.py uses: one kernel that compacts and stores into every peer's buffer over NVLink, with sequence
+numbers and acknowledgements as device-side flow control.
 """
 import ctypes
 
@@ -141,23 +142,31 @@ class DetectionGatherer:
 
 class P2PDetectionGatherer:
     """The exchange step without NCCL on the critical path: ``dspmb_detection_gather_f32`` compacts this rank's
-    detections and stores them straight into every peer's gather buffer over NVLink (CUDA IPC mapped peer memory).
-    torch.distributed is only used once, at construction, to exchange the 64-byte IPC handles.
+    detections (and / or takes the per-image target statistics) and stores them straight into every peer's gather
+    buffer over NVLink (CUDA IPC mapped peer memory).  torch.distributed is only used once, at construction, to
+    exchange the 64-byte IPC handles.
 
-    submit(out, step) is one C-ABI call on the current stream; gathered(step) returns views of this rank's copy of
-    the whole batch ((world*B, K, 7) rows and (world*B,) counts) after enqueueing a wait for all peers' data.
+    Contract (SPMD): every rank calls ``submit(out, step, stats=...)`` for every step, steps counting up by one; the
+    tensors handed to submit(step) must stay untouched until submit(step + 2) has been called (the gather kernel reads
+    them on a side stream, beside the next step's kernels).
+    ``gathered(step)`` / ``gathered_stats(step)`` return this rank's copy of the whole batch for the two most recent
+    steps.  The two slots are flow-controlled on the device: a generation is only overwritten after every rank has
+    acknowledged it -- ``gathered`` acknowledges after its copy, and ``submit`` acknowledges on the consumer's behalf
+    any generation that was never read (``release``), so a rank that runs ahead waits instead of overwriting.  All
+    waits are bounded; ``check()`` reports a timeout.
     """
 
-    launches_per_submit = 1  # det_gather_kernel
+    launches_per_submit = 1  # det_gather_kernel (+ wait / ack kernels of one thread block each)
 
-    def __init__(self, batch, anchors, max_rows, device, world, rank, group=None):
+    def __init__(self, batch, anchors, max_rows, device, world, rank, group=None, stats_width=0):
         assert max_rows % 4 == 0
-        self.B, self.A, self.K, self.device, self.world, self.rank = batch, anchors, max_rows, device, world, rank
+        self.B, self.A, self.K, self.SW = batch, anchors, max_rows, stats_width
+        self.device, self.world, self.rank = torch.device(device), world, rank
         self.lib = _lib.lib()
-        self.nbytes = self.lib.dspmb_gather_buffer_bytes(batch, max_rows, world)
+        self.nbytes = self.lib.dspmb_gather_buffer_bytes(batch, max_rows, stats_width, world)
         base = ctypes.c_void_p()
         handle = ctypes.create_string_buffer(64)
-        with torch.cuda.device(device):
+        with torch.cuda.device(self.device):
             _lib.check(self.lib.dspmb_p2p_alloc(self.nbytes, ctypes.byref(base), handle))
         self.local = base.value
         handles = [None] * world
@@ -172,62 +181,113 @@ class P2PDetectionGatherer:
                 self.peers[r] = self.local
             else:
                 p = ctypes.c_void_p()
-                with torch.cuda.device(device):
+                with torch.cuda.device(self.device):
                     _lib.check(self.lib.dspmb_p2p_open(handles[r], ctypes.byref(p)))
                 self.peers[r] = p.value
                 self._opened.append(p.value)
-        self.uses = [0, 0]
-        self.side = torch.cuda.Stream(device)  # the exchange runs beside the next step's kernels
+        self.step_of = [None, None]     # step whose data currently lives in the slot
+        self.unacked = [False, False]   # ... and has not been acknowledged by this rank yet
+        self.side = torch.cuda.Stream(self.device)  # the exchange runs beside the next step's kernels
         self.ready = [torch.cuda.Event(), torch.cuda.Event()]
         self.done = [torch.cuda.Event(), torch.cuda.Event()]
-        rows = (world * batch * max_rows * 7 * 4 + 255) // 256 * 256
-        counts = (world * batch * 4 + 255) // 256 * 256
-        self._slot_bytes = rows + counts + 256
-        self._rows_bytes = rows
+        self.read = torch.cuda.Event()
         if world > 1:
             dist.barrier(group=group)  # every peer has mapped every buffer before the first store
 
-    def submit(self, out, step, valid_count=None):
-        slot = step & 1
-        compute = torch.cuda.current_stream(self.device)
-        if self.uses[slot]:
-            compute.wait_event(self.done[slot])  # the gather that read from two steps ago has finished
-        self.uses[slot] += 1
-        self.ready[slot].record(compute)
-        self.side.wait_event(self.ready[slot])
-        _lib.check(self.lib.dspmb_detection_gather_f32(
-            out.data_ptr(), valid_count.data_ptr() if valid_count is not None else None, self.B, self.A, self.K,
-            self.rank, self.world, self.peers, slot, ctypes.c_void_p(self.side.cuda_stream)))
-        self.done[slot].record(self.side)
+    def _side(self):
+        return ctypes.c_void_p(self.side.cuda_stream)
 
-    def wait(self, slot):
-        """Enqueue (on the current stream) a wait until every rank's data of the latest use of `slot` has landed."""
-        _lib.check(self.lib.dspmb_detection_gather_wait(
-            self.local, self.B, self.K, self.world, slot, self.uses[slot] * self.world * self.B,
-            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+    def _wait(self, slot, stream):
+        _lib.check(self.lib.dspmb_detection_gather_wait(self.local, self.B, self.K, self.SW, self.world, slot,
+                                                        self.step_of[slot] + 1, stream))
+
+    def _ack(self, slot):
+        """On the side stream: this rank is done with the generation in `slot`."""
+        _lib.check(self.lib.dspmb_detection_gather_ack(self.B, self.K, self.SW, self.rank, self.world, self.peers, slot,
+                                                       self.step_of[slot] + 1, self._side()))
+        self.unacked[slot] = False
+
+    def release(self, slot):
+        """Acknowledge the generation in `slot` without reading it (after all of it has arrived here)."""
+        if self.step_of[slot] is not None and self.unacked[slot]:
+            with torch.cuda.device(self.device):
+                self._wait(slot, self._side())
+                self._ack(slot)
+
+    def submit(self, out, step, valid_count=None, stats=None):
+        slot = step & 1
+        assert self.step_of[slot] is None or step == self.step_of[slot] + 2, "submit() must be called for every step"
+        compute = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            if self.step_of[slot] is not None:
+                compute.wait_event(self.done[slot])  # the gather kernel that read `out` two steps ago has finished
+            self.release(slot)
+            self.step_of[slot] = step
+            self.unacked[slot] = True
+            self.ready[slot].record(compute)
+            self.side.wait_event(self.ready[slot])
+            _lib.check(self.lib.dspmb_detection_gather_f32(
+                out.data_ptr() if out is not None else None,
+                valid_count.data_ptr() if valid_count is not None else None,
+                stats.data_ptr() if (stats is not None and self.SW) else None, self.B, self.A, self.K, self.SW,
+                self.rank, self.world, self.peers, slot, step + 1, self._side()))
+            self.done[slot].record(self.side)
+
+    def _fetch(self, step, want_rows, want_stats):
+        slot = step & 1
+        assert self.step_of[slot] == step, "only the two most recent steps are held"
+        cur = torch.cuda.current_stream(self.device)
+        n = self.world * self.B
+        rows = counts = stats = None
+        with torch.cuda.device(self.device):
+            cur.wait_stream(self.side)
+            self._wait(slot, ctypes.c_void_p(cur.cuda_stream))
+            if want_rows and self.K:
+                rows = torch.empty((n, self.K, 7), dtype=torch.float32, device=self.device)
+                counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+            if want_stats and self.SW:
+                stats = torch.empty((n, self.SW), dtype=torch.int32, device=self.device)
+            _lib.check(self.lib.dspmb_detection_gather_read(
+                self.local, self.B, self.K, self.SW, self.world, slot,
+                rows.data_ptr() if rows is not None else None, counts.data_ptr() if counts is not None else None,
+                stats.data_ptr() if stats is not None else None, ctypes.c_void_p(cur.cuda_stream)))
+            if self.unacked[slot]:  # acknowledged on the side stream, after the copies above
+                self.read.record(cur)
+                self.side.wait_event(self.read)
+                self._ack(slot)
+        return rows, counts, stats
 
     def gathered(self, step):
         """(rows (world*B, K, 7) float32, counts (world*B,) int32) copied out of this rank's buffer."""
-        slot = step & 1
-        torch.cuda.current_stream(self.device).wait_stream(self.side)
-        self.wait(slot)
-        n = self.world * self.B
-        rows = torch.empty((n, self.K, 7), dtype=torch.float32, device=self.device)
-        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
-        _lib.check(self.lib.dspmb_detection_gather_read(
-            self.local, self.B, self.K, self.world, slot, rows.data_ptr(), counts.data_ptr(),
-            ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        rows, counts, _ = self._fetch(step, True, False)
         return rows, counts
 
+    def gathered_stats(self, step):
+        """(world*B, stats_width) int32 target statistics of every image of the batch."""
+        return self._fetch(step, False, True)[2]
+
     def drain(self):
-        torch.cuda.current_stream(self.device).wait_stream(self.side)
-        for slot in (0, 1):
-            if self.uses[slot]:
-                self.wait(slot)
+        """The current stream waits until every submitted generation has fully arrived on this rank."""
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            cur.wait_stream(self.side)
+            for slot in (0, 1):
+                if self.step_of[slot] is not None:
+                    self._wait(slot, ctypes.c_void_p(cur.cuda_stream))
+
+    def check(self):
+        """False if any bounded wait of the exchange ran out (synchronises the device)."""
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            return self.lib.dspmb_gather_error(self.local, self.B, self.K, self.SW, self.world) == 0
 
     def close(self):
         with torch.cuda.device(self.device):
+            for slot in (0, 1):  # peers may still be waiting for this rank's acknowledgements
+                self.release(slot)
             torch.cuda.synchronize(self.device)
+            if self.world > 1:
+                dist.barrier()
             for p in self._opened:
                 self.lib.dspmb_p2p_close(p)
             self._opened = []

@@ -64,9 +64,10 @@ class TargetPlan:
                                   device=device)
         self.stats = torch.zeros((B, 4), dtype=torch.int32, device=device) if want_stats else None
         self._var = _lib.float_array(variances)
-        self._tail = (B, A, L, int(label_width), C, float(overlap_threshold), float(ignore_label),
+        self._head = (B, A, L, int(label_width), C, float(overlap_threshold), float(ignore_label),
                       float(negative_mining_ratio), float(negative_mining_thresh), int(minimum_negative_samples),
-                      self._var, None, _ptr(self.stats), _ptr(self.ws), self.ws.numel())
+                      self._var, None)
+        self._ws = (_ptr(self.ws), self.ws.numel())
         self.launches_per_run = None  # set by the first run() from the library's own count
 
     def new_outputs(self):
@@ -75,13 +76,18 @@ class TargetPlan:
                 torch.empty((self.B, self.A * 5), dtype=torch.float32, device=d),
                 torch.empty((self.B, self.A), dtype=torch.float32, device=d))
 
-    def run(self, anchor, label, cls_pred, outs, stream=None):
+    def new_stats(self):
+        """(B, 4) int32 [num_valid_gt, num_positive, num_negative, num_bipartite] -- pass as run(..., stats=)."""
+        return torch.zeros((self.B, 4), dtype=torch.int32, device=self.device)
+
+    def run(self, anchor, label, cls_pred, outs, stream=None, stats=None):
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         if torch.cuda.current_device() != self._index:
             with torch.cuda.device(self.device):
-                return self.run(anchor, label, cls_pred, outs, s)
+                return self.run(anchor, label, cls_pred, outs, s, stats)
+        st = self.stats if stats is None else stats
         rc = self.lib.dspmb_target_f32(anchor.data_ptr(), label.data_ptr(), cls_pred.data_ptr(), outs[0].data_ptr(),
-                                       outs[1].data_ptr(), outs[2].data_ptr(), *self._tail, s)
+                                       outs[1].data_ptr(), outs[2].data_ptr(), *self._head, _ptr(st), *self._ws, s)
         if rc:
             _lib.check(rc)
         if self.launches_per_run is None:

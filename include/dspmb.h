@@ -111,27 +111,41 @@ int dspmb_detection_compact_f32(const float *out, const int32_t *valid_count, in
                                 int32_t *counts, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
- * Fused compaction + all-gather of the detections over NVLink peer memory (multi-GPU exchange step).
- * Every rank allocates one gather buffer with dspmb_p2p_alloc(dspmb_gather_buffer_bytes(B, K, world)), publishes
- * the 64-byte CUDA IPC handle to its peers (any host channel) and maps theirs with dspmb_p2p_open.
- * dspmb_detection_gather_f32 compacts the surviving rows (id >= 0, row order, at most K -- a multiple of 4 --,
- * padded with -1) of this rank's B images and stores them into section `rank` of EVERY rank's buffer (HOST array
- * peer_bases[world] of device pointers, own buffer at index `rank`), slot 0/1, then raises the peers' `arrived`
- * counters.  Buffer layout per slot: rows (world,B,K,7) float | counts (world,B) int32 | arrived int32
- * (each part padded to 256 B).  dspmb_detection_gather_wait enqueues a kernel that returns once this rank's
- * counter for `slot` has reached `expected` (= uses of the slot so far * world * B).
+ * Fused compaction + all-gather over NVLink peer memory (the multi-GPU exchange step: surviving detections and
+ * per-image target statistics).
+ * Every rank allocates one gather buffer with dspmb_p2p_alloc(dspmb_gather_buffer_bytes(B, K, stats_width, world)),
+ * publishes the 64-byte CUDA IPC handle to its peers (any host channel) and maps theirs with dspmb_p2p_open.
+ * dspmb_detection_gather_f32 compacts the surviving rows (id >= 0, row order, at most K -- a multiple of 4, 0 to send
+ * no rows --, padded with -1) of this rank's B images, appends `stats_width` int32 per image from `stats`
+ * (B, stats_width; NULL with stats_width 0) and stores both into section `rank` of EVERY rank's buffer (HOST array
+ * peer_bases[world] of device pointers, own buffer at index `rank`), slot 0/1; the last CTA publishes the sequence
+ * number `seq` (use step + 1; it must grow by 2 between two uses of a slot) in every peer's flag word.
+ * Flow control: a slot may only be rewritten after every reader has acknowledged the previous generation -- the
+ * gather kernel itself waits (bounded) for ack >= seq - 2 from every rank, so each rank MUST call
+ * dspmb_detection_gather_ack(slot, seq) once it has finished with generation seq (after gather_wait / gather_read),
+ * whether it read the data or not.  dspmb_detection_gather_wait enqueues a kernel that returns once every rank's
+ * flag for `slot` has reached `seq`.  A wait that runs out latches an error word: dspmb_gather_error (synchronous).
+ * Buffer layout per slot: rows (world,B,K,7) float | counts (world,B) int32 | stats (world,B,stats_width) int32 |
+ * flags (world) u64, each part padded to 256 B; then acks (2,world) u64, CTA counters, error word.
  * ------------------------------------------------------------------------------------------------- */
-size_t dspmb_gather_buffer_bytes(int B, int K, int world);
+size_t dspmb_gather_buffer_bytes(int B, int K, int stats_width, int world);
 int dspmb_p2p_alloc(size_t bytes, void **dev_ptr, unsigned char *ipc_handle_out /* 64 bytes */);
 int dspmb_p2p_open(const unsigned char *ipc_handle, void **dev_ptr);
 int dspmb_p2p_close(void *dev_ptr);
 int dspmb_p2p_free(void *dev_ptr);
-int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, int B, int A, int K, int rank, int world,
-                               void *const *peer_bases, int slot, void *stream);
-int dspmb_detection_gather_wait(const void *local_base, int B, int K, int world, int slot, int expected, void *stream);
-/* Copies slot `slot` of this rank's buffer into rows_out (world*B, K, 7) and counts_out (world*B) (device, async). */
-int dspmb_detection_gather_read(const void *local_base, int B, int K, int world, int slot, float *rows_out,
-                                int32_t *counts_out, void *stream);
+int dspmb_detection_gather_f32(const float *out, const int32_t *valid_count, const int32_t *stats, int B, int A, int K,
+                               int stats_width, int rank, int world, void *const *peer_bases, int slot, long long seq,
+                               void *stream);
+int dspmb_detection_gather_wait(void *local_base, int B, int K, int stats_width, int world, int slot, long long seq,
+                                void *stream);
+int dspmb_detection_gather_ack(int B, int K, int stats_width, int rank, int world, void *const *peer_bases, int slot,
+                               long long seq, void *stream);
+/* Copies slot `slot` of this rank's buffer into rows_out (world*B, K, 7), counts_out (world*B) and stats_out
+ * (world*B, stats_width) (device, async; NULL pointers are skipped). */
+int dspmb_detection_gather_read(const void *local_base, int B, int K, int stats_width, int world, int slot,
+                                float *rows_out, int32_t *counts_out, int32_t *stats_out, void *stream);
+/* 0, or 1 if a bounded wait of the exchange ran out (synchronous read of the buffer's error word). */
+int dspmb_gather_error(const void *local_base, int B, int K, int stats_width, int world);
 
 /* Synchronises `stream` and returns the data-dependent status latched by the last target/detection call
  * that used `workspace` (0 or a DSPMB_ERR_* code). */
@@ -218,6 +232,11 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
 #define DSPMB_NUM_TUNING 9
 int dspmb_set_tuning(int knob, int value);
+
+/* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)
+ * receives per kernel [earliest CTA start, latest CTA end] in %globaltimer ns (slots: 0 stream, 1 sort, 2 pair, 3 tail,
+ * 4 resolve); NULL switches it off.  Not part of the operator boundary. */
+int dspmb_debug_trace(unsigned long long *device_buffer);
 
 /* Device self-test hooks used by the parity tests: y[i] = expf(x[i]) / logf(x[i]) through the same
  * glibc-compatible routines the kernels use.  x, y device pointers. */

@@ -1,0 +1,49 @@
+"""Device-side timeline of one detection step in graph-replay mode (dspmb_debug_trace): per kernel the earliest CTA
+start and the latest CTA end, relative to the start of the stream kernel."""
+import sys, torch
+sys.path.insert(0, '.')
+import bench
+from dspnet_b200 import _lib
+from dspnet_b200.plan import DetectionPlan
+from dspnet_b200.symbol import multibox_anchors
+dev = torch.device('cuda', 0)
+inputs, _ = bench.make_inputs(0, bench.BATCH)
+A, C = inputs['A'], inputs['C']
+anchors = multibox_anchors(bench.PRESET, device=dev)
+plan = DetectionPlan(bench.BATCH, A, C, dev, **bench.DET_PARAMS)
+prob = [torch.from_numpy(inputs['prob']).to(dev) for _ in range(4)]
+loc = [torch.from_numpy(inputs['loc']).to(dev) for _ in range(4)]
+out = [plan.new_output() for _ in range(4)]
+for i in range(2000):
+    plan.run(prob[i % 4], loc[i % 4], anchors, out[i % 4])
+torch.cuda.synchronize()
+L = _lib.lib()
+if len(sys.argv) > 1 and sys.argv[1] == 'nograph':
+    L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
+names = ['stream', 'sort', 'pair', 'tail', 'resolve', 'pair:scans', 'pair:gather', 'pair:units', 'pair:waited', 'sort:staged', 'sort:bucket-sorted', 'sort:fallback-sorted']
+acc = [[0.0, 0.0] for _ in names]
+reps = 20
+for r in range(reps):
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
+    buf[0::2] = torch.iinfo(torch.int64).max
+    torch.cuda.synchronize()
+    L.dspmb_debug_trace(buf.data_ptr())
+    for i in range(3):
+        plan.run(prob[i % 4], loc[i % 4], anchors, out[i % 4])
+    torch.cuda.synchronize()
+    L.dspmb_debug_trace(None)
+    # only the LAST of the three steps is unambiguous for max; min comes from the first: run single steps instead
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
+    buf[0::2] = torch.iinfo(torch.int64).max
+    torch.cuda.synchronize()
+    L.dspmb_debug_trace(buf.data_ptr())
+    plan.run(prob[r % 4], loc[r % 4], anchors, out[r % 4])
+    torch.cuda.synchronize()
+    L.dspmb_debug_trace(None)
+    t = buf.cpu().tolist()
+    t0 = t[0]
+    for k in range(len(names)):
+        acc[k][0] += (t[2 * k] - t0) / 1e3 / reps
+        acc[k][1] += (t[2 * k + 1] - t0) / 1e3 / reps
+for k, n in enumerate(names):
+    print('%-22s start %7.2f us   end %7.2f us' % (n, acc[k][0], acc[k][1]))
