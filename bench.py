@@ -689,9 +689,10 @@ def main():
             dplan.run(prob_sets[s], loc_sets[s], anchors, out_sets[s])
         for s in range(rotate):  # every workspace-dependent phase input exists for every rotating set
             det_run(s)
-        if (dplan.launches_per_run or 0) >= 4:
-            names = [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_pair_kernel+det_tail_kernel"),
-                     (8, "det_resolve_kernel")]
+        pipeline = lib.dspmb_set_tuning(_lib.TUNE_DET_PIPELINE, 1)
+        lib.dspmb_set_tuning(_lib.TUNE_DET_PIPELINE, pipeline)
+        if pipeline and C in (21, 9) and not DET_PARAMS["force_suppress"]:
+            names = [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_pair_kernel")]
         else:
             names = [(1, "det_stream_kernel"), (2, "det_sort_kernel"), (4, "det_nms_kernel")]
         kernels.update(time_phases(det_run, names))

@@ -220,14 +220,14 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_NMS_SMEM_ROWS 2      /* largest segment staged in shared memory by the sweep NMS (max 1024) */
 #define DSPMB_TUNE_SORT_SMEM_KEYS 3     /* 64-bit sort keys kept in shared memory (default/max 8192)           */
 #define DSPMB_TUNE_PHASES 4             /* bit mask of the launches a detection/target call performs (default 31:
-                                           1 stream, 2 sort (+rank) / match, 4 nms or pair tests, 8 resolve) --
+                                           1 stream, 2 sort (+rank) / match, 4 nms or pair tests + resolve / select) --
                                            bench.py times one at a time                                             */
 #define DSPMB_TUNE_GRAPH_CACHE 5        /* 1 (default): a detection/target call repeated with identical arguments is
                                            captured into a CUDA graph on its second sighting and replayed from then
                                            on (one cudaGraphLaunch instead of 3-4 kernel launches); 0: always launch */
-#define DSPMB_TUNE_DET_PIPELINE 6       /* 1 (default): detection runs stream -> {sort || class pair tests} -> resolve
-                                           (fork/join inside the cached graph) where its preconditions hold;
-                                           0: stream -> sort+rank -> nms in final row order                         */
+#define DSPMB_TUNE_DET_PIPELINE 6       /* 1 (default): detection runs stream -> {sort || class pair tests + resolve}
+                                           (the pair kernel is a programmatic dependent of the sort kernel) where its
+                                           preconditions hold; 0: stream -> sort+rank -> nms in final row order      */
 #define DSPMB_TUNE_TARGET_PIPELINE 7    /* 1 (default): multi-CTA target matcher; 0: one CTA per image              */
 #define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
 #define DSPMB_NUM_TUNING 9

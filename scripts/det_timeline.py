@@ -20,7 +20,7 @@ torch.cuda.synchronize()
 L = _lib.lib()
 if len(sys.argv) > 1 and sys.argv[1] == 'nograph':
     L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
-names = ['stream', 'sort', 'pair', 'tail', 'resolve', 'pair:scans', 'pair:gather', 'pair:units', 'pair:waited', 'sort:staged', 'sort:bucket-sorted', 'sort:fallback-sorted']
+names = ['stream', 'sort', 'pair', 'tail', 'resolve', 'pair:scans', 'pair:gather', 'pair:units', 'pair:waited', 'sort:staged', 'sort:bucket-sorted', 'sort:fallback-sorted', 'res:headscan', 'res:ordered', 'res:rounds']
 acc = [[0.0, 0.0] for _ in names]
 reps = 20
 for r in range(reps):
@@ -41,9 +41,11 @@ for r in range(reps):
     torch.cuda.synchronize()
     L.dspmb_debug_trace(None)
     t = buf.cpu().tolist()
+    maxrounds = max(globals().get('maxrounds', 0), t[31])
     t0 = t[0]
     for k in range(len(names)):
         acc[k][0] += (t[2 * k] - t0) / 1e3 / reps
         acc[k][1] += (t[2 * k + 1] - t0) / 1e3 / reps
 for k, n in enumerate(names):
     print('%-22s start %7.2f us   end %7.2f us' % (n, acc[k][0], acc[k][1]))
+print('max fixed-point rounds', maxrounds)
