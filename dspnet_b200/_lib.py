@@ -89,6 +89,7 @@ def lib():
     L.dspmb_detection_gather_ack.argtypes = [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_int, c_ll, c_void_p]
     L.dspmb_detection_gather_read.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.dspmb_debug_trace.argtypes = [c_void_p]
+    L.dspmb_debug_stamps.argtypes = [c_void_p]
     L.dspmb_gather_error.argtypes = [c_void_p, c_int, c_int, c_int, c_int]
     L.dspmb_status.argtypes = [c_void_p, c_void_p]
     L.dspmb_nms_workspace_bytes.argtypes = [c_int]

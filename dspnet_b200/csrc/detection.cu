@@ -74,6 +74,19 @@ struct TraceScope {
   }
 };
 
+// Per-CTA phase stamps of the pair kernel (dspmb_debug_trace with a second buffer): 10 x uint64 per CTA, written once.
+__device__ unsigned long long *g_stamps = nullptr;
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DSPMB_STAMP(k)                                                                          \
+  do {                                                                                          \
+    if (g_stamps && threadIdx.x == 0)                                                           \
+      g_stamps[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 10 + (k)] = now_ns();            \
+  } while (0)
+
 __device__ __forceinline__ void trace_point(int slot) {  // latest time any CTA passed this point
   if (g_trace && threadIdx.x == 0) {
     unsigned long long t;
@@ -1812,55 +1825,46 @@ __device__ __forceinline__ int lower_bound_i32(const int *v, int n, int x) {  //
   return lo;
 }
 
+constexpr int kResolveCand = 128;  // nodes with an earlier neighbour that get a compact neighbour list
+constexpr int kResolveNbr = 8;     // entries of such a list; longer ones fall back to the bit-mask walk
+
 struct ResolveScratch {
   int *hq, *tmpq, *tmpr;      // [kNmsMaskRows] head positions of the class, ordered / as found (+ their ranks)
   unsigned short *hm, *hp;    // [kNmsMaskRows] member of head node k / head node of member m (0xffff: none)
   unsigned short *open;       // [2 * kNmsMaskRows] nodes that have an earlier neighbour
   unsigned char *status;      // [2 * kNmsMaskRows] 0 undecided, 1 kept, 2 suppressed
+  unsigned short *nbr;        // [kResolveCand * kResolveNbr] earlier neighbours (node ids) of the listed nodes
+  unsigned char *nnbr;        // [kResolveCand] their number (0xff: too many, walk the mask)
   int *counter;               // [2]
 };
 
 // Part of the resolve that does not depend on the sort: call (whole CTA) before griddepcontrol.wait.
 __device__ __forceinline__ void resolve_prepare(const int n, const ResolveScratch s) {
   for (int q = threadIdx.x; q < n; q += blockDim.x) s.hp[q] = (unsigned short)0xffffu;
-  for (int q = threadIdx.x; q < 2 * n; q += blockDim.x) s.status[q] = 0;
+  for (int q = threadIdx.x; q < 2 * n; q += blockDim.x) s.status[q] = 1;  // kept unless an earlier neighbour says no
   if (threadIdx.x < 2) s.counter[threadIdx.x] = 0;
   __syncthreads();
 }
 
-// Status of node q from the nodes that precede it in final order: 2 (suppressed) as soon as one earlier neighbour
-// is kept, 1 (kept) once all of them are suppressed, 0 while that is still open.
-__device__ __forceinline__ int resolve_node(const int q, const int nh, const int m0, const int W,
-                                            const unsigned long long *mask, const unsigned long long *rowany,
-                                            const unsigned long long *selfadj, const ResolveScratch &s,
-                                            const volatile unsigned char *status) {
+// Earlier neighbours of node q in final order, as node ids: calls f(id) for each.
+template <typename F>
+__device__ __forceinline__ void for_each_earlier(const int q, const int nh, const int m0, const int W,
+                                                 const unsigned long long *mask, const unsigned long long *rowany,
+                                                 const unsigned long long *selfadj, const ResolveScratch &s, F f) {
   const bool tail = q >= nh;
   const int m = tail ? m0 + (q - nh) : (int)s.hm[q];
-  bool any_alive = false, any_open = false;
   if ((rowany[m >> 6] >> (m & 63)) & 1ull) {
     for (int w = 0; w < W; ++w) {
       for (unsigned long long bits = mask[m * W + w]; bits; bits &= bits - 1) {
         const int j = (w << 6) + __ffsll((long long)bits) - 1;
         const int hj = s.hp[j];
-        if (hj != 0xffff && (tail || hj < q)) {  // the head copy of member j precedes this node
-          const int st = status[hj];
-          any_alive |= st == 1;
-          any_open |= st == 0;
-        }
-        if (tail && j >= m0 && j < m) {  // the tail copy of member j precedes this tail node
-          const int st = status[nh + j - m0];
-          any_alive |= st == 1;
-          any_open |= st == 0;
-        }
+        if (hj != 0xffff && (tail || hj < q)) f(hj);          // the head copy of member j precedes this node
+        if (tail && j >= m0 && j < m) f(nh + j - m0);         // the tail copy of member j precedes this tail node
       }
     }
   }
-  if (tail && s.hp[m] != 0xffff && ((selfadj[m >> 6] >> (m & 63)) & 1ull)) {  // its own copy in the sorted head
-    const int st = status[s.hp[m]];
-    any_alive |= st == 1;
-    any_open |= st == 0;
-  }
-  return any_alive ? 2 : (any_open ? 0 : 1);
+  // a tail row's own copy in the sorted head
+  if (tail && s.hp[m] != 0xffff && ((selfadj[m >> 6] >> (m & 63)) & 1ull)) f((int)s.hp[m]);
 }
 
 // Greedy resolve of one segment (n <= kNmsMaskRows members in rank order, symmetric mask with row stride W) in the
@@ -1882,7 +1886,7 @@ __device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, 
     }
   }
   __syncthreads();
-  trace_point(12);
+  DSPMB_STAMP(5);
   const int nh = s.counter[0];
   for (int k = threadIdx.x; k < nh; k += blockDim.x) {
     const int myq = s.tmpq[k];
@@ -1897,39 +1901,69 @@ __device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, 
   // Nodes in final order: q < nh is head row hm[q]; q >= nh is tail member m0 + (q - nh).  The greedy loop of
   // multibox_detection.cc:153-167 keeps a node iff no EARLIER adjacent node is kept.  Evaluated as a fixed point: a
   // node is suppressed as soon as one earlier neighbour is known kept and kept once all of them are known suppressed;
-  // the earliest open node always decides.  Round one runs on all nodes (most have no earlier neighbour and are
-  // kept at once); the few that stay open are listed and one warp iterates on the list -- real overlap graphs settle
-  // in a handful of rounds.
+  // the earliest open node always decides.  Only nodes that HAVE an earlier neighbour take part (the others are kept,
+  // which is what resolve_prepare wrote): they are listed once, densely, together with the node ids of those
+  // neighbours, and the rounds -- a handful for real overlap graphs -- only chase those short lists.
   const int ns = nh + (n - m0);
   __syncthreads();
-  trace_point(13);
-  for (int q = threadIdx.x; q < ns; q += blockDim.x) {
-    const int st = resolve_node(q, nh, m0, W, mask, rowany, selfadj, s, s.status);
-    if (st) s.status[q] = (unsigned char)st;
-    else s.open[atomicAdd(&s.counter[1], 1)] = (unsigned short)q;
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nopen = s.counter[1];
-    volatile unsigned char *status = s.status;
-    int rounds = 1;
-    while (nopen) {
-      ++rounds;
-      bool open = false;
-      for (int i = threadIdx.x; i < nopen; i += 32) {
-        const int q = s.open[i];
-        if (status[q]) continue;
-        const int st = resolve_node(q, nh, m0, W, mask, rowany, selfadj, s, status);
-        if (st) status[q] = (unsigned char)st;
-        else open = true;
-      }
-      __syncwarp();
-      if (!__any_sync(kFullMask, open)) break;
+  DSPMB_STAMP(6);
+  for (int q0 = 0; q0 < ns; q0 += blockDim.x) {
+    const int q = q0 + (int)threadIdx.x;
+    bool has = false;
+    if (q < ns) {
+      const bool tail = q >= nh;
+      const int m = tail ? m0 + (q - nh) : (int)s.hm[q];
+      has = ((rowany[m >> 6] >> (m & 63)) & 1ull) || (tail && s.hp[m] != 0xffff);
     }
-    if (g_trace && threadIdx.x == 0) atomicMax(g_trace + 31, (unsigned long long)rounds);
+    const unsigned bal = __ballot_sync(kFullMask, has);
+    if (bal) {
+      int base = 0;
+      if (lane_id() == 0) base = atomicAdd(&s.counter[1], __popc(bal));
+      base = __shfl_sync(kFullMask, base, 0);
+      if (has) s.open[base + __popc(bal & ((1u << lane_id()) - 1u))] = (unsigned short)q;
+    }
   }
   __syncthreads();
-  trace_point(14);
+  const int nopen = s.counter[1];
+  volatile unsigned char *status = s.status;
+  for (int i = threadIdx.x; i < nopen; i += blockDim.x) {  // neighbour lists; a node without any is kept
+    const int q = s.open[i];
+    int cnt = 0;
+    for_each_earlier(q, nh, m0, W, mask, rowany, selfadj, s, [&](int id) {
+      if (i < kResolveCand && cnt < kResolveNbr) s.nbr[i * kResolveNbr + cnt] = (unsigned short)id;
+      ++cnt;
+    });
+    if (i < kResolveCand) s.nnbr[i] = cnt <= kResolveNbr ? (unsigned char)cnt : (unsigned char)0xff;
+    if (cnt) status[q] = 0;
+  }
+  __syncthreads();
+  while (true) {
+    bool open = false;
+    for (int i = threadIdx.x; i < nopen; i += blockDim.x) {
+      const int q = s.open[i];
+      if (status[q]) continue;
+      bool any_alive = false, any_open = false;
+      const int cnt = i < kResolveCand ? (int)s.nnbr[i] : 0xff;
+      if (cnt != 0xff) {
+        for (int k = 0; k < cnt; ++k) {
+          const int st = status[s.nbr[i * kResolveNbr + k]];
+          any_alive |= st == 1;
+          any_open |= st == 0;
+        }
+      } else {
+        for_each_earlier(q, nh, m0, W, mask, rowany, selfadj, s, [&](int id) {
+          const int st = status[id];
+          any_alive |= st == 1;
+          any_open |= st == 0;
+        });
+      }
+      if (any_alive) status[q] = 2;
+      else if (!any_open) status[q] = 1;
+      else open = true;
+    }
+    if (!__syncthreads_or(open)) break;
+  }
+  DSPMB_STAMP(7);
   // ids: a suppressed row gets -1 and keeps everything else (multibox_detection.cc:163); the tail rows receive their
   // id here in either case (the sort kernel copies the other six columns)
   float *out = a.out + (size_t)b * a.A * 7;
@@ -1940,6 +1974,7 @@ __device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, 
       out[(size_t)ranks[m0 + (q - nh)] * 7] = s.status[q] == 2 ? -1.f : (float)c;
     }
   }
+  DSPMB_STAMP(8);
 }
 
 __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_constant__ PairArgs a,
@@ -1951,6 +1986,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   constexpr int kWarps = kNmsThreads / 32;
   static_assert(kNmsMaskRows * 16 >= 3 * kNmsMaskRows * 4 + 2 * kNmsMaskRows * 2, "hq / tmpq / tmpr / open alias the box stage");
   static_assert(kWarps * kNmsQueue * 2 >= 2 * kNmsMaskRows * 2 + 2 * kNmsMaskRows, "hm / hp / status alias the queues");
+  static_assert(kBytes - kOffCol >= kResolveCand * kResolveNbr * 2 + kResolveCand, "neighbour lists alias the packed boxes");
   __shared__ __align__(16) unsigned char smem_raw[kBytes];
   __shared__ int sm_tbase[kV2MaxTiles], sm_mbase[kV2MaxTiles];
   __shared__ unsigned short sm_coff[kV2MaxTiles];
@@ -1961,6 +1997,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   __shared__ unsigned char unit_tab[64];
   __shared__ int sm_nunits, sm_next, sm_ctr[2];
   TraceScope trace_(2);
+  DSPMB_STAMP(0);
 
   const int b = blockIdx.y, c = blockIdx.x, T = a.T;
   const unsigned lane = lane_id(), warp = warp_id();
@@ -2061,7 +2098,7 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   }
   for (int q = threadIdx.x; q < n * W; q += blockDim.x) mask[q] = 0ull;
   __syncthreads();
-  trace_point(6);
+  DSPMB_STAMP(2);
 
   // ---- bounding box of every 32-row group (unit culling) and the self bits ----
   const int ngroups = npad >> 5;
@@ -2156,12 +2193,14 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   rs.hm = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue);
   rs.hp = rs.hm + kNmsMaskRows;
   rs.status = reinterpret_cast<unsigned char *>(rs.hp + kNmsMaskRows);
+  rs.nbr = reinterpret_cast<unsigned short *>(smem_raw + kOffCol);  // the packed filter boxes are dead as well
+  rs.nnbr = reinterpret_cast<unsigned char *>(rs.nbr + kResolveCand * kResolveNbr);
   rs.counter = sm_ctr;
   resolve_prepare(n, rs);
-  trace_point(7);
+  DSPMB_STAMP(3);
   // the sort grid has completed and flushed: head_rank and the head rows of `out` are final
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  trace_point(8);
+  DSPMB_STAMP(4);
   resolve_segment(a, b, c, n, V, mask, ranks, rowany, selfadj, rs);
 }
 
@@ -2221,6 +2260,11 @@ extern "C" int dspmb_detection_compact_f32(const float *out, const int32_t *vali
 
 extern "C" int dspmb_debug_trace(unsigned long long *device_buffer) {
   DSPMB_CUDA_TRY(cudaMemcpyToSymbol(g_trace, &device_buffer, sizeof(device_buffer)));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_debug_stamps(unsigned long long *device_buffer) {
+  DSPMB_CUDA_TRY(cudaMemcpyToSymbol(g_stamps, &device_buffer, sizeof(device_buffer)));
   return DSPMB_OK;
 }
 

@@ -49,3 +49,21 @@ for r in range(reps):
 for k, n in enumerate(names):
     print('%-22s start %7.2f us   end %7.2f us' % (n, acc[k][0], acc[k][1]))
 print('max fixed-point rounds', maxrounds)
+
+# per-CTA phase stamps of the pair kernel (no contended atomics): mean / max duration of every phase
+st = torch.zeros(640 * 10, dtype=torch.int64, device=dev)
+torch.cuda.synchronize()
+L.dspmb_debug_stamps(st.data_ptr())
+plan.run(prob[0], loc[0], anchors, out[0])
+torch.cuda.synchronize()
+L.dspmb_debug_stamps(None)
+t = st.cpu().view(640, 10).double() / 1e3
+lab = ['scans', 'gather', 'units', 'wait', 'headscan', 'order', 'rounds', 'ids']
+ok = (t[:, 8] > 0)
+t = t[ok]
+print('pair kernel CTAs with a resolve:', int(ok.sum()))
+for k, name in enumerate(lab):
+    d = t[:, k + 1] - t[:, k]
+    print('  %-9s mean %6.2f  max %6.2f us' % (name, d.mean().item(), d.max().item()))
+print('  %-9s mean %6.2f  max %6.2f us' % ('total', (t[:, 8] - t[:, 0]).mean().item(), (t[:, 8] - t[:, 0]).max().item()))
+print('  first start %.2f, last end %.2f (span)' % (0.0, (t[:, 8].max() - t[:, 0].min()).item()))
