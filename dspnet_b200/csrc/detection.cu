@@ -1248,31 +1248,64 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7)) row_cls[V + threadIdx.x] = (unsigned short)0xffffu;
   if (a.tail_copy && nkeep < V) {
     // Fork/join pipeline: this CTA also moves the image's tail rows [nkeep, V) from the tiles' slots to their pass-1
-    // positions (one warp per tile) -- the pair-test kernel runs far longer than the sort, so the copy is hidden.  The
-    // id column is left out: the resolve owns it for every tail row of its class.
+    // positions.  The id column is left out: the resolve owns it for every tail row of its class.
+    // one warp per tile, three tiles at a time: the loads of all three runs are issued before the first store, so a
+    // warp's share of the copy costs a few memory round trips instead of a dozen
     const int nwarps = (int)(blockDim.x >> 5);
-    for (int t = (int)warp; t < T; t += nwarps) {
-      const int base = tbase[t];
-      const int nt = (t + 1 < T ? tbase[t + 1] : V) - base;
-      const int skip = min(nt, max(0, nkeep - base));
-      if (skip >= nt) continue;
-      const size_t slot0 = (size_t)b * a.Apad + (size_t)t * a.tile;
-      const float *src = a.slot_rows + slot0 * 7;
-      float *dst = out + (size_t)base * 7;
-      const int end = nt * 7;
-      for (int q = skip * 7 + (int)lane; q < end; q += 128) {
-        float v[4];
+    constexpr int kU = 3;
+    for (int t0 = (int)warp; t0 < T; t0 += kU * nwarps) {
+      int base[kU], nt[kU], skip[kU];
+      const float *src[kU];
+      int maxend = 0, maxrows = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = q + 32 * k < end ? src[q + 32 * k] : 0.f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (q + 32 * k < end && (q + 32 * k) % 7 != 0) dst[q + 32 * k] = v[k];
+      for (int u = 0; u < kU; ++u) {
+        const int t = t0 + u * nwarps;
+        base[u] = nt[u] = skip[u] = 0;
+        src[u] = a.slot_rows;
+        if (t < T) {
+          base[u] = tbase[t];
+          nt[u] = (t + 1 < T ? tbase[t + 1] : V) - base[u];
+          skip[u] = min(nt[u], max(0, nkeep - base[u]));
+          src[u] = a.slot_rows + ((size_t)b * a.Apad + (size_t)t * a.tile) * 7;
+          if (skip[u] < nt[u]) {
+            maxend = max(maxend, nt[u] * 7);
+            maxrows = max(maxrows, nt[u]);
+          }
+        }
       }
-      const unsigned short *sc = a.slot_cls + (size_t)b * a.cls_stride + (size_t)t * a.tile;
-      const float4 *sbx = a.slot_box + slot0;
-      for (int q = skip + (int)lane; q < nt; q += 32) {
-        row_cls[base + q] = sc[q];
-        row_box[base + q] = sbx[q];
+      for (int q = (int)lane; q < maxend; q += 64) {
+        float v[kU][2];
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int idx = q + 32 * k;
+            v[u][k] = (idx >= skip[u] * 7 && idx < nt[u] * 7) ? src[u][idx] : 0.f;
+          }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int idx = q + 32 * k;
+            if (idx >= skip[u] * 7 && idx < nt[u] * 7 && idx % 7 != 0) out[(size_t)base[u] * 7 + idx] = v[u][k];
+          }
+      }
+      for (int q = (int)lane; q < maxrows; q += 32) {
+        unsigned short cl[kU];
+        float4 bx[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const int t = t0 + u * nwarps;
+          const bool on = q >= skip[u] && q < nt[u];
+          cl[u] = on ? a.slot_cls[(size_t)b * a.cls_stride + (size_t)t * a.tile + q] : (unsigned short)0;
+          bx[u] = on ? a.slot_box[(size_t)b * a.Apad + (size_t)t * a.tile + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (q >= skip[u] && q < nt[u]) {
+            row_cls[base[u] + q] = cl[u];
+            row_box[base[u] + q] = bx[u];
+          }
       }
     }
   }
