@@ -34,16 +34,17 @@ constexpr unsigned kKeySentinel = 0xffffffffu;  // "not a mining candidate"
 
 struct TargetWorkspace {
   WsHeader *header;
-  int *gcount;     // (B) valid ground truths
-  int *thr_count;  // (B) threshold-stage positives (zeroed per call)
-  unsigned long long *colbest;  // (B, L) best (iou, anchor) per gt (zeroed per call)
+  int *gcount;     // (B) valid ground truths | (B) label-padding status, written by tile 0 of every image
+  int *thr_count;  // (B, Tmax) threshold-stage positives of every tile
+  unsigned long long *colbest;  // (B, Tmax, L) best (iou, anchor) per tile and gt (0: none)
   unsigned *key;   // (B, A) mining keys
   int *amb_list;      // (B, A) anchors inside the pivot's error band
   unsigned *amb_key;  // (B, A) their exact keys
-  size_t zero_begin, zero_bytes;
   size_t bytes;
 };
 
+// Nothing in the workspace needs zeroing: every CTA of the stream kernel owns its slots (the match kernel reduces
+// them), so the operator is two launches and no memset node.
 TargetWorkspace carve(void *base, int B, int A, int L) {
   TargetWorkspace w;
   size_t off = 0;
@@ -53,11 +54,10 @@ TargetWorkspace carve(void *base, int B, int A, int L) {
     return (char *)base + o;
   };
   w.header = (WsHeader *)take(sizeof(WsHeader));
-  w.zero_begin = 0;
-  w.gcount = (int *)take(sizeof(int) * B);
-  w.thr_count = (int *)take(sizeof(int) * B);
-  w.colbest = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * L);
-  w.zero_bytes = off;
+  const size_t Tmax = (size_t)ceil_div(A, kStreamThreads);
+  w.gcount = (int *)take(sizeof(int) * 2 * B);
+  w.thr_count = (int *)take(sizeof(int) * B * Tmax);
+  w.colbest = (unsigned long long *)take(sizeof(unsigned long long) * (size_t)B * Tmax * L);
   w.key = (unsigned *)take(sizeof(unsigned) * (size_t)B * A);
   w.amb_list = (int *)take(sizeof(int) * (size_t)B * A);
   w.amb_key = (unsigned *)take(sizeof(unsigned) * (size_t)B * A);
@@ -239,11 +239,13 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   const int G = count_valid_gt(lab, a.L, W, &sm_int);
   if (t == 0 && threadIdx.x == 0) {
     a.gcount[b] = G;
+    int bad = DSPMB_OK;
     if (G < a.L) {  // CHECK_EQ on the first padding row, multibox_target.cc:98-101
       const float *row = lab + (size_t)G * W;
-      if (row[1] != -1.0f || row[2] != -1.0f || row[3] != -1.0f || row[4] != -1.0f)
-        atomicMin(&a.header->status, DSPMB_ERR_LABEL_PADDING);
+      if (row[1] != -1.0f || row[2] != -1.0f || row[3] != -1.0f || row[4] != -1.0f) bad = DSPMB_ERR_LABEL_PADDING;
     }
+    a.gcount[a.B + b] = bad;                   // latched into the header by the match kernel
+    if (b == 0) a.header->status = DSPMB_OK;   // nobody else touches the header during this launch
   }
   for (int k = threadIdx.x; k < G; k += blockDim.x) {
     const float *row = lab + (size_t)k * W;
@@ -475,12 +477,9 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   npos = warp_sum_i32(npos);
   if (lane_id() == 0 && npos) atomicAdd(&sm_pos, npos);
   __syncthreads();
-  if (threadIdx.x == 0 && sm_pos) atomicAdd(&a.thr_count[b], sm_pos);
-  unsigned long long *gcol = a.colbest + (size_t)b * a.L;
-  for (int k = threadIdx.x; k < G; k += blockDim.x) {
-    const unsigned long long ck = sm_col[k];
-    if (ck) atomicMax(&gcol[k], ck);
-  }
+  if (threadIdx.x == 0) a.thr_count[(size_t)b * a.T + t] = sm_pos;
+  unsigned long long *gcol = a.colbest + ((size_t)b * a.T + t) * a.L;
+  for (int k = threadIdx.x; k < G; k += blockDim.x) gcol[k] = sm_col[k];
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -506,14 +505,20 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ unsigned long long red_smem[kMatchThreads / 32];
   __shared__ unsigned hist[256];
-  __shared__ int sm_state, sm_arg, sm_nmatch, sm_dup, sm_carry;
+  __shared__ int sm_state, sm_arg, sm_nmatch, sm_dup, sm_carry, sm_thr;
   __shared__ unsigned sm_prefix;
   __shared__ int sm_need;
+  constexpr int kLowBuckets = 2 * kMatchThreads, kPivotList = 1024;
+  __shared__ unsigned bucket[kLowBuckets], plist[kPivotList];
+  __shared__ int scan_smem[kMatchThreads / 32 + 1];
+  __shared__ int sm_np, sm_pb, sm_before;
+  __shared__ unsigned sm_kmin, sm_kmax;
 
   const int b = blockIdx.x;
   const int A = a.A, L = a.L, W = a.W;
   const int G = a.gcount[b];
   int32_t *stats = a.stats_out ? a.stats_out + 4 * b : nullptr;
+  if (threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
   if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values
     if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     return;
@@ -531,17 +536,30 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
 
   const float *lab = a.labels + (size_t)b * L * W;
   const float4 *anchors = reinterpret_cast<const float4 *>(a.anchors);
-  unsigned long long *gcol = a.colbest + (size_t)b * L;
   for (int k = threadIdx.x; k < G; k += blockDim.x) {
     const float *row = lab + (size_t)k * W;
     sm_gt[k] = make_float4(row[1], row[2], row[3], row[4]);
-    sm_col[k] = gcol[k];
+    sm_col[k] = 0ull;
     done[k] = 0;
   }
   for (int w = threadIdx.x; w < nwords; w += blockDim.x) bits[w] = 0u;
   if (threadIdx.x == 0) {
     sm_nmatch = 0;
     sm_dup = 0;
+    sm_thr = 0;
+  }
+  __syncthreads();
+  {  // column maxima and positive counts of the image's tiles (each written by its own stream CTA, no atomics there)
+    const unsigned long long *tcol = a.colbest + (size_t)b * a.T * L;
+    for (int idx = threadIdx.x; idx < a.T * G; idx += blockDim.x) {
+      const int t = idx / G, k = idx - t * G;
+      const unsigned long long ck = tcol[(size_t)t * L + k];
+      if (ck) atomicMax(&sm_col[k], ck);
+    }
+    int pos = 0;
+    for (int t = threadIdx.x; t < a.T; t += blockDim.x) pos += a.thr_count[(size_t)b * a.T + t];
+    pos = warp_sum_i32(pos);
+    if (lane_id() == 0 && pos) atomicAdd(&sm_thr, pos);
   }
   __syncthreads();
 
@@ -718,7 +736,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (a.match_out) a.match_out[row] = k;
   }
   __syncthreads();
-  const int num_positive = a.thr_count[b] + nmatch - sm_dup;
+  const int num_positive = sm_thr + nmatch - sm_dup;
 
   // ---- hard-negative mining (multibox_target.cc:182-241) ----
   int num_negative = 0;
@@ -755,7 +773,81 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     sm_prefix = 0u;
     sm_need = num_negative;
   }
-  for (int pass = 0; pass < 4; ++pass) {
+  // Fast path: one 2048-bucket histogram over the range the candidate keys actually span (the bit patterns of
+  // positive floats order like the floats) replaces the four 8-bit radix passes: the bucket that holds the
+  // num_negative-th smallest key follows from a prefix sum, and the key itself from ranking the members of that one
+  // bucket.  A bucket too crowded to rank (massive ties) or too few candidates leave it to the radix passes below.
+  bool have_q = false;
+  if (kKeysInSmem) {
+    unsigned kmin = kKeySentinel, kmax = 0u;
+    for (int j = threadIdx.x; j < A; j += blockDim.x) {
+      const unsigned kv = skeys[j];
+      if (kv != kKeySentinel) {
+        kmin = min(kmin, kv);
+        kmax = max(kmax, kv);
+      }
+    }
+    kmin = __reduce_min_sync(kFullMask, kmin);
+    kmax = __reduce_max_sync(kFullMask, kmax);
+    if (threadIdx.x == 0) {
+      sm_kmin = kKeySentinel;
+      sm_kmax = 0u;
+      sm_np = 0;
+    }
+    for (int i = threadIdx.x; i < kLowBuckets; i += blockDim.x) bucket[i] = 0u;
+    __syncthreads();
+    if (lane_id() == 0) {
+      atomicMin(&sm_kmin, kmin);
+      atomicMax(&sm_kmax, kmax);
+    }
+    __syncthreads();
+    kmin = sm_kmin;
+    kmax = sm_kmax;
+    if (kmin != kKeySentinel) {  // CTA-uniform: at least one candidate
+      int shift = 0;
+      while (((kmax - kmin) >> shift) >= (unsigned)kLowBuckets) ++shift;
+      for (int j = threadIdx.x; j < A; j += blockDim.x) {
+        const unsigned kv = skeys[j];
+        if (kv != kKeySentinel) atomicAdd(&bucket[(kv - kmin) >> shift], 1u);
+      }
+      __syncthreads();
+      const unsigned c0 = bucket[2 * threadIdx.x], c1 = bucket[2 * threadIdx.x + 1];
+      int total;
+      const int ex = block_scan_excl((int)(c0 + c1), scan_smem, &total);  // total = number of candidates
+      if (ex < num_negative && ex + (int)c0 >= num_negative) {
+        sm_pb = 2 * threadIdx.x;
+        sm_before = ex;
+      } else if (ex + (int)c0 < num_negative && ex + (int)(c0 + c1) >= num_negative) {
+        sm_pb = 2 * threadIdx.x + 1;
+        sm_before = ex + (int)c0;
+      }
+      __syncthreads();
+      if (num_negative <= total) {  // otherwise the radix path reports the missing candidates
+        const unsigned P = (unsigned)sm_pb;
+        const int r = num_negative - sm_before;  // 1-based rank of the wanted key inside bucket P
+        const int cP = (int)bucket[P];
+        if (cP <= kPivotList) {
+          for (int j = threadIdx.x; j < A; j += blockDim.x) {
+            const unsigned kv = skeys[j];
+            if (kv != kKeySentinel && ((kv - kmin) >> shift) == P) plist[atomicAdd(&sm_np, 1)] = kv;
+          }
+          __syncthreads();
+          for (int i = threadIdx.x; i < cP; i += blockDim.x) {
+            const unsigned v = plist[i];
+            int lo = 0, hi = 0;
+            for (int x = 0; x < cP; ++x) {
+              lo += plist[x] < v ? 1 : 0;
+              hi += plist[x] <= v ? 1 : 0;
+            }
+            if (lo < r && r <= hi) sm_prefix = v;  // equal keys write the same value
+          }
+          __syncthreads();
+          have_q = true;
+        }
+      }
+    }
+  }
+  for (int pass = 0; pass < (have_q ? 0 : 4); ++pass) {
     const int shift = 24 - 8 * pass;
     const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
@@ -947,10 +1039,6 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
 
   return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](const LaunchCtx &ctx) -> int {
   cudaStream_t stream = ctx.stream;
-  if (tuning(DSPMB_TUNE_PHASES) & 1) {
-    DSPMB_CUDA_TRY(cudaMemsetAsync((char *)workspace + w.zero_begin, 0, w.zero_bytes, stream));
-    ++ctx.launches;
-  }
 
   const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
                              (uintptr_t)cls_target | (uintptr_t)match_out;
@@ -996,12 +1084,12 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
                        sizeof(int) * (size_t)((L + 3) & ~3) +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
-  const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 180 * 1024;
+  const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 170 * 1024;
   const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
   DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 28);
-  DSPMB_REQUIRE(smem2 <= 200 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
-  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 200 * 1024);
-  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 200 * 1024);
+  DSPMB_REQUIRE(smem2 <= 190 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 190 * 1024);  // + ~31 KB static
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 190 * 1024);
   const int phases = tuning(DSPMB_TUNE_PHASES);
   dim3 grid1(ta.T, B);
   if (phases & 1) {
