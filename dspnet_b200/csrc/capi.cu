@@ -38,8 +38,8 @@ static int detect_host_libm_mode() {
 
 constexpr int kNumTuning = DSPMB_NUM_TUNING;
 // knobs may be set from one thread while another launches: relaxed atomics (each call reads a knob once)
-static std::atomic<int> g_tuning[kNumTuning] = {{2}, {320}, {1024}, {8192}, {31}, {1}, {1}, {1}, {1}};
-static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 31, 1, 1, 1, 1};
+static std::atomic<int> g_tuning[kNumTuning] = {{2}, {320}, {1024}, {8192}, {31}, {1}, {1}, {1}, {1}, {0}, {0}, {1}};
+static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 31, 1, 1, 1, 1, 1 << 20, 1 << 20, 4};
 int tuning(int knob) { return g_tuning[knob].load(std::memory_order_relaxed); }
 
 int libm_fma_mode() {
@@ -108,12 +108,23 @@ CaptureSet g_capture[kMaxDevices];
 int LaunchCtx::fork() const {
   if (!forked()) return DSPMB_OK;
   DSPMB_CUDA_TRY(cudaEventRecord(ev_fork, stream));
-  for (int i = 0; i < kSides; ++i) DSPMB_CUDA_TRY(cudaStreamWaitEvent(side[i], ev_fork, 0));
+  for (int i = 0; i < kSides; ++i) {
+    DSPMB_CUDA_TRY(cudaStreamWaitEvent(side[i], ev_fork, 0));
+    used[i] = true;
+  }
+  return DSPMB_OK;
+}
+int LaunchCtx::fork_side(int i) const {
+  if (!forked()) return DSPMB_OK;
+  DSPMB_CUDA_TRY(cudaEventRecord(ev_fork, stream));
+  DSPMB_CUDA_TRY(cudaStreamWaitEvent(side[i], ev_fork, 0));
+  used[i] = true;
   return DSPMB_OK;
 }
 int LaunchCtx::join() const {
   if (!forked()) return DSPMB_OK;
   for (int i = 0; i < kSides; ++i) {
+    if (!used[i]) continue;  // a side stream that never joined the capture cannot be recorded on
     DSPMB_CUDA_TRY(cudaEventRecord(ev_join[i], side[i]));
     DSPMB_CUDA_TRY(cudaStreamWaitEvent(stream, ev_join[i], 0));
   }
@@ -197,7 +208,11 @@ int graph_cached_launch(const void *key_, size_t key_len, cudaStream_t stream,
       DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.main, cudaStreamNonBlocking));
       DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_fork, cudaEventDisableTiming));
       for (int i = 0; i < LaunchCtx::kSides; ++i) {
-        DSPMB_CUDA_TRY(cudaStreamCreateWithFlags(&cs.side[i], cudaStreamNonBlocking));
+        // highest priority: the few latency-bound CTAs of a side branch take freed SM slots before the next wave of
+        // the HBM-bound kernel on the main branch does
+        int prio_lo = 0, prio_hi = 0;
+        DSPMB_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DSPMB_CUDA_TRY(cudaStreamCreateWithPriority(&cs.side[i], cudaStreamNonBlocking, prio_hi));
         DSPMB_CUDA_TRY(cudaEventCreateWithFlags(&cs.ev_join[i], cudaEventDisableTiming));
       }
     }

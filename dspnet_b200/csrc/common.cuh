@@ -99,10 +99,12 @@ struct LaunchCtx {
   cudaStream_t stream = nullptr;
   cudaStream_t side[kSides] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kSides] = {nullptr, nullptr};
+  mutable bool used[kSides] = {false, false};  // side streams that joined the capture
   mutable int launches = 0;  // kernels (and memset nodes) the operator enqueued; read back by dspmb_last_launch_count
   bool forked() const { return side[0] != nullptr; }
   cudaStream_t branch(int i) const { return side[i] ? side[i] : stream; }
   int fork() const;  // both side streams wait for everything enqueued on `stream` so far
+  int fork_side(int i) const;  // side stream i waits for everything enqueued on `stream` so far
   int join() const;  // `stream` waits for both side streams
 };
 int graph_cached_launch(const void *key, size_t key_len, cudaStream_t stream,

@@ -55,7 +55,7 @@ constexpr int kNmsSmemRows = 1024;    // rows of a larger NMS segment staged in 
 
 // Optional device-side timeline (dspmb_debug_trace): per kernel the earliest CTA start and the latest CTA end in
 // %globaltimer nanoseconds, so that the overlap of the graph's branches can be read off without a profiler.
-__device__ unsigned long long *g_trace = nullptr;
+__constant__ unsigned long long *g_trace = nullptr;  // constant bank: the disabled check costs one LDC, no global load
 struct TraceScope {
   int slot;
   __device__ __forceinline__ explicit TraceScope(int s) : slot(s) {
@@ -75,7 +75,7 @@ struct TraceScope {
 };
 
 // Per-CTA phase stamps of the pair kernel (dspmb_debug_trace with a second buffer): 10 x uint64 per CTA, written once.
-__device__ unsigned long long *g_stamps = nullptr;
+__constant__ unsigned long long *g_stamps = nullptr;
 __device__ __forceinline__ unsigned long long now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -120,11 +120,14 @@ struct DetWorkspace {
   unsigned short *crank;      // (B, cls_stride) their index inside the tile's run
   unsigned *tile_cls;         // (B, kV2ClsPad, Tmax) per (class, tile): offset | count << 16 inside the tile's run
   int *head_rank;             // (B, Apad) pass-1 rank of the row sorted to head position q
+  int2 *head_list;            // (B, kHeadCap) (head position, pass-1 rank) of the head rows grouped by class, position order
+  int *head_off;              // (B, kV2ClsPad + 1) start of every class in head_list
   size_t bytes;
 };
 
 constexpr int kV2ClsPad = 32;    // foreground classes the fork/join pipeline supports
 constexpr int kV2MaxTiles = 512; // tiles per image whose bases fit its shared-memory tables
+constexpr int kHeadCap = 1024;   // largest nms_topk whose head the sort kernel hands over as per-class lists
 
 
 inline int next_pow2(int v) {
@@ -166,6 +169,8 @@ DetWorkspace carve(void *base, int B, int A, int C) {
   w.crank = (unsigned short *)take(sizeof(unsigned short) * B * ((Apad + 7) & ~(size_t)7));
   w.tile_cls = (unsigned *)take(sizeof(unsigned) * (size_t)B * kV2ClsPad * Tmax);
   w.head_rank = (int *)take(sizeof(int) * B * Apad);
+  w.head_list = (int2 *)take(sizeof(int2) * (size_t)B * kHeadCap);
+  w.head_off = (int *)take(sizeof(int) * (size_t)B * (kV2ClsPad + 1));
   w.bytes = off;
   return w;
 }
@@ -186,6 +191,7 @@ struct StreamArgs {
   int clip;
   float vx, vy, vw, vh;
   int fma_build;
+  int prefetch;               // L2 prefetch distance in CTAs of launch order (0: none)
 };
 
 __device__ __forceinline__ float clip01(float v) {
@@ -468,6 +474,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                : "memory");
 }
 
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
 struct PipeArgs {
   StreamArgs s;
   int num_tiles;    // B * T
@@ -614,6 +624,20 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
     for (int j = 0; j < NFG; ++j) bulk_g2s(&sm.u.cls[j][0], cp + (size_t)j * A, rows * 4, &full_bar);
     bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
     bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
+  } else if (threadIdx.x == 32 && a.prefetch > 0) {
+    // The CTAs resident on an SM run their load and compute phases more or less together, which leaves DRAM idle
+    // while they compute.  One thread of another warp asks L2 for the tile a CTA `prefetch` launches ahead will load
+    // (cp.async.bulk.prefetch.L2: no registers, no shared memory, no completion to wait for), so that the DRAM
+    // queues stay full whatever the SMs are doing and the later CTA's bulk copies are L2 hits.
+    const int lin = b * (int)gridDim.x + t + a.prefetch;
+    const int pb = lin / (int)gridDim.x, pt = lin - pb * (int)gridDim.x;
+    if (pb < (int)gridDim.y) {
+      const int pbegin = pt * kTile, prow = min(kTile, A - pbegin);
+      const float *cp = a.cls_prob + ((size_t)pb * a.C + 1) * A + pbegin;
+#pragma unroll 4
+      for (int j = 0; j < NFG; ++j) bulk_prefetch_l2(cp + (size_t)j * A, prow * 4);
+      bulk_prefetch_l2(a.loc_pred + ((size_t)pb * A + pbegin) * 5, prow * 20);
+    }
   }
   {  // `out = -1` for this tile's rows (multibox_detection-inl.h:103) while the copies are in flight
     float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
@@ -856,6 +880,10 @@ struct SortArgs {
   float4 *row_box;
   unsigned long long *sort_keys;
   int *head_rank;                   // (B, Apad) pass-1 rank of every head row (fork/join pipeline), or null
+  int2 *head_list;                  // per-class head lists (fork/join pipeline with 0 < nms_topk <= kHeadCap), or null
+  int *head_off;
+  const unsigned *tile_cls;         // (B, kV2ClsPad, T) per (class, tile) offset | count << 16 (fork/join pipeline)
+  int nfg, mask_rows;
   int *valid_count_out;
   WsHeader *header;
   int A, T, tile, Apad, cls_stride, npad_max, niter_max;
@@ -955,7 +983,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ unsigned bucket[kBuckets];
   __shared__ unsigned long long stage_a[kBucketCap];
   __shared__ unsigned sm_kmin, sm_kmax;
-  __shared__ int sm_pivot;
+  __shared__ int sm_pivot, sm_need_rows;
   const int b = blockIdx.x;  // image in x: the sort-role CTAs (y == 0) of all images are scheduled first
   // Programmatic dependent launch: the pair-test kernel enqueued behind this one may start once every CTA of this
   // grid is resident and has passed this point -- it runs beside the sort and only waits for it before its resolve.
@@ -970,8 +998,20 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   // rank base of every tile (block scan over the tile counts) and V
   const int *cnt = a.tile_count + (size_t)b * T;
   int *tbase = T <= kSortSmemTiles ? sm_tbase : a.tile_base + (size_t)b * T;
-  if (threadIdx.x == 0) carry_smem = 0;
+  if (threadIdx.x == 0) {
+    carry_smem = 0;
+    sm_need_rows = 0;
+  }
   __syncthreads();
+  if (a.tail_copy && (int)warp_id() < a.nfg) {
+    // Fork/join pipeline: does any class of this image exceed the pair kernel's shared-memory mask?  Only then does
+    // that kernel fall back to the NMS on final-order rows, which reads row_cls / row_box of the tail (copied below).
+    const unsigned *tc = a.tile_cls + ((size_t)b * kV2ClsPad + warp_id()) * T;
+    int members = 0;
+    for (int t = (int)lane_id(); t < T; t += 32) members += (int)(tc[t] >> 16);
+    members = warp_sum_i32(members);
+    if (lane_id() == 0 && members > a.mask_rows) sm_need_rows = 1;
+  }
   for (int base = 0; base < T; base += blockDim.x) {
     const int i = base + threadIdx.x;
     const int v = i < T ? cnt[i] : 0;
@@ -1223,6 +1263,7 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   float *out = a.out + (size_t)b * A * 7;
   unsigned short *row_cls = a.row_cls + (size_t)b * a.cls_stride;
   float4 *row_box = a.row_box + (size_t)b * A;
+  int my_p = 0, my_c = -1;  // this thread's head row (per-class head lists: nkeep <= blockDim.x)
   for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {
     const int p = (int)(unsigned)(sel[r] & 0xffffffffull);
     int lo = 0, hi = T - 1;
@@ -1242,53 +1283,69 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
     o[6] = s6;
     row_cls[r] = (unsigned short)s0;
     row_box[r] = make_float4(s2, s3, s4, s5);
-    if (a.head_rank) a.head_rank[(size_t)b * a.Apad + r] = p | ((int)s0 << 24);  // pass-1 rank | class << 24
+    if (a.head_list) {
+      my_p = p;
+      my_c = (int)s0;
+    } else if (a.head_rank) {
+      a.head_rank[(size_t)b * a.Apad + r] = p | ((int)s0 << 24);  // pass-1 rank | class << 24
+    }
+  }
+  if (a.head_list) {
+    // Per-class head lists for the resolve of the pair kernel: a stable counting sort of the <= kHeadCap head rows by
+    // class (one row per thread, so thread order == head position order).  Lanes of a warp with the same class find
+    // each other with MATCH.ANY; per-(warp, class) counts are scanned over the warps by the warp that owns the class,
+    // the class totals over the classes by warp 0.  Each pair CTA then reads only its own ~nkeep/classes entries, in
+    // order, instead of filtering and ordering all nkeep head positions.
+    static_assert(kSortThreads == 1024 && kV2ClsPad == 32, "one (warp, class) table entry per thread");
+    unsigned *wc = bucket;                                   // [32 warps][32 classes], dead after the sort
+    int *ctot = reinterpret_cast<int *>(hist256);            // [32] class totals, then [32..63] class offsets
+    wc[threadIdx.x] = 0u;
+    __syncthreads();
+    const bool on = my_c >= 0 && my_c < kV2ClsPad;
+    const unsigned peers = __match_any_sync(kFullMask, on ? my_c : -1);
+    const int within = __popc(peers & ((1u << lane) - 1u));
+    if (on && within == 0) wc[warp * 32 + my_c] = (unsigned)__popc(peers);
+    __syncthreads();
+    {  // warp `c` scans the counts of class c over the 32 warps (lane = warp index)
+      const int v = (int)wc[lane * 32 + warp];
+      const int incl = warp_scan_incl(v);
+      wc[lane * 32 + warp] = (unsigned)(incl - v);
+      if (lane == 31) ctot[warp] = incl;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int v = ctot[lane];
+      const int incl = warp_scan_incl(v);
+      ctot[32 + lane] = incl - v;
+      int *ho = a.head_off + (size_t)b * (kV2ClsPad + 1);
+      ho[lane] = incl - v;
+      if (lane == 31) ho[32] = incl;
+    }
+    __syncthreads();
+    if (on) a.head_list[(size_t)b * kHeadCap + ctot[32 + my_c] + (int)wc[warp * 32 + my_c] + within] = make_int2((int)threadIdx.x, my_p);
   }
   // the NMS kernel reads row_cls eight entries at a time: define the entries between V and the next multiple of 8
   if (threadIdx.x < 8 && V + (int)threadIdx.x < ((V + 7) & ~7)) row_cls[V + threadIdx.x] = (unsigned short)0xffffu;
-  if (a.tail_copy && nkeep < V) {
-    // Fork/join pipeline: this CTA also moves the image's tail rows [nkeep, V) from the tiles' slots to their pass-1
-    // positions.  The id column is left out: the resolve owns it for every tail row of its class.
-    // one warp per tile, three tiles at a time: the loads of all three runs are issued before the first store, so a
-    // warp's share of the copy costs a few memory round trips instead of a dozen
+  if (a.tail_copy && nkeep < V && sm_need_rows) {
+    // Fork/join pipeline, rare case: a class of this image is too large for the pair kernel's shared-memory mask and
+    // will take the NMS on final-order rows, which reads row_cls / row_box of the tail rows [nkeep, V) as well.  (The
+    // tail rows of `out` themselves are written by the pair kernel, each class its own.)  One warp per tile, three
+    // tiles at a time: all loads of the three runs are issued before the first store.
     const int nwarps = (int)(blockDim.x >> 5);
     constexpr int kU = 3;
     for (int t0 = (int)warp; t0 < T; t0 += kU * nwarps) {
       int base[kU], nt[kU], skip[kU];
-      const float *src[kU];
-      int maxend = 0, maxrows = 0;
+      int maxrows = 0;
 #pragma unroll
       for (int u = 0; u < kU; ++u) {
         const int t = t0 + u * nwarps;
         base[u] = nt[u] = skip[u] = 0;
-        src[u] = a.slot_rows;
         if (t < T) {
           base[u] = tbase[t];
           nt[u] = (t + 1 < T ? tbase[t + 1] : V) - base[u];
           skip[u] = min(nt[u], max(0, nkeep - base[u]));
-          src[u] = a.slot_rows + ((size_t)b * a.Apad + (size_t)t * a.tile) * 7;
-          if (skip[u] < nt[u]) {
-            maxend = max(maxend, nt[u] * 7);
-            maxrows = max(maxrows, nt[u]);
-          }
+          if (skip[u] < nt[u]) maxrows = max(maxrows, nt[u]);
         }
-      }
-      for (int q = (int)lane; q < maxend; q += 64) {
-        float v[kU][2];
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int idx = q + 32 * k;
-            v[u][k] = (idx >= skip[u] * 7 && idx < nt[u] * 7) ? src[u][idx] : 0.f;
-          }
-#pragma unroll
-        for (int u = 0; u < kU; ++u)
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const int idx = q + 32 * k;
-            if (idx >= skip[u] * 7 && idx < nt[u] * 7 && idx % 7 != 0) out[(size_t)base[u] * 7 + idx] = v[u][k];
-          }
       }
       for (int q = (int)lane; q < maxrows; q += 32) {
         unsigned short cl[kU];
@@ -1815,10 +1872,27 @@ struct PairArgs {
   float4 *row_box;
   const int *nms_rows;   // resolve kernel only
   const int *head_rank;
+  const int2 *head_list;   // per-class head lists written by the sort kernel (0 < nms_topk <= kHeadCap), or null
+  const int *head_off;
   int A, T, tile, Apad, cls_stride, nfg;
   float nms_threshold;
   int nms_topk, mask_rows;
 };
+
+// Pass-1 row of a tail member (rank >= nkeep), copied from its tile slot to its final position `rank`; the resolve
+// later overwrites the id of suppressed rows only (multibox_detection.cc:163).
+__device__ __forceinline__ void copy_tail_row(const PairArgs &a, int b, size_t slot, int rank) {
+  const float *src = a.slot_rows + ((size_t)b * a.Apad + slot) * 7;
+  const float s0 = src[0], s1 = src[1], s2 = src[2], s3 = src[3], s4 = src[4], s5 = src[5], s6 = src[6];
+  float *o = a.out + ((size_t)b * a.A + rank) * 7;
+  o[0] = s0;
+  o[1] = s1;
+  o[2] = s2;
+  o[3] = s3;
+  o[4] = s4;
+  o[5] = s5;
+  o[6] = s6;
+}
 
 
 // Exclusive block scan of one 64-bit value per thread (two packed 32-bit counters); `smem`: blockDim.x/32 + 1 words.
@@ -1909,26 +1983,43 @@ __device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, 
   const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
   const int W = (n + 63) >> 6;
   // head rows of this class (their positions q in the sorted head; every one of them is a member, so <= n)
-  const int *hinfo = a.head_rank + (size_t)b * a.Apad;  // rank | class << 24, written by the sort kernel (another SM)
-  for (int q = threadIdx.x; q < nkeep; q += blockDim.x) {
-    const int info = __ldcg(hinfo + q);
-    if ((info >> 24) == c) {
-      const int k = atomicAdd(&s.counter[0], 1);
-      s.tmpq[k] = q;
-      s.tmpr[k] = info & 0xffffff;
+  int nh;
+  if (a.head_list) {
+    // the sort kernel (another SM) handed over this class's head rows already grouped and in position order
+    const int *ho = a.head_off + (size_t)b * (kV2ClsPad + 1);
+    const int off0 = __ldcg(ho + c);
+    nh = __ldcg(ho + c + 1) - off0;
+    const int2 *hl = a.head_list + (size_t)b * kHeadCap + off0;
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+      const int2 e = __ldcg(hl + k);  // (head position, pass-1 rank)
+      const int m = lower_bound_i32(ranks, n, e.y);
+      s.hq[k] = e.x;
+      s.hm[k] = (unsigned short)m;
+      s.hp[m] = (unsigned short)k;
     }
-  }
-  __syncthreads();
-  DSPMB_STAMP(5);
-  const int nh = s.counter[0];
-  for (int k = threadIdx.x; k < nh; k += blockDim.x) {
-    const int myq = s.tmpq[k];
-    int ord = 0;
-    for (int i = 0; i < nh; ++i) ord += s.tmpq[i] < myq ? 1 : 0;
-    const int m = lower_bound_i32(ranks, n, s.tmpr[k]);
-    s.hq[ord] = myq;
-    s.hm[ord] = (unsigned short)m;
-    s.hp[m] = (unsigned short)ord;
+    DSPMB_STAMP(5);
+  } else {
+    const int *hinfo = a.head_rank + (size_t)b * a.Apad;  // rank | class << 24, written by the sort kernel (another SM)
+    for (int q = threadIdx.x; q < nkeep; q += blockDim.x) {
+      const int info = __ldcg(hinfo + q);
+      if ((info >> 24) == c) {
+        const int k = atomicAdd(&s.counter[0], 1);
+        s.tmpq[k] = q;
+        s.tmpr[k] = info & 0xffffff;
+      }
+    }
+    __syncthreads();
+    DSPMB_STAMP(5);
+    nh = s.counter[0];
+    for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+      const int myq = s.tmpq[k];
+      int ord = 0;
+      for (int i = 0; i < nh; ++i) ord += s.tmpq[i] < myq ? 1 : 0;
+      const int m = lower_bound_i32(ranks, n, s.tmpr[k]);
+      s.hq[ord] = myq;
+      s.hm[ord] = (unsigned short)m;
+      s.hp[m] = (unsigned short)ord;
+    }
   }
   const int m0 = lower_bound_i32(ranks, n, nkeep);  // members m0 .. n-1 are the tail rows of the class
   // Nodes in final order: q < nh is head row hm[q]; q >= nh is tail member m0 + (q - nh).  The greedy loop of
@@ -1997,16 +2088,10 @@ __device__ __forceinline__ void resolve_segment(const PairArgs &a, const int b, 
     if (!__syncthreads_or(open)) break;
   }
   DSPMB_STAMP(7);
-  // ids: a suppressed row gets -1 and keeps everything else (multibox_detection.cc:163); the tail rows receive their
-  // id here in either case (the sort kernel copies the other six columns)
+  // ids: a suppressed row gets -1 and keeps everything else (multibox_detection.cc:163)
   float *out = a.out + (size_t)b * a.A * 7;
-  for (int q = threadIdx.x; q < ns; q += blockDim.x) {
-    if (q < nh) {
-      if (s.status[q] == 2) out[(size_t)s.hq[q] * 7] = -1.f;
-    } else {
-      out[(size_t)ranks[m0 + (q - nh)] * 7] = s.status[q] == 2 ? -1.f : (float)c;
-    }
-  }
+  for (int q = threadIdx.x; q < ns; q += blockDim.x)
+    if (s.status[q] == 2) out[(size_t)(q < nh ? s.hq[q] : ranks[m0 + (q - nh)]) * 7] = -1.f;
   DSPMB_STAMP(8);
 }
 
@@ -2015,11 +2100,12 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   constexpr int kOffMask = kNmsMaskRows * 16, kOffArea = kOffMask + kNmsMaskRows * 5 * 8;
   constexpr int kOffRank = kOffArea + kNmsMaskRows * 4, kOffQueue = kOffRank + kNmsMaskRows * 4;
   constexpr int kOffCol = kOffQueue + (kNmsThreads / 32) * kNmsQueue * 2, kOffRow = kOffCol + kNmsMaskRows * 4;
-  constexpr int kBytes = kOffRow + kNmsMaskRows * 4;
+  constexpr int kOffSlot = kOffRow + kNmsMaskRows * 4;
+  constexpr int kBytes = kOffSlot + kNmsMaskRows * 4;
   constexpr int kWarps = kNmsThreads / 32;
   static_assert(kNmsMaskRows * 16 >= 3 * kNmsMaskRows * 4 + 2 * kNmsMaskRows * 2, "hq / tmpq / tmpr / open alias the box stage");
   static_assert(kWarps * kNmsQueue * 2 >= 2 * kNmsMaskRows * 2 + 2 * kNmsMaskRows, "hm / hp / status alias the queues");
-  static_assert(kBytes - kOffCol >= kResolveCand * kResolveNbr * 2 + kResolveCand, "neighbour lists alias the packed boxes");
+  static_assert(kOffSlot - kOffCol >= kResolveCand * kResolveNbr * 2 + kResolveCand, "neighbour lists alias the packed boxes");
   __shared__ __align__(16) unsigned char smem_raw[kBytes];
   __shared__ int sm_tbase[kV2MaxTiles], sm_mbase[kV2MaxTiles];
   __shared__ unsigned short sm_coff[kV2MaxTiles];
@@ -2064,18 +2150,35 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
     __syncthreads();
   }
   const int V = (int)(unsigned)sm_carry, n = (int)(sm_carry >> 32);
+  const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
   static_assert(kBytes >= kNmsBodyBytes, "the final-order path reuses this kernel's stage");
+  // member m of the class (rank order) -> tile, slot inside the tile's run, pass-1 rank
+  auto locate = [&](int m, size_t *cslot, size_t *slot) -> int {
+    int lo = 0, hi = T;  // first tile whose member base exceeds m
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (sm_mbase[mid] <= m) lo = mid + 1; else hi = mid;
+    }
+    const int t = lo - 1;
+    *cslot = (size_t)t * a.tile + sm_coff[t] + (m - sm_mbase[t]);
+    const int k = (int)a.crank[(size_t)b * a.cls_stride + *cslot];
+    *slot = (size_t)t * a.tile + k;
+    return sm_tbase[t] + k;
+  };
   if (V < 1 || n < 1 || n > a.mask_rows) {
+    if (V >= 1 && n > a.mask_rows) {
+      // a segment too large for the shared-memory mask: its tail rows are moved here like everybody's ...
+      for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        size_t cslot, slot;
+        const int rank = locate(m, &cslot, &slot);
+        if (rank >= nkeep) copy_tail_row(a, b, slot, rank);
+      }
+    }
     // every CTA waits for the sort grid before it exits, so that the completion of THIS grid implies the sort's
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (V >= 1 && n > a.mask_rows) {
-      // a segment too large for the shared-memory mask: chunk-sweep NMS on the rows in FINAL order, which the sort
-      // grid has just completed (row_cls / row_box); it left the tail's id column to the resolve
-      const int nkeep = (a.nms_topk > 0 && a.nms_topk < V) ? a.nms_topk : V;
-      const unsigned short *rcls = a.row_cls + (size_t)b * a.cls_stride;
-      float *out = a.out + (size_t)b * a.A * 7;
-      for (int r = nkeep + threadIdx.x; r < V; r += blockDim.x)
-        if (__ldcg(rcls + r) == (unsigned short)c) out[(size_t)r * 7] = (float)c;
+      // ... then chunk-sweep NMS on the rows in FINAL order, which the sort grid has just completed (row_cls / row_box
+      // of every row of the image: the sort kernel saw the same class sizes and copied the tail's as well)
       __syncthreads();
       nms_final_order_body(na, b, c, smem_raw);
     }
@@ -2090,19 +2193,16 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   unsigned short *queue = reinterpret_cast<unsigned short *>(smem_raw + kOffQueue) + warp * kNmsQueue;
   unsigned *colpack = reinterpret_cast<unsigned *>(smem_raw + kOffCol);
   unsigned *rowpack = reinterpret_cast<unsigned *>(smem_raw + kOffRow);
+  int *mslot = reinterpret_cast<int *>(smem_raw + kOffSlot);  // slot of member m inside the image's tile slots
   const NmsThr thr = make_thr(a.nms_threshold);
   const int W = (n + 63) >> 6, npad = (n + 31) & ~31;
   for (int m = threadIdx.x; m < npad; m += blockDim.x) {
     unsigned cp = 0x7f7f7f7fu, rp = 0x80808080u;  // padded / degenerate rows: reach nothing, are reached by nothing
     if (m < n) {
-      int lo = 0, hi = T;  // first tile whose member base exceeds m
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (sm_mbase[mid] <= m) lo = mid + 1; else hi = mid;
-      }
-      const int t = lo - 1;
-      const size_t s0 = (size_t)t * a.tile + sm_coff[t] + (m - sm_mbase[t]);
-      ranks[m] = sm_tbase[t] + (int)a.crank[(size_t)b * a.cls_stride + s0];
+      size_t s0, slot;
+      const int rank = locate(m, &s0, &slot);
+      ranks[m] = rank;
+      mslot[m] = (int)slot;
       const float4 bi = stage_box(__ldg(a.cbox + (size_t)b * a.Apad + s0), &areas[m]);
       boxes[m] = bi;
       if (bi.x < __int_as_float(0x7f800000)) {
@@ -2172,6 +2272,34 @@ __global__ void __launch_bounds__(kNmsThreads, 6) det_pair_kernel(const __grid_c
   const int nunits = sm_nunits;
   unsigned *mask32 = reinterpret_cast<unsigned *>(mask);
   unsigned *rowany32 = reinterpret_cast<unsigned *>(rowany);
+  if (warp == kWarps - 1) {
+    // Tail rows [nkeep, V) keep their pass-1 content at their pass-1 position (multibox_detection.cc:146-151): the
+    // class's members of rank >= nkeep are moved from their tile slots to `out` by ONE warp while the others start on
+    // the units (it joins them afterwards): a flat loop over (member, column) elements, eight independent loads in
+    // flight per lane, so the copy costs a handful of memory round trips beside the pair tests instead of before them.
+    // The resolve later overwrites the id of suppressed rows only.
+    const int mt = lower_bound_i32(ranks, n, nkeep);
+    const int total = (n - mt) * 7;
+    const float *srows = a.slot_rows + (size_t)b * a.Apad * 7;
+    float *orows = a.out + (size_t)b * a.A * 7;
+    for (int base = 0; base < total; base += 256) {
+      float v[8];
+      int dst[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int idx = base + k * 32 + (int)lane;
+        const int mm = (idx * 9363) >> 16, col = idx - mm * 7;  // idx / 7 for idx < 13107
+        dst[k] = -1;
+        if (idx < total) {
+          v[k] = srows[(size_t)mslot[mt + mm] * 7 + col];
+          dst[k] = ranks[mt + mm] * 7 + col;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (dst[k] >= 0) orows[dst[k]] = v[k];
+    }
+  }
   while (true) {  // the warps draw units from a shared counter (diagonal units and culled neighbourhoods differ in cost)
     int u = 0;
     if (lane == 0) u = atomicAdd(&sm_next, 1);
@@ -2301,9 +2429,33 @@ extern "C" int dspmb_debug_stamps(unsigned long long *device_buffer) {
   return DSPMB_OK;
 }
 
+// The batch is processed as up to kMaxSplit groups of consecutive images (DSPMB_TUNE_DET_SPLIT): the select / sort /
+// pair tests / resolve of group g only depend on the stream kernel of group g, so inside the library's CUDA graph they
+// run on a parallel branch while the stream kernel of group g + 1 -- which is HBM-bound and leaves most issue slots
+// idle -- is reading its class tensor.  Every group owns its own slice of the workspace.
+constexpr int kMaxSplit = 4;
+static int split_groups(int B, int want) {
+  int g = want < 1 ? 1 : (want > kMaxSplit ? kMaxSplit : want);
+  while (g > 1 && B / g < 4) --g;  // at least four images per group
+  return g;
+}
+static size_t split_workspace_bytes(int B, int A, int C, int groups) {
+  size_t total = 0;
+  for (int g = 0; g < groups; ++g) {
+    const int b0 = (int)((long long)B * g / groups), b1 = (int)((long long)B * (g + 1) / groups);
+    total += align_up(carve(nullptr, b1 - b0, A, C).bytes, 256);
+  }
+  return total;
+}
+
 extern "C" size_t dspmb_detection_workspace_bytes(int B, int A, int C) {
   if (B <= 0 || A <= 0 || C <= 0) return 0;
-  return carve(nullptr, B, A, C).bytes;
+  size_t need = 0;
+  for (int g = 1; g <= kMaxSplit; ++g) {
+    const size_t n = split_workspace_bytes(B, A, C, split_groups(B, g));
+    need = n > need ? n : need;
+  }
+  return need;
 }
 
 extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const float *anchors, float *out,
@@ -2317,12 +2469,11 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   DSPMB_REQUIRE(A < (1 << 24), "MultiBoxDetection: more than 2^24 anchors are not supported");
   DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxDetection: anchors must be 16-byte aligned");
   if (B == 0) return DSPMB_OK;
-  const size_t need = carve(nullptr, B, A, C).bytes;
+  const size_t need = dspmb_detection_workspace_bytes(B, A, C);
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
     set_error("MultiBoxDetection: workspace must be 256-byte aligned and >= %zu bytes (got %zu)", need, workspace_bytes);
     return DSPMB_ERR_WORKSPACE;
   }
-  DetWorkspace w = carve(workspace, B, A, C);
   const int nms_debug = getenv("DSPMB_NMS_DEBUG") ? atoi(getenv("DSPMB_NMS_DEBUG")) : 0;
 
   struct {
@@ -2336,7 +2487,27 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   key.f[0] = threshold, key.f[1] = nms_threshold;
   for (int k = 0; k < 4; ++k) key.f[2 + k] = variances[k];
 
+  const float *const cls_prob_all = cls_prob, *const loc_pred_all = loc_pred;
+  float *const out_all = out;
+  int32_t *const valid_all = valid_count_out;
+  const int B_all = B;
   return graph_cached_launch(&key, sizeof(key), (cudaStream_t)stream_, [&](const LaunchCtx &ctx) -> int {
+  const bool vec4_all = (A % 4 == 0) && (((uintptr_t)cls_prob_all | (uintptr_t)out_all | (uintptr_t)loc_pred_all) & 15) == 0;
+  const int variant_all = tuning(DSPMB_TUNE_DET_STREAM_VARIANT);
+  const bool v2_all = tuning(DSPMB_TUNE_DET_PIPELINE) != 0 && vec4_all && (C == 21 || C == 9) && variant_all == 2 &&
+                      !force_suppress && nms_threshold > 0.f && nms_threshold <= 1.f && C - 1 <= kV2ClsPad &&
+                      ceil_div(A, 256) <= kV2MaxTiles;
+  const int groups = v2_all ? split_groups(B_all, tuning(DSPMB_TUNE_DET_SPLIT)) : 1;
+  size_t ws_off = 0;
+  for (int grp = 0; grp < groups; ++grp) {
+  const int b0 = (int)((long long)B_all * grp / groups), B = (int)((long long)B_all * (grp + 1) / groups) - b0;
+  const float *cls_prob = cls_prob_all + (size_t)b0 * C * A, *loc_pred = loc_pred_all + (size_t)b0 * A * 5;
+  float *out = out_all + (size_t)b0 * A * 7;
+  int32_t *valid_count_out = valid_all ? valid_all + b0 : nullptr;
+  DetWorkspace w = carve((char *)workspace + ws_off, B, A, C);
+  ws_off += align_up(w.bytes, 256);
+  // the stream kernels of all groups run back to back on the main branch; everything after a group's stream kernel
+  // goes to a side branch (alternating between the two) when the call is being captured into the library's graph
   cudaStream_t stream = ctx.stream;
   const bool vec4 = (A % 4 == 0) && (((uintptr_t)cls_prob | (uintptr_t)out | (uintptr_t)loc_pred) & 15) == 0;
   // TMA-fed persistent kernel whenever the ring fits (2..4 stages); plain kernels otherwise
@@ -2389,6 +2560,7 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   sa.vw = variances[2];
   sa.vh = variances[3];
   sa.fma_build = libm_fma_mode();
+  sa.prefetch = tuning(DSPMB_TUNE_DET_PREFETCH);
   const int phases = tuning(DSPMB_TUNE_PHASES);
   if (!(phases & 1)) {
     // stream phase skipped (per-phase timing: the workspace still holds the previous call's records)
@@ -2434,6 +2606,11 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   }
   if (phases & 1) ++ctx.launches;
   DSPMB_CUDA_TRY(cudaGetLastError());
+  if (groups > 1 && ctx.forked()) {
+    const int rc = ctx.fork_side(grp % LaunchCtx::kSides);
+    if (rc != DSPMB_OK) return rc;
+    stream = ctx.side[grp % LaunchCtx::kSides];
+  }
 
   SortArgs so;
   so.out = out;
@@ -2450,7 +2627,13 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   so.row_cls = w.row_cls;
   so.row_box = w.row_box;
   so.sort_keys = w.sort_keys;
+  const bool head_lists = v2 && nms_topk > 0 && nms_topk <= kHeadCap;
   so.head_rank = v2 ? w.head_rank : nullptr;
+  so.head_list = head_lists ? w.head_list : nullptr;
+  so.head_off = w.head_off;
+  so.tile_cls = w.tile_cls;
+  so.nfg = C - 1;
+  so.mask_rows = tuning(DSPMB_TUNE_NMS_MASK_ROWS);
   so.tail_copy = v2 ? 1 : 0;
   so.valid_count_out = valid_count_out;
   so.header = w.header;
@@ -2519,6 +2702,8 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
       pa.row_box = w.row_box;
       pa.nms_rows = w.nms_rows;
       pa.head_rank = w.head_rank;
+      pa.head_list = head_lists ? w.head_list : nullptr;
+      pa.head_off = w.head_off;
       pa.A = A;
       pa.T = T;
       pa.tile = tile;
@@ -2549,6 +2734,8 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
+  }  // groups
+  if (groups > 1 && ctx.forked()) return ctx.join();
   return DSPMB_OK;
   });
 }

@@ -230,7 +230,17 @@ const char *dspmb_profile_kernel_name(int slot);
                                            preconditions hold; 0: stream -> sort+rank -> nms in final row order      */
 #define DSPMB_TUNE_TARGET_PIPELINE 7    /* 1 (default): multi-CTA target matcher; 0: one CTA per image              */
 #define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
-#define DSPMB_NUM_TUNING 9
+#define DSPMB_TUNE_DET_PREFETCH 9        /* detection stream kernel: CTA start issues an L2 prefetch for the tile this many
+                                           CTAs ahead in launch order (default 0 = off: measured 54.6 us/step without,
+                                           57.0 us with a distance of one resident wave -- the kernel is not short of
+                                           requests in flight)                                                       */
+#define DSPMB_TUNE_TARGET_PREFETCH 10    /* same for the target stream kernel                                        */
+#define DSPMB_TUNE_DET_SPLIT 11           /* detection fork/join pipeline: image groups whose post-processing overlaps the
+                                           stream kernel of the next group inside the graph (default 1 = no split, max 4;
+                                           measured at SSD-512 B=32: 54.0 / 56.2 / 61.7 / 69.5 us for 1 / 2 / 3 / 4 groups:
+                                           the 1024-thread sort CTAs of a group only find room once the next group's
+                                           stream CTAs have drained, and the stream kernel itself slows down)          */
+#define DSPMB_NUM_TUNING 12
 int dspmb_set_tuning(int knob, int value);
 
 /* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)

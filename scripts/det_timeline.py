@@ -18,8 +18,15 @@ for i in range(2000):
     plan.run(prob[i % 4], loc[i % 4], anchors, out[i % 4])
 torch.cuda.synchronize()
 L = _lib.lib()
-if len(sys.argv) > 1 and sys.argv[1] == 'nograph':
-    L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
+for kv in sys.argv[1:]:
+    if kv == 'nograph':
+        L.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
+    else:
+        k, v = kv.split('=')
+        L.dspmb_set_tuning(int(k), int(v))
+for i in range(20):
+    plan.run(prob[i % 4], loc[i % 4], anchors, out[i % 4])
+torch.cuda.synchronize()
 names = ['stream', 'sort', 'pair', 'tail', 'resolve', 'pair:scans', 'pair:gather', 'pair:units', 'pair:waited', 'sort:staged', 'sort:bucket-sorted', 'sort:fallback-sorted', 'res:headscan', 'res:ordered', 'res:rounds']
 acc = [[0.0, 0.0] for _ in names]
 reps = 20
