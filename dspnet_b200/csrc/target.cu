@@ -23,6 +23,8 @@
 //                         maximum is an upper bound, so it is recomputed only when it reaches the top), output
 //                         fix-up of the <= G matched anchors, then an MSB-first radix select (4 x 8 bit) of the
 //                         num_negative smallest (probability, anchor) keys with an ordered tie pass.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dspmb {
@@ -31,6 +33,28 @@ namespace {
 constexpr int kStreamThreads = 128;
 constexpr int kMatchThreads = 1024;
 constexpr unsigned kKeySentinel = 0xffffffffu;  // "not a mining candidate"
+
+// Optional per-CTA phase stamps of the match kernel (dspmb_debug_target_stamps): 12 x uint64 %globaltimer values per
+// image.  The pointer lives in constant memory, so the disabled check is one LDC.
+__constant__ unsigned long long *g_tstamps = nullptr;
+__constant__ unsigned long long *g_sstamps = nullptr;  // stream kernel: 8 stamps per CTA
+#define DSPMB_SSTAMP(k)                                                                         \
+  do {                                                                                          \
+    if (g_sstamps && threadIdx.x == 0) {                                                        \
+      unsigned long long t_;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                    \
+      g_sstamps[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (k)] = t_;                  \
+    }                                                                                           \
+  } while (0)
+#define DSPMB_TSTAMP_IMG(img, k)                                                                \
+  do {                                                                                          \
+    if (g_tstamps && threadIdx.x == 0) {                                                        \
+      unsigned long long t_;                                                                    \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                    \
+      g_tstamps[(size_t)(img) * 12 + (k)] = t_;                                                 \
+    }                                                                                           \
+  } while (0)
+#define DSPMB_TSTAMP(k) DSPMB_TSTAMP_IMG(blockIdx.x, k)
 
 struct TargetWorkspace {
   WsHeader *header;
@@ -105,19 +129,15 @@ __device__ __forceinline__ unsigned long long col_key(float iou, int anchor) {
   return ((unsigned long long)__float_as_uint(iou) << 32) | (unsigned)(0xffffffffu - (unsigned)anchor);
 }
 
-// Number of leading valid label rows (multibox_target.cc:95-105).  All threads of the CTA must call.
-__device__ int count_valid_gt(const float *lab, int L, int W, int *smem_min) {
-  if (threadIdx.x == 0) *smem_min = L;
-  __syncthreads();
-  int first = L;
-  for (int l = threadIdx.x; l < L; l += blockDim.x)
-    if (lab[(size_t)l * W] == -1.0f) {
-      first = l;
-      break;
-    }
-  if (first < L) atomicMin(smem_min, first);
-  __syncthreads();
-  return *smem_min;
+// Number of leading valid label rows (multibox_target.cc:95-105), computed by every warp on its own (32 label rows per
+// ballot): no shared memory, no block barrier.
+__device__ __forceinline__ int count_valid_gt_warp(const float *lab, int L, int W) {
+  for (int l0 = 0; l0 < L; l0 += 32) {
+    const int l = l0 + (int)lane_id();
+    const unsigned pad = __ballot_sync(kFullMask, l < L && __ldg(lab + (size_t)l * W) == -1.0f);
+    if (pad) return l0 + __ffs(pad) - 1;
+  }
+  return L;
 }
 
 // exp(d) for d <= 0 in fp32 through MUFU.EX2: the product d*log2(e) is rounded once (absolute error <= 2^-18 for
@@ -125,6 +145,16 @@ __device__ int count_valid_gt(const float *lab, int L, int W, int *smem_min) {
 __device__ __forceinline__ float exp_approx(float d) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmul(d, 1.4426950408889634f)));
+  return r;
+}
+// exp(x - mx) with the subtraction folded into one fused multiply-add: ex2(x*log2e - mx*log2e), `nml` = -mx*log2e
+// rounded once.  The argument differs from (x - mx)*log2e by <= 2^-24 |mx*log2e| + 2^-24 |arg| (two roundings of
+// magnitudes <= |mx| log2e each); for the |logits| <= 64 a softmax sees that is an absolute error <= 1.1e-5 in the
+// exponent, i.e. a relative error <= 7.7e-6 of the result -- inside the bound delta the match kernel's band assumes.
+// Only used while |mx| <= 64 (the caller checks), where the rounding of nml is <= 2^-18.
+__device__ __forceinline__ float exp_approx_fma(float x, float nml) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(__fmaf_rn(x, 1.4426950408889634f, nml)));
   return r;
 }
 
@@ -196,7 +226,6 @@ __device__ __forceinline__ float iou_target_fast(float4 a, float area_a, float4 
 template <int VEC, int NC, bool kFma>
 __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ int sm_int;
   __shared__ int sm_pos;
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);                                  // [L]
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + a.L);       // [L]
@@ -236,7 +265,9 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     for (int v = 0; v < VEC; ++v) an[v] = __ldg(reinterpret_cast<const float4 *>(a.anchors) + i0 + v);
   }
 
-  const int G = count_valid_gt(lab, a.L, W, &sm_int);
+  DSPMB_SSTAMP(0);
+  const int G = count_valid_gt_warp(lab, a.L, W);
+  DSPMB_SSTAMP(1);
   if (t == 0 && threadIdx.x == 0) {
     a.gcount[b] = G;
     int bad = DSPMB_OK;
@@ -256,6 +287,7 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   }
   if (threadIdx.x == 0) sm_pos = 0;
   __syncthreads();
+  DSPMB_SSTAMP(2);
 
   float best_iou[VEC], area[VEC];
   int best_k[VEC];
@@ -289,40 +321,77 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   }
 
   // ---- fused IoU + row first-max + column max (multibox_target-inl.h:137-161, .cc:113-134,158-166) ----
-  for (int k = 0; k < G; ++k) {
-    const float4 g = sm_gt[k];
-    if (!(bb.z > g.x && g.z > bb.x && bb.w > g.y && g.w > bb.y)) {  // warp-uniform
-      if (k == 0) {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          best_iou[v] = 0.0f;
-          best_k[v] = 0;
-        }
-      }
-      continue;
+  // The warp first lists the gts that reach its bounding box (32 gts per ballot, gt order kept), then walks the list
+  // two gts at a time: the four IoUs of an iteration (two anchors x two gts) are independent, so their divisions and
+  // the two warp-wide column maxima overlap instead of queueing behind a branch per gt.
+  unsigned short *wlist = reinterpret_cast<unsigned short *>(sm_garea + a.L) + warp_id() * a.L;
+  int nlist = 0;
+  bool gt0_listed = false;
+  for (int k0 = 0; k0 < G; k0 += 32) {
+    const int k = k0 + (int)lane_id();
+    bool reach = false;
+    if (k < G) {
+      const float4 g = sm_gt[k];
+      reach = bb.z > g.x && g.z > bb.x && bb.w > g.y && g.w > bb.y;
     }
-    const float ga = sm_garea[k];
-    unsigned long long tkey = 0ull;
+    const unsigned m = __ballot_sync(kFullMask, reach);
+    if (reach) wlist[nlist + __popc(m & ((1u << lane_id()) - 1u))] = (unsigned short)k;
+    if (k0 == 0) gt0_listed = (m & 1u) != 0u;
+    nlist += __popc(m);
+  }
+  __syncwarp();
+  if (G > 0 && !gt0_listed) {  // gt 0 has IoU 0 with every anchor of the warp: the row's first maximum so far
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      best_iou[v] = 0.0f;
+      best_k[v] = 0;
+    }
+  }
+  for (int i = 0; i < nlist; i += 2) {
+    const bool two = i + 1 < nlist;
+    const int k0 = wlist[i], k1 = two ? (int)wlist[i + 1] : k0;
+    const float4 g0 = sm_gt[k0], g1 = sm_gt[k1];
+    const float ga0 = sm_garea[k0], ga1 = sm_garea[k1];
+    unsigned long long tkey0 = 0ull, tkey1 = 0ull;
     if (active) {
+      float iou0[VEC], iou1[VEC];
 #pragma unroll
       for (int v = 0; v < VEC; ++v) {
-        const float iou = iou_target_fast(an[v], area[v], g, ga);
-        if (iou > best_iou[v]) {
-          best_iou[v] = iou;
-          best_k[v] = k;
+        iou0[v] = iou_target_fast(an[v], area[v], g0, ga0);
+        iou1[v] = iou_target_fast(an[v], area[v], g1, ga1);
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        if (iou0[v] > best_iou[v]) {
+          best_iou[v] = iou0[v];
+          best_k[v] = k0;
         }
-        if (iou > 1e-6f) {
-          const unsigned long long ck = col_key(iou, i0 + v);
-          tkey = ck > tkey ? ck : tkey;
+        if (two && iou1[v] > best_iou[v]) {
+          best_iou[v] = iou1[v];
+          best_k[v] = k1;
+        }
+        if (iou0[v] > 1e-6f) {
+          const unsigned long long ck = col_key(iou0[v], i0 + v);
+          tkey0 = ck > tkey0 ? ck : tkey0;
+        }
+        if (two && iou1[v] > 1e-6f) {
+          const unsigned long long ck = col_key(iou1[v], i0 + v);
+          tkey1 = ck > tkey1 ? ck : tkey1;
         }
       }
     }
-    if (__any_sync(kFullMask, tkey != 0ull)) {
-      const unsigned long long wk = warp_max_u64(tkey);
-      if (lane_id() == 0) atomicMax(&sm_col[k], wk);
+    const bool any0 = __any_sync(kFullMask, tkey0 != 0ull), any1 = __any_sync(kFullMask, tkey1 != 0ull);
+    if (any0) {
+      const unsigned long long wk = warp_max_u64(tkey0);
+      if (lane_id() == 0) atomicMax(&sm_col[k0], wk);
+    }
+    if (any1) {
+      const unsigned long long wk = warp_max_u64(tkey1);
+      if (lane_id() == 0) atomicMax(&sm_col[k1], wk);
     }
   }
 
+  DSPMB_SSTAMP(3);
   // ---- threshold-stage positives + mining keys ----
   bool pos[VEC];
   unsigned key[VEC];
@@ -360,10 +429,24 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
 #pragma unroll
           for (int v = 0; v < VEC; ++v)
             mx[v] = fmaxf(mx[v], xr[c][v]);
+        float nml[VEC];
+        bool small = true;
 #pragma unroll
-        for (int c = 0; c < NC; ++c)
+        for (int v = 0; v < VEC; ++v) {
+          nml[v] = -fmul(mx[v], 1.4426950408889634f);
+          small = small && fabsf(mx[v]) <= 64.0f;
+        }
+        if (small) {  // the error bound of exp_approx_fma needs |mx| <= 64; larger logits take the two-step form
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) sum[v] = fadd(sum[v], exp_approx(fsub(xr[c][v], mx[v])));
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sum[v] = fadd(sum[v], exp_approx_fma(xr[c][v], nml[v]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) sum[v] = fadd(sum[v], exp_approx(fsub(xr[c][v], mx[v])));
+        }
       } else {
 #pragma unroll 4
         for (int c = 0; c < C; ++c) {
@@ -418,6 +501,7 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     }
   }
 
+  DSPMB_SSTAMP(4);
   // ---- outputs ----
   if (active) {
     const size_t row0 = (size_t)b * A + i0;
@@ -473,6 +557,7 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     }
   }
 
+  DSPMB_SSTAMP(5);
   // ---- publish the CTA's column maxima and positive count ----
   npos = warp_sum_i32(npos);
   if (lane_id() == 0 && npos) atomicAdd(&sm_pos, npos);
@@ -480,6 +565,7 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
   if (threadIdx.x == 0) a.thr_count[(size_t)b * a.T + t] = sm_pos;
   unsigned long long *gcol = a.colbest + ((size_t)b * a.T + t) * a.L;
   for (int k = threadIdx.x; k < G; k += blockDim.x) gcol[k] = sm_col[k];
+  DSPMB_SSTAMP(6);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -516,6 +602,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
 
   const int b = blockIdx.x;
   const int A = a.A, L = a.L, W = a.W;
+  DSPMB_TSTAMP(0);
   const int G = a.gcount[b];
   int32_t *stats = a.stats_out ? a.stats_out + 4 * b : nullptr;
   if (threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
@@ -562,6 +649,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (lane_id() == 0 && pos) atomicAdd(&sm_thr, pos);
   }
   __syncthreads();
+  DSPMB_TSTAMP(1);
 
   // ---- bipartite stage (multibox_target.cc:113-149) ----
   // Fast path: if the cached best anchors of the gts are pairwise distinct, the greedy loop never meets a stale
@@ -698,6 +786,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
   }
   const int nmatch = sm_nmatch;
+  DSPMB_TSTAMP(2);
 
   // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
   // a group of lanes per matched anchor (16, or 4 when there are more than 64 matches so that one round covers
@@ -736,6 +825,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (a.match_out) a.match_out[row] = k;
   }
   __syncthreads();
+  DSPMB_TSTAMP(3);
   const int num_positive = sm_thr + nmatch - sm_dup;
 
   // ---- hard-negative mining (multibox_target.cc:182-241) ----
@@ -767,6 +857,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
   }
   auto key_at = [&](int j) -> unsigned { return kKeysInSmem ? skeys[j] : gkeys[j]; };
+  DSPMB_TSTAMP(4);
   // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
   // (larger than the bits of any probability), so they are only reached if there are too few candidates.
   if (threadIdx.x == 0) {
@@ -914,6 +1005,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
     __syncthreads();
   }
+  DSPMB_TSTAMP(5);
   const unsigned qkey = sm_prefix;  // the num_negative-th smallest APPROXIMATE key
   if (qkey == kKeySentinel) {
     // the num_negative-th smallest key is a non-candidate: CHECK_GE(temp.size(), num_negative) fails
@@ -955,6 +1047,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   n_in_local = warp_sum_i32(n_in_local);
   if (lane_id() == 0 && n_in_local) atomicAdd(&sm_carry, n_in_local);
   __syncthreads();
+  DSPMB_TSTAMP(6);
   const int n_amb = sm_dup;
   const int need = num_negative - sm_carry;
   if (need < 0 || need > n_amb) {  // would mean the error bound was violated
@@ -986,12 +1079,607 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
     if (rank < need) ct[jq] = 0.0f;
   }
+  DSPMB_TSTAMP(7);
+}
+
+
+// ----------------------------------------------------------------------------------------------------
+// Cluster version of the matcher (the default): one thread-block CLUSTER of kMatchCluster CTAs per image instead of
+// one 1024-thread CTA.  The single-CTA kernel is pure latency (0.43 waves, four passes over the image's A mining keys
+// by one CTA); here every CTA owns a slice of A / kMatchCluster anchors and their keys in its shared memory, and the
+// CTAs talk through distributed shared memory (cluster.map_shared_rank) and the hardware cluster barrier (~0.2 us):
+//   * reduction of the stream kernel's per-tile column maxima: tiles dealt round-robin, CTA 0 combines the partials;
+//   * bipartite stage: CTA 0 runs the (mostly one-shot) greedy assignment; when a cached column maximum is stale, all
+//     CTAs recompute that column over their anchor slices and hand their partial maxima to CTA 0;
+//   * fix-up of the matched anchors by CTA 0, which also patches their keys in the owners' shared memory;
+//   * mining: MSB-first radix select with 11-bit digits taken straight from the float bits of the probability
+//     (p <= 1 keeps bit 30 clear, so bits 29..19 are digit one): every CTA histograms its slice, every CTA sums the
+//     kMatchCluster histograms through DSMEM and finds the pivot bin redundantly (no broadcast round); as soon as the
+//     pivot bin holds <= 256 keys they are pushed into CTA 0's list and ranked there; the final pass (selected /
+//     ambiguous band) again runs on the slices, and CTA 0 re-evaluates the few ambiguous anchors bit-exactly.
+constexpr int kMatchCluster = 8;
+constexpr int kClusterThreads = 256;
+constexpr int kClusterSliceMax = 12288;   // keys per CTA kept in shared memory (48 KB)
+constexpr int kDigitBins = 2048;
+constexpr int kPivotCap = 2048;   // pivot-bin keys ranked directly, one per thread of the cluster
+static_assert(kPivotCap == kMatchCluster * kClusterThreads, "one pivot-bin key per thread of the cluster");
+
+// Warp-aggregated histogram update of one key per lane: background probabilities cluster (most of an image's keys
+// share one or two digits), so plain shared-memory atomics would serialise.  The digit of the first hit lane is
+// counted for the whole warp with one ballot; the lanes with another digit add themselves.
+__device__ __forceinline__ void hist_add_warp(unsigned *h, unsigned digit, bool hit) {
+  const unsigned act = __ballot_sync(kFullMask, hit);
+  if (act == 0u) return;
+  const int leader = __ffs(act) - 1;
+  const unsigned d0 = __shfl_sync(kFullMask, digit, leader);
+  const unsigned same = __ballot_sync(kFullMask, hit && digit == d0);
+  if ((int)lane_id() == leader) atomicAdd(&h[d0], (unsigned)__popc(same));
+  else if (hit && digit != d0) atomicAdd(&h[digit], 1u);
+}
+
+struct ClusterCtl {
+  int state, k, num_negative, err;
+  unsigned qkey;
+  int have_q;
+};
+
+template <bool kFma>
+__global__ void __cluster_dims__(kMatchCluster, 1, 1) __launch_bounds__(kClusterThreads)
+    target_match_cluster_kernel(const __grid_constant__ TargetArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ unsigned long long red_smem[kClusterThreads / 32];
+  __shared__ unsigned long long sm_part[kMatchCluster];
+  __shared__ unsigned hist[2][kDigitBins], hsum[kDigitBins];
+  __shared__ unsigned plist[kPivotCap];
+  __shared__ int sm_npatch, sm_lcnt, sm_off;
+  __shared__ int scan_smem[kClusterThreads / 32 + 1];
+  __shared__ ClusterCtl ctl;
+  __shared__ int sm_arg, sm_nmatch, sm_dup, sm_thr, sm_thr_part, sm_np, sm_carry, sm_amb, sm_pb, sm_before, sm_cp, sm_total;
+
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / kMatchCluster;
+  const int A = a.A, L = a.L, W = a.W;
+  if (rank == 0) DSPMB_TSTAMP_IMG(b, 0);
+  const int G = a.gcount[b];
+  int32_t *stats = a.stats_out ? a.stats_out + 4 * b : nullptr;
+  if (rank == 0 && threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
+  if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values (uniform over the cluster)
+    if (rank == 0 && threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    return;
+  }
+  // slices: CTA r owns anchors [r * slice, min(A, (r + 1) * slice)), slice a multiple of 32
+  const int slice = (((A + kMatchCluster - 1) / kMatchCluster) + 31) & ~31;
+  const int s0 = min(A, rank * slice), s1 = min(A, s0 + slice);
+  const int nwords_all = (A + 31) / 32, nwords_slice = slice / 32;
+  // dynamic smem (same layout in every CTA, so that DSMEM offsets coincide):
+  //   [gt: L float4][col: L u64][colp: L u64][m_anchor: L int][m_gt: L int][ord: L int][bits_all: ceil(A/32) u32]
+  //   [bits: slice/32 u32][skeys: slice u32][patch_bin: L u16][patch_owner: L u16]
+  float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);
+  unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + L);
+  unsigned long long *sm_colp = sm_col + L;
+  int *m_anchor = reinterpret_cast<int *>(sm_colp + L);
+  int *m_gt = m_anchor + L;
+  int *ord = m_gt + L;
+  unsigned *bits_all = reinterpret_cast<unsigned *>(ord + ((L + 3) & ~3));
+  unsigned *bits = bits_all + ((nwords_all + 3) & ~3);
+  unsigned *skeys = bits + ((nwords_slice + 3) & ~3);
+  unsigned short *patch_bin = reinterpret_cast<unsigned short *>(skeys + slice);  // matched anchors: first digit of their
+  unsigned short *patch_owner = patch_bin + L;                                     // key and the CTA that held it
+  const int kPatchCap = L;  // at most G <= L anchors are matched
+
+  const float *lab = a.labels + (size_t)b * L * W;
+  const float4 *anchors = reinterpret_cast<const float4 *>(a.anchors);
+  const bool mining = a.mining_ratio > 0.f;
+  // ---- phase 0 (every CTA): gts, this CTA's share of the tile reductions, its key slice ----
+  for (int k = threadIdx.x; k < G; k += blockDim.x) {
+    const float *row = lab + (size_t)k * W;
+    sm_gt[k] = make_float4(row[1], row[2], row[3], row[4]);
+    sm_col[k] = 0ull;
+    sm_colp[k] = 0ull;
+  }
+  if (rank == 0)
+    for (int w = threadIdx.x; w < nwords_all; w += blockDim.x) bits_all[w] = 0u;
+  if (threadIdx.x == 0) {
+    sm_nmatch = 0;
+    sm_dup = 0;
+    sm_thr = 0;
+    sm_thr_part = 0;
+    sm_np = 0;
+    sm_carry = 0;
+    sm_amb = 0;
+    ctl.state = kStateDone;
+    ctl.num_negative = 0;
+    ctl.err = 0;
+    ctl.have_q = 0;
+    sm_npatch = 0;
+    sm_lcnt = 0;
+  }
+  if (mining)
+    for (int i = threadIdx.x; i < kDigitBins; i += blockDim.x) hist[0][i] = 0u;
+  if (mining) {
+    const unsigned *gkeys = a.key + (size_t)b * A;
+    if ((A & 3) == 0 && (reinterpret_cast<uintptr_t>(gkeys) & 15) == 0) {
+      const uint4 *g4 = reinterpret_cast<const uint4 *>(gkeys + s0);
+      uint4 *s4 = reinterpret_cast<uint4 *>(skeys);
+#pragma unroll 4
+      for (int j = threadIdx.x; j < ((s1 - s0) >> 2); j += blockDim.x) s4[j] = g4[j];
+    } else {
+#pragma unroll 4
+      for (int j = threadIdx.x; j < s1 - s0; j += blockDim.x) skeys[j] = gkeys[s0 + j];
+    }
+  }
+  __syncthreads();
+  if (mining) {
+    // first digit (bits 29..19) of this slice's keys.  The histogram does not depend on num_negative, so it is built
+    // here, off the critical path; the keys of the anchors the bipartite stage matches later are taken out again
+    // through the patch list.
+    for (int base = 0; base < s1 - s0; base += blockDim.x) {
+      const int j = base + (int)threadIdx.x;
+      const unsigned kv = j < s1 - s0 ? skeys[j] : kKeySentinel;
+      hist_add_warp(hist[0], (kv >> 19) & (unsigned)(kDigitBins - 1), kv != kKeySentinel);
+    }
+  }
+  {
+    const unsigned long long *tcol = a.colbest + (size_t)b * a.T * L;
+    const int ntl = (a.T - rank + kMatchCluster - 1) / kMatchCluster;  // tiles rank, rank + CS, ...
+    for (int idx = threadIdx.x; idx < ntl * G; idx += blockDim.x) {
+      const int tl = idx / G, k = idx - tl * G;
+      const unsigned long long ck = tcol[(size_t)(rank + tl * kMatchCluster) * L + k];
+      if (ck) atomicMax(&sm_colp[k], ck);
+    }
+    int pos = 0;
+    for (int t = rank + (int)threadIdx.x * kMatchCluster; t < a.T; t += (int)blockDim.x * kMatchCluster)
+      pos += a.thr_count[(size_t)b * a.T + t];
+    pos = warp_sum_i32(pos);
+    if (lane_id() == 0 && pos) atomicAdd(&sm_thr_part, pos);
+  }
+  cluster.sync();  // #1: partial maxima / counts, every key slice and its first-digit histogram are in place
+  if (mining && rank != 0) {
+    // cluster total of the first-digit histograms, while CTA 0 is matching (it copies the result afterwards)
+    for (int i = threadIdx.x; i < kDigitBins; i += blockDim.x) {
+      unsigned t = 0u;
+#pragma unroll
+      for (int r = 0; r < kMatchCluster; ++r) t += cluster.map_shared_rank(hist[0], r)[i];
+      hsum[i] = t;
+      if (rank == 1) hist[1][i] = t;  // the copy CTA 0 picks up (hsum itself is patched in place later)
+    }
+  }
+  if (rank == 0) {
+    for (int k = threadIdx.x; k < G; k += blockDim.x) {
+      unsigned long long m = 0ull;
+#pragma unroll
+      for (int r = 0; r < kMatchCluster; ++r) {
+        const unsigned long long o = *cluster.map_shared_rank(&sm_colp[k], r);
+        m = o > m ? o : m;
+      }
+      sm_col[k] = m;
+    }
+    if (threadIdx.x < kMatchCluster) atomicAdd(&sm_thr, *cluster.map_shared_rank(&sm_thr_part, threadIdx.x));
+    __syncthreads();
+    DSPMB_TSTAMP_IMG(b, 1);
+  }
+
+  // ---- bipartite stage (multibox_target.cc:113-149): CTA 0 decides, everybody recomputes stale columns ----
+  bool distinct = true;
+  int n_ord = 0, head = 0;
+  if (rank == 0) {
+    int clash = 0;
+    for (int k = threadIdx.x; k < G; k += blockDim.x) {
+      const unsigned long long ck = sm_col[k];
+      if (ck == 0ull) continue;
+      const unsigned mine = (unsigned)(ck & 0xffffffffull);
+      for (int kk = 0; kk < G; ++kk)
+        if (kk != k && sm_col[kk] != 0ull && (unsigned)(sm_col[kk] & 0xffffffffull) == mine) clash = 1;
+    }
+    distinct = __syncthreads_or(clash) == 0;
+    if (distinct) {
+      // cached best anchors pairwise distinct: the greedy loop never meets a stale maximum, assign all at once
+      for (int k = threadIdx.x; k < G; k += blockDim.x) {
+        const unsigned long long ck = sm_col[k];
+        if (ck == 0ull) continue;
+        const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
+        const int n = atomicAdd(&sm_nmatch, 1);
+        m_anchor[n] = j;
+        m_gt[n] = k;
+      }
+      __syncthreads();
+    } else {
+      // sorted list of the gts with a candidate (cached key descending, lower gt first), walked by one thread
+      if (threadIdx.x == 0) sm_arg = 0;
+      __syncthreads();
+      for (int k = threadIdx.x; k < G; k += blockDim.x) {
+        const unsigned long long ck = sm_col[k];
+        if (ck == 0ull) continue;
+        int r = 0;
+        for (int kk = 0; kk < G; ++kk) {
+          const unsigned long long o = sm_col[kk];
+          r += (o > ck || (o == ck && kk < k)) ? 1 : 0;
+        }
+        ord[r] = k;
+        atomicAdd(&sm_arg, 1);
+      }
+      __syncthreads();
+      n_ord = sm_arg;
+      __syncthreads();
+    }
+  }
+  while (true) {
+    if (rank == 0) {
+      if (!distinct && threadIdx.x == 0) {
+        int state = kStateDone;
+        while (head < n_ord) {
+          const int k = ord[head];
+          const unsigned long long ck = sm_col[k];
+          const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
+          if ((bits_all[j >> 5] >> (j & 31)) & 1u) {
+            state = kStateRecompute;  // cached maximum points at an anchor that has been taken since
+            break;
+          }
+          const int n = sm_nmatch;
+          m_anchor[n] = j;
+          m_gt[n] = k;
+          sm_nmatch = n + 1;
+          bits_all[j >> 5] |= 1u << (j & 31);
+          ++head;
+        }
+        ctl.state = state;
+        ctl.k = state == kStateRecompute ? ord[head] : 0;
+        sm_arg = head;
+      }
+      __syncthreads();
+      if (ctl.state == kStateDone) break;  // CTA 0 leaves the loop WITHOUT the barrier: it arrives at (a) after the fix-up
+      head = sm_arg;
+    }
+    cluster.sync();  // (a) recompute round: ctl of CTA 0 is final
+    const int state = *cluster.map_shared_rank(&ctl.state, 0);
+    if (state == kStateDone) break;  // ranks != 0 only (CTA 0 broke out above)
+    const int k = *cluster.map_shared_rank(&ctl.k, 0);
+    // this CTA's slice of the matched-anchor bitmap, then the column maximum of gt k over its unmatched anchors
+    {
+      const unsigned *rb = cluster.map_shared_rank(bits_all, 0) + (s0 >> 5);
+      for (int w = threadIdx.x; w < ((s1 - s0 + 31) >> 5); w += blockDim.x) bits[w] = rb[w];
+    }
+    __syncthreads();
+    const float4 g = sm_gt[k];
+    unsigned long long tkey = 0ull;
+    for (int j0 = s0 + (int)threadIdx.x; j0 < s1; j0 += 4 * (int)blockDim.x) {
+      float4 an4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * (int)blockDim.x;
+        an4[u] = j < s1 ? __ldg(anchors + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * (int)blockDim.x;
+        if (j >= s1 || ((bits[(j - s0) >> 5] >> ((j - s0) & 31)) & 1u)) continue;
+        const float4 an = an4[u];
+        if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
+        const float iou = iou_target(an, g);
+        if (iou > 1e-6f) {
+          const unsigned long long ck = col_key(iou, j);
+          tkey = ck > tkey ? ck : tkey;
+        }
+      }
+    }
+    const unsigned long long pm = block_max_u64(tkey, red_smem);
+    if (threadIdx.x == 0) *cluster.map_shared_rank(&sm_part[rank], 0) = pm;
+    cluster.sync();  // (b) the partial maxima are in CTA 0
+    if (rank == 0) {
+      unsigned long long bm = 0ull;
+#pragma unroll
+      for (int r = 0; r < kMatchCluster; ++r) bm = sm_part[r] > bm ? sm_part[r] : bm;
+      // re-insert gt k behind the entries that still rank before it (a gt without candidate leaves the list)
+      int base = head + 1;
+      while (true) {
+        const int pos = base + (int)threadIdx.x;
+        int e = -1;
+        bool before = false;
+        if (pos < n_ord) {
+          e = ord[pos];
+          const unsigned long long ek = sm_col[e];
+          before = bm == 0ull || ek > bm || (ek == bm && e < k);
+        }
+        const int moved = __syncthreads_count(before);
+        if (before) ord[pos - 1] = e;
+        base += moved;
+        if (moved < (int)blockDim.x) break;
+      }
+      if (threadIdx.x == 0) {
+        ord[base - 1] = k;
+        sm_col[k] = bm;
+      }
+      if (bm == 0ull) --n_ord;
+      __syncthreads();
+    }
+  }
+
+  int num_negative = 0;
+  if (rank == 0) {
+    const int nmatch = sm_nmatch;
+    DSPMB_TSTAMP_IMG(b, 2);
+    // ---- fix up the bipartite-matched anchors; their mining keys are taken out of the owners' slices ----
+    const int gs = nmatch > (int)(blockDim.x >> 4) ? 4 : 16;
+    for (int q = (int)threadIdx.x / gs; q < nmatch; q += (int)blockDim.x / gs) {
+      const int sub = threadIdx.x & (gs - 1);
+      const int j = m_anchor[q], k = m_gt[q];
+      const float4 an = __ldg(anchors + j);
+      float max_iou = -1.0f;
+      for (int kk = sub; kk < G; kk += gs) {
+        const float4 g = sm_gt[kk];
+        const bool reach = an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y;
+        const float iou = reach ? iou_target(an, g) : 0.0f;
+        if (iou > max_iou) max_iou = iou;
+      }
+      const unsigned gmask = (gs == 16 ? 0xffffu : 0xfu) << (lane_id() & ~(unsigned)(gs - 1));
+      for (int m = gs >> 1; m > 0; m >>= 1) {
+        const float o = __shfl_xor_sync(gmask, max_iou, m);
+        if (o > max_iou) max_iou = o;
+      }
+      if (sub != 0) continue;
+      if (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) atomicAdd(&sm_dup, 1);  // counted by the stream kernel
+      const size_t row = (size_t)b * A + j;
+      const float *lrow = lab + (size_t)k * W;
+      float enc[5];
+      encode_loc(an, lrow, a, enc);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        a.loc_target[row * 5 + c] = enc[c];
+        a.loc_mask[row * 5 + c] = 1.0f;
+      }
+      a.cls_target[row] = fadd(lrow[0], 1.0f);
+      if (mining) {
+        const int owner = j / slice;
+        const unsigned old = atomicExch(cluster.map_shared_rank(&skeys[j - owner * slice], owner), kKeySentinel);
+        if (old != kKeySentinel) {
+          const int n = atomicAdd(&sm_npatch, 1);
+          if (n < kPatchCap) {
+            patch_bin[n] = (unsigned short)((old >> 19) & (unsigned)(kDigitBins - 1));
+            patch_owner[n] = (unsigned short)owner;
+          }
+        }
+      }
+      if (a.match_out) a.match_out[row] = k;
+    }
+    __syncthreads();
+    DSPMB_TSTAMP_IMG(b, 3);
+    DSPMB_TSTAMP_IMG(b, 4);
+    const int num_positive = sm_thr + nmatch - sm_dup;
+    if (mining) {  // multibox_target.cc:186-189
+      num_negative = (int)fmul((float)num_positive, a.mining_ratio);
+      if (num_negative > A - num_positive) num_negative = A - num_positive;
+      if (num_negative < 0) num_negative = 0;
+    }
+    if (threadIdx.x == 0) {
+      if (stats) {
+        stats[0] = G;
+        stats[1] = num_positive;
+        stats[2] = mining ? num_negative : A - num_positive;
+        stats[3] = nmatch;
+      }
+      ctl.state = kStateDone;
+      ctl.num_negative = num_negative;
+    }
+    cluster.sync();  // (a), final round: state == done, num_negative and the patched key slices are visible
+  }
+  num_negative = *cluster.map_shared_rank(&ctl.num_negative, 0);
+  if (num_negative <= 0) {
+    cluster.sync();  // nobody leaves while its shared memory may still be read
+    return;
+  }
+
+  // ---- hard-negative mining (multibox_target.cc:182-241): MSB-first select, 11 + 11 + 8 bits ----
+  const int nloc = s1 - s0;
+  unsigned prefix = 0u, prefix_mask = 0u;
+  int need = num_negative;
+  bool exact_key = false;
+  int cp = 0;
+  const int npatch = *cluster.map_shared_rank(&sm_npatch, 0);
+  const unsigned short *rpb = cluster.map_shared_rank(patch_bin, 0), *rpo = cluster.map_shared_rank(patch_owner, 0);
+  for (int level = 0; level < 3; ++level) {
+    const int shift = level == 0 ? 19 : (level == 1 ? 8 : 0);
+    const int nbins = level == 2 ? 256 : kDigitBins;
+    unsigned *h = hist[level & 1];
+    if (level == 0 && npatch <= kPatchCap) {
+      // first digit: histogram and cluster total were prepared before num_negative was known; take the matched
+      // anchors' keys out of the total
+      if (rank == 0) {
+        const unsigned *rs = cluster.map_shared_rank(hist[1], 1);
+        for (int i = threadIdx.x; i < kDigitBins; i += blockDim.x) hsum[i] = rs[i];
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < npatch; i += blockDim.x) atomicSub(&hsum[rpb[i]], 1u);
+      __syncthreads();
+    } else {
+      if (level == 1) cluster.sync();  // CTA 0 has copied the first-level total out of CTA 1's hist[1]
+      for (int i = threadIdx.x; i < nbins; i += blockDim.x) h[i] = 0u;
+      __syncthreads();
+      for (int base = 0; base < nloc; base += blockDim.x) {
+        const int j = base + (int)threadIdx.x;
+        const unsigned kv = j < nloc ? skeys[j] : kKeySentinel;
+        hist_add_warp(h, (kv >> shift) & (unsigned)(nbins - 1), kv != kKeySentinel && (kv & prefix_mask) == prefix);
+      }
+      cluster.sync();  // every CTA's histogram of this level is complete
+      // every CTA sums the histograms on its own (same result everywhere): coalesced DSMEM reads
+      for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+        unsigned t = 0u;
+#pragma unroll
+        for (int r = 0; r < kMatchCluster; ++r) t += cluster.map_shared_rank(h, r)[i];
+        hsum[i] = t;
+      }
+      __syncthreads();
+    }
+    const int per = nbins / (int)blockDim.x;  // 8 or 1 consecutive bins per thread
+    unsigned c[8];
+    int tot = 0;
+    for (int i = 0; i < per; ++i) c[i] = hsum[threadIdx.x * per + i];
+    for (int i = 0; i < per; ++i) tot += (int)c[i];
+    int total;
+    const int ex = block_scan_excl(tot, scan_smem, &total);
+    if (ex < need && ex + tot >= need) {
+      int acc = ex;
+      for (int i = 0; i < per; ++i) {
+        if (acc + (int)c[i] >= need) {
+          sm_pb = (int)threadIdx.x * per + i;
+          sm_before = acc;
+          sm_cp = (int)c[i];
+          break;
+        }
+        acc += (int)c[i];
+      }
+    }
+    if (threadIdx.x == 0) sm_total = total;
+    __syncthreads();
+    if (level == 0 && sm_total < need) {
+      // fewer candidates than num_negative: CHECK_GE(temp.size(), num_negative) fails (multibox_target.cc:236)
+      if (rank == 0 && threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_MINING_CANDIDATES);
+      cluster.sync();
+      return;
+    }
+    prefix |= (unsigned)sm_pb << shift;
+    prefix_mask |= (unsigned)(nbins - 1) << shift;
+    need -= sm_before;
+    cp = sm_cp;
+    __syncthreads();  // sm_pb / sm_before / sm_cp are re-written by the next level
+    if (level == 2) {
+      exact_key = true;  // all 30 bits fixed: the pivot key itself
+      break;
+    }
+    if (cp <= kPivotCap) break;  // few enough to rank directly, one key per thread of the cluster
+  }
+  unsigned qkey = prefix;
+  if (!exact_key) {
+    // The pivot bin's keys are copied into EVERY CTA's list at identical positions: CTA r's keys start behind those
+    // of the lower ranks (their counts are the histogram entries, minus patched keys at the first level); CTA r then
+    // ranks entries [256 r, 256 r + 256) against the whole list, and the thread that holds the need-th smallest key
+    // tells everybody.
+    const int level_done = prefix_mask == (0x7ffu << 19) ? 0 : 1;
+    const unsigned pbin = (prefix >> (level_done == 0 ? 19 : 8)) & (unsigned)(kDigitBins - 1);
+    if (threadIdx.x < 32) {
+      int cnt = 0;
+      if ((int)lane_id() < rank) {
+        cnt = (int)cluster.map_shared_rank(hist[level_done & 1], (int)lane_id())[pbin];
+        if (level_done == 0 && npatch <= kPatchCap)
+          for (int i = 0; i < npatch; ++i) cnt -= (rpb[i] == pbin && rpo[i] == lane_id()) ? 1 : 0;
+      }
+      cnt = warp_sum_i32(cnt);
+      if (lane_id() == 0) sm_off = cnt;
+    }
+    __syncthreads();
+    const int off = sm_off;
+    for (int j = threadIdx.x; j < nloc; j += blockDim.x) {
+      const unsigned kv = skeys[j];
+      if (kv != kKeySentinel && (kv & prefix_mask) == prefix) {
+        const int pos = off + atomicAdd(&sm_lcnt, 1);
+#pragma unroll
+        for (int r = 0; r < kMatchCluster; ++r) cluster.map_shared_rank(plist, r)[pos] = kv;
+      }
+    }
+    cluster.sync();  // every CTA holds the complete list
+    {
+      const int i = rank * (int)blockDim.x + (int)threadIdx.x;
+      if (i < cp) {
+        const unsigned v = plist[i];
+        int lo = 0, hi = 0;
+        for (int x = 0; x < cp; ++x) {
+          const unsigned o = plist[x];
+          lo += o < v ? 1 : 0;
+          hi += o <= v ? 1 : 0;
+        }
+        if (lo < need && need <= hi) {  // equal keys write the same value
+#pragma unroll
+          for (int r = 0; r < kMatchCluster; ++r) *cluster.map_shared_rank(&ctl.qkey, r) = v;
+        }
+      }
+    }
+    cluster.sync();  // qkey is final everywhere
+    qkey = ctl.qkey;
+  }
+  if (rank == 0) DSPMB_TSTAMP_IMG(b, 5);
+  // Keys q approximate the reference's probabilities p with |q - p| <= delta * p: keys below Q(1-3 delta) are certainly
+  // selected, keys above Q(1+3 delta) certainly not, the band in between is re-evaluated exactly (CTA 0, below).
+  const float Q = __uint_as_float(qkey);
+  const unsigned klo = __float_as_uint(fmul(Q, 1.0f - 3.0f * a.delta));
+  const unsigned khi = __float_as_uint(fmul(Q, 1.0f + 3.0f * a.delta));
+  float *ct = a.cls_target + (size_t)b * A;
+  int *amb_list = a.amb_list + (size_t)b * A;
+  unsigned *amb_key = a.amb_key + (size_t)b * A;
+  {
+    int *ramb = cluster.map_shared_rank(&sm_amb, 0);
+    int n_in_local = 0;
+    for (int base = 0; base < nloc; base += blockDim.x) {
+      const int j = base + threadIdx.x;
+      const unsigned kv = j < nloc ? skeys[j] : kKeySentinel;
+      if (kv < klo) {
+        ct[s0 + j] = 0.0f;
+        ++n_in_local;
+      }
+      const bool amb = kv >= klo && kv <= khi;
+      const unsigned m = __ballot_sync(kFullMask, amb);
+      if (m) {
+        int wbase = 0;
+        if (lane_id() == 0) wbase = atomicAdd(ramb, __popc(m));
+        wbase = __shfl_sync(kFullMask, wbase, 0);
+        if (amb) amb_list[wbase + __popc(m & ((1u << lane_id()) - 1u))] = s0 + j;
+      }
+    }
+    n_in_local = warp_sum_i32(n_in_local);
+    if (lane_id() == 0 && n_in_local) atomicAdd(cluster.map_shared_rank(&sm_carry, 0), n_in_local);
+  }
+  __threadfence();  // the ambiguous list (global memory) is read by CTA 0 after the barrier
+  cluster.sync();
+  if (rank != 0) return;
+  DSPMB_TSTAMP_IMG(b, 6);
+  const int n_amb = sm_amb;
+  const int need2 = num_negative - sm_carry;
+  if (need2 < 0 || need2 > n_amb) {  // would mean the error bound was violated
+    if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_INTERNAL);
+    return;
+  }
+  const float *p_cls = a.cls_preds + (size_t)b * a.C * A;
+  if (n_amb <= 4 * (int)(blockDim.x >> 5)) {  // a handful: one warp each (latency); many: one thread each (throughput)
+    for (int q = (int)warp_id(); q < n_amb; q += (int)(blockDim.x >> 5)) {
+      const int j = __ldcg(amb_list + q);
+      const float pe = exact_bg_prob_warp<kFma>(p_cls, j, A, a.C);
+      if (lane_id() == 0) amb_key[q] = __float_as_uint(pe);
+    }
+  } else {
+    for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+      const int j = __ldcg(amb_list + q);
+      const float pe = exact_bg_prob<kFma>(p_cls, j, A, a.C);
+      amb_key[q] = __float_as_uint(pe);
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+    const unsigned kq = amb_key[q];
+    const int jq = __ldcg(amb_list + q);
+    int rnk = 0;
+    for (int i = 0; i < n_amb; ++i) {
+      const unsigned ki = amb_key[i];
+      rnk += (ki < kq || (ki == kq && __ldcg(amb_list + i) < jq)) ? 1 : 0;
+    }
+    if (rnk < need2) ct[jq] = 0.0f;
+  }
+  DSPMB_TSTAMP_IMG(b, 7);
 }
 
 }  // namespace
 }  // namespace dspmb
 
 using namespace dspmb;
+
+extern "C" int dspmb_debug_target_stamps(unsigned long long *device_buffer) {
+  DSPMB_CUDA_TRY(cudaMemcpyToSymbol(g_tstamps, &device_buffer, sizeof(device_buffer)));
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_debug_target_stream_stamps(unsigned long long *device_buffer) {
+  DSPMB_CUDA_TRY(cudaMemcpyToSymbol(g_sstamps, &device_buffer, sizeof(device_buffer)));
+  return DSPMB_OK;
+}
 
 extern "C" size_t dspmb_target_workspace_bytes(int B, int A, int L, int C) {
   (void)C;
@@ -1080,13 +1768,14 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   ta.vh = variances[3];
   ta.fma_build = libm_fma_mode();
 
-  const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L;
+  const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L +
+                       sizeof(unsigned short) * (size_t)L * (kStreamThreads / 32);
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
                        sizeof(int) * (size_t)((L + 3) & ~3) +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
   const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 170 * 1024;
   const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
-  DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 28);
+  DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 36);
   DSPMB_REQUIRE(smem2 <= 190 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
   DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 190 * 1024);  // + ~31 KB static
   DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 190 * 1024);
@@ -1118,7 +1807,23 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
-  if (phases & 2) {
+  // cluster matcher: key slices and the matched-anchor bitmap must fit in the CTAs' shared memory
+  const int cslice = (((A + kMatchCluster - 1) / kMatchCluster) + 31) & ~31;
+  const size_t smem3 = (sizeof(float4) + 2 * sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
+                       sizeof(int) * (size_t)((L + 3) & ~3) + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3) +
+                       sizeof(unsigned) * (size_t)(((cslice / 32) + 3) & ~3) + sizeof(unsigned) * (size_t)cslice +
+                       2 * sizeof(unsigned short) * (size_t)L;
+  const bool use_cluster = tuning(DSPMB_TUNE_TARGET_PIPELINE) != 0 && cslice <= kClusterSliceMax && smem3 <= 150 * 1024;
+  if ((phases & 2) && use_cluster) {
+    ProfileScope _p(kSlotTargetMatch, stream);
+    DSPMB_ENSURE_DYN_SMEM(target_match_cluster_kernel<true>, 150 * 1024);
+    DSPMB_ENSURE_DYN_SMEM(target_match_cluster_kernel<false>, 150 * 1024);
+    if (ta.fma_build)
+      target_match_cluster_kernel<true><<<B * kMatchCluster, kClusterThreads, smem3, stream>>>(ta);
+    else
+      target_match_cluster_kernel<false><<<B * kMatchCluster, kClusterThreads, smem3, stream>>>(ta);
+    ++ctx.launches;
+  } else if (phases & 2) {
     ProfileScope _p(kSlotTargetMatch, stream);
     if (keys_in_smem)
       target_match_kernel<true><<<B, kMatchThreads, smem2_total, stream>>>(ta);

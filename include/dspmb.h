@@ -228,7 +228,11 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_DET_PIPELINE 6       /* 1 (default): detection runs stream -> {sort || class pair tests + resolve}
                                            (the pair kernel is a programmatic dependent of the sort kernel) where its
                                            preconditions hold; 0: stream -> sort+rank -> nms in final row order      */
-#define DSPMB_TUNE_TARGET_PIPELINE 7    /* 1 (default): multi-CTA target matcher; 0: one CTA per image              */
+#define DSPMB_TUNE_TARGET_PIPELINE 7    /* 1: thread-block-cluster target matcher (8 CTAs per image, DSMEM histograms);
+                                           0 (default): one 1024-thread CTA per image -- measured at SSD-512 B=64:
+                                           84.6 us/step with one CTA, 88.8 us with the cluster (the matcher is a chain
+                                           of ~8 dependent global-memory round trips and barriers, not a throughput
+                                           problem, so eight times the threads buy nothing)                          */
 #define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
 #define DSPMB_TUNE_DET_PREFETCH 9        /* detection stream kernel: CTA start issues an L2 prefetch for the tile this many
                                            CTAs ahead in launch order (default 0 = off: measured 54.6 us/step without,
