@@ -6,7 +6,22 @@
 //
 // The reference's gpu path argsorts on the host, cudaMallocs per call, computes the FULL N x N/64 mask (the
 // lower-triangle early-out is commented out, nms_kernel.cu:39), copies the mask to the host and sweeps it there.
-// Here everything stays on the device and on the caller's stream:
+// Here everything stays on the device and on the caller's stream.  Default (DSPMB_TUNE_NMS_PIPELINE = 1), work
+// O(N x kept) instead of O(N^2) and workspace O(N) instead of the N x N/64 mask:
+//   sort                N <= 16384: one CTA, bitonic network in shared memory; larger: multi-CTA bitonic (every CTA
+//                       sorts a 4096-key tile in shared memory, the wide strides are one compare-exchange pass over
+//                       global memory each, the narrow ones are finished per tile in shared memory again);
+//   nms_gather_kernel   sorted boxes as float4 + precomputed fp32 areas (cpu_nms.pyx:24) + optional class;
+//   then, per chunk of 1024 boxes in score order (greedy NMS only ever needs a box compared with the boxes KEPT before
+//   it -- 21 k of 200 k on the benchmark sweep):
+//     nms_cull_kernel     every CTA stages a slab of 128 kept boxes in shared memory and tests the chunk against it
+//                         (four chained compares on x2+1 / y2+1 decide "cannot overlap"; the few pairs that pass take
+//                         the reference's IoU and its threshold rule); a suppressed box gets its dead flag;
+//     nms_resolve_kernel  one CTA: ordered compaction of the chunk's survivors, their upper-triangular bit mask in
+//                         shared memory, greedy resolve on 64-bit words, survivors appended to the kept list (boxes
+//                         for the later chunks' cull + original indices = the output, already in score order).
+// DSPMB_TUNE_NMS_PIPELINE = 0 keeps the first implementation (full mask, kept for A/B runs and as a second opinion in
+// the tests):
 //   nms_sort_kernel     64-bit keys (~score | ~index) sorted by a bitonic network (shared memory up to 16K keys,
 //                       global above) => descending score, ties to the higher index like a stable
 //                       argsort()[::-1];
@@ -193,14 +208,394 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int N, int W, co
   if (threadIdx.x == 0) *num_keep = sm_carry;
 }
 
+
+// ====================================================================================================
+// Chunked pipeline (default)
+// ====================================================================================================
+constexpr int kChunk = 1024;        // boxes per greedy step
+constexpr int kSlab = 128;          // kept boxes per cull CTA
+constexpr int kCullThreads = 256;   // 4 chunk boxes per thread
+constexpr int kTileKeys = 4096;     // keys per CTA of the multi-CTA bitonic sort
+
+struct NmsPipe {
+  unsigned long long *keys;  // npad sort keys
+  int *order;                // N sorted position -> original row
+  float4 *box;               // N sorted boxes
+  float *area, *cls;         // N
+  unsigned char *dead;       // N: suppressed by an earlier kept box
+  float4 *kbox;              // kept boxes, score order (x2 / y2 are stored as x2 + 1 / y2 + 1 rounded up, see cull)
+  float4 *kraw;              // kept boxes as given
+  float *karea, *kcls;
+  int *nkept;                // [0] number of kept boxes so far
+  size_t bytes;
+};
+
+NmsPipe carve_pipe(void *base, int N) {
+  NmsPipe w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 256);
+    return (char *)base + o;
+  };
+  const size_t npad = (size_t)next_pow2(N < 2 ? 2 : N);
+  w.keys = (unsigned long long *)take(sizeof(unsigned long long) * npad);
+  w.order = (int *)take(sizeof(int) * (size_t)N);
+  w.box = (float4 *)take(sizeof(float4) * (size_t)N);
+  w.area = (float *)take(sizeof(float) * (size_t)N);
+  w.cls = (float *)take(sizeof(float) * (size_t)N);
+  w.dead = (unsigned char *)take((size_t)N);
+  w.kbox = (float4 *)take(sizeof(float4) * (size_t)N);
+  w.kraw = (float4 *)take(sizeof(float4) * (size_t)N);
+  w.karea = (float *)take(sizeof(float) * (size_t)N);
+  w.kcls = (float *)take(sizeof(float) * (size_t)N);
+  w.nkept = (int *)take(256);
+  w.bytes = off;
+  return w;
+}
+
+// ---- multi-CTA bitonic sort of npad (power of two, >= kTileKeys) 64-bit keys, ascending ----
+__global__ void __launch_bounds__(1024) nms_keys_kernel(const float *__restrict__ dets, int N, int dim, int npad,
+                                                        unsigned long long *__restrict__ keys, unsigned char *__restrict__ dead,
+                                                        int *__restrict__ nkept) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *nkept = 0;
+  if (i < N) dead[i] = 0;
+  if (i >= npad) return;
+  unsigned long long k = ~0ull;
+  if (i < N) k = ((unsigned long long)(~float_order_key(dets[(size_t)i * dim + 4])) << 32) | (0xffffffffu - (unsigned)i);
+  keys[i] = k;
+}
+
+// compare-exchange steps j = j_hi .. 1 of merge stage k on a tile of kTileKeys keys held in shared memory; with
+// full != 0 the tile is sorted from scratch first (stages 2 .. kTileKeys)
+__global__ void __launch_bounds__(1024) nms_bitonic_tile_kernel(unsigned long long *__restrict__ keys, int k_stage, int full) {
+  __shared__ unsigned long long sk[kTileKeys];
+  const int base = blockIdx.x * kTileKeys;
+  for (int i = threadIdx.x; i < kTileKeys; i += blockDim.x) sk[i] = keys[base + i];
+  __syncthreads();
+  for (int k = full ? 2 : k_stage; k <= k_stage; k <<= 1) {
+    for (int j = min(k >> 1, kTileKeys >> 1); j > 0; j >>= 1) {
+      for (int q = threadIdx.x; q < (kTileKeys >> 1); q += blockDim.x) {
+        const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+        const int hi = lo | j;
+        const bool up = ((base + lo) & k) == 0;
+        const unsigned long long x = sk[lo], y = sk[hi];
+        if ((x > y) == up) {
+          sk[lo] = y;
+          sk[hi] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kTileKeys; i += blockDim.x) keys[base + i] = sk[i];
+}
+
+// one compare-exchange pass with stride j >= kTileKeys of merge stage k over global memory
+__global__ void __launch_bounds__(256) nms_bitonic_global_kernel(unsigned long long *__restrict__ keys, int npad, int k, int j) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= (npad >> 1)) return;
+  const int lo = ((q & ~(j - 1)) << 1) | (q & (j - 1));
+  const int hi = lo | j;
+  const bool up = (lo & k) == 0;
+  const unsigned long long x = keys[lo], y = keys[hi];
+  if ((x > y) == up) {
+    keys[lo] = y;
+    keys[hi] = x;
+  }
+}
+
+__global__ void nms_order_kernel(const unsigned long long *__restrict__ keys, int N, int *__restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) order[i] = (int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull));
+}
+
+// single-CTA variant for N <= kSortSmemKeys: keys, sort and order in one launch (also clears the pipeline's state)
+__global__ void __launch_bounds__(kSortThreads) nms_sort_small_kernel(const float *__restrict__ dets, int N, int dim, int npad,
+                                                                       int *__restrict__ order, unsigned char *__restrict__ dead,
+                                                                       int *__restrict__ nkept) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem);
+  if (threadIdx.x == 0) *nkept = 0;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    unsigned long long k = ~0ull;
+    if (i < N) {
+      k = ((unsigned long long)(~float_order_key(dets[(size_t)i * dim + 4])) << 32) | (0xffffffffu - (unsigned)i);
+      dead[i] = 0;
+    }
+    keys[i] = k;
+  }
+  __syncthreads();
+  bitonic_sort_u64(keys, npad);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull));
+}
+
+__global__ void nms_clear_kernel(int N, unsigned char *__restrict__ dead, int *__restrict__ nkept) {  // presorted input
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) *nkept = 0;
+  if (i < N) dead[i] = 0;
+}
+
+// The reference's suppression rule on one pair (cpu_nms.pyx:57-65 / nms_kernel.cu:24-32,71); a = the kept box.
+__device__ __forceinline__ bool nms_suppresses(float4 a, float area_a, float4 b, float area_b, double thresh, float thresh_f,
+                                               int mode) {
+  const float iou = iou_plus1(a, area_a, b, area_b);
+  return mode == 0 ? ((double)iou >= thresh) : (iou > thresh_f);
+}
+
+// Chunk [c0, c0 + kChunk) against the kept boxes [0, nk): CTA s (grid-stride) stages kept boxes [128 s, 128 s + 128)
+// in shared memory, every thread runs its four chunk boxes over them.  "Cannot overlap" is four compares on
+// coordinates with the +1 of the pixel convention folded in and rounded UP (x2p = RU(x2 + 1) >= x2 + 1, so
+// x2p_j < x1_i implies RN(RN(xx2 - xx1) + 1) <= 0, i.e. the reference's w is 0): conservative, never drops a pair the
+// reference would suppress as long as the threshold is positive (no_filter otherwise).
+template <bool kUseClass>
+__global__ void __launch_bounds__(kCullThreads) nms_cull_kernel(int N, int c0, double thresh, int mode, int no_filter,
+                                                                const float4 *__restrict__ box, const float *__restrict__ area,
+                                                                const float *__restrict__ cls, const float4 *__restrict__ kbox,
+                                                                const float4 *__restrict__ kraw, const float *__restrict__ karea,
+                                                                const float *__restrict__ kcls, const int *__restrict__ nkept,
+                                                                unsigned char *__restrict__ dead) {
+  __shared__ float4 sb[kSlab], sr[kSlab];
+  __shared__ float sa[kSlab], sc[kSlab];
+  const int nk = *nkept;
+  if ((int)blockIdx.x * kSlab >= nk) return;
+  constexpr int kPer = kChunk / kCullThreads;
+  float4 b[kPer], bp[kPer];
+  float ar[kPer], cl[kPer];
+  bool live[kPer];
+  const float thresh_f = (float)thresh;
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int i = c0 + u * kCullThreads + (int)threadIdx.x;
+    live[u] = i < N && dead[i] == 0;
+    b[u] = live[u] ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ar[u] = live[u] ? area[i] : 0.f;
+    cl[u] = (kUseClass && live[u]) ? cls[i] : 0.f;
+    bp[u] = make_float4(b[u].x, b[u].y, __fadd_ru(b[u].z, 1.0f), __fadd_ru(b[u].w, 1.0f));
+  }
+  for (int s0 = (int)blockIdx.x * kSlab; s0 < nk; s0 += (int)gridDim.x * kSlab) {
+    const int ns = min(kSlab, nk - s0);
+    __syncthreads();
+    if ((int)threadIdx.x < ns) {
+      sb[threadIdx.x] = kbox[s0 + threadIdx.x];
+      sr[threadIdx.x] = kraw[s0 + threadIdx.x];
+      sa[threadIdx.x] = karea[s0 + threadIdx.x];
+      if (kUseClass) sc[threadIdx.x] = kcls[s0 + threadIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+      if (!live[u]) continue;
+      for (int j = 0; j < ns; ++j) {
+        const float4 k = sb[j];  // (x1, y1, RU(x2 + 1), RU(y2 + 1)) of the kept box
+        if (!no_filter && !(k.z >= b[u].x && bp[u].z >= k.x && k.w >= b[u].y && bp[u].w >= k.y)) continue;
+        if (kUseClass && sc[j] != cl[u]) continue;
+        if (nms_suppresses(sr[j], sa[j], b[u], ar[u], thresh, thresh_f, mode)) {
+          live[u] = false;
+          dead[c0 + u * kCullThreads + (int)threadIdx.x] = 1;
+          break;
+        }
+      }
+    }
+  }
+}
+
+// Greedy resolve of the chunk's survivors (one CTA of 1024 threads) and append to the kept list.
+constexpr int kResolveThreads = 1024;
+template <bool kUseClass>
+__global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int c0, double thresh, int mode, int no_filter,
+                                                                      const float4 *__restrict__ box, const float *__restrict__ area,
+                                                                      const float *__restrict__ cls, const int *__restrict__ order,
+                                                                      const unsigned char *__restrict__ dead, float4 *__restrict__ kbox,
+                                                                      float4 *__restrict__ kraw, float *__restrict__ karea,
+                                                                      float *__restrict__ kcls, int *__restrict__ nkept,
+                                                                      int32_t *__restrict__ keep, int32_t *__restrict__ num_keep,
+                                                                      int last) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  // [sbox: kChunk float4][sbp: kChunk float4][sarea][scls][sidx: kChunk int][mask: S x W u64, S <= kChunk]
+  float4 *sbox = reinterpret_cast<float4 *>(dyn_smem);
+  float4 *sbp = sbox + kChunk;
+  float *sarea = reinterpret_cast<float *>(sbp + kChunk);
+  float *scls = sarea + kChunk;
+  int *sidx = reinterpret_cast<int *>(scls + kChunk);
+  unsigned long long *mask = reinterpret_cast<unsigned long long *>(sidx + kChunk);
+  __shared__ int scan_smem[kResolveThreads / 32 + 1];
+  __shared__ unsigned long long rowany[kChunk / 64], remv_sm[kChunk / 64];
+  const float thresh_f = (float)thresh;
+  const int i = c0 + (int)threadIdx.x;
+  const int alive = (i < N && dead[i] == 0) ? 1 : 0;
+  int S;
+  const int pos = block_scan_excl(alive, scan_smem, &S);
+  if (alive) {
+    const float4 b = box[i];
+    sbox[pos] = b;
+    sbp[pos] = make_float4(b.x, b.y, __fadd_ru(b.z, 1.0f), __fadd_ru(b.w, 1.0f));
+    sarea[pos] = area[i];
+    if (kUseClass) scls[pos] = cls[i];
+    sidx[pos] = order ? order[i] : i;
+  }
+  if (threadIdx.x < kChunk / 64) rowany[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int nk0 = *nkept;
+  if (S > 0) {
+    const int W = (S + 63) >> 6;
+    // mask[r * W + w] bit t: survivor r suppresses survivor 64 w + t (> r).  One warp per 32 rows and 64 columns
+    // (lane = row, the column box is a broadcast read), upper triangle only; warps draw (row group, word) units
+    // round-robin so that the triangle's imbalance is spread.
+    const int ngroups = (S + 31) >> 5;
+    const unsigned warp = warp_id(), lane = lane_id(), nwarps = blockDim.x >> 5;
+    for (int u = (int)warp; u < ngroups * W; u += (int)nwarps) {
+      const int rg = u / W, w = u - rg * W;
+      const int r = (rg << 5) + (int)lane;
+      if ((w << 6) + 63 <= (rg << 5)) {  // word entirely at or left of the diagonal
+        if (r < S) mask[r * W + w] = 0ull;
+        continue;
+      }
+      unsigned long long bits = 0ull;
+      if (r < S) {
+        const float4 b = sbox[r], bp = sbp[r];
+        const float ar = sarea[r];
+        const float cr = kUseClass ? scls[r] : 0.f;
+        const int j1 = min(S, (w << 6) + 64);
+        for (int j = max(w << 6, (rg << 5) + 1); j < j1; ++j) {
+          const float4 k = sbp[j];
+          const bool reach = no_filter || (k.z >= b.x && bp.z >= k.x && k.w >= b.y && bp.w >= k.y);
+          if (j > r && reach && (!kUseClass || scls[j] == cr) &&
+              nms_suppresses(b, ar, sbox[j], sarea[j], thresh, thresh_f, mode))
+            bits |= 1ull << (j & 63);
+        }
+        mask[r * W + w] = bits;
+      }
+      const unsigned any = __ballot_sync(kFullMask, bits != 0ull);
+      if (lane == 0 && any) atomicOr(&rowany[rg >> 1], (unsigned long long)any << ((rg & 1) * 32));
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // lane w owns word w of the removed set; per 64-row chunk only the rows that suppress something are visited
+      unsigned long long remv = 0ull;
+      for (int c = 0; c < W; ++c) {
+        unsigned long long cur = __shfl_sync(kFullMask, remv, c);
+        unsigned long long live = 0ull;
+        for (unsigned long long cand = rowany[c]; cand; cand &= cand - 1) {
+          const int t = __ffsll((long long)cand) - 1;
+          if (!((cur >> t) & 1ull)) {
+            live |= 1ull << t;
+            cur |= mask[((c << 6) + t) * W + c];
+          }
+        }
+        if ((int)lane == c) remv = cur;
+        if ((int)lane > c && (int)lane < W) {
+          unsigned long long acc = 0ull;
+          for (unsigned long long rem = live; rem; rem &= rem - 1) {
+            const int t = __ffsll((long long)rem) - 1;
+            acc |= mask[((c << 6) + t) * W + lane];
+          }
+          remv |= acc;
+        }
+      }
+      if ((int)lane < W) remv_sm[lane] = remv;
+    }
+    __syncthreads();
+  }
+  // ordered append of the survivors that stay
+  const int q = (int)threadIdx.x;
+  const int stays = (q < S && !((remv_sm[q >> 6] >> (q & 63)) & 1ull)) ? 1 : 0;
+  int added;
+  const int kp = block_scan_excl(stays, scan_smem, &added);
+  if (stays) {
+    const int d = nk0 + kp;
+    kbox[d] = sbp[q];
+    kraw[d] = sbox[q];
+    karea[d] = sarea[q];
+    if (kUseClass) kcls[d] = scls[q];
+    keep[d] = sidx[q];
+  }
+  if (threadIdx.x == 0) {
+    *nkept = nk0 + added;
+    if (last) *num_keep = nk0 + added;
+  }
+}
+
 }  // namespace
 }  // namespace dspmb
 
 using namespace dspmb;
 
+// The chunked pipeline needs O(N) bytes; the full-mask implementation (DSPMB_TUNE_NMS_PIPELINE = 0) N^2 / 8 more, so
+// its workspace is only promised up to 32768 boxes (beyond that the knob is ignored).
+constexpr int kFullMaskMaxN = 32768;
 extern "C" size_t dspmb_nms_workspace_bytes(int N) {
   if (N <= 0) return 256;
-  return carve(nullptr, N).bytes;
+  const size_t pipe = carve_pipe(nullptr, N).bytes;
+  const size_t full = N <= kFullMaskMaxN ? carve(nullptr, N).bytes : 0;
+  return pipe > full ? pipe : full;
+}
+
+static int nms_pipeline(const float *dets, int N, int dim, double thresh, int mode, int class_col, int presorted,
+                        int32_t *keep, int32_t *num_keep, void *workspace, cudaStream_t stream) {
+  NmsPipe w = carve_pipe(workspace, N);
+  const int *order = nullptr;
+  if (!presorted) {
+    const int npad = next_pow2(N < 2 ? 2 : N);
+    ProfileScope _p(kSlotNmsSort, stream);
+    if (npad <= kSortSmemKeys) {
+      DSPMB_ENSURE_DYN_SMEM(nms_sort_small_kernel, kSortSmemKeys * 8);
+      nms_sort_small_kernel<<<1, kSortThreads, sizeof(unsigned long long) * npad, stream>>>(dets, N, dim, npad, w.order, w.dead,
+                                                                                           w.nkept);
+    } else {
+      nms_keys_kernel<<<ceil_div(npad, 1024), 1024, 0, stream>>>(dets, N, dim, npad, w.keys, w.dead, w.nkept);
+      const int tiles = npad / kTileKeys;
+      nms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(w.keys, kTileKeys, 1);
+      for (int k = 2 * kTileKeys; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j >= kTileKeys; j >>= 1)
+          nms_bitonic_global_kernel<<<ceil_div(npad >> 1, 256), 256, 0, stream>>>(w.keys, npad, k, j);
+        nms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(w.keys, k, 0);
+      }
+      nms_order_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(w.keys, N, w.order);
+    }
+    DSPMB_CUDA_TRY(cudaGetLastError());
+    order = w.order;
+  } else {
+    nms_clear_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(N, w.dead, w.nkept);
+    DSPMB_CUDA_TRY(cudaGetLastError());
+  }
+  {
+    ProfileScope _p(kSlotNmsGather, stream);
+    nms_gather_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(dets, N, dim, class_col, order, w.box, w.area, w.cls);
+  }
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  // a non-positive threshold suppresses pairs that do not overlap at all: no geometric filter then
+  const int no_filter = mode == 0 ? !(thresh > 0.0) : !((float)thresh >= 0.f);
+  const size_t smem_res = (size_t)kChunk * (16 + 16 + 4 + 4 + 4) + sizeof(unsigned long long) * (size_t)kChunk * (kChunk / 64);
+  DSPMB_ENSURE_DYN_SMEM(nms_resolve_kernel<true>, smem_res);
+  DSPMB_ENSURE_DYN_SMEM(nms_resolve_kernel<false>, smem_res);
+  for (int c0 = 0; c0 < N; c0 += kChunk) {
+    if (c0 > 0) {
+      // at most c0 boxes can have been kept so far; CTAs whose slab lies beyond the actual count return at once
+      int grid = ceil_div(c0, kSlab);
+      if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
+      ProfileScope _p(kSlotNmsTile, stream);
+      if (class_col >= 0)
+        nms_cull_kernel<true><<<grid, kCullThreads, 0, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, w.kbox,
+                                                                  w.kraw, w.karea, w.kcls, w.nkept, w.dead);
+      else
+        nms_cull_kernel<false><<<grid, kCullThreads, 0, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, w.kbox,
+                                                                   w.kraw, w.karea, w.kcls, w.nkept, w.dead);
+    }
+    const int last = c0 + kChunk >= N;
+    ProfileScope _p(kSlotNmsReduce, stream);
+    if (class_col >= 0)
+      nms_resolve_kernel<true><<<1, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
+                                                                         w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
+                                                                         num_keep, last);
+    else
+      nms_resolve_kernel<false><<<1, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
+                                                                          w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
+                                                                          num_keep, last);
+  }
+  DSPMB_CUDA_TRY(cudaGetLastError());
+  return DSPMB_OK;
 }
 
 extern "C" int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, int mode, int class_col,
@@ -216,11 +611,13 @@ extern "C" int dspmb_nms_f32(const float *dets, int N, int dim, double thresh, i
     return DSPMB_OK;
   }
   DSPMB_REQUIRE(dets && keep, "nms: NULL tensor");
-  const size_t need = carve(nullptr, N).bytes;
+  const size_t need = dspmb_nms_workspace_bytes(N);
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
     set_error("nms: workspace must be 256-byte aligned and >= %zu bytes (got %zu)", need, workspace_bytes);
     return DSPMB_ERR_WORKSPACE;
   }
+  if (tuning(DSPMB_TUNE_NMS_PIPELINE) != 0 || N > kFullMaskMaxN)
+    return nms_pipeline(dets, N, dim, thresh, mode, class_col, presorted, keep, num_keep, workspace, stream);
   NmsWorkspace w = carve(workspace, N);
   const int W = ceil_div(N, 64);
   DSPMB_REQUIRE((size_t)W * 8 <= 200 * 1024, "nms: more than %d boxes are not supported", 200 * 1024 / 8 * 64);

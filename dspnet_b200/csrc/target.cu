@@ -857,6 +857,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
   }
   auto key_at = [&](int j) -> unsigned { return kKeysInSmem ? skeys[j] : gkeys[j]; };
+  __syncthreads();  // the staged keys are read by other threads from here on (racecheck: staging vs. the min/max pass)
   DSPMB_TSTAMP(4);
   // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
   // (larger than the bits of any probability), so they are only reached if there are too few candidates.
