@@ -13,6 +13,8 @@ static thread_local char g_error[512] = "";
 static thread_local int g_last_launches = 0;
 static std::atomic<int> g_libm_mode{-1};
 
+void note_launches(int n) { g_last_launches = n; }
+
 void set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -62,8 +64,8 @@ std::vector<ProfileRecord> g_profile_records;
 const char *const kSlotNames[kNumKernelSlots] = {
     "prior_kernel",        "det_stream_kernel", "det_sort_kernel", "det_nms_kernel",  "target_stream_kernel",
     "target_match_kernel", "nms_sort_kernel",   "nms_gather_kernel", "nms_mask_kernel", "nms_scan_kernel",
-    "det_compact_kernel",  "det_pair_kernel",   "det_resolve_kernel", "target_fixup_kernel", "nms_tile_kernel",
-    "nms_reduce_kernel",   "softmax_det_kernel", "multibox_loss_kernel"};
+    "det_compact_kernel",  "det_pair_kernel",   "det_resolve_kernel", "target_fixup_kernel", "nms_cull_kernel",
+    "nms_resolve_kernel",  "softmax_det_kernel", "multibox_loss_kernel"};
 }  // namespace
 
 void profile_mark(int slot, cudaStream_t stream, bool begin) {

@@ -20,6 +20,7 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // ---- host-side error plumbing -------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 int cuda_fail(cudaError_t e, const char *what);
+void note_launches(int n);  // kernels the calling thread's last operator call enqueued (dspmb_last_launch_count)
 int libm_fma_mode();  // 0 / 1, resolved from dspmb_set_libm_mode / host CPU flags
 int tuning(int knob);  // current value of a DSPMB_TUNE_* knob
 

@@ -30,6 +30,8 @@
 //   nms_scan_kernel     one CTA: 64-row chunks; the diagonal words are resolved serially in registers, the rows
 //                       of the surviving boxes are OR-ed into a shared-memory bit vector with all loads in flight
 //                       at once; then an ordered compaction writes the kept original indices.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace dspmb {
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(int N, int W, co
 // ====================================================================================================
 constexpr int kChunk = 1024;        // boxes per greedy step
 constexpr int kSlab = 128;          // kept boxes per cull CTA
-constexpr int kCullThreads = 256;   // 4 chunk boxes per thread
+constexpr int kCullThreads = 1024;  // one chunk box per thread (32 warps keep the issue slots of the SM busy)
 constexpr int kTileKeys = 4096;     // keys per CTA of the multi-CTA bitonic sort
 
 struct NmsPipe {
@@ -313,8 +315,10 @@ __global__ void nms_order_kernel(const unsigned long long *__restrict__ keys, in
 
 // single-CTA variant for N <= kSortSmemKeys: keys, sort and order in one launch (also clears the pipeline's state)
 __global__ void __launch_bounds__(kSortThreads) nms_sort_small_kernel(const float *__restrict__ dets, int N, int dim, int npad,
-                                                                       int *__restrict__ order, unsigned char *__restrict__ dead,
-                                                                       int *__restrict__ nkept) {
+                                                                       int class_col, int *__restrict__ order,
+                                                                       unsigned char *__restrict__ dead, int *__restrict__ nkept,
+                                                                       float4 *__restrict__ box, float *__restrict__ area,
+                                                                       float *__restrict__ cls) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem);
   if (threadIdx.x == 0) *nkept = 0;
@@ -328,7 +332,15 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_small_kernel(const floa
   }
   __syncthreads();
   bitonic_sort_u64(keys, npad);
-  for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = (int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull));
+  for (int i = threadIdx.x; i < N; i += blockDim.x) {  // order + the gather of nms_gather_kernel, no second launch
+    const int src = (int)(0xffffffffu - (unsigned)(keys[i] & 0xffffffffull));
+    order[i] = src;
+    const float *d = dets + (size_t)src * dim;
+    const float x1 = d[0], y1 = d[1], x2 = d[2], y2 = d[3];
+    box[i] = make_float4(x1, y1, x2, y2);
+    area[i] = fmul(fadd(fsub(x2, x1), 1.0f), fadd(fsub(y2, y1), 1.0f));  // cpu_nms.pyx:24
+    if (class_col >= 0) cls[i] = d[class_col];
+  }
 }
 
 __global__ void nms_clear_kernel(int N, unsigned char *__restrict__ dead, int *__restrict__ nkept) {  // presorted input
@@ -344,11 +356,55 @@ __device__ __forceinline__ bool nms_suppresses(float4 a, float area_a, float4 b,
   return mode == 0 ? ((double)iou >= thresh) : (iou > thresh_f);
 }
 
+// Dense evaluation of a warp's candidate pairs.  Every lane holds `cand`, the columns (bits) of ITS row that passed the
+// cheap filter; a warp that ran the exact test inside the filter loop would take that divergent branch whenever ANY
+// lane has a hit -- with 4 % of the pairs overlapping that is 3 iterations out of 4, two lanes busy.  Instead the
+// (row lane, column bit) pairs are compacted into a per-warp queue and `test(row_lane, bit)` runs on full warps.
+constexpr int kQueue = 256;
+template <typename F>
+__device__ __forceinline__ void warp_dense_pairs(unsigned cand, unsigned short *queue, F test) {
+  const unsigned lane = lane_id();
+  const int cnum = __popc(cand);
+  const int incl = warp_scan_incl(cnum);
+  const int total = __shfl_sync(kFullMask, incl, 31);
+  for (int base = 0; base < total; base += kQueue) {
+    int pos = incl - cnum - base;
+    for (unsigned m = cand; m; m &= m - 1, ++pos)
+      if (pos >= 0 && pos < kQueue) queue[pos] = (unsigned short)((lane << 5) | (unsigned)(__ffs(m) - 1));
+    __syncwarp();
+    const int qn = min(kQueue, total - base);
+    for (int q = (int)lane; q < qn; q += 32) {
+      const unsigned e = queue[q];
+      test((int)(e >> 5), (int)(e & 31u));
+    }
+    __syncwarp();
+  }
+}
+
+// Filter bits of one row against 32 staged columns (x1, y1, RU(x2 + 1), RU(y2 + 1)): four chained compares and one
+// predicated OR per pair, no branch.  "Cannot overlap" folds the +1 of the pixel convention in, rounded UP
+// (x2p = RU(x2 + 1) >= x2 + 1, so x2p_j < x1_i implies RN(RN(xx2 - xx1) + 1) <= 0, i.e. the reference's w is 0):
+// conservative, never drops a pair the reference would suppress as long as the threshold is positive.
+__device__ __forceinline__ unsigned filter_bits32(float4 rowp, const float4 *colp) {
+  unsigned cand = 0u;
+#pragma unroll
+  for (int jj = 0; jj < 32; ++jj) {
+    const float4 k = colp[jj];
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.ge.f32 p, %1, %2;\n\t"
+        "setp.ge.and.f32 p, %3, %4, p;\n\t"
+        "setp.ge.and.f32 p, %5, %6, p;\n\t"
+        "setp.ge.and.f32 p, %7, %8, p;\n\t"
+        "@p or.b32 %0, %0, %9;\n\t}"
+        : "+r"(cand)
+        : "f"(k.z), "f"(rowp.x), "f"(rowp.z), "f"(k.x), "f"(k.w), "f"(rowp.y), "f"(rowp.w), "f"(k.y), "r"(1u << jj));
+  }
+  return cand;
+}
+
 // Chunk [c0, c0 + kChunk) against the kept boxes [0, nk): CTA s (grid-stride) stages kept boxes [128 s, 128 s + 128)
-// in shared memory, every thread runs its four chunk boxes over them.  "Cannot overlap" is four compares on
-// coordinates with the +1 of the pixel convention folded in and rounded UP (x2p = RU(x2 + 1) >= x2 + 1, so
-// x2p_j < x1_i implies RN(RN(xx2 - xx1) + 1) <= 0, i.e. the reference's w is 0): conservative, never drops a pair the
-// reference would suppress as long as the threshold is positive (no_filter otherwise).
+// and the chunk in shared memory; warp w owns chunk boxes [128 w, 128 w + 128), 32 at a time (lane = box): filter bits
+// against the slab 32 kept boxes at a time, then the dense exact tests; a suppressed box gets its dead flag.
 template <bool kUseClass>
 __global__ void __launch_bounds__(kCullThreads) nms_cull_kernel(int N, int c0, double thresh, int mode, int no_filter,
                                                                 const float4 *__restrict__ box, const float *__restrict__ area,
@@ -356,55 +412,74 @@ __global__ void __launch_bounds__(kCullThreads) nms_cull_kernel(int N, int c0, d
                                                                 const float4 *__restrict__ kraw, const float *__restrict__ karea,
                                                                 const float *__restrict__ kcls, const int *__restrict__ nkept,
                                                                 unsigned char *__restrict__ dead) {
-  __shared__ float4 sb[kSlab], sr[kSlab];
+  __shared__ float4 sb[kSlab], sr[kSlab];        // kept: filter form / as given
   __shared__ float sa[kSlab], sc[kSlab];
+  __shared__ float4 cb[kChunk];                  // chunk boxes as given
+  __shared__ float ca[kChunk], cc[kChunk];
+  __shared__ unsigned char cdead[kChunk];
+  __shared__ unsigned short queues[kCullThreads / 32][kQueue];
   const int nk = *nkept;
   if ((int)blockIdx.x * kSlab >= nk) return;
-  constexpr int kPer = kChunk / kCullThreads;
-  float4 b[kPer], bp[kPer];
-  float ar[kPer], cl[kPer];
-  bool live[kPer];
   const float thresh_f = (float)thresh;
-#pragma unroll
-  for (int u = 0; u < kPer; ++u) {
-    const int i = c0 + u * kCullThreads + (int)threadIdx.x;
-    live[u] = i < N && dead[i] == 0;
-    b[u] = live[u] ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-    ar[u] = live[u] ? area[i] : 0.f;
-    cl[u] = (kUseClass && live[u]) ? cls[i] : 0.f;
-    bp[u] = make_float4(b[u].x, b[u].y, __fadd_ru(b[u].z, 1.0f), __fadd_ru(b[u].w, 1.0f));
+  for (int q = threadIdx.x; q < kChunk; q += blockDim.x) {
+    const int i = c0 + q;
+    const bool on = i < N && dead[i] == 0;
+    cb[q] = on ? box[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ca[q] = on ? area[i] : 0.f;
+    if (kUseClass) cc[q] = on ? cls[i] : 0.f;
+    cdead[q] = on ? 0 : 1;
   }
+  const unsigned warp = warp_id(), lane = lane_id();
+  unsigned short *queue = queues[warp];
   for (int s0 = (int)blockIdx.x * kSlab; s0 < nk; s0 += (int)gridDim.x * kSlab) {
     const int ns = min(kSlab, nk - s0);
     __syncthreads();
-    if ((int)threadIdx.x < ns) {
-      sb[threadIdx.x] = kbox[s0 + threadIdx.x];
-      sr[threadIdx.x] = kraw[s0 + threadIdx.x];
-      sa[threadIdx.x] = karea[s0 + threadIdx.x];
-      if (kUseClass) sc[threadIdx.x] = kcls[s0 + threadIdx.x];
+    if ((int)threadIdx.x < kSlab) {
+      const bool on = (int)threadIdx.x < ns;
+      // padding entries can reach nothing: x1 = +inf fails "x2p_row >= x1"
+      sb[threadIdx.x] = on ? kbox[s0 + threadIdx.x] : make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
+      if (on) {
+        sr[threadIdx.x] = kraw[s0 + threadIdx.x];
+        sa[threadIdx.x] = karea[s0 + threadIdx.x];
+        if (kUseClass) sc[threadIdx.x] = kcls[s0 + threadIdx.x];
+      }
     }
     __syncthreads();
-#pragma unroll
-    for (int u = 0; u < kPer; ++u) {
-      if (!live[u]) continue;
-      for (int j = 0; j < ns; ++j) {
-        const float4 k = sb[j];  // (x1, y1, RU(x2 + 1), RU(y2 + 1)) of the kept box
-        if (!no_filter && !(k.z >= b[u].x && bp[u].z >= k.x && k.w >= b[u].y && bp[u].w >= k.y)) continue;
-        if (kUseClass && sc[j] != cl[u]) continue;
-        if (nms_suppresses(sr[j], sa[j], b[u], ar[u], thresh, thresh_f, mode)) {
-          live[u] = false;
-          dead[c0 + u * kCullThreads + (int)threadIdx.x] = 1;
-          break;
-        }
+    constexpr int kRounds = kChunk / kCullThreads;  // 4 x 32 boxes per warp
+    for (int u = 0; u < kRounds; ++u) {
+      const int r0 = ((int)warp * kRounds + u) << 5;  // first chunk box of this round
+      const int r = r0 + (int)lane;
+      if (__all_sync(kFullMask, cdead[r] != 0)) continue;
+      const float4 b = cb[r];
+      const float4 bp = make_float4(b.x, b.y, __fadd_ru(b.z, 1.0f), __fadd_ru(b.w, 1.0f));
+      for (int jw = 0; jw < ns; jw += 32) {
+        unsigned cand = no_filter ? (ns - jw >= 32 ? 0xffffffffu : (1u << (ns - jw)) - 1u) : filter_bits32(bp, sb + jw);
+        if (cdead[r]) cand = 0u;
+        warp_dense_pairs(cand, queue, [&](int rl, int jj) {
+          const int rr = r0 + rl, j = jw + jj;
+          if (cdead[rr]) return;
+          if (kUseClass && sc[j] != cc[rr]) return;
+          if (nms_suppresses(sr[j], sa[j], cb[rr], ca[rr], thresh, thresh_f, mode)) cdead[rr] = 1;
+        });
       }
     }
   }
+  __syncthreads();
+  for (int q = threadIdx.x; q < kChunk; q += blockDim.x) {
+    const int i = c0 + q;
+    if (i < N && cdead[q] && dead[i] == 0) dead[i] = 1;
+  }
 }
 
-// Greedy resolve of the chunk's survivors (one CTA of 1024 threads) and append to the kept list.
+// Greedy resolve of the chunk's survivors and append to the kept list.  One thread-block CLUSTER of kResolveCluster
+// CTAs: every CTA compacts the chunk (redundantly, it is 1024 flags) and takes every kResolveCluster-th strip of
+// pair-test units; hits are OR-ed into the mask of CTA 0 through distributed shared memory (they are rare: a box
+// suppresses a fraction of a box on average), and after one cluster barrier CTA 0 resolves and appends alone.  With
+// one CTA the 528 units of a full first chunk took 30 us -- at N = 1000 that was most of the call.
 constexpr int kResolveThreads = 1024;
+constexpr int kResolveCluster = 8;
 template <bool kUseClass>
-__global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int c0, double thresh, int mode, int no_filter,
+__global__ void __cluster_dims__(kResolveCluster, 1, 1) __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int c0, double thresh, int mode, int no_filter,
                                                                       const float4 *__restrict__ box, const float *__restrict__ area,
                                                                       const float *__restrict__ cls, const int *__restrict__ order,
                                                                       const unsigned char *__restrict__ dead, float4 *__restrict__ kbox,
@@ -421,7 +496,11 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int
   int *sidx = reinterpret_cast<int *>(scls + kChunk);
   unsigned long long *mask = reinterpret_cast<unsigned long long *>(sidx + kChunk);
   __shared__ int scan_smem[kResolveThreads / 32 + 1];
-  __shared__ unsigned long long rowany[kChunk / 64], remv_sm[kChunk / 64];
+  __shared__ unsigned long long rowany[kChunk / 64], remv_sm[kChunk / 64], diagany[kChunk / 64];
+  __shared__ unsigned short queues[kResolveThreads / 32][kQueue];
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
   const float thresh_f = (float)thresh;
   const int i = c0 + (int)threadIdx.x;
   const int alive = (i < N && dead[i] == 0) ? 1 : 0;
@@ -435,55 +514,68 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int
     if (kUseClass) scls[pos] = cls[i];
     sidx[pos] = order ? order[i] : i;
   }
-  if (threadIdx.x < kChunk / 64) rowany[threadIdx.x] = 0ull;
+  if (threadIdx.x < kChunk / 64) {
+    rowany[threadIdx.x] = 0ull;
+    diagany[threadIdx.x] = 0ull;
+  }
   __syncthreads();
   const int nk0 = *nkept;
   if (S > 0) {
     const int W = (S + 63) >> 6;
-    // mask[r * W + w] bit t: survivor r suppresses survivor 64 w + t (> r).  One warp per 32 rows and 64 columns
-    // (lane = row, the column box is a broadcast read), upper triangle only; warps draw (row group, word) units
-    // round-robin so that the triangle's imbalance is spread.
+    // mask[r * W + w] bit t: survivor r suppresses survivor 64 w + t (> r).  Units of 32 rows x 32 columns (lane = row)
+    // of the upper triangle, dealt round-robin to the warps: branch-free filter bits, then the dense exact tests
+    // (warp_dense_pairs); hits are OR-ed into the 32-bit halves of the mask words with shared-memory atomics.
     const int ngroups = (S + 31) >> 5;
     const unsigned warp = warp_id(), lane = lane_id(), nwarps = blockDim.x >> 5;
-    for (int u = (int)warp; u < ngroups * W; u += (int)nwarps) {
-      const int rg = u / W, w = u - rg * W;
-      const int r = (rg << 5) + (int)lane;
-      if ((w << 6) + 63 <= (rg << 5)) {  // word entirely at or left of the diagonal
-        if (r < S) mask[r * W + w] = 0ull;
-        continue;
+    unsigned *mask32 = reinterpret_cast<unsigned *>(cluster.map_shared_rank(mask, 0));       // CTA 0 owns the mask
+    unsigned *rowany32 = reinterpret_cast<unsigned *>(cluster.map_shared_rank(rowany, 0));
+    unsigned *diagany32 = reinterpret_cast<unsigned *>(cluster.map_shared_rank(diagany, 0));
+    unsigned short *queue = queues[warp];
+    if (crank == 0)
+      for (int q2 = threadIdx.x; q2 < S * W; q2 += blockDim.x) mask[q2] = 0ull;
+    for (int q2 = S + (int)threadIdx.x; q2 < (ngroups << 5); q2 += blockDim.x)  // padding columns reach nothing
+      sbp[q2] = make_float4(__int_as_float(0x7f800000), 0.f, 0.f, 0.f);
+    cluster.sync();  // CTA 0's mask is cleared before anybody ORs into it
+    const int nunits = ngroups * (ngroups + 1) / 2;
+    for (int u = crank * (int)nwarps + (int)warp; u < nunits; u += kResolveCluster * (int)nwarps) {
+      int rg = 0, rem = u;  // unit u -> (row group, column group >= row group), row-major over the triangle
+      while (rem >= ngroups - rg) {
+        rem -= ngroups - rg;
+        ++rg;
       }
-      unsigned long long bits = 0ull;
+      const int cg = rg + rem;
+      const int r = (rg << 5) + (int)lane, jb = cg << 5;
+      unsigned cand = 0u;
       if (r < S) {
-        const float4 b = sbox[r], bp = sbp[r];
-        const float ar = sarea[r];
-        const float cr = kUseClass ? scls[r] : 0.f;
-        const int j1 = min(S, (w << 6) + 64);
-        for (int j = max(w << 6, (rg << 5) + 1); j < j1; ++j) {
-          const float4 k = sbp[j];
-          const bool reach = no_filter || (k.z >= b.x && bp.z >= k.x && k.w >= b.y && bp.w >= k.y);
-          if (j > r && reach && (!kUseClass || scls[j] == cr) &&
-              nms_suppresses(b, ar, sbox[j], sarea[j], thresh, thresh_f, mode))
-            bits |= 1ull << (j & 63);
-        }
-        mask[r * W + w] = bits;
+        cand = no_filter ? 0xffffffffu : filter_bits32(sbp[r], sbp + jb);
+        if (S - jb < 32) cand &= (1u << (S - jb)) - 1u;
+        if (cg == rg) cand &= lane == 31 ? 0u : ~0u << (lane + 1);  // j > r
       }
-      const unsigned any = __ballot_sync(kFullMask, bits != 0ull);
-      if (lane == 0 && any) atomicOr(&rowany[rg >> 1], (unsigned long long)any << ((rg & 1) * 32));
+      warp_dense_pairs(cand, queue, [&](int rl, int jj) {
+        const int rr = (rg << 5) + rl, j = jb + jj;
+        if (kUseClass && scls[j] != scls[rr]) return;
+        if (nms_suppresses(sbox[rr], sarea[rr], sbox[j], sarea[j], thresh, thresh_f, mode)) {
+          atomicOr(&mask32[rr * 2 * W + cg], 1u << jj);
+          atomicOr(&rowany32[rg], 1u << rl);
+          if ((cg >> 1) == (rg >> 1)) atomicOr(&diagany32[rg], 1u << rl);  // suppresses inside its own 64-row block
+        }
+      });
     }
-    __syncthreads();
+    cluster.sync();  // every hit has landed in CTA 0
+    if (crank != 0) return;
     if (warp == 0) {
       // lane w owns word w of the removed set; per 64-row chunk only the rows that suppress something are visited
       unsigned long long remv = 0ull;
       for (int c = 0; c < W; ++c) {
+        // Only rows that suppress something inside their own 64-row block form a serial chain (bit t of `cur` can only
+        // be set by a row < t of the same block or by an earlier block); the other rows of the block that suppress
+        // anything at all are live iff their bit is clear once the chain is through.
         unsigned long long cur = __shfl_sync(kFullMask, remv, c);
-        unsigned long long live = 0ull;
-        for (unsigned long long cand = rowany[c]; cand; cand &= cand - 1) {
+        for (unsigned long long cand = diagany[c]; cand; cand &= cand - 1) {
           const int t = __ffsll((long long)cand) - 1;
-          if (!((cur >> t) & 1ull)) {
-            live |= 1ull << t;
-            cur |= mask[((c << 6) + t) * W + c];
-          }
+          if (!((cur >> t) & 1ull)) cur |= mask[((c << 6) + t) * W + c];
         }
+        const unsigned long long live = rowany[c] & ~cur;
         if ((int)lane == c) remv = cur;
         if ((int)lane > c && (int)lane < W) {
           unsigned long long acc = 0ull;
@@ -497,6 +589,11 @@ __global__ void __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int
       if ((int)lane < W) remv_sm[lane] = remv;
     }
     __syncthreads();
+  }
+  else {
+    cluster.sync();  // (same barrier count on the S == 0 path)
+    cluster.sync();
+    if (crank != 0) return;
   }
   // ordered append of the survivors that stay
   const int q = (int)threadIdx.x;
@@ -536,33 +633,42 @@ static int nms_pipeline(const float *dets, int N, int dim, double thresh, int mo
                         int32_t *keep, int32_t *num_keep, void *workspace, cudaStream_t stream) {
   NmsPipe w = carve_pipe(workspace, N);
   const int *order = nullptr;
+  bool gathered = false;
+  int launches = 0;
   if (!presorted) {
     const int npad = next_pow2(N < 2 ? 2 : N);
     ProfileScope _p(kSlotNmsSort, stream);
     if (npad <= kSortSmemKeys) {
       DSPMB_ENSURE_DYN_SMEM(nms_sort_small_kernel, kSortSmemKeys * 8);
-      nms_sort_small_kernel<<<1, kSortThreads, sizeof(unsigned long long) * npad, stream>>>(dets, N, dim, npad, w.order, w.dead,
-                                                                                           w.nkept);
+      nms_sort_small_kernel<<<1, kSortThreads, sizeof(unsigned long long) * npad, stream>>>(
+          dets, N, dim, npad, class_col, w.order, w.dead, w.nkept, w.box, w.area, w.cls);
+      gathered = true;
+      ++launches;
     } else {
       nms_keys_kernel<<<ceil_div(npad, 1024), 1024, 0, stream>>>(dets, N, dim, npad, w.keys, w.dead, w.nkept);
       const int tiles = npad / kTileKeys;
       nms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(w.keys, kTileKeys, 1);
+      launches += 2;
       for (int k = 2 * kTileKeys; k <= npad; k <<= 1) {
-        for (int j = k >> 1; j >= kTileKeys; j >>= 1)
+        for (int j = k >> 1; j >= kTileKeys; j >>= 1, ++launches)
           nms_bitonic_global_kernel<<<ceil_div(npad >> 1, 256), 256, 0, stream>>>(w.keys, npad, k, j);
         nms_bitonic_tile_kernel<<<tiles, 1024, 0, stream>>>(w.keys, k, 0);
+        ++launches;
       }
       nms_order_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(w.keys, N, w.order);
+      ++launches;
     }
     DSPMB_CUDA_TRY(cudaGetLastError());
     order = w.order;
   } else {
     nms_clear_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(N, w.dead, w.nkept);
+    ++launches;
     DSPMB_CUDA_TRY(cudaGetLastError());
   }
-  {
+  if (!gathered) {
     ProfileScope _p(kSlotNmsGather, stream);
     nms_gather_kernel<<<ceil_div(N, 256), 256, 0, stream>>>(dets, N, dim, class_col, order, w.box, w.area, w.cls);
+    ++launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   // a non-positive threshold suppresses pairs that do not overlap at all: no geometric filter then
@@ -584,17 +690,19 @@ static int nms_pipeline(const float *dets, int N, int dim, double thresh, int mo
                                                                    w.kraw, w.karea, w.kcls, w.nkept, w.dead);
     }
     const int last = c0 + kChunk >= N;
+    launches += c0 > 0 ? 2 : 1;
     ProfileScope _p(kSlotNmsReduce, stream);
     if (class_col >= 0)
-      nms_resolve_kernel<true><<<1, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
+      nms_resolve_kernel<true><<<kResolveCluster, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
                                                                          w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
                                                                          num_keep, last);
     else
-      nms_resolve_kernel<false><<<1, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
+      nms_resolve_kernel<false><<<kResolveCluster, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
                                                                           w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
                                                                           num_keep, last);
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
+  note_launches(launches);
   return DSPMB_OK;
 }
 

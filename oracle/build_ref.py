@@ -8,7 +8,10 @@
   cpu_nms_ref*.so      cython/cpu_nms.pyx with the 3-token numpy-2 / Cython-3 patch of SURVEY.md section 8c
                        (np.int_t -> np.intp_t, dtype=np.int -> np.intp, `np.float thresh` -> `double thresh`),
                        applied on the fly to a scratch copy under oracle/_ref/;
-  bbox_ref*.so         cython/bbox.pyx (bbox_overlaps_cython) with `np.float` -> `np.float64`.
+  bbox_ref*.so         cython/bbox.pyx (bbox_overlaps_cython) with `np.float` -> `np.float64`;
+  libgpu_nms_ref.so    cython/nms_kernel.cu + gpu_nms.hpp, UNMODIFIED, compiled with nvcc for sm_100a: the reference's own
+                       GPU NMS (`_nms`: cudaMalloc, H2D, full N x N/64 mask, D2H, host sweep), used only as the same-box
+                       speed comparator of bench.py --workload nms.
 
 The reference's own build (MXNet's make/cmake with the operators dropped into src/operator/contrib) cannot be run:
 MXNet is neither vendored nor installable here.
@@ -75,6 +78,13 @@ def build_bbox():
     os.unlink(pyx)
 
 
+def build_gpu_nms():
+    """The reference's nms_kernel.cu as it is (the file includes "gpu_nms.hpp" from its own directory)."""
+    subprocess.check_call(["nvcc", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC",
+                           "-cudart", "static", "-w", os.path.join(REF, "cython", "nms_kernel.cu"), "-o",
+                           os.path.join(OUT, "libgpu_nms_ref.so")])
+
+
 def main():
     if not os.path.isdir(os.path.join(REF, "operator")):
         print("build_ref: %s not present, keeping the prebuilt oracle/_ref/ (if any)" % REF)
@@ -89,6 +99,10 @@ def main():
         build_bbox()
     except Exception as e:
         print("build_ref: bbox not built (%r)" % (e,))
+    try:
+        build_gpu_nms()
+    except Exception as e:
+        print("build_ref: gpu_nms comparator not built (%r)" % (e,))
     print("build_ref: ok ->", sorted(os.listdir(OUT)))
     return 0
 

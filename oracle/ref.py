@@ -116,3 +116,30 @@ def bbox_overlaps_cython(boxes, query_boxes):
         spec.loader.exec_module(_bbox)
     return _bbox.bbox_overlaps_cython(np.ascontiguousarray(boxes, dtype=np.float64),
                                       np.ascontiguousarray(query_boxes, dtype=np.float64))
+
+
+_gpu_nms = None
+
+
+def gpu_nms_available():
+    return os.path.exists(os.path.join(_DIR, "libgpu_nms_ref.so"))
+
+
+def gpu_nms_sorted(sorted_dets, thresh, device_id=0):
+    """The reference's own GPU NMS, `_nms` of cython/nms_kernel.cu:91-144 compiled unmodified for sm_100a (speed
+    comparator only).  Same contract as the C++ function: rows already in descending score order, host pointers in and
+    out, synchronous; returns the kept sorted positions."""
+    global _gpu_nms
+    if _gpu_nms is None:
+        L = ctypes.CDLL(os.path.join(_DIR, "libgpu_nms_ref.so"))
+        f = getattr(L, "_Z4_nmsPiS_PKfiifi")  # void _nms(int*, int*, const float*, int, int, float, int)
+        f.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_float),
+                      ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int]
+        f.restype = None
+        _gpu_nms = f
+    d = np.ascontiguousarray(sorted_dets, dtype=np.float32)
+    keep = np.empty(d.shape[0], np.int32)
+    num = ctypes.c_int(0)
+    _gpu_nms(keep.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), ctypes.byref(num),
+             d.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), d.shape[0], d.shape[1], float(thresh), device_id)
+    return keep[: num.value]
