@@ -10,6 +10,7 @@ Public surface (reference operator / helper names):
 
 All compute runs in libdspmb.so (hand-written CUDA behind the C ABI of include/dspmb.h); there is no CPU path.
 """
-from .ops import MultiBoxDetection, MultiBoxPrior, MultiBoxTarget, DspmbError, multibox_prior_concat  # noqa: F401
+from .ops import (MultiBoxDetection, MultiBoxDetectionFromHeads, MultiBoxPrior, MultiBoxTarget, DspmbError,  # noqa: F401
+                  multibox_prior_concat)
 
 __version__ = "0.1.0"

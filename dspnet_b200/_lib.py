@@ -31,7 +31,8 @@ EXPORTS = (
     "dspmb_p2p_open", "dspmb_p2p_close", "dspmb_p2p_free", "dspmb_detection_gather_f32", "dspmb_detection_gather_wait", "dspmb_detection_gather_read",
     "dspmb_detection_gather_ack", "dspmb_gather_error",
     "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32", "dspmb_last_launch_count",
-    "dspmb_debug_trace",
+    "dspmb_debug_trace", "dspmb_detection_heads_workspace_bytes", "dspmb_detection_heads_f32",
+    "dspmb_multibox_loss_workspace_bytes", "dspmb_multibox_loss_f32",
 )
 
 
@@ -75,6 +76,14 @@ def lib():
     L.dspmb_detection_workspace_bytes.restype = c_size_t
     L.dspmb_detection_f32.argtypes = [c_void_p] * 4 + [c_int] * 3 + [c_float, c_int, fp, c_float, c_int, c_int,
                                                                      c_void_p, c_void_p, c_size_t, c_void_p]
+    L.dspmb_detection_heads_workspace_bytes.argtypes = [c_int, c_int, c_int, ip, ip, c_int]
+    L.dspmb_detection_heads_workspace_bytes.restype = c_size_t
+    L.dspmb_detection_heads_f32.argtypes = [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ip, ip, c_int, c_void_p,
+                                            c_void_p, c_int, c_int, c_int, c_float, c_int, fp, c_float, c_int, c_int,
+                                            c_void_p, c_void_p, c_size_t, c_void_p]
+    L.dspmb_multibox_loss_workspace_bytes.argtypes = [c_int, c_int]
+    L.dspmb_multibox_loss_workspace_bytes.restype = c_size_t
+    L.dspmb_multibox_loss_f32.argtypes = [c_void_p] * 8 + [c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]
     L.dspmb_detection_compact_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.dspmb_set_tuning.argtypes = [c_int, c_int]
     c_ll = ctypes.c_longlong

@@ -137,10 +137,13 @@ inline int next_pow2(int v) {
 }
 
 // Layout is a pure function of (B, A, C); T and Apad are bounded with the smallest tile (128 anchors).
-DetWorkspace carve(void *base, int B, int A, int C) {
+DetWorkspace carve(void *base, int B, int A, int C, int tiles_min = 0, size_t slots_min = 0) {
   DetWorkspace w;
-  const size_t Tmax = (size_t)ceil_div(A, kStreamThreads);
-  const size_t Apad = (((size_t)A + 3) & ~(size_t)3) + 4 * kStreamThreads;  // multiple of 4: 128-bit key loads
+  // the head-fed stream kernel cuts tiles at scale boundaries: a few more tiles and slots than A alone implies
+  const size_t Tdef = (size_t)ceil_div(A, kStreamThreads);
+  const size_t Tmax = Tdef > (size_t)tiles_min ? Tdef : (size_t)tiles_min;
+  const size_t Adef = (((size_t)A + 3) & ~(size_t)3) + 4 * kStreamThreads;  // multiple of 4: 128-bit key loads
+  const size_t Apad = Adef > slots_min ? Adef : slots_min;
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -602,6 +605,75 @@ struct BulkSmem {
   unsigned short idx[kTile], id[kTile];
 };
 
+// Second half of a stream CTA, shared by the cls_prob-fed and the head-fed kernels: `total` survivors are listed in
+// anchor order in sm.score / sm.idx / sm.id; they are decoded on dense lanes, staged and flushed into the tile's slots
+// (slot_begin + k), and -- fork/join pipeline -- copied once more grouped by class for the pair-test kernel.
+template <int NFG, int kThreads, int kVec, bool kV2, typename Smem>
+__device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const int b, const int t, const int slot_begin,
+                                            const int total) {
+  constexpr int kTile = kThreads * kVec;
+  __syncthreads();  // survivor list complete; the class rows are dead from here on
+  for (int j = threadIdx.x; j < total; j += kThreads) {
+    const int l = sm.idx[j];
+    const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
+    stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
+  }
+  __syncthreads();  // the staged rows are complete
+  flush_rows(a, sm.u.rows, b, slot_begin, total);
+  if constexpr (kV2) {
+    // Class-grouped copy of the tile's boxes for the pair-test kernel: a stable counting sort of the <= kTile
+    // survivors by class.  Lanes of a warp that hold the same class find each other with MATCH.ANY; the lowest of
+    // them records the group's size per (round, warp); a 32-lane pass turns the table into offsets.  The table
+    // aliases the loc_pred stage, which is dead once the rows are staged.
+    static_assert(NFG <= kV2ClsPad, "tile_cls holds kV2ClsPad classes");
+    constexpr int kWarps = kThreads / 32, kParts = kVec * kWarps;
+    static_assert(sizeof(float) * kTile * 5 >= (kParts * 32 + 33) * sizeof(unsigned short) + kParts * sizeof(unsigned),
+                  "class table does not fit in the loc stage");
+    unsigned short(*cnt)[32] = reinterpret_cast<unsigned short(*)[32]>(sm.loc);
+    unsigned short *coff = reinterpret_cast<unsigned short *>(sm.loc) + kParts * 32;  // [33]
+    unsigned *present = reinterpret_cast<unsigned *>(coff + 34);                      // [kParts], 4-byte aligned
+    const unsigned lane = lane_id(), warp = warp_id();
+    int within[kVec], cc[kVec];
+#pragma unroll
+    for (int r = 0; r < kVec; ++r) {
+      const int j = r * kThreads + (int)threadIdx.x;
+      const bool valid = j < total;
+      cc[r] = valid ? (int)sm.u.rows.cls[j] : 0xffff;
+      const unsigned m = __match_any_sync(kFullMask, cc[r]);
+      within[r] = __popc(m & ((1u << lane) - 1u));
+      const bool leader = valid && within[r] == 0;
+      if (leader) cnt[r * kWarps + warp][cc[r]] = (unsigned short)__popc(m);
+      const unsigned pres = __reduce_or_sync(kFullMask, leader ? 1u << cc[r] : 0u);
+      if (lane == 0) present[r * kWarps + warp] = pres;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      int run = 0;
+#pragma unroll
+      for (int q = 0; q < kParts; ++q) {
+        const int v = (present[q] >> lane) & 1u ? (int)cnt[q][lane] : 0;
+        cnt[q][lane] = (unsigned short)run;
+        run += v;
+      }
+      const int off = warp_scan_incl(run) - run;
+      coff[lane] = (unsigned short)off;
+      if ((int)lane < NFG) a.tile_cls[((size_t)b * kV2ClsPad + lane) * a.T + t] = (unsigned)off | ((unsigned)run << 16);
+    }
+    __syncthreads();
+    float4 *gb = a.cbox + (size_t)b * a.Apad + slot_begin;
+    unsigned short *gr = a.crank + (size_t)b * a.cls_stride + slot_begin;
+#pragma unroll
+    for (int r = 0; r < kVec; ++r) {
+      const int j = r * kThreads + (int)threadIdx.x;
+      if (j < total) {
+        const int pos = (int)coff[cc[r]] + (int)cnt[r * kWarps + warp][cc[r]] + within[r];
+        gb[pos] = sm.u.rows.box[j];
+        gr[pos] = (unsigned short)j;
+      }
+    }
+  }
+}
+
 template <int NFG, int kThreads, int kVec, bool kV2>
 __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
   constexpr int kTile = kThreads * kVec;
@@ -692,66 +764,265 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
       sm.id[pos] = (unsigned short)id[k];
       ++pos;
     }
-  __syncthreads();  // survivor list complete; the class rows are dead from here on
-  for (int j = threadIdx.x; j < total; j += kThreads) {
-    const int l = sm.idx[j];
-    const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
-    stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
+  finish_tile<NFG, kThreads, kVec, kV2>(a, sm, b, t, tile_begin, total);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Head-fed stream kernel: MultiBoxDetection straight from the per-scale conv outputs.
+// The reference graph (symbol/common.py:399-432, symbol/symbol_builder.py:156-165) runs, per scale, transpose ->
+// Flatten, then Concat -> Reshape -> transpose -> SoftmaxActivation(mode='channel') and only then MultiBoxDetection:
+// four full passes over the class tensor (66 MB at SSD-512, batch 32) before the operator reads it a fifth time.
+// Here a CTA owns a tile of whole cells of one scale (<= 256 anchors): it reads the C logits and 5 loc values of
+// every anchor of the tile directly from the NCHW heads (a thread walks one (cell, anchor-in-cell) pair, so that
+// consecutive threads read consecutive cells of one channel plane: coalesced), keeps the logits in shared memory and
+// never materialises cls_prob.
+//   * every anchor: channel softmax in fp32 with MUFU.EX2 (relative error < 3e-5) -> largest foreground probability;
+//     anchors whose approximate score is below threshold (1 - 1e-4) are below the threshold exactly as well;
+//   * the others (the survivors and a thin band) are re-evaluated bit-exactly on dense lanes: glibc expf of every
+//     class (one (candidate, class) pair per thread), fp32 sum in class order, one division -- the softmax
+//     multibox_target.cc:220-231 spells out, which oracle_softmax_channel restates -- then the first-maximum arg-max on
+//     the rounded probabilities and the exact threshold test of multibox_detection.cc:79-100;
+//   * from there on the tile is finished exactly like one of the cls_prob-fed kernel (finish_tile).
+constexpr int kMaxScales = 8;
+constexpr int kHeadThreads = 128, kHeadTile = 256, kHeadBatch = 64;
+struct HeadsArgs {
+  const float *cls[kMaxScales], *loc[kMaxScales];   // (B, na*C, H, W) / (B, na*5, H, W)
+  int hw[kMaxScales], na[kMaxScales], cpt[kMaxScales];  // cells per map, anchors per cell, cells per tile
+  int tile_off[kMaxScales + 1];                     // first tile of every scale
+  int anchor_off[kMaxScales];                       // first anchor of every scale
+  int nscales;
+};
+
+template <int C>
+struct HeadSmem {
+  union {
+    float xs[C][kHeadTile];            // logits of the tile, [class][anchor in tile]
+    RowStage<kHeadTile> rows;          // finished rows of the survivors (after the exact phase)
+  } u;
+  float loc[kHeadTile * 5];
+  float4 anc[kHeadTile];
+  float score[kHeadTile];              // approximate score per anchor, then exact score per survivor (rank order)
+  unsigned short idx[kHeadTile], id[kHeadTile];
+  unsigned short cand[kHeadTile];      // candidates of the exact phase, anchor order
+  float es[kHeadBatch][C];             // exact exponentials of one batch of candidates
+  float cmx[kHeadBatch];
+  unsigned short cq[kHeadBatch];       // plane-order index of the batch's candidates
+  float fscore[kHeadTile];             // exact score of every candidate (candidate order)
+  unsigned short fid[kHeadTile];       // its class, 0 = below the threshold
+};
+
+template <int C, bool kV2>
+__global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __grid_constant__ StreamArgs a,
+                                                                        const __grid_constant__ HeadsArgs h) {
+  constexpr int NFG = C - 1;
+  TraceScope trace_(0);
+  extern __shared__ __align__(128) unsigned char head_smem_raw[];
+  HeadSmem<C> &sm = *reinterpret_cast<HeadSmem<C> *>(head_smem_raw);
+  __shared__ int scan_smem[kHeadThreads / 32 + 1];
+  const int b = blockIdx.y, t = blockIdx.x;
+  int k = 0;
+  while (k + 1 < h.nscales && t >= h.tile_off[k + 1]) ++k;
+  const int na = h.na[k], HW = h.hw[k];
+  const int cell0 = (t - h.tile_off[k]) * h.cpt[k];
+  const int ncells = min(h.cpt[k], HW - cell0);
+  const int n = ncells * na;                       // anchors of this tile
+  const int a0 = h.anchor_off[k] + cell0 * na;     // first anchor of the tile
+  const float *cls = h.cls[k] + (size_t)b * na * C * HW + cell0;
+  const float *loc = h.loc[k] + (size_t)b * na * 5 * HW + cell0;
+
+  {  // `out = -1` for this tile's rows (multibox_detection-inl.h:103)
+    float *ob = a.out + ((size_t)b * a.A + a0) * 7;
+    if (((uintptr_t)ob & 15) == 0 && (n & 3) == 0) {
+      const float4 m1 = make_float4(-1.f, -1.f, -1.f, -1.f);
+      for (int x = threadIdx.x * 4; x < n * 7; x += kHeadThreads * 4) *reinterpret_cast<float4 *>(ob + x) = m1;
+    } else {
+      for (int x = threadIdx.x; x < n * 7; x += kHeadThreads) ob[x] = -1.f;
+    }
   }
-  __syncthreads();  // the staged rows are complete
-  flush_rows(a, sm.u.rows, b, tile_begin, total);
-  if constexpr (kV2) {
-    // Class-grouped copy of the tile's boxes for the pair-test kernel: a stable counting sort of the <= kTile
-    // survivors by class.  Lanes of a warp that hold the same class find each other with MATCH.ANY; the lowest of
-    // them records the group's size per (round, warp); a 32-lane pass turns the table into offsets.  The table
-    // aliases the loc_pred stage, which is dead once the rows are staged.
-    static_assert(NFG <= kV2ClsPad, "tile_cls holds kV2ClsPad classes");
-    constexpr int kWarps = kThreads / 32, kParts = kVec * kWarps;
-    static_assert(sizeof(float) * kTile * 5 >= (kParts * 32 + 33) * sizeof(unsigned short) + kParts * sizeof(unsigned),
-                  "class table does not fit in the loc stage");
-    unsigned short(*cnt)[32] = reinterpret_cast<unsigned short(*)[32]>(sm.loc);
-    unsigned short *coff = reinterpret_cast<unsigned short *>(sm.loc) + kParts * 32;  // [33]
-    unsigned *present = reinterpret_cast<unsigned *>(coff + 34);                      // [kParts], 4-byte aligned
-    const unsigned lane = lane_id(), warp = warp_id();
-    int within[kVec], cc[kVec];
+  for (int j = threadIdx.x; j < n; j += kHeadThreads)
+    sm.anc[j] = __ldg(reinterpret_cast<const float4 *>(a.anchors) + a0 + j);
+  const bool all_cand = !(a.threshold > 1e-30f);
+  const float thr_lo = fmul(a.threshold, 1.0f - 1e-4f);
+  // ---- loads + approximate softmax ----
+  // The logits of the tile live in shared memory as xs[class][ai * ncells + cell] ("plane order": the order of the
+  // NCHW heads, so global loads and shared stores are both contiguous over the cells); anchor j = cell * na + ai.
+  // A thread takes two neighbouring cells of one anchor-in-cell plane (64-bit loads) when the tile allows it.
+  const bool pairs = ((ncells | cell0 | HW) & 1) == 0 && (((uintptr_t)h.cls[k] | (uintptr_t)h.loc[k]) & 7) == 0;
+  if (pairs) {
+    const int half = ncells >> 1;
+    for (int p = threadIdx.x; p < half * na; p += kHeadThreads) {
+      const int ai = p / half, cell = (p - ai * half) * 2;
+      const int q = ai * ncells + cell;  // plane-order index of the first of the two anchors
+      const float *pc = cls + (size_t)ai * C * HW + cell;
+      float2 x[C];
 #pragma unroll
-    for (int r = 0; r < kVec; ++r) {
-      const int j = r * kThreads + (int)threadIdx.x;
-      const bool valid = j < total;
-      cc[r] = valid ? (int)sm.u.rows.cls[j] : 0xffff;
-      const unsigned m = __match_any_sync(kFullMask, cc[r]);
-      within[r] = __popc(m & ((1u << lane) - 1u));
-      const bool leader = valid && within[r] == 0;
-      if (leader) cnt[r * kWarps + warp][cc[r]] = (unsigned short)__popc(m);
-      const unsigned pres = __reduce_or_sync(kFullMask, leader ? 1u << cc[r] : 0u);
-      if (lane == 0) present[r * kWarps + warp] = pres;
+      for (int c = 0; c < C; ++c) {
+        x[c] = ld_stream_f2(pc);
+        pc += HW;
+      }
+      const float *pl = loc + (size_t)ai * 5 * HW + cell;
+      const int j0 = cell * na + ai, j1 = j0 + na;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const float2 v = ld_stream_f2(pl);
+        pl += HW;
+        sm.loc[j0 * 5 + d] = v.x;
+        sm.loc[j1 * 5 + d] = v.y;
+      }
+      float2 mx = x[0], best = x[1];
+#pragma unroll
+      for (int c = 1; c < C; ++c) {
+        mx.x = fmaxf(mx.x, x[c].x);
+        mx.y = fmaxf(mx.y, x[c].y);
+        if (c > 1) {
+          best.x = fmaxf(best.x, x[c].x);
+          best.y = fmaxf(best.y, x[c].y);
+        }
+      }
+      float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        *reinterpret_cast<float2 *>(&sm.u.xs[c][q]) = x[c];
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmul(fsub(x[c].x, mx.x), 1.4426950408889634f)));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmul(fsub(x[c].y, mx.y), 1.4426950408889634f)));
+        sum.x = fadd(sum.x, e0);
+        sum.y = fadd(sum.y, e1);
+      }
+      float b0, b1;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b0) : "f"(fmul(fsub(best.x, mx.x), 1.4426950408889634f)));
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(b1) : "f"(fmul(fsub(best.y, mx.y), 1.4426950408889634f)));
+      sm.score[j0] = fdiv(b0, sum.x);
+      sm.score[j1] = fdiv(b1, sum.y);
+    }
+  } else {
+    for (int p = threadIdx.x; p < n; p += kHeadThreads) {
+      const int ai = p / ncells, cell = p - ai * ncells;
+      const int j = cell * na + ai;  // anchor index inside the tile (cell-major, symbol/common.py:399-400)
+      const float *pc = cls + (size_t)ai * C * HW + cell;
+      float x[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        x[c] = ld_stream_f1(pc);
+        pc += HW;
+      }
+      const float *pl = loc + (size_t)ai * 5 * HW + cell;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        sm.loc[j * 5 + d] = ld_stream_f1(pl);
+        pl += HW;
+      }
+      float mx = x[0];
+#pragma unroll
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
+      float sum = 0.f, best = x[1];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        sm.u.xs[c][p] = x[c];
+        float e;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmul(fsub(x[c], mx), 1.4426950408889634f)));
+        sum = fadd(sum, e);
+        if (c > 1) best = fmaxf(best, x[c]);
+      }
+      float eb;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(eb) : "f"(fmul(fsub(best, mx), 1.4426950408889634f)));
+      sm.score[j] = fdiv(eb, sum);
+    }
+  }
+  __syncthreads();
+  // ---- candidates of the exact phase, in anchor order (two consecutive anchors per thread) ----
+  const int l0 = threadIdx.x * 2;
+  int ncand_mine = 0;
+  bool cnd[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    cnd[v] = l0 + v < n && (all_cand || sm.score[l0 + v] >= thr_lo);
+    ncand_mine += cnd[v];
+  }
+  int ncand;
+  int cpos = block_scan_excl(ncand_mine, scan_smem, &ncand);
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+    if (cnd[v]) sm.cand[cpos++] = (unsigned short)(l0 + v);
+  __syncthreads();
+  // ---- exact phase, kHeadBatch candidates at a time ----
+  for (int c0 = 0; c0 < ncand; c0 += kHeadBatch) {
+    const int nb = min(kHeadBatch, ncand - c0);
+    if ((int)threadIdx.x < nb) {
+      const int j = sm.cand[c0 + threadIdx.x];
+      const int cell = j / na, q = (j - cell * na) * ncells + cell;
+      float mx = sm.u.xs[0][q];
+#pragma unroll
+      for (int c = 1; c < C; ++c) {
+        const float v = sm.u.xs[c][q];
+        if (v > mx) mx = v;
+      }
+      sm.cmx[threadIdx.x] = mx;
+      sm.cq[threadIdx.x] = (unsigned short)q;
     }
     __syncthreads();
-    if (warp == 0) {
-      int run = 0;
-#pragma unroll
-      for (int q = 0; q < kParts; ++q) {
-        const int v = (present[q] >> lane) & 1u ? (int)cnt[q][lane] : 0;
-        cnt[q][lane] = (unsigned short)run;
-        run += v;
-      }
-      const int off = warp_scan_incl(run) - run;
-      coff[lane] = (unsigned short)off;
-      if ((int)lane < NFG) a.tile_cls[((size_t)b * kV2ClsPad + lane) * a.T + t] = (unsigned)off | ((unsigned)run << 16);
+    for (int q = threadIdx.x; q < nb * C; q += kHeadThreads) {
+      const int kk = q / C, c = q - kk * C;
+      sm.es[kk][c] = libm::expf_glibc(fsub(sm.u.xs[c][sm.cq[kk]], sm.cmx[kk]), a.fma_build);
     }
     __syncthreads();
-    float4 *gb = a.cbox + (size_t)b * a.Apad + tile_begin;
-    unsigned short *gr = a.crank + (size_t)b * a.cls_stride + tile_begin;
+    if ((int)threadIdx.x < nb) {
+      const float *e = sm.es[threadIdx.x];
+      float sum = 0.f;
 #pragma unroll
-    for (int r = 0; r < kVec; ++r) {
-      const int j = r * kThreads + (int)threadIdx.x;
-      if (j < total) {
-        const int pos = (int)coff[cc[r]] + (int)cnt[r * kWarps + warp][cc[r]] + within[r];
-        gb[pos] = sm.u.rows.box[j];
-        gr[pos] = (unsigned short)j;
-      }
+      for (int c = 0; c < C; ++c) sum = fadd(sum, e[c]);
+      // first maximum of the rounded probabilities over the foreground classes (strict >, multibox_detection.cc:84-91):
+      // RN(e/sum) is monotone in e, so it is the first class whose quotient equals the quotient of the largest e
+      float emax = e[1];
+      int cbest = 1;
+#pragma unroll
+      for (int c = 2; c < C; ++c)
+        if (e[c] > emax) {
+          emax = e[c];
+          cbest = c;
+        }
+      const float pmax = fdiv(emax, sum);
+      for (int c = 1; c < cbest; ++c)
+        if (e[c] >= fmul(emax, 0.999999f) && fdiv(e[c], sum) == pmax) {
+          cbest = c;
+          break;
+        }
+      sm.fscore[c0 + threadIdx.x] = pmax;
+      sm.fid[c0 + threadIdx.x] = (unsigned short)((pmax < a.threshold) ? 0 : cbest);
     }
+    __syncthreads();
   }
+  // ---- survivors in anchor order ----
+  int nvalid = 0;
+  bool ok[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int q = l0 + v;
+    ok[v] = q < ncand && sm.fid[q] != 0;
+    nvalid += ok[v];
+  }
+  int total;
+  int pos = block_scan_excl(nvalid, scan_smem, &total);
+  if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
+  float sc[2];
+  unsigned short ci[2], cj[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+    if (ok[v]) {
+      sc[v] = sm.fscore[l0 + v];
+      ci[v] = sm.fid[l0 + v];
+      cj[v] = sm.cand[l0 + v];
+    }
+  __syncthreads();  // sm.score is about to change meaning (approximate per anchor -> exact per survivor)
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+    if (ok[v]) {
+      sm.score[pos] = sc[v];
+      sm.idx[pos] = cj[v];
+      sm.id[pos] = ci[v];
+      ++pos;
+    }
+  finish_tile<NFG, kHeadThreads, kHeadTile / kHeadThreads, kV2>(a, sm, b, t, t * kHeadTile, total);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -2458,18 +2729,85 @@ extern "C" size_t dspmb_detection_workspace_bytes(int B, int A, int C) {
   return need;
 }
 
+static int detection_run(const HeadsArgs *heads, const float *cls_prob, const float *loc_pred, const float *anchors,
+                         float *out, int B, int A, int C, float threshold, int clip, const float *variances,
+                         float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
+                         size_t workspace_bytes, void *stream_);
+
 extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const float *anchors, float *out,
                                    int B, int A, int C, float threshold, int clip, const float *variances,
                                    float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out,
                                    void *workspace, size_t workspace_bytes, void *stream_) {
+  DSPMB_REQUIRE(cls_prob && loc_pred, "MultiBoxDetection: NULL tensor");
+  return detection_run(nullptr, cls_prob, loc_pred, anchors, out, B, A, C, threshold, clip, variances, nms_threshold,
+                       force_suppress, nms_topk, valid_count_out, workspace, workspace_bytes, stream_);
+}
+
+// Tile table of the head-fed stream kernel: whole cells per tile, scale by scale.
+static int heads_describe(const float *const *cls_heads, const float *const *loc_heads, const int *head_hw,
+                          const int *head_na, int nscales, int A, HeadsArgs *h) {
+  DSPMB_REQUIRE(nscales >= 1 && nscales <= kMaxScales, "MultiBoxDetection (heads): 1..%d scales supported (got %d)", kMaxScales,
+                nscales);
+  DSPMB_REQUIRE(cls_heads && loc_heads && head_hw && head_na, "MultiBoxDetection (heads): NULL table");
+  memset(h, 0, sizeof(*h));
+  h->nscales = nscales;
+  int tiles = 0, anchors = 0;
+  for (int k = 0; k < nscales; ++k) {
+    const int hw = head_hw[2 * k] * head_hw[2 * k + 1], na = head_na[k];
+    DSPMB_REQUIRE(hw > 0 && na > 0 && na <= kHeadTile, "MultiBoxDetection (heads): bad scale %d (H*W=%d, anchors/cell=%d)", k, hw, na);
+    DSPMB_REQUIRE(cls_heads[k] && loc_heads[k], "MultiBoxDetection (heads): NULL head %d", k);
+    h->cls[k] = cls_heads[k];
+    h->loc[k] = loc_heads[k];
+    h->hw[k] = hw;
+    h->na[k] = na;
+    h->cpt[k] = kHeadTile / na;
+    h->tile_off[k] = tiles;
+    h->anchor_off[k] = anchors;
+    tiles += ceil_div(hw, h->cpt[k]);
+    anchors += hw * na;
+  }
+  h->tile_off[nscales] = tiles;
+  DSPMB_REQUIRE(anchors == A, "MultiBoxDetection (heads): the heads hold %d anchors, the anchor tensor %d", anchors, A);
+  return DSPMB_OK;
+}
+
+extern "C" size_t dspmb_detection_heads_workspace_bytes(int B, int A, int C, const int *head_hw, const int *head_na,
+                                                        int nscales) {
+  if (B <= 0 || A <= 0 || C <= 0 || !head_hw || !head_na || nscales < 1 || nscales > kMaxScales) return 0;
+  int tiles = 0;
+  for (int k = 0; k < nscales; ++k) {
+    if (head_na[k] <= 0 || head_na[k] > kHeadTile) return 0;
+    tiles += ceil_div(head_hw[2 * k] * head_hw[2 * k + 1], kHeadTile / head_na[k]);
+  }
+  return carve(nullptr, B, A, C, tiles, (size_t)tiles * kHeadTile).bytes;
+}
+
+extern "C" int dspmb_detection_heads_f32(const float *const *cls_heads, const float *const *loc_heads, const int *head_hw,
+                                         const int *head_na, int nscales, const float *anchors, float *out, int B, int A,
+                                         int C, float threshold, int clip, const float *variances, float nms_threshold,
+                                         int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
+                                         size_t workspace_bytes, void *stream_) {
+  HeadsArgs h;
+  const int rc = heads_describe(cls_heads, loc_heads, head_hw, head_na, nscales, A, &h);
+  if (rc != DSPMB_OK) return rc;
+  DSPMB_REQUIRE(C == 21 || C == 9, "MultiBoxDetection (heads): built for 21 (VOC) and 9 (Cityscapes) classes, got %d", C);
+  return detection_run(&h, nullptr, nullptr, anchors, out, B, A, C, threshold, clip, variances, nms_threshold,
+                       force_suppress, nms_topk, valid_count_out, workspace, workspace_bytes, stream_);
+}
+
+static int detection_run(const HeadsArgs *heads, const float *cls_prob, const float *loc_pred, const float *anchors,
+                         float *out, int B, int A, int C, float threshold, int clip, const float *variances,
+                         float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
+                         size_t workspace_bytes, void *stream_) {
   // Shape CHECKs of MultiBoxDetectionProp::InferShape (multibox_detection-inl.h:149-171).
   DSPMB_REQUIRE(B >= 0 && A > 0 && C > 0, "MultiBoxDetection: bad shape B=%d A=%d C=%d", B, A, C);
-  DSPMB_REQUIRE(cls_prob && loc_pred && anchors && out && variances, "MultiBoxDetection: NULL tensor");
+  DSPMB_REQUIRE(anchors && out && variances, "MultiBoxDetection: NULL tensor");
   DSPMB_REQUIRE(B <= 65535 && C <= 65535, "MultiBoxDetection: batch / classes > 65535 not supported in one call");
   DSPMB_REQUIRE(A < (1 << 24), "MultiBoxDetection: more than 2^24 anchors are not supported");
   DSPMB_REQUIRE(((uintptr_t)anchors & 15) == 0, "MultiBoxDetection: anchors must be 16-byte aligned");
   if (B == 0) return DSPMB_OK;
-  const size_t need = dspmb_detection_workspace_bytes(B, A, C);
+  const int Th = heads ? heads->tile_off[heads->nscales] : 0;
+  const size_t need = heads ? carve(nullptr, B, A, C, Th, (size_t)Th * kHeadTile).bytes : dspmb_detection_workspace_bytes(B, A, C);
   if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
     set_error("MultiBoxDetection: workspace must be 256-byte aligned and >= %zu bytes (got %zu)", need, workspace_bytes);
     return DSPMB_ERR_WORKSPACE;
@@ -2480,8 +2818,10 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
     const void *p[6];
     int i[7];
     float f[6];
+    HeadsArgs h;
   } key;
   memset(&key, 0, sizeof(key));
+  if (heads) key.h = *heads;
   key.p[0] = cls_prob, key.p[1] = loc_pred, key.p[2] = anchors, key.p[3] = out, key.p[4] = valid_count_out, key.p[5] = workspace;
   key.i[0] = B, key.i[1] = A, key.i[2] = C, key.i[3] = clip, key.i[4] = force_suppress, key.i[5] = nms_topk, key.i[6] = nms_debug;
   key.f[0] = threshold, key.f[1] = nms_threshold;
@@ -2497,14 +2837,15 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const bool v2_all = tuning(DSPMB_TUNE_DET_PIPELINE) != 0 && vec4_all && (C == 21 || C == 9) && variant_all == 2 &&
                       !force_suppress && nms_threshold > 0.f && nms_threshold <= 1.f && C - 1 <= kV2ClsPad &&
                       ceil_div(A, 256) <= kV2MaxTiles;
-  const int groups = v2_all ? split_groups(B_all, tuning(DSPMB_TUNE_DET_SPLIT)) : 1;
+  const int groups = (v2_all && !heads) ? split_groups(B_all, tuning(DSPMB_TUNE_DET_SPLIT)) : 1;
   size_t ws_off = 0;
   for (int grp = 0; grp < groups; ++grp) {
   const int b0 = (int)((long long)B_all * grp / groups), B = (int)((long long)B_all * (grp + 1) / groups) - b0;
-  const float *cls_prob = cls_prob_all + (size_t)b0 * C * A, *loc_pred = loc_pred_all + (size_t)b0 * A * 5;
+  const float *cls_prob = heads ? nullptr : cls_prob_all + (size_t)b0 * C * A;
+  const float *loc_pred = heads ? nullptr : loc_pred_all + (size_t)b0 * A * 5;
   float *out = out_all + (size_t)b0 * A * 7;
   int32_t *valid_count_out = valid_all ? valid_all + b0 : nullptr;
-  DetWorkspace w = carve((char *)workspace + ws_off, B, A, C);
+  DetWorkspace w = carve((char *)workspace + ws_off, B, A, C, Th, (size_t)Th * kHeadTile);
   ws_off += align_up(w.bytes, 256);
   // the stream kernels of all groups run back to back on the main branch; everything after a group's stream kernel
   // goes to a side branch (alternating between the two) when the call is being captured into the library's graph
@@ -2527,13 +2868,17 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const int bulk_threads = variant == 3 ? 256 : 128, bulk_vec = variant == 5 ? 4 : 2;
   const bool bulk_variant = bulk_ok && (variant == 2 || variant == 3 || variant == 5);
   const bool reg_variant = vec4 && !bulk_variant && variant > 2 && (C == 21 || C == 9);
-  const int tile = stages ? kPipeTile : (bulk_variant ? bulk_threads * bulk_vec : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1)));
-  const int T = ceil_div(A, tile);
-  const int Apad = ((A + 3) & ~3) + 4 * kStreamThreads;
+  const int tile = heads ? kHeadTile
+                         : (stages ? kPipeTile
+                                   : (bulk_variant ? bulk_threads * bulk_vec
+                                                   : (reg_variant ? kRegThreads * 4 : kStreamThreads * (vec4 ? 4 : 1))));
+  const int T = heads ? Th : ceil_div(A, tile);
+  const int Adef = ((A + 3) & ~3) + 4 * kStreamThreads;
+  const int Apad = heads && Th * kHeadTile > Adef ? Th * kHeadTile : Adef;
   const bool nms_on = nms_threshold > 0.f && nms_threshold <= 1.f && (C > 1 || force_suppress);
-  // fork/join pipeline: per-class segments, the default stream kernel, tile tables that fit in shared memory
-  const bool v2 = tuning(DSPMB_TUNE_DET_PIPELINE) != 0 && bulk_variant && variant == 2 && !stages && !force_suppress &&
-                  nms_on && T <= kV2MaxTiles && C - 1 <= kV2ClsPad;
+  // fork/join pipeline: per-class segments, the default (or the head-fed) stream kernel, tile tables that fit in shared memory
+  const bool v2 = tuning(DSPMB_TUNE_DET_PIPELINE) != 0 && (heads || (bulk_variant && variant == 2 && !stages)) &&
+                  !force_suppress && nms_on && T <= kV2MaxTiles && C - 1 <= kV2ClsPad;
 
   StreamArgs sa;
   sa.cls_prob = cls_prob;
@@ -2564,6 +2909,20 @@ extern "C" int dspmb_detection_f32(const float *cls_prob, const float *loc_pred,
   const int phases = tuning(DSPMB_TUNE_PHASES);
   if (!(phases & 1)) {
     // stream phase skipped (per-phase timing: the workspace still holds the previous call's records)
+  } else if (heads) {
+    dim3 gridh(T, B);
+    ProfileScope _p(kSlotDetStream, stream);
+#define DSPMB_LAUNCH_HEADS(CC, V2)                                                                    \
+  do {                                                                                                \
+    constexpr size_t kBytes = sizeof(HeadSmem<CC>);                                                   \
+    DSPMB_ENSURE_DYN_SMEM((det_stream_heads_kernel<CC, V2>), kBytes);                                 \
+    det_stream_heads_kernel<CC, V2><<<gridh, kHeadThreads, kBytes, stream>>>(sa, *heads);             \
+  } while (0)
+    if (C == 21 && v2) DSPMB_LAUNCH_HEADS(21, true);
+    else if (C == 21) DSPMB_LAUNCH_HEADS(21, false);
+    else if (v2) DSPMB_LAUNCH_HEADS(9, true);
+    else DSPMB_LAUNCH_HEADS(9, false);
+#undef DSPMB_LAUNCH_HEADS
   } else if (stages) {
     PipeArgs pa;
     pa.s = sa;

@@ -19,7 +19,8 @@ import torch
 from . import _lib
 from ._lib import DspmbError  # noqa: F401  (re-export)
 
-__all__ = ["MultiBoxPrior", "MultiBoxTarget", "MultiBoxDetection", "multibox_prior_concat", "DspmbError"]
+__all__ = ["MultiBoxPrior", "MultiBoxTarget", "MultiBoxDetection", "MultiBoxDetectionFromHeads", "multibox_prior_concat",
+           "DspmbError"]
 
 _workspaces = {}
 
@@ -229,3 +230,52 @@ def MultiBoxDetection(cls_prob, loc_pred, anchor, clip=True, threshold=0.01, bac
     outs = [out] + ([valid] if return_valid_count else [])
     outs = _back(outs, to_host)
     return outs if return_valid_count else outs[0]
+
+
+def MultiBoxDetectionFromHeads(cls_heads, loc_heads, anchor, num_classes, clip=True, threshold=0.01, background_id=0,
+                               nms_threshold=0.5, force_suppress=False, variances=(0.1, 0.1, 0.2, 0.2), nms_topk=-1,
+                               return_valid_count=False):
+    """The inference tail of the SSD graph in one operator -- what
+    symbol/symbol_builder.py:156-165 builds from multibox_layer's per-scale heads (symbol/common.py:399-432):
+    transpose / Flatten / Concat / Reshape / transpose, ``SoftmaxActivation(mode='channel')`` and MultiBoxDetection.
+
+    cls_heads[k] (B, na_k*C, H_k, W_k) and loc_heads[k] (B, na_k*5, H_k, W_k) are the conv outputs (CUDA tensors, NCHW),
+    anchor (1, A, 4) the concatenated MultiBoxPrior boxes.  Returns (B, A, 7) like MultiBoxDetection; the (B, C, A)
+    probability tensor is never materialised.  Built for C = 21 and C = 9."""
+    if len(cls_heads) != len(loc_heads) or not cls_heads:
+        raise DspmbError(_lib.ERR_BAD_ARG, "MultiBoxDetectionFromHeads: one class head and one loc head per scale")
+    C = int(num_classes)
+    cls_heads = [h.contiguous() for h in cls_heads]
+    loc_heads = [h.contiguous() for h in loc_heads]
+    dev = cls_heads[0].device
+    B = cls_heads[0].shape[0]
+    hw, na = [], []
+    for ch, lh in zip(cls_heads, loc_heads):
+        if not (ch.is_cuda and lh.is_cuda and ch.dtype == torch.float32 and lh.dtype == torch.float32 and ch.dim() == 4
+                and lh.dim() == 4):
+            raise DspmbError(_lib.ERR_BAD_ARG, "MultiBoxDetectionFromHeads: heads must be 4-D float32 CUDA tensors")
+        n = ch.shape[1] // C
+        if ch.shape[1] != n * C or lh.shape[1] != n * 5 or ch.shape[0] != B or lh.shape[0] != B or ch.shape[2:] != lh.shape[2:]:
+            raise DspmbError(_lib.ERR_BAD_ARG, "MultiBoxDetectionFromHeads: head shapes do not match (B, na*C, H, W) / (B, na*5, H, W)")
+        hw += [int(ch.shape[2]), int(ch.shape[3])]
+        na.append(int(n))
+    anchor, _ = _as_device(anchor, "anchor")
+    A = anchor.shape[1]
+    var = _tuple(variances, "variances")
+    if len(var) != 4:
+        raise DspmbError(_lib.ERR_BAD_ARG, "MultiBoxDetection: variance size must be 4")
+    out = torch.empty((B, A, 7), dtype=torch.float32, device=dev)
+    valid = torch.empty((B,), dtype=torch.int32, device=dev) if return_valid_count else None
+    L_ = _lib.lib()
+    k = len(cls_heads)
+    cp = (ctypes.c_void_p * k)(*[h.data_ptr() for h in cls_heads])
+    lp = (ctypes.c_void_p * k)(*[h.data_ptr() for h in loc_heads])
+    hw_a, na_a = _lib.int_array(hw), _lib.int_array(na)
+    with torch.cuda.device(dev):
+        nbytes = L_.dspmb_detection_heads_workspace_bytes(B, A, C, hw_a, na_a, k)
+        ws = _workspace("detection_heads", max(int(nbytes), 256), dev)
+        _lib.check(L_.dspmb_detection_heads_f32(cp, lp, hw_a, na_a, k, _ptr(anchor), _ptr(out), B, A, C, threshold,
+                                                int(bool(clip)), _lib.float_array(var), nms_threshold,
+                                                int(bool(force_suppress)), int(nms_topk), _ptr(valid), _ptr(ws),
+                                                ws.numel(), _stream()))
+    return (out, valid) if return_valid_count else out

@@ -50,6 +50,49 @@ class DetectionPlan:
         return out
 
 
+class DetectionHeadsPlan:
+    """MultiBoxDetectionFromHeads (dspnet_b200.ops) for fixed shapes: the pointer tables of the per-scale heads are
+    built once per set of head tensors (``bind``), a run is one C-ABI call."""
+
+    def __init__(self, B, A, C, head_shapes, device, clip=True, threshold=0.01, nms_threshold=0.5, force_suppress=False,
+                 variances=(0.1, 0.1, 0.2, 0.2), nms_topk=-1):
+        """head_shapes: [(H, W, anchors_per_cell), ...] per scale."""
+        self.B, self.A, self.C, self.device = B, A, C, torch.device(device)
+        self._index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.lib = _lib.lib()
+        self.k = len(head_shapes)
+        self._hw = _lib.int_array([v for (h, w, _) in head_shapes for v in (h, w)])
+        self._na = _lib.int_array([n for (_, _, n) in head_shapes])
+        with torch.cuda.device(device):
+            nbytes = self.lib.dspmb_detection_heads_workspace_bytes(B, A, C, self._hw, self._na, self.k)
+            self.ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        self._var = _lib.float_array(variances)
+        self._tail = (B, A, C, float(threshold), int(bool(clip)), self._var, float(nms_threshold),
+                      int(bool(force_suppress)), int(nms_topk), None, _ptr(self.ws), self.ws.numel())
+        self.launches_per_run = None
+
+    def new_output(self):
+        return torch.empty((self.B, self.A, 7), dtype=torch.float32, device=self.device)
+
+    def bind(self, cls_heads, loc_heads):
+        """Pointer tables for one set of head tensors (keep the tensors alive while the binding is used)."""
+        return ((ctypes.c_void_p * self.k)(*[h.data_ptr() for h in cls_heads]),
+                (ctypes.c_void_p * self.k)(*[h.data_ptr() for h in loc_heads]))
+
+    def run(self, binding, anchor, out, stream=None):
+        s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if torch.cuda.current_device() != self._index:
+            with torch.cuda.device(self.device):
+                return self.run(binding, anchor, out, s)
+        rc = self.lib.dspmb_detection_heads_f32(binding[0], binding[1], self._hw, self._na, self.k, anchor.data_ptr(),
+                                                out.data_ptr(), *self._tail, s)
+        if rc:
+            _lib.check(rc)
+        if self.launches_per_run is None:
+            self.launches_per_run = self.lib.dspmb_last_launch_count()
+        return out
+
+
 class TargetPlan:
     """MultiBoxTarget (operator/multibox_target-inl.h:59-80 parameters) for fixed shapes."""
 

@@ -93,3 +93,39 @@ def nms_boxes(seed, n, with_class=False, num_classes=20):
     if with_class:
         cols.append(r.integers(0, num_classes, n))
     return np.stack(cols, axis=1).astype(np.float32)
+
+
+def heads_from_logits(preset, logits, loc):
+    """Per-scale conv outputs that multibox_layer (symbol/common.py:399-432) would turn into the given
+    ``logits`` (B, C, A) and ``loc`` (B, A*5): class heads (B, na*C, H, W) and loc heads (B, na*5, H, W), NCHW with
+    channel = anchor_in_cell * C + class.  (The inverse of the transpose / Flatten / Concat / Reshape / transpose
+    chain, so that head-fed and tensor-fed runs see the same numbers.)"""
+    B, C, A = logits.shape
+    loc = loc.reshape(B, A, 5)
+    cls_heads, loc_heads, a0 = [], [], 0
+    for fm in preset.maps:
+        na = len(fm.sizes) + len(fm.ratios) - 1
+        n = fm.height * fm.width * na
+        blk = logits[:, :, a0:a0 + n].reshape(B, C, fm.height, fm.width, na)          # (B, C, H, W, na)
+        cls_heads.append(np.ascontiguousarray(np.transpose(blk, (0, 4, 1, 2, 3)).reshape(B, na * C, fm.height, fm.width)))
+        lb = loc[:, a0:a0 + n].reshape(B, fm.height, fm.width, na, 5)                    # (B, H, W, na, 5)
+        loc_heads.append(np.ascontiguousarray(np.transpose(lb, (0, 3, 4, 1, 2)).reshape(B, na * 5, fm.height, fm.width)))
+        a0 += n
+    assert a0 == A
+    return cls_heads, loc_heads
+
+
+def det_logits(config_id, batch, num_classes, num_anchors, first_image=0):
+    """(B, C, A) raw logits with the same mixture as cls_prob() (before its softmax): background boosted by N(8,1) on
+    97 % of the anchors, one foreground logit boosted by N(6,2) on the rest."""
+    out = np.empty((batch, num_classes, num_anchors), np.float32)
+    for b in range(batch):
+        r = _rng(config_id + 2, first_image + b)
+        x = r.standard_normal((num_classes, num_anchors), dtype=np.float32)
+        bg = r.random(num_anchors) < 0.97
+        x[0] += np.where(bg, r.normal(8.0, 1.0, num_anchors), 0).astype(np.float32)
+        fg_cls = r.integers(1, num_classes, num_anchors)
+        boost = np.where(bg, 0, r.normal(6.0, 2.0, num_anchors)).astype(np.float32)
+        x[fg_cls, np.arange(num_anchors)] += boost
+        out[b] = x
+    return out

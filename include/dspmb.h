@@ -103,6 +103,37 @@ int dspmb_detection_f32(const float *cls_prob, const float *loc_pred, const floa
                         int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
                         size_t workspace_bytes, void *stream);
 
+/* MultiBoxDetection fed by the per-scale prediction heads -- replaces, in ONE operator,
+ * the chain of symbol/common.py:399-412,424-432 and symbol/symbol_builder.py:161-165:
+ *   per scale  transpose(0,2,3,1) -> Flatten, then Concat -> Reshape(0,-1,C) -> transpose(0,2,1)
+ *   -> SoftmaxActivation(mode='channel') -> MultiBoxDetection.
+ * cls_heads[k] (B, na_k*C, H_k, W_k), loc_heads[k] (B, na_k*5, H_k, W_k): device pointers to the conv outputs (NCHW,
+ * channel = anchor_in_cell * C + class); head_hw = {H_0, W_0, H_1, W_1, ...}; head_na[k] = anchors per cell.  The class
+ * tensor (B,C,A) is never written: the stream kernel reads the logits, evaluates the channel softmax (bit-exact glibc
+ * expf for every anchor that can reach the threshold) and continues as dspmb_detection_f32.  C = 21 or 9; at most 8
+ * scales; anchors as in dspmb_detection_f32 (scale-major, cell-major, then anchor-in-cell: the order
+ * dspmb_prior_multi_f32 produces). */
+size_t dspmb_detection_heads_workspace_bytes(int B, int A, int C, const int *head_hw, const int *head_na, int nscales);
+int dspmb_detection_heads_f32(const float *const *cls_heads, const float *const *loc_heads, const int *head_hw,
+                              const int *head_na, int nscales, const float *anchors, float *out, int B, int A, int C,
+                              float threshold, int clip, const float *variances, float nms_threshold,
+                              int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
+                              size_t workspace_bytes, void *stream);
+
+/* Forward of the training graph behind MultiBoxTarget and the MultiBoxMetric statistics
+ * -- replaces symbol/symbol_builder.py:82-88 (SoftmaxOutput(ignore_label=-1, use_ignore, multi_output,
+ * normalization='valid') forward = channel softmax; MakeLoss(smooth_l1(loc_mask * (loc_preds - loc_target), scalar=1)))
+ * and the reductions of train/metric.py:27-46, in one pass over the tensors:
+ *   cls_prob (B,C,A) and loc_loss (B,A*5): optional outputs (NULL: not written);
+ *   stats (B,4) double, device: [#(cls_target >= 0), sum -log(prob[label] + eps), sum(loc_loss), #(loc_loss > 0)]
+ *   (the last one is the count MakeLoss(normalization='valid') divides its gradient by).
+ * Softmax as in multibox_target.cc:220-231 (MXNet's kernel is not part of the reference tree), bit-exact expf/logf. */
+size_t dspmb_multibox_loss_workspace_bytes(int B, int A);
+int dspmb_multibox_loss_f32(const float *cls_preds, const float *loc_preds, const float *loc_target,
+                            const float *loc_mask, const float *cls_target, float *cls_prob, float *loc_loss,
+                            double *stats, int B, int A, int C, float eps, void *workspace, size_t workspace_bytes,
+                            void *stream);
+
 /* Ordered compaction of the surviving detections: for every image the rows of `out` (B,A,7) with id >= 0, in
  * row order, at most K of them, into dst (B,K,7) (padded with -1) and their number into counts (B) -- the
  * `det[:,0] >= 0` filter of detect/multitask_detector.py:268-271 / multi_solver.py:419-432, on the device.

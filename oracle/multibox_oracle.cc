@@ -520,6 +520,29 @@ int oracle_cpu_nms(const float *dets, int ndets, int dim, const int64_t *order, 
   return nkeep;
 }
 
+// Channel softmax of the class head, SURVEY.md section 8f row f1: `SoftmaxActivation(mode='channel')`
+// (symbol/symbol_builder.py:161-162) and the forward of `SoftmaxOutput(multi_output=True)` (:82-84) on cls_preds
+// (B, C, A).  The arithmetic lives in MXNet, which is not part of the reference tree, so this restates the softmax the
+// reference itself spells out for the same tensor in multibox_target.cc:220-231 -- running maximum over the classes,
+// fp32 sum of expf(x - max) in class order, one division per value -- and declares it the pin ("parity unpinned"
+// against MXNet's own kernel, which evaluates the same three steps per position).
+void oracle_softmax_channel(const float *x, float *out, int B, int C, int A) {
+  for (int b = 0; b < B; ++b) {
+    const float *xb = x + (size_t)b * C * A;
+    float *ob = out + (size_t)b * C * A;
+    for (int a = 0; a < A; ++a) {
+      float mx = xb[a];
+      for (int c = 1; c < C; ++c) {
+        float t = xb[(size_t)c * A + a];
+        if (t > mx) mx = t;
+      }
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum += expf(xb[(size_t)c * A + a] - mx);
+      for (int c = 0; c < C; ++c) ob[(size_t)c * A + a] = expf(xb[(size_t)c * A + a] - mx) / sum;
+    }
+  }
+}
+
 // libm probes used by tests to check the CUDA library's glibc-compatible expf/logf.
 float oracle_expf(float x) { return expf(x); }
 float oracle_logf(float x) { return logf(x); }

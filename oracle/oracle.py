@@ -66,6 +66,8 @@ def lib():
         dp = ctypes.POINTER(ctypes.c_double)
         L.oracle_bbox_overlaps.argtypes = [dp, ctypes.c_int, dp, ctypes.c_int, dp]
         L.oracle_bbox_overlaps.restype = None
+        L.oracle_softmax_channel.argtypes = [fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oracle_softmax_channel.restype = None
         L.oracle_expf_array.argtypes = [fp, fp, ctypes.c_long]
         L.oracle_logf_array.argtypes = [fp, fp, ctypes.c_long]
         _lib = L
@@ -158,6 +160,67 @@ def multibox_detection(cls_prob, loc_pred, anchor, clip=True, threshold=0.01, ba
     if rc:
         raise OracleError(rc)
     return (out, valid) if return_valid else out
+
+
+def head_layout(cls_heads, loc_heads, num_classes):
+    """The layout shuffles of multibox_layer (symbol/common.py:399-432), numpy only: per scale the conv outputs
+    (B, na*C, H, W) / (B, na*5, H, W) are transposed to NHWC and flattened, the scales concatenated, the class tensor
+    reshaped to (B, A, C) and transposed to (B, C, A).  Returns (cls_preds (B, C, A), loc_preds (B, A*5))."""
+    cls = [np.ascontiguousarray(np.transpose(_f32(h), (0, 2, 3, 1))).reshape(h.shape[0], -1) for h in cls_heads]
+    loc = [np.ascontiguousarray(np.transpose(_f32(h), (0, 2, 3, 1))).reshape(h.shape[0], -1) for h in loc_heads]
+    cls_preds = np.concatenate(cls, axis=1)
+    cls_preds = cls_preds.reshape(cls_preds.shape[0], -1, num_classes)
+    cls_preds = np.ascontiguousarray(np.transpose(cls_preds, (0, 2, 1)))
+    return cls_preds, np.ascontiguousarray(np.concatenate(loc, axis=1))
+
+
+def softmax_channel(cls_preds):
+    """SoftmaxActivation(mode='channel') / SoftmaxOutput forward on (B, C, A): the softmax of multibox_target.cc:220-231
+    per position (see oracle_softmax_channel; MXNet's own kernel is not in the reference tree)."""
+    x = _f32(cls_preds)
+    B, C, A = x.shape
+    out = np.empty_like(x)
+    lib().oracle_softmax_channel(_p(x), _p(out), B, C, A)
+    return out
+
+
+def multibox_detection_from_heads(cls_heads, loc_heads, anchor, num_classes, **kw):
+    """symbol/symbol_builder.py:156-165: multibox_layer -> SoftmaxActivation(channel) -> MultiBoxDetection."""
+    cls_preds, loc_preds = head_layout(cls_heads, loc_heads, num_classes)
+    return multibox_detection(softmax_channel(cls_preds), loc_preds, anchor, **kw)
+
+
+def smooth_l1(x, sigma=1.0):
+    """mx.symbol.smooth_l1(scalar=sigma), element-wise in fp32: 0.5 (sigma x)^2 if |x| < 1/sigma^2 else |x| - 0.5/sigma^2
+    (MXNet mshadow_op::smooth_l1_loss; documented formula, MXNet itself is not in the reference tree)."""
+    x = _f32(x)
+    s2 = np.float32(sigma) * np.float32(sigma)
+    ax = np.abs(x)
+    quad = np.float32(0.5) * (x * x) * s2
+    lin = ax - np.float32(0.5) / s2
+    return np.where(ax < np.float32(1.0) / s2, quad, lin).astype(np.float32)
+
+
+def multibox_training_outputs(cls_preds, loc_preds, loc_target, loc_mask, cls_target, eps=1e-8):
+    """Forward of the training graph after MultiBoxTarget (symbol/symbol_builder.py:82-88) and the statistics of
+    MultiBoxMetric.update (train/metric.py:27-46):
+        cls_prob  = SoftmaxOutput(cls_preds, cls_target, ignore_label=-1, multi_output)   -> channel softmax
+        loc_loss  = MakeLoss(smooth_l1(loc_mask * (loc_preds - loc_target), scalar=1))    -> element-wise
+        valid     = #(cls_target >= 0);  ce = sum -log(prob[label] + eps) over those;  sl1 = sum(loc_loss)
+    Sums are accumulated in float64 here (numpy's float32 pairwise order is an implementation detail of numpy)."""
+    prob = softmax_channel(cls_preds)
+    diff = _f32(loc_mask) * (_f32(loc_preds) - _f32(loc_target))
+    loc_loss = smooth_l1(diff, 1.0)
+    label = _f32(cls_target)
+    B, C, A = prob.shape
+    stats = np.zeros((B, 3), np.float64)
+    for b in range(B):
+        m = np.nonzero(label[b] >= 0)[0]
+        p = prob[b, label[b, m].astype(np.int64), m]
+        stats[b, 0] = m.size
+        stats[b, 1] = (-np.log(p + np.float32(eps))).astype(np.float64).sum()
+        stats[b, 2] = loc_loss[b].astype(np.float64).sum()
+    return prob, loc_loss, stats
 
 
 def cpu_nms(dets, thresh, mode="cpu"):
