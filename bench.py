@@ -12,6 +12,10 @@ Workloads (one per BASELINE.json config; the default is configs[1], the one the 
     ssd300      SSD-300 prior + target + detection, batch 1                                     configs[0]
     dspnet_cs   DSPNet Cityscapes 1024x512 head, prior + target + detection, 16 images split    configs[3]
     nms         standalone NMS sweep 1k-200k boxes, force_suppress on / off                     configs[4]
+    detection_heads  SURVEY 8f row f1: SSD-512 detection fed by the per-scale conv heads (layout shuffles + channel
+                     softmax fused into the stream kernel), 32 images per GPU
+    train_tail       SURVEY 8f row f2: SSD-512 MultiBoxTarget + training-graph forward (softmax, masked smooth-L1) +
+                     MultiBoxMetric statistics, 64 images split over the GPUs
 
 A step is one pass of the workload's operators over one batch of synthetic head tensors.  Inputs rotate over resident
 copies whose total footprint exceeds the 126 MB L2 (or, for the small configs, L2 is flushed between event-timed
@@ -53,6 +57,12 @@ WORKLOADS = {
                       name="dspnet_cityscapes_1024x512_prior_target_detection_batch16"),
     "nms": dict(metric="nms_sweep_boxes_per_s", name="standalone_nms_sweep_1k_200k_iou045_force_on_off",
                 scaling="weak"),
+    "detection_heads": dict(preset="ssd512", batch=32, scaling="weak", ops=("detection_heads",), config_id=2, max_gt=8,
+                            metric="ssd512_multibox_detection_from_heads_images_per_s",
+                            name="ssd512_voc21_layout_softmax_multibox_detection_nms_batch32"),
+    "train_tail": dict(preset="ssd512", batch=64, scaling="strong", ops=("target", "loss"), config_id=2, max_gt=8,
+                       metric="ssd512_multibox_target_loss_metric_images_per_s",
+                       name="ssd512_voc21_multibox_target_softmax_smoothl1_metric_batch64"),
 }
 # the names older scripts use for the default workload
 PRESET, BATCH = WORKLOADS["detection"]["preset"], WORKLOADS["detection"]["batch"]
@@ -271,6 +281,22 @@ def run_reference(args):
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
+    if args.workload in ("detection_heads", "train_tail"):
+        B = w["batch"]
+        inputs = extra_inputs(args.workload, 0, B)
+        anchors = oracle_anchors(w["preset"])
+        value, done, dt = extra_cpu_time(args.workload, inputs, anchors, threads, args.steps, budget_s=120.0)
+        line = {"impl": "reference", "metric": w["metric"], "value": value, "unit": "images/s", "n_gpus": args.gpus,
+                "steps": done, "warmup": args.warmup, "ms_per_step": 1e3 * dt / done, "higher_is_better": True,
+                "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "preset": w["preset"], "batch_per_gpu": B, "anchors": inputs["A"],
+                           "classes": inputs["C"]},
+                "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                                 "sample": "%d steps x one B=%d batch, image slices over %d host threads" % (done, B, threads)},
+                "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
     # weak workloads: one GPU's batch (what one step of the GPU arm processes per GPU); strong: the whole batch
     B = w["batch"]
     inputs, _ = make_inputs(0, B, args.workload)
@@ -338,6 +364,263 @@ class E2EPipeline:
                 p.copy_(o, non_blocking=True)
             self.ev_out[k].record(self.s_out)
         self.n = i + 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8f rows f1 / f2 (the callers either side of the hot path)
+# ---------------------------------------------------------------------------------------------------------------
+def extra_inputs(workload, first_image, B):
+    from dspnet_b200 import presets, synth
+    w = WORKLOADS[workload]
+    p = presets.PRESETS[w["preset"]]
+    A, C = presets.num_anchors(p), p.num_classes
+    d = dict(A=A, C=C, L=p.label_slots, B=B, preset=w["preset"])
+    if workload == "detection_heads":
+        d["logits"] = synth.det_logits(w["config_id"], B, C, A, first_image=first_image)
+        d["loc"] = synth.loc_pred(w["config_id"], B, A, first_image=first_image)
+        d["cls_heads"], d["loc_heads"] = synth.heads_from_logits(p, d["logits"], d["loc"])
+        d["shapes"] = [(fm.height, fm.width, len(fm.sizes) + len(fm.ratios) - 1) for fm in p.maps]
+    else:
+        d["lab"] = synth.labels(w["config_id"], B, p.label_slots, C, max_gt=w["max_gt"], first_image=first_image)
+        d["logits"] = synth.cls_preds(w["config_id"], B, C, A, first_image=first_image)
+        d["loc"] = synth.loc_pred(w["config_id"], B, A, first_image=first_image)
+    return d
+
+
+def extra_cpu_pass(workload, inputs, anchors, threads, collect=False):
+    """The reference graph of the row on the host, image slices over the host threads: f1 = layout shuffles (numpy) ->
+    channel softmax -> MultiBoxDetection; f2 = MultiBoxTarget -> softmax / smooth-L1 / metric sums."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    M, _ = cpu_backend()
+    B = inputs["B"]
+    n = max(1, min(threads, B))
+    bounds = [(i * B // n, (i + 1) * B // n) for i in range(n)]
+
+    def run(be):
+        b, e = be
+        if workload == "detection_heads":
+            cp, lp = O.head_layout([h[b:e] for h in inputs["cls_heads"]], [h[b:e] for h in inputs["loc_heads"]], inputs["C"])
+            return M.multibox_detection(O.softmax_channel(cp), lp, anchors, **DET_PARAMS)
+        tgt = M.multibox_target(anchors, inputs["lab"][b:e], inputs["logits"][b:e], **TGT_PARAMS)
+        return tgt, O.multibox_training_outputs(inputs["logits"][b:e], inputs["loc"][b:e], *tgt)
+    if n == 1:
+        parts = [run(bounds[0])]
+    else:
+        with ThreadPoolExecutor(n) as ex:
+            parts = list(ex.map(run, bounds))
+    return parts if collect else None
+
+
+def extra_cpu_time(workload, inputs, anchors, threads, steps, budget_s):
+    extra_cpu_pass(workload, inputs, anchors, threads)
+    done, t0 = 0, time.perf_counter()
+    while done < steps:
+        extra_cpu_pass(workload, inputs, anchors, threads)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return inputs["B"] * done / dt, done, dt
+
+
+def run_extra(args, torch, dist, dev, rank, world):
+    import ctypes
+    import numpy as np
+    from dspnet_b200 import _lib
+    from dspnet_b200.plan import DetectionHeadsPlan, TargetPlan
+    from dspnet_b200.symbol import multibox_anchors
+    from dspnet_b200.loss import multibox_training_outputs
+    wl = args.workload
+    w = WORKLOADS[wl]
+    lib = _lib.lib()
+    Bg = w["batch"] if w["scaling"] == "weak" else max(1, w["batch"] // world)
+    inputs = extra_inputs(wl, rank * Bg, Bg)
+    A, C, L = inputs["A"], inputs["C"], inputs["L"]
+    anchors = multibox_anchors(w["preset"], device=dev)
+    rotate = 4
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    if wl == "detection_heads":
+        plan = DetectionHeadsPlan(Bg, A, C, inputs["shapes"], dev, **DET_PARAMS)
+        sets = []
+        for _ in range(rotate):
+            ch, lh = [t(h) for h in inputs["cls_heads"]], [t(h) for h in inputs["loc_heads"]]
+            sets.append((ch, lh, plan.bind(ch, lh), plan.new_output()))
+        abytes = 4 * Bg * C * A + 20 * Bg * A + 16 * A + 28 * Bg * A  # every class row is read now (softmax), 28 B/anchor out
+        avoided = 2 * 4 * Bg * C * A                                   # cls_prob written by the softmax, read by the operator
+        avoided_shuffles = 3 * 2 * 4 * Bg * C * A                      # transpose, concat, transpose of the class tensor
+
+        def step(i):
+            s = sets[i % rotate]
+            plan.run(s[2], anchors, s[3])
+        launches = lambda: plan.launches_per_run
+        names = [(1, "det_stream_heads_kernel"), (2, "det_sort_kernel"), (4, "det_pair_kernel")]
+    else:
+        tplan = TargetPlan(Bg, A, L, C, dev, **TGT_PARAMS)
+        lab_d = t(inputs["lab"])
+        sets = [(t(inputs["logits"]), t(inputs["loc"]), tplan.new_outputs(), tplan.new_stats()) for _ in range(rotate)]
+        ws = torch.empty(max(int(lib.dspmb_multibox_loss_workspace_bytes(Bg, A)), 256), dtype=torch.uint8, device=dev)
+        stats = [torch.empty((Bg, 4), dtype=torch.float64, device=dev) for _ in range(rotate)]
+        p = lambda x: ctypes.c_void_p(x.data_ptr())
+        # statistics-only pass behind the target: three loc tensors + labels are read (64 B / anchor), the logits only
+        # for the labelled anchors (a few percent; not counted), 32 B of sums per image are written
+        loss_bytes = 64 * Bg * A + 32 * Bg
+        abytes = tgt_algorithmic_bytes(Bg, A, C, L) + loss_bytes
+        # the reference graph writes cls_prob and loc_loss and the metric reads them back (plus SoftmaxOutput's own read
+        # of cls_preds, which the statistics kernel skips for unlabelled anchors)
+        avoided = 2 * 4 * Bg * C * A + 2 * 20 * Bg * A + 4 * Bg * C * A
+
+        def step(i):
+            s = sets[i % rotate]
+            tplan.run(anchors, lab_d, s[0], s[2], stats=s[3])
+            rc = lib.dspmb_multibox_loss_f32(p(s[0]), p(s[1]), p(s[2][0]), p(s[2][1]), p(s[2][2]), None, None,
+                                             p(stats[i % rotate]), Bg, A, C, ctypes.c_float(1e-8), p(ws), ws.numel(),
+                                             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if rc:
+                _lib.check(rc)
+        launches = lambda: (tplan.launches_per_run or 0) + 2
+        names = None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index) if rank == 0 else None
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    soak = 0 if args.no_soak else 4000
+    for i in range(soak):
+        step(i)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    block_ms = []
+    for _ in range(1 if args.no_soak else 9):
+        barrier()
+        ev0.record()
+        for k in range(args.steps):
+            step(k)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        block_ms.append(ms)
+    ms = sorted(block_ms)[len(block_ms) // 2]
+    # per-kernel times (profile events around every launch, direct launches)
+    cache_was = lib.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, 0)
+    lib.dspmb_profile_enable(1)
+    for k in range(20):
+        step(k)
+    torch.cuda.synchronize()
+    ms_k, ln_k = (ctypes.c_float * 32)(), (ctypes.c_int * 32)()
+    nslots = lib.dspmb_profile_read(ms_k, ln_k, 32)
+    lib.dspmb_profile_enable(0)
+    lib.dspmb_set_tuning(_lib.TUNE_GRAPH_CACHE, cache_was)
+    lib.dspmb_profile_kernel_name.restype = ctypes.c_char_p
+    kernels = {lib.dspmb_profile_kernel_name(i).decode(): ms_k[i] / 20 for i in range(nslots) if ln_k[i]}
+    if wl == "detection_heads" and "det_stream_kernel" in kernels:
+        kernels["det_stream_heads_kernel"] = kernels.pop("det_stream_kernel")
+    # parity of the last outputs against the oracle's walk through the reference graph
+    M, kind = cpu_backend()
+    ref_anchors = oracle_anchors(w["preset"])
+    want = extra_cpu_pass(wl, inputs, ref_anchors, os.cpu_count() or 1, collect=True)
+    if wl == "detection_heads":
+        got = sets[(args.steps - 1) % rotate][3].cpu().numpy()
+        exp = np.concatenate(want, axis=0)
+        ok = bool(np.array_equal(got.view(np.uint32), exp.view(np.uint32)))
+        checked = ["detection (B,A,7) bit-exact against head_layout -> softmax_channel -> multibox_detection"]
+    else:
+        s = sets[(args.steps - 1) % rotate]
+        ok = True
+        for k in range(3):
+            g = s[2][k].cpu().numpy()
+            e = np.concatenate([pp[0][k] for pp in want], axis=0).reshape(g.shape)
+            ok = ok and bool(((g.view(np.uint32) == e.view(np.uint32)) | ((g == 0) & (e == 0))).all())
+        st = stats[(args.steps - 1) % rotate].cpu().numpy()
+        est = np.concatenate([pp[1][2] for pp in want], axis=0)
+        ok = ok and bool(np.array_equal(st[:, 0], est[:, 0])) and bool(np.allclose(st[:, 1:3], est[:, 1:3], rtol=1e-6))
+        checked = ["loc_target / loc_mask / cls_target bit-exact", "valid count exact, cross-entropy and smooth-L1 sums to 1e-6"]
+    if world > 1:
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = int(flag.item()) == 1
+    # end to end with host buffers through the public operators
+    e2e = None
+    if not args.no_e2e:
+        from dspnet_b200 import MultiBoxDetectionFromHeads, MultiBoxTarget
+        if wl == "detection_heads":
+            host_in = list(inputs["cls_heads"]) + list(inputs["loc_heads"])
+            k = len(inputs["cls_heads"])
+
+            def e2e_run(*d):
+                return [MultiBoxDetectionFromHeads(list(d[:k]), list(d[k:]), anchors, C, **DET_PARAMS)]
+        else:
+            host_in = [inputs["lab"], inputs["logits"], inputs["loc"]]
+
+            def e2e_run(lab, logits, loc):
+                lt, lm, ct = MultiBoxTarget(anchors, lab, logits, **TGT_PARAMS)
+                _, _, st = multibox_training_outputs(logits, loc, lt, lm, ct, want_cls_prob=False, want_loc_loss=False)
+                return [lt, lm, ct, st]
+        pipe = E2EPipeline(torch, dev, host_in, e2e_run)
+        e2e_steps = max(3, args.steps)
+        for _ in range(4):
+            pipe.step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe.step()
+        torch.cuda.synchronize()
+        e2e_ms = 1e3 * (time.perf_counter() - t0)
+        barrier()
+        if world > 1:
+            tt = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        e2e = {"value": Bg * world * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(pipe.h2d),
+               "d2h_bytes_per_step": int(pipe.d2h), "steps": e2e_steps,
+               "api": ("dspnet_b200.MultiBoxDetectionFromHeads" if wl == "detection_heads" else
+                       "dspnet_b200.MultiBoxTarget + dspnet_b200.loss.multibox_training_outputs (statistics only)") +
+                      "; pinned host -> device copy of every input, the operators, every output copied back"}
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    step_ms = ms / args.steps
+    dominant = max(kernels, key=kernels.get)
+    rk = "det_stream_heads_kernel" if wl == "detection_heads" else "multibox_loss_kernel"
+    rbytes = abytes if wl == "detection_heads" else loss_bytes
+    achieved = rbytes / (kernels[rk] * 1e-3) / 1e9
+    line = {"metric": w["metric"], "value": Bg * world * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "preset": w["preset"], "batch_per_gpu": Bg, "anchors": A, "classes": C,
+                       "l2": "inputs/outputs rotate over %d resident sets (> 126 MB L2)" % rotate,
+                       "parallelism": "one GPU" if world == 1 else "images sharded, %d per GPU, no exchange" % Bg,
+                       "survey_row": "8f " + ("f1" if wl == "detection_heads" else "f2")},
+            "soak_steps": soak, "timed_blocks": len(block_ms), "block_ms": [round(x, 4) for x in block_ms],
+            "roofline": {"bound": "hbm", "kernel": rk, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": kernel_traffic(rk), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": rbytes, "kernel_ms": kernels[rk], "all_kernels_ms": kernels,
+                         "dominant_kernel": dominant, "whole_op_frac": abytes / (step_ms * 1e-3) / 1e9 / peak,
+                         "whole_op_algorithmic_bytes": abytes,
+                         "hbm_bytes_the_fusion_removes": avoided,
+                         "note": ("cls_prob (B,C,A) is neither written by a softmax pass nor read by the operator; the "
+                                  "reference graph additionally moves the class tensor through transpose / Concat / "
+                                  "transpose (%d more bytes)" % avoided_shuffles) if wl == "detection_heads" else
+                                 "the metric's inputs (cls_prob, loc_loss) stay in registers; only (B,4) sums are written"},
+            "e2e": e2e, "gpu_launches": args.steps * launches(), "launches_per_step": launches(),
+            "parity_check": {"result": "ok" if ok else "MISMATCH", "checked": checked,
+                             "against": "oracle restatement of the reference graph (MXNet's softmax / smooth_l1 are not "
+                                        "in the reference tree: parity pinned on multibox_target.cc:220-231's softmax)"},
+            "clocks": clocks}
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, done, dt = extra_cpu_time(wl, inputs, ref_anchors, threads, steps=10, budget_s=20.0)
+        line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": threads, "kind": "port",
+                                "sample": "%d steps x one B=%d batch: layout shuffles / softmax (oracle) + the reference "
+                                          "operator, image slices over %d host threads" % (done, Bg, threads)}
+    print(json.dumps(line))
 
 
 def run_nms(args, torch, dist, dev, rank, world):
@@ -532,6 +815,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "nms":
         run_nms(args, torch, dist, dev, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    if args.workload in ("detection_heads", "train_tail"):
+        run_extra(args, torch, dist, dev, rank, world)
         if world > 1:
             dist.destroy_process_group()
         return

@@ -177,6 +177,136 @@ __global__ void __launch_bounds__(kLossThreads) multibox_loss_kernel(const __gri
   }
 }
 
+
+// Statistics-only variant (cls_prob not requested): the cross-entropy needs the probability of the LABELLED class of
+// the anchors with a label only -- a few percent of them when hard-negative mining is on -- and every probability
+// costs C bit-exact expf evaluations in fp64, which is what the kernel above spends its time on (33 M of them at
+// SSD-512, batch 64).  Here a CTA first streams its loc tensors and labels (the logits are not touched), lists its
+// labelled anchors in shared memory, and then evaluates the softmax of only those, kLossBatch anchors at a time with
+// one (anchor, class) pair per thread.  Same arithmetic, same fixed-order fp64 sums.
+constexpr int kLossBatch = 64;
+template <int VEC>
+__global__ void __launch_bounds__(kLossThreads) multibox_metric_kernel(const __grid_constant__ LossArgs a) {
+  __shared__ double red[kLossThreads / 32][4];
+  __shared__ bool last;
+  __shared__ unsigned short list[kLossThreads * VEC];
+  __shared__ unsigned char llab[kLossThreads * VEC];
+  __shared__ int scan_smem[kLossThreads / 32 + 1];
+  __shared__ float cmx[kLossBatch];
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  float *es = reinterpret_cast<float *>(dyn_smem);  // [kLossBatch][C]
+  const int b = blockIdx.y, t = blockIdx.x, A = a.A, C = a.C;
+  const int tile0 = t * kLossThreads * VEC;
+  const int i0 = tile0 + (int)threadIdx.x * VEC;
+  double s_valid = 0.0, s_ce = 0.0, s_l1 = 0.0, s_pos = 0.0;
+  float lab[VEC];
+  int nmine = 0;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) lab[v] = -1.f;
+  if (i0 < A) {
+    const size_t row0 = (size_t)b * A + i0;
+    const float *pp = a.loc_preds + row0 * 5, *pt = a.loc_target + row0 * 5, *pm = a.loc_mask + row0 * 5;
+    float *po = a.loc_loss ? a.loc_loss + row0 * 5 : nullptr;
+    if constexpr (VEC == 4) {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const float4 p4 = ld_stream_f4(pp + 4 * q), t4 = ld_stream_f4(pt + 4 * q), m4 = ld_stream_f4(pm + 4 * q);
+        float4 l4;
+        l4.x = smooth_l1_unit(fmul(m4.x, fsub(p4.x, t4.x)));
+        l4.y = smooth_l1_unit(fmul(m4.y, fsub(p4.y, t4.y)));
+        l4.z = smooth_l1_unit(fmul(m4.z, fsub(p4.z, t4.z)));
+        l4.w = smooth_l1_unit(fmul(m4.w, fsub(p4.w, t4.w)));
+        if (po) st_stream_f4(po + 4 * q, l4);
+        s_l1 += (double)l4.x + (double)l4.y + (double)l4.z + (double)l4.w;
+        s_pos += (l4.x > 0.f) + (l4.y > 0.f) + (l4.z > 0.f) + (l4.w > 0.f);
+      }
+      const float4 l4 = ld_stream_f4(a.cls_target + row0);
+      lab[0] = l4.x, lab[1] = l4.y, lab[2] = l4.z, lab[3] = l4.w;
+    } else {
+      for (int q = 0; q < 5 * VEC; ++q) {
+        const float l = smooth_l1_unit(fmul(pm[q], fsub(pp[q], pt[q])));
+        if (po) po[q] = l;
+        s_l1 += (double)l;
+        s_pos += l > 0.f;
+      }
+      lab[0] = a.cls_target[row0];
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) nmine += lab[v] >= 0.f;
+  }
+  s_valid = (double)nmine;
+  int nlist;
+  int pos = block_scan_excl(nmine, scan_smem, &nlist);
+#pragma unroll
+  for (int v = 0; v < VEC; ++v)
+    if (lab[v] >= 0.f) {
+      list[pos] = (unsigned short)(threadIdx.x * VEC + v);
+      // a label outside [0, C) indexes outside the probabilities in the reference too (numpy would raise): class 0 here
+      llab[pos] = (unsigned char)((lab[v] < (float)C && lab[v] < 256.f) ? (int)lab[v] : 0);
+      ++pos;
+    }
+  __syncthreads();
+  const float *cp = a.cls_preds + (size_t)b * C * A + tile0;
+  for (int c0 = 0; c0 < nlist; c0 += kLossBatch) {
+    const int nb = min(kLossBatch, nlist - c0);
+    for (int q = threadIdx.x; q < nb * C; q += kLossThreads) {  // logits of the batch: class-major reads
+      const int c = q / nb, k = q - c * nb;
+      es[k * C + c] = __ldg(cp + (size_t)c * A + list[c0 + k]);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+      const float *x = es + threadIdx.x * C;
+      float mx = x[0];
+      for (int c = 1; c < C; ++c)
+        if (x[c] > mx) mx = x[c];
+      cmx[threadIdx.x] = mx;
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < nb * C; q += kLossThreads) {
+      const int k = q / C;
+      es[q] = libm::expf_glibc(fsub(es[q], cmx[k]), a.fma_build);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nb) {
+      const float *e = es + threadIdx.x * C;
+      float sum = 0.f;
+      for (int c = 0; c < C; ++c) sum = fadd(sum, e[c]);
+      const float p = fdiv(e[llab[c0 + threadIdx.x]], sum);
+      s_ce -= (double)libm::logf_glibc(fadd(p, a.eps), a.fma_build);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    s_valid += __shfl_xor_sync(kFullMask, s_valid, m);
+    s_ce += __shfl_xor_sync(kFullMask, s_ce, m);
+    s_l1 += __shfl_xor_sync(kFullMask, s_l1, m);
+    s_pos += __shfl_xor_sync(kFullMask, s_pos, m);
+  }
+  if (lane_id() == 0) {
+    red[warp_id()][0] = s_valid;
+    red[warp_id()][1] = s_ce;
+    red[warp_id()][2] = s_l1;
+    red[warp_id()][3] = s_pos;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+    for (int w = 0; w < kLossThreads / 32; ++w) v += red[w][threadIdx.x];
+    a.partial[((size_t)b * a.T + t) * 4 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&a.arrived[b], 1u) == (unsigned)a.T - 1u;
+  __syncthreads();
+  if (last && threadIdx.x < 4) {
+    __threadfence();
+    double v = 0.0;
+    for (int tt = 0; tt < a.T; ++tt) v += __ldcg(a.partial + ((size_t)b * a.T + tt) * 4 + threadIdx.x);
+    a.stats[(size_t)b * 4 + threadIdx.x] = v;
+  }
+}
+
 }  // namespace
 }  // namespace dspmb
 
@@ -232,7 +362,13 @@ extern "C" int dspmb_multibox_loss_f32(const float *cls_preds, const float *loc_
   dim3 grid(la.T, B);
   {
     ProfileScope _p(kSlotLoss, stream);
-    if (vec4 && C == 21)
+    const size_t smem_es = sizeof(float) * (size_t)kLossBatch * C;
+    if (!cls_prob && smem_es <= 40 * 1024) {  // statistics (and loc_loss) only: softmax of the labelled anchors alone
+      if (vec4)
+        multibox_metric_kernel<4><<<grid, kLossThreads, smem_es, stream>>>(la);
+      else
+        multibox_metric_kernel<1><<<grid, kLossThreads, smem_es, stream>>>(la);
+    } else if (vec4 && C == 21)
       multibox_loss_kernel<4, 21><<<grid, kLossThreads, 0, stream>>>(la);
     else if (vec4 && C == 9)
       multibox_loss_kernel<4, 9><<<grid, kLossThreads, 0, stream>>>(la);
