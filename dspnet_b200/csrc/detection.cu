@@ -593,14 +593,18 @@ __global__ void __launch_bounds__(kPipeThreads) det_stream_tma_kernel(const __gr
 // are in flight, then consumes the tile from shared memory.  ~40 registers and ~32 KB of shared memory per CTA
 // give 7 CTAs/SM whose load and compute phases interleave freely (the hardware CTA scheduler replaces a software
 // pipeline).  The row staging aliases the class rows, which are dead once the arg-max is done.
-template <int NFG, int kTile>
+template <int NFG, int kTile, bool kLean = false>
 struct BulkSmem {
   union {
     float cls[NFG][kTile];       // class rows of the tile (bulk copies)
     RowStage<kTile> rows;        // finished rows of the survivors (after the arg-max)
   } u;
-  float loc[kTile * 5];
-  float4 anc[kTile];
+  // kLean: loc_pred and the anchors are NOT staged -- only the survivors (one anchor in five) need them, and they
+  // fetch their 5 + 4 floats from global memory themselves; the CTA then needs 22.7 KB instead of 31.7 KB of shared
+  // memory, 9 CTAs fit on an SM instead of 7, and 9 KB less per tile go through the TMA engine.  `loc` shrinks to the
+  // scratch the class table of the fork/join pipeline needs.
+  float loc[kLean ? 192 : kTile * 5];
+  float4 anc[kLean ? 1 : kTile];
   float score[kTile];            // survivors in rank order
   unsigned short idx[kTile], id[kTile];
 };
@@ -608,15 +612,21 @@ struct BulkSmem {
 // Second half of a stream CTA, shared by the cls_prob-fed and the head-fed kernels: `total` survivors are listed in
 // anchor order in sm.score / sm.idx / sm.id; they are decoded on dense lanes, staged and flushed into the tile's slots
 // (slot_begin + k), and -- fork/join pipeline -- copied once more grouped by class for the pair-test kernel.
-template <int NFG, int kThreads, int kVec, bool kV2, typename Smem>
+template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false, typename Smem>
 __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const int b, const int t, const int slot_begin,
-                                            const int total) {
-  constexpr int kTile = kThreads * kVec;
+                                            const int total, const int anchor_begin = 0) {
   __syncthreads();  // survivor list complete; the class rows are dead from here on
   for (int j = threadIdx.x; j < total; j += kThreads) {
     const int l = sm.idx[j];
-    const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
-    stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
+    if constexpr (kLean) {
+      const float *lp = a.loc_pred + ((size_t)b * a.A + anchor_begin + l) * 5;
+      const float l5[5] = {__ldg(lp), __ldg(lp + 1), __ldg(lp + 2), __ldg(lp + 3), __ldg(lp + 4)};
+      const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + anchor_begin + l);
+      stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], an, l5);
+    } else {
+      const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
+      stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
+    }
   }
   __syncthreads();  // the staged rows are complete
   flush_rows(a, sm.u.rows, b, slot_begin, total);
@@ -627,7 +637,7 @@ __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const
     // aliases the loc_pred stage, which is dead once the rows are staged.
     static_assert(NFG <= kV2ClsPad, "tile_cls holds kV2ClsPad classes");
     constexpr int kWarps = kThreads / 32, kParts = kVec * kWarps;
-    static_assert(sizeof(float) * kTile * 5 >= (kParts * 32 + 33) * sizeof(unsigned short) + kParts * sizeof(unsigned),
+    static_assert(sizeof(sm.loc) >= (kParts * 32 + 34) * sizeof(unsigned short) + kParts * sizeof(unsigned),
                   "class table does not fit in the loc stage");
     unsigned short(*cnt)[32] = reinterpret_cast<unsigned short(*)[32]>(sm.loc);
     unsigned short *coff = reinterpret_cast<unsigned short *>(sm.loc) + kParts * 32;  // [33]
@@ -674,12 +684,12 @@ __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const
   }
 }
 
-template <int NFG, int kThreads, int kVec, bool kV2>
+template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false>
 __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
   constexpr int kTile = kThreads * kVec;
   TraceScope trace_(0);
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
-  BulkSmem<NFG, kTile> &sm = *reinterpret_cast<BulkSmem<NFG, kTile> *>(bulk_smem_raw);
+  BulkSmem<NFG, kTile, kLean> &sm = *reinterpret_cast<BulkSmem<NFG, kTile, kLean> *>(bulk_smem_raw);
   __shared__ __align__(8) unsigned long long full_bar;
   __shared__ int scan_smem[kThreads / 32 + 1];
   const int b = blockIdx.y, t = blockIdx.x;
@@ -690,12 +700,14 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
   if (threadIdx.x == 0) {
     mbar_init(&full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(&full_bar, (unsigned)(rows * 4 * NFG + rows * 20 + rows * 16));
+    mbar_expect_tx(&full_bar, (unsigned)(rows * 4 * NFG + (kLean ? 0 : rows * 20 + rows * 16)));
     const float *cp = a.cls_prob + ((size_t)b * a.C + 1) * A + tile_begin;
 #pragma unroll 4
     for (int j = 0; j < NFG; ++j) bulk_g2s(&sm.u.cls[j][0], cp + (size_t)j * A, rows * 4, &full_bar);
-    bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
-    bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
+    if constexpr (!kLean) {
+      bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
+      bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
+    }
   } else if (threadIdx.x == 32 && a.prefetch > 0) {
     // The CTAs resident on an SM run their load and compute phases more or less together, which leaves DRAM idle
     // while they compute.  One thread of another warp asks L2 for the tile a CTA `prefetch` launches ahead will load
@@ -764,7 +776,7 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
       sm.id[pos] = (unsigned short)id[k];
       ++pos;
     }
-  finish_tile<NFG, kThreads, kVec, kV2>(a, sm, b, t, tile_begin, total);
+  finish_tile<NFG, kThreads, kVec, kV2, kLean>(a, sm, b, t, tile_begin, total, tile_begin);
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -2944,7 +2956,16 @@ static int detection_run(const HeadsArgs *heads, const float *cls_prob, const fl
     DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, TH, VEC, V2>), kBytes);                                    \
     det_stream_bulk_kernel<NFG, TH, VEC, V2><<<grid1, TH, kBytes, stream>>>(sa);                                  \
   } while (0)
-      if (C == 21 && v2) DSPMB_LAUNCH_BULK(20, 128, 2, true);
+#define DSPMB_LAUNCH_BULK_LEAN(NFG)                                                                               \
+  do {                                                                                                            \
+    constexpr size_t kBytes = sizeof(BulkSmem<NFG, 256, true>);                                                   \
+    DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, 128, 2, true, true>), kBytes);                             \
+    det_stream_bulk_kernel<NFG, 128, 2, true, true><<<grid1, 128, kBytes, stream>>>(sa);                          \
+  } while (0)
+      const bool lean = tuning(DSPMB_TUNE_DET_LEAN) != 0;
+      if (C == 21 && v2 && lean) DSPMB_LAUNCH_BULK_LEAN(20);
+      else if (v2 && lean) DSPMB_LAUNCH_BULK_LEAN(8);
+      else if (C == 21 && v2) DSPMB_LAUNCH_BULK(20, 128, 2, true);
       else if (v2) DSPMB_LAUNCH_BULK(8, 128, 2, true);
       else if (C == 21 && variant == 2) DSPMB_LAUNCH_BULK(20, 128, 2, false);
       else if (C == 21 && variant == 3) DSPMB_LAUNCH_BULK(20, 256, 2, false);
@@ -2953,6 +2974,7 @@ static int detection_run(const HeadsArgs *heads, const float *cls_prob, const fl
       else if (variant == 3) DSPMB_LAUNCH_BULK(8, 256, 2, false);
       else DSPMB_LAUNCH_BULK(8, 128, 4, false);
 #undef DSPMB_LAUNCH_BULK
+#undef DSPMB_LAUNCH_BULK_LEAN
     }
     else if (reg_variant && C == 21)
       det_stream_reg_kernel<20, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);

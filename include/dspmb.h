@@ -275,7 +275,10 @@ const char *dspmb_profile_kernel_name(int slot);
                                            measured at SSD-512 B=32: 54.0 / 56.2 / 61.7 / 69.5 us for 1 / 2 / 3 / 4 groups:
                                            the 1024-thread sort CTAs of a group only find room once the next group's
                                            stream CTAs have drained, and the stream kernel itself slows down)          */
-#define DSPMB_NUM_TUNING 12
+#define DSPMB_TUNE_DET_LEAN 12            /* 1: the TMA-fed detection stream kernel stages only the class rows; survivors
+                                           fetch their loc_pred / anchor values from global memory (9 instead of 7
+                                           CTAs per SM); 0: loc_pred and anchors are staged by bulk copies as well   */
+#define DSPMB_NUM_TUNING 13
 int dspmb_set_tuning(int knob, int value);
 
 /* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)
