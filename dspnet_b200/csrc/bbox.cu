@@ -42,7 +42,8 @@ __global__ void __launch_bounds__(kBboxThreads) bbox_overlaps_kernel(const doubl
     q[c].y1 = query[(size_t)kk * 4 + 3];
     q[c].area = __dmul_rn(__dadd_rn(__dsub_rn(q[c].x1, q[c].x0), 1.0), __dadd_rn(__dsub_rn(q[c].y1, q[c].y0), 1.0));
   }
-  const bool pair_store = (K & 1) == 0 && k + 1 < K;  // row starts are 16-byte aligned when K is even
+  // row starts are 16-byte aligned when K is even AND the output tensor itself is (a C-ABI caller may pass a view)
+  const bool pair_store = (K & 1) == 0 && k + 1 < K && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   const int rows = min(kBboxRows, N - n0);
   for (int r = 0; r < rows; ++r) {
     const int n = n0 + r;

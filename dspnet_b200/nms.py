@@ -9,6 +9,15 @@ two different comparison rules; each name keeps its own
     gpu_nms, nms     suppress iff iou > float32(thresh)       (``rule='gt'``)
 
 Unlike the reference's gpu_nms nothing is sorted, swept or allocated on the host.
+
+Deliberate differences from the reference helpers:
+  * everything is computed in float32 (what the Cython helpers do: their signatures are ``np.float32_t``);
+    ``detect/nms.py::nms`` would keep float64 input in float64 -- float64 arrays are converted here;
+  * equal scores are ordered like a stable ``argsort()[::-1]`` (ties: higher index first).  numpy's default argsort is
+    not stable, so for tied scores the reference's own order is unspecified and parity is only defined for tie-free
+    scores (SURVEY.md section 8c);
+  * ``evalmap.postfilter`` pads / truncates to ``max_rows`` and returns the per-image counts; the reference's
+    ``multi_solver.py:429`` raises when more than 200 rows survive -- compare ``counts`` with ``max_rows`` for that.
 """
 import ctypes
 

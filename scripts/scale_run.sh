@@ -1,19 +1,16 @@
 #!/bin/bash
-# Runs ON THE GPU BOX under `gpurun --gpus 8`: the driver's scaling sequence N = 1, 2, 4, 8.
+# On a multi-GPU box (gpurun --gpus N): bench.py under torchrun at the given N for the given workloads.
+#   N=8 bash scripts/scale_run.sh detection target
+N=${N:-2}
 mkdir -p gpurun_out
-for n in ${SCALE_NS:-1 2 4 8}; do
-  if [ "$n" = "1" ]; then
-    timeout 200 python bench.py --gpus 1 --steps 200 --warmup 20 2>/dev/null | tail -1 > gpurun_out/scale_$n.json
-  else
-    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) \
-      bench.py --gpus $n --steps 200 --warmup 20 2>/dev/null | tail -1 > gpurun_out/scale_$n.json
-  fi
-  python - <<PY
-import json
-try:
-    d = json.loads(open("gpurun_out/scale_$n.json").read().strip().splitlines()[-1])
-    print("SCALE", d["n_gpus"], round(d["value"]), d["ms_per_step"], d.get("gather_check"), round(d["e2e"]["value"]))
-except Exception as e:
-    print("SCALE n=$n failed", repr(e)[:200])
+for wl in ${@:-detection}; do
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
+      bench.py --gpus $N --workload $wl --steps 200 --warmup 20 > gpurun_out/scale_${wl}_n$N.json 2> gpurun_out/scale_${wl}_n$N.err
+  tail -2 gpurun_out/scale_${wl}_n$N.err
+  python - $wl $N <<'PY'
+import json, sys
+d = json.loads(open("gpurun_out/scale_%s_n%s.json" % (sys.argv[1], sys.argv[2])).read().strip().splitlines()[-1])
+print(sys.argv[1], "N", d["n_gpus"], "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 5), "e2e", round(d["e2e"]["value"]),
+      "parity", d["parity_check"]["result"], "gather", d.get("gather_check"), d["config"].get("parallelism"))
 PY
 done

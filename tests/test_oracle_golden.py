@@ -111,3 +111,15 @@ def test_oracle_semantics_spot_checks(oracle):
     lab = np.full((1, 3, 6), -1, np.float32)
     lt, lm, ct = oracle.multibox_target(anchors, lab, np.zeros((1, 2, 3), np.float32), negative_mining_ratio=3)
     assert not lt.any() and not lm.any() and (ct == -1).all()
+
+
+def test_py_nms_equals_the_reference_file(oracle):
+    """oracle.py_nms against the reference's own detect/nms.py::nms (its two Cython imports stubbed), SURVEY 8c."""
+    from oracle import ref_pynms as RP
+    if not RP.available():
+        pytest.skip("/root/reference not present (GPU box): the pin is checked in the build container")
+    from dspnet_b200 import synth
+    for seed, n in ((1, 50), (2, 400), (3, 1500)):
+        dets = synth.nms_boxes(seed, n)
+        for thr in (0.3, 0.45, 0.7):
+            assert oracle.py_nms(dets, thr) == RP.nms(dets, thr)
