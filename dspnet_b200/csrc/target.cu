@@ -635,6 +635,18 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     sm_dup = 0;
     sm_thr = 0;
   }
+  // The mining keys are only needed after the matching, but their 100 KB take two microseconds to arrive: start the
+  // copy into shared memory now (cp.async: no registers, nobody waits) and let it fly beside the column reduction and
+  // the bipartite stage; the fix-up below patches the matched anchors' keys in the staged copy.
+  const unsigned *gkeys = a.key + (size_t)b * A;
+  const bool async_keys = kKeysInSmem && a.mining_ratio > 0.f && (A & 3) == 0 && (reinterpret_cast<uintptr_t>(gkeys) & 15) == 0;
+  if (async_keys) {
+    for (int j = threadIdx.x; j < (A >> 2); j += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(skeys + 4 * j)),
+                   "l"(gkeys + 4 * j)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   __syncthreads();
   {  // column maxima and positive counts of the image's tiles (each written by its own stream CTA, no atomics there)
     const unsigned long long *tcol = a.colbest + (size_t)b * a.T * L;
@@ -787,6 +799,10 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   }
   const int nmatch = sm_nmatch;
   DSPMB_TSTAMP(2);
+  if (async_keys) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();  // every thread's share of the staged keys is in shared memory before the fix-up patches it
+  }
 
   // ---- fix up the bipartite-matched anchors (they override whatever the threshold stage wrote) ----
   // a group of lanes per matched anchor (16, or 4 when there are more than 64 matches so that one round covers
@@ -822,6 +838,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     }
     a.cls_target[row] = fadd(lrow[0], 1.0f);
     a.key[row] = kKeySentinel;
+    if (async_keys) skeys[j] = kKeySentinel;
     if (a.match_out) a.match_out[row] = k;
   }
   __syncthreads();
@@ -843,9 +860,9 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   }
   if (num_negative <= 0) return;
 
-  const unsigned *gkeys = a.key + (size_t)b * A;
-  // Stage the keys in shared memory (the fix-up above has already replaced the matched anchors' keys).
-  if (kKeysInSmem) {
+  // Stage the keys in shared memory (the fix-up above has already replaced the matched anchors' keys) unless the
+  // asynchronous copy has done it.
+  if (kKeysInSmem && !async_keys) {
     if ((A & 3) == 0 && (reinterpret_cast<uintptr_t>(gkeys) & 15) == 0) {  // 128-bit loads, all in flight at once
       const uint4 *g4 = reinterpret_cast<const uint4 *>(gkeys);
       uint4 *s4 = reinterpret_cast<uint4 *>(skeys);
@@ -1733,7 +1750,14 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
                              (uintptr_t)cls_target | (uintptr_t)match_out;
   const bool vec4 = (A % 4 == 0) && (align_or & 15) == 0;
   // register-resident variants: 2 anchors/thread (about 85 registers => 6 CTAs/SM) unless knob 0 says otherwise
-  const int tvec = (vec4 && (C == 21 || C == 9) && tuning(DSPMB_TUNE_DET_STREAM_VARIANT) != 4) ? 2 : 4;
+  int tvec = (vec4 && (C == 21 || C == 9) && tuning(DSPMB_TUNE_DET_STREAM_VARIANT) != 4) ? 2 : 4;
+  // Small batches are latency bound by the CTAs of images with many ground truths (every warp of a large-anchor tile
+  // walks the whole gt list, two IoUs per anchor and gt): up to about two waves of CTAs (measured: 8 and 16 images
+  // of SSD-512), one anchor per thread shortens that chain and still fills the machine.
+  const int small_mode = tuning(DSPMB_TUNE_TARGET_SMALL);  // 0 never, 1 (default) by size, 2 always
+  if (vec4 && (C == 21 || C == 9) && tvec == 2 &&
+      (small_mode == 2 || (small_mode == 1 && (long long)B * ceil_div(A, 2 * kStreamThreads) <= 12LL * kNumSMs)))
+    tvec = 1;
   const int tile = kStreamThreads * (vec4 ? tvec : 1);
 
   TargetArgs ta;
@@ -1792,7 +1816,11 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     else                                                                               \
       target_stream_kernel<V, N, false><<<grid1, kStreamThreads, smem1, stream>>>(ta); \
   } while (0)
-    if (vec4 && C == 21 && tvec == 2)
+    if (vec4 && C == 21 && tvec == 1)
+      DSPMB_LAUNCH_TS(1, 21);
+    else if (vec4 && C == 9 && tvec == 1)
+      DSPMB_LAUNCH_TS(1, 9);
+    else if (vec4 && C == 21 && tvec == 2)
       DSPMB_LAUNCH_TS(2, 21);
     else if (vec4 && C == 9 && tvec == 2)
       DSPMB_LAUNCH_TS(2, 9);

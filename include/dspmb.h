@@ -278,7 +278,10 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_DET_LEAN 12            /* 1: the TMA-fed detection stream kernel stages only the class rows; survivors
                                            fetch their loc_pred / anchor values from global memory (9 instead of 7
                                            CTAs per SM); 0: loc_pred and anchors are staged by bulk copies as well   */
-#define DSPMB_NUM_TUNING 13
+#define DSPMB_TUNE_TARGET_SMALL 13        /* target stream kernel with ONE anchor per thread: 0 never, 1 (default) when the
+                                           two-anchor grid is at most about two waves of CTAs (latency-bound batches:
+                                           55.5 -> 53.0 us at 8 images of SSD-512, 57.5 -> 55.4 us at 16), 2 always       */
+#define DSPMB_NUM_TUNING 14
 int dspmb_set_tuning(int knob, int value);
 
 /* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)
