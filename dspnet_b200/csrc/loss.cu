@@ -37,6 +37,32 @@ __device__ __forceinline__ float smooth_l1_unit(float d) {  // mx.symbol.smooth_
   return ad < 1.0f ? fmul(0.5f, fmul(d, d)) : fsub(ad, 0.5f);
 }
 
+
+// Masked smooth-L1 of one warp's block of the (B, A*5) tensors: the loss is element-wise, so the warp walks its
+// 32 x VEC anchors x 5 contiguous floats as full 128-bit lines (lane l takes float4 l, l + 32, ...) instead of every
+// lane reading its own 80-byte piece in five 16-byte steps, which moves every 32-byte sector through L1 twice.
+template <int VEC>
+__device__ __forceinline__ void warp_loc_loss(const LossArgs &a, size_t warp_row0, int warp_anchors, double &s_l1, double &s_pos) {
+  const float *pp = a.loc_preds + warp_row0 * 5, *pt = a.loc_target + warp_row0 * 5, *pm = a.loc_mask + warp_row0 * 5;
+  float *po = a.loc_loss ? a.loc_loss + warp_row0 * 5 : nullptr;
+  const int n4 = warp_anchors * 5 / 4;  // warp_anchors is a multiple of 4
+#pragma unroll
+  for (int q0 = 0; q0 < 32 * VEC * 5 / 4; q0 += 32) {
+    const int q = q0 + (int)lane_id();
+    if (q < n4) {
+      const float4 p4 = ld_stream_f4(pp + 4 * q), t4 = ld_stream_f4(pt + 4 * q), m4 = ld_stream_f4(pm + 4 * q);
+      float4 l4;
+      l4.x = smooth_l1_unit(fmul(m4.x, fsub(p4.x, t4.x)));
+      l4.y = smooth_l1_unit(fmul(m4.y, fsub(p4.y, t4.y)));
+      l4.z = smooth_l1_unit(fmul(m4.z, fsub(p4.z, t4.z)));
+      l4.w = smooth_l1_unit(fmul(m4.w, fsub(p4.w, t4.w)));
+      if (po) st_stream_f4(po + 4 * q, l4);
+      s_l1 += (double)l4.x + (double)l4.y + (double)l4.z + (double)l4.w;
+      s_pos += (l4.x > 0.f) + (l4.y > 0.f) + (l4.z > 0.f) + (l4.w > 0.f);
+    }
+  }
+}
+
 template <int VEC, int NC>
 __global__ void __launch_bounds__(kLossThreads) multibox_loss_kernel(const __grid_constant__ LossArgs a) {
   __shared__ double red[kLossThreads / 32][4];
@@ -45,6 +71,10 @@ __global__ void __launch_bounds__(kLossThreads) multibox_loss_kernel(const __gri
   const int C = NC > 0 ? NC : a.C;
   const int i0 = (t * kLossThreads + (int)threadIdx.x) * VEC;
   double s_valid = 0.0, s_ce = 0.0, s_l1 = 0.0, s_pos = 0.0;
+  if constexpr (VEC == 4) {
+    const int w0 = (t * kLossThreads + (int)warp_id() * 32) * VEC;  // first anchor of this warp
+    if (w0 < A) warp_loc_loss<VEC>(a, (size_t)b * A + w0, min(32 * VEC, A - w0), s_l1, s_pos);
+  }
   if (i0 < A) {
     const size_t row0 = (size_t)b * A + i0;
     // ---- localisation loss: 5 values per anchor, VEC anchors = 5 * VEC consecutive floats ----
@@ -52,18 +82,7 @@ __global__ void __launch_bounds__(kLossThreads) multibox_loss_kernel(const __gri
       const float *pp = a.loc_preds + row0 * 5, *pt = a.loc_target + row0 * 5, *pm = a.loc_mask + row0 * 5;
       float *po = a.loc_loss ? a.loc_loss + row0 * 5 : nullptr;
       if constexpr (VEC == 4) {
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const float4 p4 = ld_stream_f4(pp + 4 * q), t4 = ld_stream_f4(pt + 4 * q), m4 = ld_stream_f4(pm + 4 * q);
-          float4 l4;
-          l4.x = smooth_l1_unit(fmul(m4.x, fsub(p4.x, t4.x)));
-          l4.y = smooth_l1_unit(fmul(m4.y, fsub(p4.y, t4.y)));
-          l4.z = smooth_l1_unit(fmul(m4.z, fsub(p4.z, t4.z)));
-          l4.w = smooth_l1_unit(fmul(m4.w, fsub(p4.w, t4.w)));
-          if (po) st_stream_f4(po + 4 * q, l4);
-          s_l1 += (double)l4.x + (double)l4.y + (double)l4.z + (double)l4.w;
-          s_pos += (l4.x > 0.f) + (l4.y > 0.f) + (l4.z > 0.f) + (l4.w > 0.f);
-        }
+        (void)pp, (void)pt, (void)pm, (void)po;  // walked warp-wide above (coalesced)
       } else {
         for (int q = 0; q < 5 * VEC; ++q) {
           const float l = smooth_l1_unit(fmul(pm[q], fsub(pp[q], pt[q])));
@@ -203,23 +222,16 @@ __global__ void __launch_bounds__(kLossThreads) multibox_metric_kernel(const __g
   int nmine = 0;
 #pragma unroll
   for (int v = 0; v < VEC; ++v) lab[v] = -1.f;
+  if constexpr (VEC == 4) {
+    const int w0 = tile0 + (int)warp_id() * 32 * VEC;  // first anchor of this warp
+    if (w0 < A) warp_loc_loss<VEC>(a, (size_t)b * A + w0, min(32 * VEC, A - w0), s_l1, s_pos);
+  }
   if (i0 < A) {
     const size_t row0 = (size_t)b * A + i0;
     const float *pp = a.loc_preds + row0 * 5, *pt = a.loc_target + row0 * 5, *pm = a.loc_mask + row0 * 5;
     float *po = a.loc_loss ? a.loc_loss + row0 * 5 : nullptr;
     if constexpr (VEC == 4) {
-#pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        const float4 p4 = ld_stream_f4(pp + 4 * q), t4 = ld_stream_f4(pt + 4 * q), m4 = ld_stream_f4(pm + 4 * q);
-        float4 l4;
-        l4.x = smooth_l1_unit(fmul(m4.x, fsub(p4.x, t4.x)));
-        l4.y = smooth_l1_unit(fmul(m4.y, fsub(p4.y, t4.y)));
-        l4.z = smooth_l1_unit(fmul(m4.z, fsub(p4.z, t4.z)));
-        l4.w = smooth_l1_unit(fmul(m4.w, fsub(p4.w, t4.w)));
-        if (po) st_stream_f4(po + 4 * q, l4);
-        s_l1 += (double)l4.x + (double)l4.y + (double)l4.z + (double)l4.w;
-        s_pos += (l4.x > 0.f) + (l4.y > 0.f) + (l4.z > 0.f) + (l4.w > 0.f);
-      }
+      (void)pp, (void)pt, (void)pm, (void)po;  // the loc tensors are walked warp-wide above
       const float4 l4 = ld_stream_f4(a.cls_target + row0);
       lab[0] = l4.x, lab[1] = l4.y, lab[2] = l4.z, lab[3] = l4.w;
     } else {

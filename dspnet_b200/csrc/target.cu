@@ -32,6 +32,10 @@ namespace {
 
 constexpr int kStreamThreads = 128;
 constexpr int kMatchThreads = 1024;
+#ifndef DSPMB_TARGET_MIN_BLOCKS
+#define DSPMB_TARGET_MIN_BLOCKS 5
+#endif
+constexpr int kTargetMinBlocks = DSPMB_TARGET_MIN_BLOCKS;  // CTAs per SM the stream kernel is compiled for
 constexpr unsigned kKeySentinel = 0xffffffffu;  // "not a mining candidate"
 
 // Optional per-CTA phase stamps of the match kernel (dspmb_debug_target_stamps): 12 x uint64 %globaltimer values per
@@ -224,7 +228,7 @@ __device__ __forceinline__ float iou_target_fast(float4 a, float area_a, float4 
 // thread keeps its NC x VEC logits in registers (one HBM read, no re-load for the second softmax pass); NC == 0:
 // runtime class count, second pass re-reads through L1/L2.  kFma: which glibc build of expf/logf to reproduce.
 template <int VEC, int NC, bool kFma>
-__global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __grid_constant__ TargetArgs a) {
+__global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_stream_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ int sm_pos;
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);                                  // [L]
@@ -503,6 +507,12 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
 
   DSPMB_SSTAMP(4);
   // ---- outputs ----
+  bool any_pos = false;
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) any_pos |= pos[v];
+  const bool zero_warp = (VEC == 2 || VEC == 4) && __all_sync(kFullMask, active && !any_pos) &&
+                         ((reinterpret_cast<uintptr_t>(a.loc_target) | reinterpret_cast<uintptr_t>(a.loc_mask)) & 15) == 0 &&
+                         (((size_t)b * A + (i0 - (int)lane_id() * VEC)) & 3) == 0;
   if (active) {
     const size_t row0 = (size_t)b * A + i0;
     float ct[VEC];
@@ -525,11 +535,28 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
       }
     }
     float *plt = a.loc_target + row0 * 5, *plm = a.loc_mask + row0 * 5;
-    if constexpr (VEC == 4) {
+    // Most warps hold no positive anchor at all (99 % of the anchors are not matched): their 32 x VEC x 5 zeros of
+    // loc_target and loc_mask are one contiguous block each, written as full 128-bit lines by consecutive lanes instead
+    // of 40-byte pieces per lane (a fifth of the sectors through L1 / TEX).  `zero_warp` is set before the divergent
+    // part: the whole warp is active, lies inside the image and its block starts 16-byte aligned.
+    if (zero_warp) {
+      const size_t wrow0 = (size_t)b * A + (i0 - (int)lane_id() * VEC);  // first anchor of the warp
+      float *zt = a.loc_target + wrow0 * 5, *zm = a.loc_mask + wrow0 * 5;
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      constexpr int kVec4 = 32 * VEC * 5 / 4;  // float4 per warp and tensor
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        st_stream_f4(plt + 4 * q, make_float4(lt[4 * q], lt[4 * q + 1], lt[4 * q + 2], lt[4 * q + 3]));
-        st_stream_f4(plm + 4 * q, make_float4(lm[4 * q], lm[4 * q + 1], lm[4 * q + 2], lm[4 * q + 3]));
+      for (int q = (int)lane_id(); q < kVec4; q += 32) {
+        st_stream_f4(zt + 4 * q, z4);
+        st_stream_f4(zm + 4 * q, z4);
+      }
+    }
+    if constexpr (VEC == 4) {
+      if (!zero_warp) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          st_stream_f4(plt + 4 * q, make_float4(lt[4 * q], lt[4 * q + 1], lt[4 * q + 2], lt[4 * q + 3]));
+          st_stream_f4(plm + 4 * q, make_float4(lm[4 * q], lm[4 * q + 1], lm[4 * q + 2], lm[4 * q + 3]));
+        }
       }
       *reinterpret_cast<float4 *>(a.cls_target + row0) = make_float4(ct[0], ct[1], ct[2], ct[3]);
       *reinterpret_cast<uint4 *>(a.key + row0) = make_uint4(key[0], key[1], key[2], key[3]);
@@ -537,10 +564,12 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
         *reinterpret_cast<int4 *>(a.match_out + row0) =
             make_int4(pos[0] ? best_k[0] : -1, pos[1] ? best_k[1] : -1, pos[2] ? best_k[2] : -1, pos[3] ? best_k[3] : -1);
     } else if constexpr (VEC == 2) {
+      if (!zero_warp) {
 #pragma unroll
-      for (int q = 0; q < 5; ++q) {
-        reinterpret_cast<float2 *>(plt)[q] = make_float2(lt[2 * q], lt[2 * q + 1]);
-        reinterpret_cast<float2 *>(plm)[q] = make_float2(lm[2 * q], lm[2 * q + 1]);
+        for (int q = 0; q < 5; ++q) {
+          reinterpret_cast<float2 *>(plt)[q] = make_float2(lt[2 * q], lt[2 * q + 1]);
+          reinterpret_cast<float2 *>(plm)[q] = make_float2(lm[2 * q], lm[2 * q + 1]);
+        }
       }
       *reinterpret_cast<float2 *>(a.cls_target + row0) = make_float2(ct[0], ct[1]);
       *reinterpret_cast<uint2 *>(a.key + row0) = make_uint2(key[0], key[1]);
@@ -557,7 +586,6 @@ __global__ void __launch_bounds__(kStreamThreads) target_stream_kernel(const __g
     }
   }
 
-  DSPMB_SSTAMP(5);
   // ---- publish the CTA's column maxima and positive count ----
   npos = warp_sum_i32(npos);
   if (lane_id() == 0 && npos) atomicAdd(&sm_pos, npos);
