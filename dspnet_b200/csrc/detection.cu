@@ -612,7 +612,7 @@ struct BulkSmem {
 // Second half of a stream CTA, shared by the cls_prob-fed and the head-fed kernels: `total` survivors are listed in
 // anchor order in sm.score / sm.idx / sm.id; they are decoded on dense lanes, staged and flushed into the tile's slots
 // (slot_begin + k), and -- fork/join pipeline -- copied once more grouped by class for the pair-test kernel.
-template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false, typename Smem>
+template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false, bool kLocPlane = false, typename Smem>
 __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const int b, const int t, const int slot_begin,
                                             const int total, const int anchor_begin = 0) {
   __syncthreads();  // survivor list complete; the class rows are dead from here on
@@ -623,6 +623,13 @@ __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const
       const float l5[5] = {__ldg(lp), __ldg(lp + 1), __ldg(lp + 2), __ldg(lp + 3), __ldg(lp + 4)};
       const float4 an = __ldg(reinterpret_cast<const float4 *>(a.anchors) + anchor_begin + l);
       stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], an, l5);
+    } else if constexpr (kLocPlane) {  // loc staged as [value][plane-order index] (head-fed kernel)
+      // (gathering the survivors' loc values from the global planes instead -- five cold 32-byte sectors per survivor in
+      // the decode phase -- measured 60.4 instead of 51.7 us)
+      constexpr int kT = kThreads * kVec;
+      const int q = sm.idxq[j];
+      const float l5[5] = {sm.loc[q], sm.loc[kT + q], sm.loc[2 * kT + q], sm.loc[3 * kT + q], sm.loc[4 * kT + q]};
+      stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
     } else {
       const float l5[5] = {sm.loc[l * 5], sm.loc[l * 5 + 1], sm.loc[l * 5 + 2], sm.loc[l * 5 + 3], sm.loc[l * 5 + 4]};
       stage_row(a, sm.u.rows, j, (int)sm.id[j], sm.score[j], sm.anc[l], l5);
@@ -807,18 +814,17 @@ struct HeadsArgs {
 
 template <int C>
 struct HeadSmem {
-  union {
-    float xs[C][kHeadTile];            // logits of the tile, [class][anchor in tile]
-    RowStage<kHeadTile> rows;          // finished rows of the survivors (after the exact phase)
+  struct {
+    RowStage<kHeadTile> rows;          // finished rows of the survivors
   } u;
-  float loc[kHeadTile * 5];
+  float loc[kHeadTile * 5];            // [value][plane-order index]
   float4 anc[kHeadTile];
   float score[kHeadTile];              // approximate score per anchor, then exact score per survivor (rank order)
   unsigned short idx[kHeadTile], id[kHeadTile];
+  unsigned short idxq[kHeadTile];      // plane-order index of survivor j (loc is staged as [value][plane index])
   unsigned short cand[kHeadTile];      // candidates of the exact phase, anchor order
   float es[kHeadBatch][C];             // exact exponentials of one batch of candidates
   float cmx[kHeadBatch];
-  unsigned short cq[kHeadBatch];       // plane-order index of the batch's candidates
   float fscore[kHeadTile];             // exact score of every candidate (candidate order)
   unsigned short fid[kHeadTile];       // its class, 0 = below the threshold
 };
@@ -864,7 +870,6 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
     const int half = ncells >> 1;
     for (int p = threadIdx.x; p < half * na; p += kHeadThreads) {
       const int ai = p / half, cell = (p - ai * half) * 2;
-      const int q = ai * ncells + cell;  // plane-order index of the first of the two anchors
       const float *pc = cls + (size_t)ai * C * HW + cell;
       float2 x[C];
 #pragma unroll
@@ -872,14 +877,13 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
         x[c] = ld_stream_f2(pc);
         pc += HW;
       }
+      const int q = ai * ncells + cell;  // plane-order index of the first of the two anchors
       const float *pl = loc + (size_t)ai * 5 * HW + cell;
       const int j0 = cell * na + ai, j1 = j0 + na;
 #pragma unroll
       for (int d = 0; d < 5; ++d) {
-        const float2 v = ld_stream_f2(pl);
+        *reinterpret_cast<float2 *>(&sm.loc[d * kHeadTile + q]) = ld_stream_f2(pl);  // plane order: no bank conflicts
         pl += HW;
-        sm.loc[j0 * 5 + d] = v.x;
-        sm.loc[j1 * 5 + d] = v.y;
       }
       float2 mx = x[0], best = x[1];
 #pragma unroll
@@ -894,7 +898,6 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
       float2 sum = make_float2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        *reinterpret_cast<float2 *>(&sm.u.xs[c][q]) = x[c];
         float e0, e1;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmul(fsub(x[c].x, mx.x), 1.4426950408889634f)));
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmul(fsub(x[c].y, mx.y), 1.4426950408889634f)));
@@ -921,16 +924,16 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
       const float *pl = loc + (size_t)ai * 5 * HW + cell;
 #pragma unroll
       for (int d = 0; d < 5; ++d) {
-        sm.loc[j * 5 + d] = ld_stream_f1(pl);
+        sm.loc[d * kHeadTile + p] = ld_stream_f1(pl);
         pl += HW;
       }
+
       float mx = x[0];
 #pragma unroll
       for (int c = 1; c < C; ++c) mx = fmaxf(mx, x[c]);
       float sum = 0.f, best = x[1];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        sm.u.xs[c][p] = x[c];
         float e;
         asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmul(fsub(x[c], mx), 1.4426950408889634f)));
         sum = fadd(sum, e);
@@ -961,21 +964,26 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
   for (int c0 = 0; c0 < ncand; c0 += kHeadBatch) {
     const int nb = min(kHeadBatch, ncand - c0);
     if ((int)threadIdx.x < nb) {
+      // the candidate's logits come from global memory again (L2 hits: the tile was read a microsecond ago) -- keeping
+      // all 21 x 256 logits of the tile in shared memory for the one anchor in five that needs them cost half the
+      // occupancy
       const int j = sm.cand[c0 + threadIdx.x];
-      const int cell = j / na, q = (j - cell * na) * ncells + cell;
-      float mx = sm.u.xs[0][q];
+      const int cell = j / na, ai = j - cell * na;
+      const float *pc = cls + (size_t)ai * C * HW + cell;
+      float *x = sm.es[threadIdx.x];
+      float mx = __int_as_float(0xff800000);
 #pragma unroll
-      for (int c = 1; c < C; ++c) {
-        const float v = sm.u.xs[c][q];
-        if (v > mx) mx = v;
+      for (int c = 0; c < C; ++c) {
+        const float v = __ldg(pc + (size_t)c * HW);
+        x[c] = v;
+        if (c == 0 || v > mx) mx = v;
       }
       sm.cmx[threadIdx.x] = mx;
-      sm.cq[threadIdx.x] = (unsigned short)q;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < nb * C; q += kHeadThreads) {
       const int kk = q / C, c = q - kk * C;
-      sm.es[kk][c] = libm::expf_glibc(fsub(sm.u.xs[c][sm.cq[kk]], sm.cmx[kk]), a.fma_build);
+      sm.es[kk][c] = libm::expf_glibc(fsub(sm.es[kk][c], sm.cmx[kk]), a.fma_build);
     }
     __syncthreads();
     if ((int)threadIdx.x < nb) {
@@ -1017,13 +1025,15 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
   int pos = block_scan_excl(nvalid, scan_smem, &total);
   if (threadIdx.x == 0) a.tile_count[(size_t)b * a.T + t] = total;
   float sc[2];
-  unsigned short ci[2], cj[2];
+  unsigned short ci[2], cj[2], cqv[2];
 #pragma unroll
   for (int v = 0; v < 2; ++v)
     if (ok[v]) {
       sc[v] = sm.fscore[l0 + v];
       ci[v] = sm.fid[l0 + v];
       cj[v] = sm.cand[l0 + v];
+      const int cell = cj[v] / na;
+      cqv[v] = (unsigned short)((cj[v] - cell * na) * ncells + cell);
     }
   __syncthreads();  // sm.score is about to change meaning (approximate per anchor -> exact per survivor)
 #pragma unroll
@@ -1031,10 +1041,11 @@ __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __
     if (ok[v]) {
       sm.score[pos] = sc[v];
       sm.idx[pos] = cj[v];
+      sm.idxq[pos] = cqv[v];
       sm.id[pos] = ci[v];
       ++pos;
     }
-  finish_tile<NFG, kHeadThreads, kHeadTile / kHeadThreads, kV2>(a, sm, b, t, t * kHeadTile, total);
+  finish_tile<NFG, kHeadThreads, kHeadTile / kHeadThreads, kV2, false, true>(a, sm, b, t, t * kHeadTile, total);
 }
 
 // ----------------------------------------------------------------------------------------------------

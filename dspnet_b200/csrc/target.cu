@@ -244,7 +244,21 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
   const bool mining = a.mining_ratio > 0.f;
   const int C = NC > 0 ? NC : a.C;
 
-  // ---- issue every global load of this thread first: logits (register-resident when NC > 0) and anchors ----
+  // ---- issue every global load of this thread first.  The label loads go out BEFORE the 21 logit loads: the warp
+  // needs them first (valid-gt count, gt staging), and queued behind the logits they were the kernel's largest stall.
+  // Thread k < L fetches label row k speculatively, every lane the class fields of rows lane, lane + 32, .. + 96.
+  float4 gsp = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((int)threadIdx.x < a.L) {
+    const float *row = lab + (size_t)threadIdx.x * W;
+    gsp = make_float4(__ldg(row + 1), __ldg(row + 2), __ldg(row + 3), __ldg(row + 4));
+  }
+  float cfield[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int l = r * 32 + (int)lane_id();
+    cfield[r] = l < a.L ? __ldg(lab + (size_t)l * W) : 0.f;
+  }
+  // ---- logits (register-resident when NC > 0) and anchors ----
   const float *cp = a.cls_preds + (size_t)b * C * A + i0;
   float xr[NC > 0 ? NC : 1][VEC];
   float4 an[VEC];
@@ -270,7 +284,14 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
   }
 
   DSPMB_SSTAMP(0);
-  const int G = count_valid_gt_warp(lab, a.L, W);
+  int G = -1;  // number of leading valid label rows (multibox_target.cc:95-105), every warp on its own
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int l = r * 32 + (int)lane_id();
+    const unsigned pad = __ballot_sync(kFullMask, l < a.L && cfield[r] == -1.0f);
+    if (G < 0 && pad) G = r * 32 + __ffs(pad) - 1;
+  }
+  if (G < 0) G = a.L <= 128 ? a.L : 128 + count_valid_gt_warp(lab + (size_t)128 * W, a.L - 128, W);
   DSPMB_SSTAMP(1);
   if (t == 0 && threadIdx.x == 0) {
     a.gcount[b] = G;
@@ -283,8 +304,11 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
     if (b == 0) a.header->status = DSPMB_OK;   // nobody else touches the header during this launch
   }
   for (int k = threadIdx.x; k < G; k += blockDim.x) {
-    const float *row = lab + (size_t)k * W;
-    const float4 g = make_float4(row[1], row[2], row[3], row[4]);
+    float4 g = gsp;  // row k == threadIdx.x was fetched up front
+    if (k >= (int)blockDim.x) {
+      const float *row = lab + (size_t)k * W;
+      g = make_float4(row[1], row[2], row[3], row[4]);
+    }
     sm_gt[k] = g;
     sm_garea[k] = fmul(fsub(g.z, g.x), fsub(g.w, g.y));
     sm_col[k] = 0ull;
