@@ -641,7 +641,6 @@ enum { kStateDone = 0, kStateRecompute = 1 };
 template <bool kKeysInSmem>
 __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __grid_constant__ TargetArgs a) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ unsigned long long red_smem[kMatchThreads / 32];
   __shared__ unsigned hist[256];
   __shared__ int sm_state, sm_arg, sm_nmatch, sm_dup, sm_carry, sm_thr;
   __shared__ unsigned sm_prefix;
@@ -662,13 +661,14 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     return;
   }
-  // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][ord: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
+  // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][ord: L int][slist: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + L);
   int *m_anchor = reinterpret_cast<int *>(sm_col + L);
   int *m_gt = m_anchor + L;
   int *ord = m_gt + L;  // gts with a candidate, sorted by cached key (sequential bipartite path)
-  unsigned char *done = reinterpret_cast<unsigned char *>(ord + ((L + 3) & ~3));  // keeps `skeys` 16-byte aligned
+  int *slist = ord + ((L + 3) & ~3);  // gts whose cached maximum has gone stale (batched recompute), then sort scratch
+  unsigned char *done = reinterpret_cast<unsigned char *>(slist + ((L + 3) & ~3));  // keeps `skeys` 16-byte aligned
   unsigned *bits = reinterpret_cast<unsigned *>(done + ((L + 15) / 16) * 16);
   const int nwords = (A + 31) / 32;
   unsigned *skeys = bits + ((nwords + 3) & ~3);  // [A] staged mining keys (kKeysInSmem)
@@ -794,10 +794,23 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
         __syncthreads();
         if (sm_state == kStateDone) break;
         head = sm_arg;
-        // recompute the column maximum of the head gt over the anchors that are still unmatched
-        const int k = ord[head];
-        const float4 g = sm_gt[k];
-        unsigned long long tkey = 0ull;
+        // Batched recompute.  Not only the head gt: EVERY listed gt whose cached best anchor has been taken by now is
+        // stale (gts crowd around the same anchors, so they go stale together -- with 200 gts one at a time meant ~25
+        // passes over the anchor table, 5 us each).  One pass over the unmatched anchors refreshes all of them: the
+        // stale gts are listed, their keys reset, and every anchor is tried against the list (overlap pre-test, IoU,
+        // shared-memory atomicMax only when it improves the column).
+        if (threadIdx.x == 0) sm_dup = 0;
+        __syncthreads();
+        for (int pos = head + (int)threadIdx.x; pos < n_ord; pos += blockDim.x) {
+          const int k = ord[pos];
+          const int j = (int)(0xffffffffu - (unsigned)(sm_col[k] & 0xffffffffull));
+          if ((bits[j >> 5] >> (j & 31)) & 1u) {
+            slist[atomicAdd(&sm_dup, 1)] = k;
+            sm_col[k] = 0ull;
+          }
+        }
+        __syncthreads();
+        const int nstale = sm_dup;
         // four anchors per thread in flight: the anchor table lives in L2, one dependent load per iteration would
         // put its latency on this loop twelve to twenty-four times
         for (int j0 = threadIdx.x; j0 < A; j0 += 4 * blockDim.x) {
@@ -812,41 +825,45 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
             const int j = j0 + u * (int)blockDim.x;
             if (j >= A || ((bits[j >> 5] >> (j & 31)) & 1u)) continue;
             const float4 an = an4[u];
-            // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
-            if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
-            const float iou = iou_target(an, g);
-            if (iou > 1e-6f) {
-              const unsigned long long ck = col_key(iou, j);
-              tkey = ck > tkey ? ck : tkey;
+            for (int si = 0; si < nstale; ++si) {
+              const int k = slist[si];
+              const float4 g = sm_gt[k];
+              // disjoint boxes have inter == 0 (or NaN), never > 1e-6: skip the IoU arithmetic and its division
+              if (!(an.z > g.x && g.z > an.x && an.w > g.y && g.w > an.y)) continue;
+              const float iou = iou_target(an, g);
+              if (iou > 1e-6f) {
+                const unsigned long long ck = col_key(iou, j);
+                if (ck > sm_col[k]) atomicMax(&sm_col[k], ck);
+              }
             }
           }
         }
-        const unsigned long long bm = block_max_u64(tkey, red_smem);
-        // move gt k from the head to its place among the remaining entries (bm <= its old key): the entries that
-        // still rank before it form a prefix of the rest of the list and shift up by one, a chunk of blockDim at a
-        // time; a gt without any remaining candidate (bm == 0) ends up behind the list and leaves it
-        int base = head + 1;
-        while (true) {
-          const int pos = base + (int)threadIdx.x;
-          int e = -1;
-          bool before = false;
-          if (pos < n_ord) {
-            e = ord[pos];
-            const unsigned long long ek = sm_col[e];
-            before = bm == 0ull || ek > bm || (ek == bm && e < k);
+        __syncthreads();
+        // re-rank the rest of the list by (key descending, gt ascending); gts without a remaining candidate drop out
+        const int nrem = n_ord - head;
+        if (threadIdx.x == 0) sm_dup = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nrem; i += blockDim.x) {
+          const int k = ord[head + i];
+          const unsigned long long ck = sm_col[k];
+          if (ck == 0ull) continue;
+          int r = 0;
+          for (int x = 0; x < nrem; ++x) {
+            const int kk = ord[head + x];
+            const unsigned long long o = sm_col[kk];
+            r += (o > ck || (o == ck && kk < k)) ? 1 : 0;
           }
-          const int moved = __syncthreads_count(before);  // also orders the reads above before the writes below
-          if (before) ord[pos - 1] = e;
-          base += moved;
-          if (moved < (int)blockDim.x) break;
+          slist[r] = k;  // the stale list is dead: scratch for the new order
+          atomicAdd(&sm_dup, 1);
         }
-        if (threadIdx.x == 0) {
-          ord[base - 1] = k;
-          sm_col[k] = bm;
-        }
-        if (bm == 0ull) --n_ord;  // bm is the same in every thread
+        __syncthreads();
+        const int nkeep = sm_dup;
+        for (int i = threadIdx.x; i < nkeep; i += blockDim.x) ord[head + i] = slist[i];
+        n_ord = head + nkeep;
         __syncthreads();
       }
+      if (threadIdx.x == 0) sm_dup = 0;
+      __syncthreads();
     }
   }
   const int nmatch = sm_nmatch;
@@ -1848,7 +1865,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L +
                        sizeof(unsigned short) * (size_t)L * (kStreamThreads / 32);
   const size_t smem2 = (sizeof(float4) + sizeof(unsigned long long) + 2 * sizeof(int)) * (size_t)L +
-                       sizeof(int) * (size_t)((L + 3) & ~3) +
+                       2 * sizeof(int) * (size_t)((L + 3) & ~3) +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
   const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 170 * 1024;
   const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
