@@ -36,6 +36,7 @@
 //                                  division-free threshold test with its exact fallback band on dense lanes) + a
 //                                  word-serial resolve that only visits rows that suppress something;
 //                        larger:   64-row chunks: ballot mask + serial resolve + parallel sweep of the later rows.
+#include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -477,6 +478,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                : "memory");
 }
 
+// One 2-D TMA tile copy (cp.async.bulk.tensor, SASS UTMALDG): box {kTile columns, NFG rows} of the (B*C, A) view of
+// cls_prob at element coordinates (x = first anchor, y = first class row), completion on an mbarrier.
+__device__ __forceinline__ void tma_tile_2d(void *dst, const CUtensorMap *tmap, int x, int y, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst)),
+               "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
@@ -691,8 +701,9 @@ __device__ __forceinline__ void finish_tile(const StreamArgs &a, Smem &sm, const
   }
 }
 
-template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false>
-__global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a) {
+template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false, bool kTensor = false>
+__global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a,
+                                                                   const __grid_constant__ CUtensorMap tmap) {
   constexpr int kTile = kThreads * kVec;
   TraceScope trace_(0);
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
@@ -707,10 +718,18 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
   if (threadIdx.x == 0) {
     mbar_init(&full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if constexpr (kTensor) {
+      // ONE tensor-map copy for the whole [NFG x kTile] class tile; columns beyond A are out of bounds of the map and
+      // arrive as zeros, so the transaction count is always the full box
+      static_assert(kLean, "the tensor-map variant stages the class rows only");
+      mbar_expect_tx(&full_bar, (unsigned)(kTile * 4 * NFG));
+      tma_tile_2d(&sm.u.cls[0][0], &tmap, tile_begin, b * a.C + 1, &full_bar);
+    } else {
     mbar_expect_tx(&full_bar, (unsigned)(rows * 4 * NFG + (kLean ? 0 : rows * 20 + rows * 16)));
     const float *cp = a.cls_prob + ((size_t)b * a.C + 1) * A + tile_begin;
 #pragma unroll 4
     for (int j = 0; j < NFG; ++j) bulk_g2s(&sm.u.cls[j][0], cp + (size_t)j * A, rows * 4, &full_bar);
+    }
     if constexpr (!kLean) {
       bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
       bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
@@ -2752,6 +2771,32 @@ extern "C" size_t dspmb_detection_workspace_bytes(int B, int A, int C) {
   return need;
 }
 
+// Tensor map of cls_prob viewed as a 2-D fp32 tensor (inner dimension: A anchors, outer: B*C class rows) with a box of
+// {256 anchors, nfg rows}.  cuTensorMapEncodeTiled is resolved through the runtime (no link-time libcuda dependency).
+static int make_cls_tensor_map(CUtensorMap *tmap, const float *cls_prob, int B, int C, int A, int nfg) {
+  typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                               const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      cudaGetLastError();
+      return DSPMB_ERR_CUDA;
+    }
+    encode = (EncodeFn)fn;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)A, (cuuint64_t)B * C};
+  const cuuint64_t strides[1] = {(cuuint64_t)A * sizeof(float)};
+  const cuuint32_t box[2] = {256u, (cuuint32_t)nfg};
+  const cuuint32_t estr[2] = {1u, 1u};
+  const CUresult r = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(cls_prob), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DSPMB_OK : DSPMB_ERR_CUDA;
+}
+
 static int detection_run(const HeadsArgs *heads, const float *cls_prob, const float *loc_pred, const float *anchors,
                          float *out, int B, int A, int C, float threshold, int clip, const float *variances,
                          float nms_threshold, int force_suppress, int nms_topk, int32_t *valid_count_out, void *workspace,
@@ -2965,16 +3010,30 @@ static int detection_run(const HeadsArgs *heads, const float *cls_prob, const fl
   do {                                                                                                            \
     constexpr size_t kBytes = sizeof(BulkSmem<NFG, TH * VEC>);                                                    \
     DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, TH, VEC, V2>), kBytes);                                    \
-    det_stream_bulk_kernel<NFG, TH, VEC, V2><<<grid1, TH, kBytes, stream>>>(sa);                                  \
+    det_stream_bulk_kernel<NFG, TH, VEC, V2><<<grid1, TH, kBytes, stream>>>(sa, tmap);                            \
   } while (0)
 #define DSPMB_LAUNCH_BULK_LEAN(NFG)                                                                               \
   do {                                                                                                            \
     constexpr size_t kBytes = sizeof(BulkSmem<NFG, 256, true>);                                                   \
     DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, 128, 2, true, true>), kBytes);                             \
-    det_stream_bulk_kernel<NFG, 128, 2, true, true><<<grid1, 128, kBytes, stream>>>(sa);                          \
+    det_stream_bulk_kernel<NFG, 128, 2, true, true><<<grid1, 128, kBytes, stream>>>(sa, tmap);                    \
   } while (0)
-      const bool lean = tuning(DSPMB_TUNE_DET_LEAN) != 0;
-      if (C == 21 && v2 && lean) DSPMB_LAUNCH_BULK_LEAN(20);
+#define DSPMB_LAUNCH_BULK_TENSOR(NFG)                                                                             \
+  do {                                                                                                            \
+    constexpr size_t kBytes = sizeof(BulkSmem<NFG, 256, true>);                                                   \
+    DSPMB_ENSURE_DYN_SMEM((det_stream_bulk_kernel<NFG, 128, 2, true, true, true>), kBytes);                       \
+    det_stream_bulk_kernel<NFG, 128, 2, true, true, true><<<grid1, 128, kBytes, stream>>>(sa, tmap);              \
+  } while (0)
+      const int lean = tuning(DSPMB_TUNE_DET_LEAN);
+      // 2: class tile through ONE cp.async.bulk.tensor copy (needs the tensor map; rows of A*4 bytes must be 16-byte
+      // multiples, which vec4 guarantees); 1: NFG 1-D bulk copies
+      CUtensorMap tmap;
+      memset(&tmap, 0, sizeof(tmap));
+      bool tensor = false;
+      if (v2 && lean == 2) tensor = make_cls_tensor_map(&tmap, cls_prob, B, C, A, C - 1) == DSPMB_OK;
+      if (C == 21 && v2 && tensor) DSPMB_LAUNCH_BULK_TENSOR(20);
+      else if (v2 && tensor) DSPMB_LAUNCH_BULK_TENSOR(8);
+      else if (C == 21 && v2 && lean) DSPMB_LAUNCH_BULK_LEAN(20);
       else if (v2 && lean) DSPMB_LAUNCH_BULK_LEAN(8);
       else if (C == 21 && v2) DSPMB_LAUNCH_BULK(20, 128, 2, true);
       else if (v2) DSPMB_LAUNCH_BULK(8, 128, 2, true);
@@ -2986,6 +3045,7 @@ static int detection_run(const HeadsArgs *heads, const float *cls_prob, const fl
       else DSPMB_LAUNCH_BULK(8, 128, 4, false);
 #undef DSPMB_LAUNCH_BULK
 #undef DSPMB_LAUNCH_BULK_LEAN
+#undef DSPMB_LAUNCH_BULK_TENSOR
     }
     else if (reg_variant && C == 21)
       det_stream_reg_kernel<20, kRegThreads><<<grid1, kRegThreads, 0, stream>>>(sa);

@@ -277,7 +277,9 @@ const char *dspmb_profile_kernel_name(int slot);
                                            stream CTAs have drained, and the stream kernel itself slows down)          */
 #define DSPMB_TUNE_DET_LEAN 12            /* 1: the TMA-fed detection stream kernel stages only the class rows; survivors
                                            fetch their loc_pred / anchor values from global memory (9 instead of 7
-                                           CTAs per SM); 0: loc_pred and anchors are staged by bulk copies as well   */
+                                           CTAs per SM); 2: the same with the class tile as ONE cp.async.bulk.tensor
+                                           2-D copy (tensor map, UTMALDG) instead of NFG 1-D bulk copies; 0: loc_pred
+                                           and anchors are staged by bulk copies as well                             */
 #define DSPMB_TUNE_TARGET_SMALL 13        /* target stream kernel with ONE anchor per thread: 0 never, 1 (default) when the
                                            two-anchor grid is at most about two waves of CTAs (latency-bound batches:
                                            55.5 -> 53.0 us at 8 images of SSD-512, 57.5 -> 55.4 us at 16), 2 always       */
