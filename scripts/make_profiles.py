@@ -123,7 +123,7 @@ for line in sass.splitlines():
         continue
     if cur is not None:
         cur.append(line)
-listing = [k for k in blocks if re.match(r'void det_stream_bulk_kernel<20, 128, 2, true, true>|void target_stream_kernel<2, 21, true>|void det_stream_heads_kernel<21, true>', k)]
+listing = [k for k in blocks if re.match(r'void det_stream_bulk_kernel<20, 128, 2, true, true, true>|void target_stream_kernel<2, 21, true>|void det_stream_heads_kernel<21, true>', k)]
 with open(os.path.join(P, 'sass_%s.txt' % R), 'w') as f:
     f.write('# cuobjdump -sass dspnet_b200/libdspmb.so (sm_100a only).  Part 1: opcode counts per kernel for the mnemonics that matter on this\n'
             '# path (no tensor-core opcodes anywhere: nothing here is a dense contraction; UBLKCP = cp.async.bulk TMA copy, SYNCS = mbarrier,\n'
