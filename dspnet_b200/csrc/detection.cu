@@ -734,20 +734,6 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
       bulk_g2s(sm.loc, a.loc_pred + ((size_t)b * A + tile_begin) * 5, rows * 20, &full_bar);
       bulk_g2s(sm.anc, a.anchors + (size_t)tile_begin * 4, rows * 16, &full_bar);
     }
-  } else if (threadIdx.x == 32 && a.prefetch > 0) {
-    // The CTAs resident on an SM run their load and compute phases more or less together, which leaves DRAM idle
-    // while they compute.  One thread of another warp asks L2 for the tile a CTA `prefetch` launches ahead will load
-    // (cp.async.bulk.prefetch.L2: no registers, no shared memory, no completion to wait for), so that the DRAM
-    // queues stay full whatever the SMs are doing and the later CTA's bulk copies are L2 hits.
-    const int lin = b * (int)gridDim.x + t + a.prefetch;
-    const int pb = lin / (int)gridDim.x, pt = lin - pb * (int)gridDim.x;
-    if (pb < (int)gridDim.y) {
-      const int pbegin = pt * kTile, prow = min(kTile, A - pbegin);
-      const float *cp = a.cls_prob + ((size_t)pb * a.C + 1) * A + pbegin;
-#pragma unroll 4
-      for (int j = 0; j < NFG; ++j) bulk_prefetch_l2(cp + (size_t)j * A, prow * 4);
-      bulk_prefetch_l2(a.loc_pred + ((size_t)pb * A + pbegin) * 5, prow * 20);
-    }
   }
   {  // `out = -1` for this tile's rows (multibox_detection-inl.h:103) while the copies are in flight
     float *ob = a.out + ((size_t)b * A + tile_begin) * 7;
@@ -757,6 +743,30 @@ __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_
   }
   __syncthreads();  // the barrier initialisation is visible to every waiter
   mbar_wait(&full_bar, 0u);
+  if (a.prefetch > 0 && threadIdx.x == 32) {
+    // The CTAs of a wave start together, so they also load together and compute together: DRAM is saturated while the
+    // wave's tiles arrive and IDLE while it computes (2.3 waves x ~3 us of a 24 us kernel).  Now that this CTA's own
+    // tile has landed, one thread asks L2 for the class tile of the CTA `prefetch` launches ahead -- the one that takes
+    // this CTA's place on the SM (prefetch = CTAs resident on the GPU) -- so that DRAM works through the compute
+    // phase and the successor's TMA copy is an L2 hit.  (Issued at CTA start instead, the prefetch only doubled the
+    // queue in front of the CTA's own tile: measured +2.5 us.)  No registers, no shared memory, nothing to wait for.
+    const int lin = b * (int)gridDim.x + t + a.prefetch;
+    const int pb = lin / (int)gridDim.x, pt = lin - pb * (int)gridDim.x;
+    if (pb < (int)gridDim.y) {
+      const int pbegin = pt * kTile;
+      if constexpr (kTensor) {
+        asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(&tmap), "r"(pbegin),
+                     "r"(pb * a.C + 1)
+                     : "memory");
+      } else {
+        const int prow = min(kTile, A - pbegin);
+        const float *cp = a.cls_prob + ((size_t)pb * a.C + 1) * A + pbegin;
+#pragma unroll 4
+        for (int j = 0; j < NFG; ++j) bulk_prefetch_l2(cp + (size_t)j * A, prow * 4);
+        if constexpr (!kLean) bulk_prefetch_l2(a.loc_pred + ((size_t)pb * A + pbegin) * 5, prow * 20);
+      }
+    }
+  }
 
   const int l0 = threadIdx.x * kVec;
   float score[kVec];

@@ -32,6 +32,7 @@ namespace {
 
 constexpr int kStreamThreads = 128;
 constexpr int kMatchThreads = 1024;
+constexpr int kShortCap = 4096;  // matcher: capacity of the mining shortlist (keys + anchor ids in shared memory)
 #ifndef DSPMB_TARGET_MIN_BLOCKS
 #define DSPMB_TARGET_MIN_BLOCKS 5
 #endif
@@ -108,6 +109,7 @@ struct TargetArgs {
   float overlap_threshold, ignore_label, mining_ratio, mining_thresh;
   float vx, vy, vw, vh;
   int fma_build;
+  int shortlist;  // matcher: mine on a shortlist of the keys below a sampled bound (DSPMB_TUNE_TARGET_SHORTLIST)
 };
 
 // 5-wide box encoding, operator/multibox_target.cc:30-56.
@@ -235,6 +237,8 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + a.L);       // [L]
   float *sm_garea = reinterpret_cast<float *>(sm_col + a.L);                              // [L]
 
+  // the match kernel is launched as a programmatic dependent: let its CTAs take the SMs this grid's tail frees
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b = blockIdx.y, t = blockIdx.x;
   constexpr int kTile = kStreamThreads * VEC;
   const int A = a.A, W = a.W;
@@ -646,21 +650,23 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   __shared__ unsigned sm_prefix;
   __shared__ int sm_need;
   constexpr int kLowBuckets = 2 * kMatchThreads, kPivotList = 1024;
+  constexpr int kSampleKeys = 2 * kMatchThreads;
+  constexpr int kSampleShift = 19;  // sample buckets = float bits >> 19: 16 per octave, p <= 1 stays below bucket 2033
   __shared__ unsigned bucket[kLowBuckets], plist[kPivotList];
   __shared__ int scan_smem[kMatchThreads / 32 + 1];
   __shared__ int sm_np, sm_pb, sm_before;
   __shared__ unsigned sm_kmin, sm_kmax;
+  __shared__ unsigned wmin_smem[kMatchThreads / 32];
 
   const int b = blockIdx.x;
   const int A = a.A, L = a.L, W = a.W;
-  DSPMB_TSTAMP(0);
-  const int G = a.gcount[b];
+  // The kernel is a PROGRAMMATIC dependent of the stream kernel (which triggers on entry): its CTAs become resident
+  // while the last stream CTAs drain, and everything up to griddepcontrol.wait below touches only the operator's
+  // INPUTS (labels) and shared memory -- the valid-gt count is recomputed from the labels (every warp on its own, as
+  // in the stream kernel) instead of being read back from the stream kernel's gcount[].
+  const float *lab = a.labels + (size_t)b * L * W;
+  const int G = count_valid_gt_warp(lab, L, W);
   int32_t *stats = a.stats_out ? a.stats_out + 4 * b : nullptr;
-  if (threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
-  if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values
-    if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
-    return;
-  }
   // dynamic smem: [gt: L float4][col: L u64][m_anchor: L int][m_gt: L int][ord: L int][slist: L int][done: L u8 (padded)][bits: ceil(A/32) u32]
   float4 *sm_gt = reinterpret_cast<float4 *>(dyn_smem);
   unsigned long long *sm_col = reinterpret_cast<unsigned long long *>(sm_gt + L);
@@ -673,7 +679,6 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   const int nwords = (A + 31) / 32;
   unsigned *skeys = bits + ((nwords + 3) & ~3);  // [A] staged mining keys (kKeysInSmem)
 
-  const float *lab = a.labels + (size_t)b * L * W;
   const float4 *anchors = reinterpret_cast<const float4 *>(a.anchors);
   for (int k = threadIdx.x; k < G; k += blockDim.x) {
     const float *row = lab + (size_t)k * W;
@@ -686,6 +691,15 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     sm_nmatch = 0;
     sm_dup = 0;
     sm_thr = 0;
+    sm_pb = -1;              // sample bucket of the shortlist bound
+  }
+  for (int i = threadIdx.x; i < kLowBuckets; i += blockDim.x) bucket[i] = 0u;  // sample histogram of the shortlist
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // the stream kernel's outputs are complete and visible from here
+  DSPMB_TSTAMP(0);
+  if (threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
+  if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values
+    if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    return;
   }
   // The mining keys are only needed after the matching, but their 100 KB take two microseconds to arrive: start the
   // copy into shared memory now (cp.async: no registers, nobody waits) and let it fly beside the column reduction and
@@ -702,15 +716,25 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   __syncthreads();
   {  // column maxima and positive counts of the image's tiles (each written by its own stream CTA, no atomics there)
     const unsigned long long *tcol = a.colbest + (size_t)b * a.T * L;
-    for (int idx = threadIdx.x; idx < a.T * G; idx += blockDim.x) {
-      const int t = idx / G, k = idx - t * G;
-      const unsigned long long ck = tcol[(size_t)t * L + k];
-      if (ck) atomicMax(&sm_col[k], ck);
+    // One warp per gt, lanes over the tiles, warp-wide maximum: no shared-memory atomics (a 64-bit atomicMax is a CAS
+    // loop, and with one (tile, gt) pair per thread ~96 of them hit every sm_col[k]).
+    const int nw = (int)(blockDim.x >> 5);
+    for (int k = (int)warp_id(); k < G; k += nw) {
+      unsigned long long v = 0ull;
+#pragma unroll 4
+      for (int t = (int)lane_id(); t < a.T; t += 32) {
+        const unsigned long long ck = tcol[(size_t)t * L + k];
+        v = ck > v ? ck : v;
+      }
+      v = warp_max_u64(v);
+      if (lane_id() == 0) sm_col[k] = v;
     }
-    int pos = 0;
-    for (int t = threadIdx.x; t < a.T; t += blockDim.x) pos += a.thr_count[(size_t)b * a.T + t];
-    pos = warp_sum_i32(pos);
-    if (lane_id() == 0 && pos) atomicAdd(&sm_thr, pos);
+    if ((int)warp_id() == nw - 1) {
+      int pos = 0;
+      for (int t = (int)lane_id(); t < a.T; t += 32) pos += a.thr_count[(size_t)b * a.T + t];
+      pos = warp_sum_i32(pos);
+      if (lane_id() == 0) sm_thr = pos;
+    }
   }
   __syncthreads();
   DSPMB_TSTAMP(1);
@@ -728,24 +752,27 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       for (int kk = 0; kk < G; ++kk)
         if (kk != k && sm_col[kk] != 0ull && (unsigned)(sm_col[kk] & 0xffffffffull) == mine) clash = 1;
     }
-    if (clash) sm_dup = 1;
-    __syncthreads();
-    const bool distinct = sm_dup == 0;
-    __syncthreads();
+    const bool distinct = __syncthreads_or(clash) == 0;
     if (distinct) {
-      for (int k = threadIdx.x; k < G; k += blockDim.x) {
-        const unsigned long long ck = sm_col[k];
-        if (ck == 0ull) continue;
-        const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
-        const int n = atomicAdd(&sm_nmatch, 1);
-        m_anchor[n] = j;
-        m_gt[n] = k;
-        atomicOr(&bits[j >> 5], 1u << (j & 31));
+      if (warp_id() == 0) {  // ordered compaction by ballots: no queue on one shared-memory counter
+        int base = 0;
+        for (int k0 = 0; k0 < G; k0 += 32) {
+          const int k = k0 + (int)lane_id();
+          const unsigned long long ck = k < G ? sm_col[k] : 0ull;
+          const unsigned m = __ballot_sync(kFullMask, ck != 0ull);
+          if (ck != 0ull) {
+            const int j = (int)(0xffffffffu - (unsigned)(ck & 0xffffffffull));
+            const int n = base + __popc(m & ((1u << lane_id()) - 1u));
+            m_anchor[n] = j;
+            m_gt[n] = k;
+            atomicOr(&bits[j >> 5], 1u << (j & 31));
+          }
+          base += __popc(m);
+        }
+        if (lane_id() == 0) sm_nmatch = base;
       }
       __syncthreads();
     }
-    if (threadIdx.x == 0) sm_dup = 0;
-    __syncthreads();
     if (!distinct) {
       // Sequential lazy greedy on a SORTED list: the gts with a candidate, ordered by cached key (descending; equal
       // keys -> lower gt index first, the reference's scan order).  The head of the list is the global maximum of
@@ -895,7 +922,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       if (o > max_iou) max_iou = o;
     }
     if (sub != 0) continue;
-    if (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) atomicAdd(&sm_dup, 1);  // counted by the stream kernel
+    done[q] = (a.overlap_threshold > 0.f && max_iou > a.overlap_threshold) ? 1 : 0;  // counted by the stream kernel
     const size_t row = (size_t)b * A + j;
     const float *lrow = lab + (size_t)k * W;
     float enc[5];
@@ -912,7 +939,10 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   }
   __syncthreads();
   DSPMB_TSTAMP(3);
-  const int num_positive = sm_thr + nmatch - sm_dup;
+  int ndup = 0;  // matched anchors the threshold stage had already counted (flags instead of a contended counter)
+  for (int q = (int)lane_id(); q < nmatch; q += 32) ndup += done[q];
+  ndup = warp_sum_i32(ndup);
+  const int num_positive = sm_thr + nmatch - ndup;
 
   // ---- hard-negative mining (multibox_target.cc:182-241) ----
   int num_negative = 0;
@@ -942,231 +972,345 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       for (int j = threadIdx.x; j < A; j += blockDim.x) skeys[j] = gkeys[j];
     }
   }
-  auto key_at = [&](int j) -> unsigned { return kKeysInSmem ? skeys[j] : gkeys[j]; };
   __syncthreads();  // the staged keys are read by other threads from here on (racecheck: staging vs. the min/max pass)
   DSPMB_TSTAMP(4);
-  // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
-  // (larger than the bits of any probability), so they are only reached if there are too few candidates.
-  if (threadIdx.x == 0) {
-    sm_prefix = 0u;
-    sm_need = num_negative;
-  }
-  // Fast path: one 2048-bucket histogram over the range the candidate keys actually span (the bit patterns of
-  // positive floats order like the floats) replaces the four 8-bit radix passes: the bucket that holds the
-  // num_negative-th smallest key follows from a prefix sum, and the key itself from ranking the members of that one
-  // bucket.  A bucket too crowded to rank (massive ties) or too few candidates leave it to the radix passes below.
-  bool have_q = false;
-  if (kKeysInSmem) {
-    unsigned kmin = kKeySentinel, kmax = 0u;
-    for (int j = threadIdx.x; j < A; j += blockDim.x) {
-      const unsigned kv = skeys[j];
-      if (kv != kKeySentinel) {
-        kmin = min(kmin, kv);
-        kmax = max(kmax, kv);
-      }
-    }
-    kmin = __reduce_min_sync(kFullMask, kmin);
-    kmax = __reduce_max_sync(kFullMask, kmax);
-    if (threadIdx.x == 0) {
-      sm_kmin = kKeySentinel;
-      sm_kmax = 0u;
-      sm_np = 0;
-    }
-    for (int i = threadIdx.x; i < kLowBuckets; i += blockDim.x) bucket[i] = 0u;
-    __syncthreads();
-    if (lane_id() == 0) {
-      atomicMin(&sm_kmin, kmin);
-      atomicMax(&sm_kmax, kmax);
+
+  // ---- shortlist ----
+  // The wanted keys are the num_negative SMALLEST of A (a per cent or two of the image), yet the selection below used
+  // to walk all A keys four times (range, histogram, pivot bucket, final pass): 60 % of this kernel's instructions on
+  // a single SM.  Instead: a 2048-key sample of the staged keys gives an upper bound U of the pivot (the sample's
+  // quantile of num_negative/A plus four standard deviations, rounded up to a bucket edge), ONE pass over the keys
+  // compacts everything <= U into a shortlist (key, anchor), and range / histogram / pivot / final pass then run on
+  // the shortlist alone.  U is only a guess -- the count of the shortlist verifies it: fewer than num_negative
+  // entries, an overflow of the list, or (below) an ambiguity band that reaches beyond U fall back to the full walk.
+  unsigned *sl_key = skeys + ((A + 3) & ~3);                       // [kShortCap] (kKeysInSmem only)
+  int *sl_idx = reinterpret_cast<int *>(sl_key + kShortCap);       // [kShortCap]
+  unsigned U = 0u, kmin_short = 0u;
+  int n_short = 0;
+  bool use_short = false;
+  if (kKeysInSmem && a.shortlist && (A & 3) == 0 && A >= 4 * kSampleKeys) {
+    // Sample histogram on the float bits themselves (sign 0, 8 exponent and 4 mantissa bits: 16 buckets per octave of
+    // the probability, 2032 buckets up to p = 1): no range pass, and the bound only has to be roughly right.
+    // bucket[] was zeroed at kernel start.
+    const float m = (float)num_negative * (float)kSampleKeys / (float)A;  // expected sample keys below the pivot
+    const int r_s = (int)(m + 4.0f * sqrtf(m) + 4.0f) + 1;
+    for (int s = threadIdx.x; s < kSampleKeys; s += blockDim.x) {
+      const unsigned kv = skeys[(int)(((long long)s * A) / kSampleKeys)];
+      if (kv != kKeySentinel) atomicAdd(&bucket[min(kv >> kSampleShift, (unsigned)kLowBuckets - 1u)], 1u);
     }
     __syncthreads();
-    kmin = sm_kmin;
-    kmax = sm_kmax;
-    if (kmin != kKeySentinel) {  // CTA-uniform: at least one candidate
-      int shift = 0;
-      while (((kmax - kmin) >> shift) >= (unsigned)kLowBuckets) ++shift;
-      for (int j = threadIdx.x; j < A; j += blockDim.x) {
-        const unsigned kv = skeys[j];
-        if (kv != kKeySentinel) atomicAdd(&bucket[(kv - kmin) >> shift], 1u);
-      }
-      __syncthreads();
-      const unsigned c0 = bucket[2 * threadIdx.x], c1 = bucket[2 * threadIdx.x + 1];
-      int total;
-      const int ex = block_scan_excl((int)(c0 + c1), scan_smem, &total);  // total = number of candidates
-      if (ex < num_negative && ex + (int)c0 >= num_negative) {
-        sm_pb = 2 * threadIdx.x;
-        sm_before = ex;
-      } else if (ex + (int)c0 < num_negative && ex + (int)(c0 + c1) >= num_negative) {
-        sm_pb = 2 * threadIdx.x + 1;
-        sm_before = ex + (int)c0;
-      }
-      __syncthreads();
-      if (num_negative <= total) {  // otherwise the radix path reports the missing candidates
-        const unsigned P = (unsigned)sm_pb;
-        const int r = num_negative - sm_before;  // 1-based rank of the wanted key inside bucket P
-        const int cP = (int)bucket[P];
-        if (cP <= kPivotList) {
-          for (int j = threadIdx.x; j < A; j += blockDim.x) {
-            const unsigned kv = skeys[j];
-            if (kv != kKeySentinel && ((kv - kmin) >> shift) == P) plist[atomicAdd(&sm_np, 1)] = kv;
-          }
-          __syncthreads();
-          for (int i = threadIdx.x; i < cP; i += blockDim.x) {
-            const unsigned v = plist[i];
-            int lo = 0, hi = 0;
-            for (int x = 0; x < cP; ++x) {
-              lo += plist[x] < v ? 1 : 0;
-              hi += plist[x] <= v ? 1 : 0;
-            }
-            if (lo < r && r <= hi) sm_prefix = v;  // equal keys write the same value
-          }
-          __syncthreads();
-          have_q = true;
-        }
-      }
-    }
-  }
-  for (int pass = 0; pass < (have_q ? 0 : 4); ++pass) {
-    const int shift = 24 - 8 * pass;
-    const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+    const unsigned c0 = bucket[2 * threadIdx.x], c1 = bucket[2 * threadIdx.x + 1];
+    bucket[2 * threadIdx.x] = 0u;  // ready for the selection's histogram (nobody else touches these two)
+    bucket[2 * threadIdx.x + 1] = 0u;
+    int total;
+    const int ex = block_scan_excl((int)(c0 + c1), scan_smem, &total);
+    if (ex < r_s && ex + (int)c0 >= r_s) sm_pb = 2 * threadIdx.x;
+    else if (ex + (int)c0 < r_s && ex + (int)(c0 + c1) >= r_s) sm_pb = 2 * threadIdx.x + 1;
     __syncthreads();
-    const unsigned prefix = sm_prefix;
-    // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
-    auto hist_add = [&](unsigned kv, bool in_range) {
-      const bool hit = in_range && (kv & mask) == prefix;
-      const unsigned active = __ballot_sync(kFullMask, hit);
-      if (active == 0u) return;
-      // the digit of the first hit lane is counted for the whole warp with one ballot (probabilities cluster: in the
-      // first pass that is nearly every lane); the other lanes add themselves, and their digits rarely coincide
-      const unsigned digit = (kv >> shift) & 0xffu;
-      const int leader = __ffs(active) - 1;
-      const unsigned d0 = __shfl_sync(kFullMask, digit, leader);
-      const unsigned same = __ballot_sync(kFullMask, hit && digit == d0);
-      if ((int)lane_id() == leader) atomicAdd(&hist[d0], (unsigned)__popc(same));
-      else if (hit && digit != d0) atomicAdd(&hist[digit], 1u);
-    };
-    if (kKeysInSmem && (A & 3) == 0) {  // four keys per thread and iteration: one LDS.128, four independent updates
+    const int P = sm_pb;  // -1 (set at kernel start): the sample holds fewer than r_s candidates
+    DSPMB_TSTAMP(8);
+    if (P >= 0 && P < kLowBuckets - 1) {
+      U = (((unsigned)P + 1u) << kSampleShift) - 1u;  // upper edge of the bucket; < 2^30, far below the sentinel
+      // Compaction: every thread counts its hits first (no communication), ONE warp scan and ONE shared-memory atomic
+      // per warp reserve the slots, then the thread walks its keys again and stores.  (A scan + atomic per 128 keys
+      // made this pass a 2.7 us chain of dependent shuffles and atomics.)  The smallest key of the image falls out.
       const uint4 *s4 = reinterpret_cast<const uint4 *>(skeys);
       const int n4 = A >> 2;
-      for (int base = 0; base < n4; base += blockDim.x) {
-        const int j = base + threadIdx.x;
-        const bool in = j < n4;
-        const uint4 kv = in ? s4[j] : make_uint4(0u, 0u, 0u, 0u);
-        hist_add(kv.x, in);
-        hist_add(kv.y, in);
-        hist_add(kv.z, in);
-        hist_add(kv.w, in);
+      int c = 0;
+      unsigned mymin = kKeySentinel;
+      for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+        const uint4 kv = s4[j];
+        c += (kv.x <= U ? 1 : 0) + (kv.y <= U ? 1 : 0) + (kv.z <= U ? 1 : 0) + (kv.w <= U ? 1 : 0);
+        mymin = min(min(mymin, kv.x), min(min(kv.y, kv.z), kv.w));
       }
-    } else {
-      for (int base = 0; base < A; base += blockDim.x) {
-        const int j = base + threadIdx.x;
-        hist_add(j < A ? key_at(j) : kKeySentinel, j < A);
+      const int incl = warp_scan_incl(c);
+      mymin = __reduce_min_sync(kFullMask, mymin);
+      // warp totals through shared memory and one redundant 32-wide scan per warp: 32 warps queueing on one
+      // shared-memory atomic (and a second one for the minimum) cost more than the pass itself
+      if (lane_id() == 31) {
+        scan_smem[warp_id()] = incl;
+        wmin_smem[warp_id()] = mymin;
       }
-    }
-    __syncthreads();
-    if (warp_id() == 0) {  // digit search: 8 bins per lane + warp scan
-      const unsigned lane = lane_id();
-      unsigned h[8];
-      int tot = 0;
-#pragma unroll
-      for (int d = 0; d < 8; ++d) {
-        h[d] = hist[lane * 8 + d];
-        tot += (int)h[d];
-      }
-      const int incl = warp_scan_incl(tot);
-      const int excl = incl - tot;
-      const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
-      __syncwarp();  // every lane has read sm_need before one lane overwrites it
-      if (excl < need && incl >= need) {
-        int acc = excl;
-#pragma unroll
-        for (int d = 0; d < 8; ++d) {
-          if (acc + (int)h[d] >= need) {
-            sm_need = need - acc;
-            sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
-            break;
+      __syncthreads();
+      const int nw = (int)(blockDim.x >> 5);  // <= 32
+      const int wt = (int)lane_id() < nw ? scan_smem[lane_id()] : 0;
+      const int wincl = warp_scan_incl(wt);
+      const int wbase = __shfl_sync(kFullMask, wincl - wt, (int)warp_id());
+      n_short = __shfl_sync(kFullMask, wincl, 31);
+      kmin_short = __reduce_min_sync(kFullMask, (int)lane_id() < nw ? wmin_smem[lane_id()] : kKeySentinel);
+      int pos = wbase + incl - c;
+      if (c) {
+        for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+          const uint4 kv = s4[j];
+          if (kv.x <= U) {
+            if (pos < kShortCap) sl_key[pos] = kv.x, sl_idx[pos] = 4 * j;
+            ++pos;
           }
-          acc += (int)h[d];
+          if (kv.y <= U) {
+            if (pos < kShortCap) sl_key[pos] = kv.y, sl_idx[pos] = 4 * j + 1;
+            ++pos;
+          }
+          if (kv.z <= U) {
+            if (pos < kShortCap) sl_key[pos] = kv.z, sl_idx[pos] = 4 * j + 2;
+            ++pos;
+          }
+          if (kv.w <= U) {
+            if (pos < kShortCap) sl_key[pos] = kv.w, sl_idx[pos] = 4 * j + 3;
+            ++pos;
+          }
         }
       }
+      __syncthreads();
+      use_short = n_short >= num_negative && n_short <= kShortCap;
+      DSPMB_TSTAMP(9);
     }
-    __syncthreads();
   }
-  DSPMB_TSTAMP(5);
-  const unsigned qkey = sm_prefix;  // the num_negative-th smallest APPROXIMATE key
-  if (qkey == kKeySentinel) {
-    // the num_negative-th smallest key is a non-candidate: CHECK_GE(temp.size(), num_negative) fails
-    // (multibox_target.cc:236)
-    if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_MINING_CANDIDATES);
-    return;
-  }
-  // Keys q approximate the reference's probabilities p with |q - p| <= delta * p, so the exact pivot lies in
-  // [Q/(1+delta), Q/(1-delta)]: keys below Q(1-3 delta) are certainly selected, keys above Q(1+3 delta) certainly
-  // not, and only the band in between is re-evaluated exactly and ranked by (p, anchor) like the stable sort.
-  const float Q = __uint_as_float(qkey);
-  const unsigned klo = __float_as_uint(fmul(Q, 1.0f - 3.0f * a.delta));
-  const unsigned khi = __float_as_uint(fmul(Q, 1.0f + 3.0f * a.delta));
-  if (threadIdx.x == 0) {
-    sm_carry = 0;  // surely selected
-    sm_dup = 0;    // ambiguous
-  }
-  __syncthreads();
+
   float *ct = a.cls_target + (size_t)b * A;
   int *amb_list = a.amb_list + (size_t)b * A;
   unsigned *amb_key = a.amb_key + (size_t)b * A;
-  int n_in_local = 0;
-  for (int base = 0; base < A; base += blockDim.x) {
-    const int j = base + threadIdx.x;
-    const unsigned kv = j < A ? key_at(j) : kKeySentinel;
-    if (kv < klo) {
-      ct[j] = 0.0f;
-      ++n_in_local;
+  for (int attempt = use_short ? 0 : 1; attempt < 2; ++attempt) {
+    const bool sh = attempt == 0;                                          // CTA-uniform
+    const unsigned *mk = sh ? sl_key : (kKeysInSmem ? skeys : gkeys);     // the keys this attempt selects from
+    const int mn = sh ? n_short : A;
+    __syncthreads();  // (second attempt: everybody has left the first one)
+    // MSB-first radix select of the num_negative-th smallest key.  Non-candidates carry the sentinel 0xffffffff
+    // (larger than the bits of any probability), so they are only reached if there are too few candidates.
+    if (threadIdx.x == 0) {
+      sm_prefix = 0u;
+      sm_need = num_negative;
     }
-    const bool amb = kv >= klo && kv <= khi;
-    const unsigned m = __ballot_sync(kFullMask, amb);
-    if (m) {
-      int wbase = 0;
-      if (lane_id() == 0) wbase = atomicAdd(&sm_dup, __popc(m));
-      wbase = __shfl_sync(kFullMask, wbase, 0);
-      if (amb) amb_list[wbase + __popc(m & ((1u << lane_id()) - 1u))] = j;
+    // Fast path: one 2048-bucket histogram over the range the candidate keys actually span (the bit patterns of
+    // positive floats order like the floats) replaces the four 8-bit radix passes: the bucket that holds the
+    // num_negative-th smallest key follows from a prefix sum, and the key itself from ranking the members of that one
+    // bucket.  A bucket too crowded to rank (massive ties) or too few candidates leave it to the radix passes below.
+    bool have_q = false;
+    if (kKeysInSmem) {
+      unsigned kmin = kKeySentinel, kmax = 0u;
+      if (sh) {
+        // range known from the compaction (smallest key of the image .. U); its per-thread re-zeroing of bucket[]
+        // and the barriers since then stand in for the zeroing below
+        kmin = kmin_short;
+        kmax = U;
+        if (threadIdx.x == 0) sm_np = 0;
+      } else {
+        for (int j = threadIdx.x; j < mn; j += blockDim.x) {
+          const unsigned kv = mk[j];
+          if (kv != kKeySentinel) {
+            kmin = min(kmin, kv);
+            kmax = max(kmax, kv);
+          }
+        }
+        kmin = __reduce_min_sync(kFullMask, kmin);
+        kmax = __reduce_max_sync(kFullMask, kmax);
+        if (threadIdx.x == 0) {
+          sm_kmin = kKeySentinel;
+          sm_kmax = 0u;
+          sm_np = 0;
+        }
+        for (int i = threadIdx.x; i < kLowBuckets; i += blockDim.x) bucket[i] = 0u;
+        __syncthreads();
+        if (lane_id() == 0) {
+          atomicMin(&sm_kmin, kmin);
+          atomicMax(&sm_kmax, kmax);
+        }
+        __syncthreads();
+        kmin = sm_kmin;
+        kmax = sm_kmax;
+      }
+      if (kmin != kKeySentinel) {  // CTA-uniform: at least one candidate
+        int shift = 0;
+        while (((kmax - kmin) >> shift) >= (unsigned)kLowBuckets) ++shift;
+        for (int j = threadIdx.x; j < mn; j += blockDim.x) {
+          const unsigned kv = mk[j];
+          if (kv != kKeySentinel) atomicAdd(&bucket[(kv - kmin) >> shift], 1u);
+        }
+        __syncthreads();
+        const unsigned c0 = bucket[2 * threadIdx.x], c1 = bucket[2 * threadIdx.x + 1];
+        int total;
+        const int ex = block_scan_excl((int)(c0 + c1), scan_smem, &total);  // total = number of candidates
+        if (ex < num_negative && ex + (int)c0 >= num_negative) {
+          sm_pb = 2 * threadIdx.x;
+          sm_before = ex;
+        } else if (ex + (int)c0 < num_negative && ex + (int)(c0 + c1) >= num_negative) {
+          sm_pb = 2 * threadIdx.x + 1;
+          sm_before = ex + (int)c0;
+        }
+        __syncthreads();
+        DSPMB_TSTAMP(10);
+        if (num_negative <= total) {  // otherwise the radix path reports the missing candidates
+          const unsigned P = (unsigned)sm_pb;
+          const int r = num_negative - sm_before;  // 1-based rank of the wanted key inside bucket P
+          const int cP = (int)bucket[P];
+          if (cP <= kPivotList) {
+            for (int j = threadIdx.x; j < mn; j += blockDim.x) {
+              const unsigned kv = mk[j];
+              if (kv != kKeySentinel && ((kv - kmin) >> shift) == P) plist[atomicAdd(&sm_np, 1)] = kv;
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < cP; i += blockDim.x) {
+              const unsigned v = plist[i];
+              int lo = 0, hi = 0;
+              for (int x = 0; x < cP; ++x) {
+                lo += plist[x] < v ? 1 : 0;
+                hi += plist[x] <= v ? 1 : 0;
+              }
+              if (lo < r && r <= hi) sm_prefix = v;  // equal keys write the same value
+            }
+            __syncthreads();
+            have_q = true;
+          }
+        }
+      }
     }
-  }
-  n_in_local = warp_sum_i32(n_in_local);
-  if (lane_id() == 0 && n_in_local) atomicAdd(&sm_carry, n_in_local);
-  __syncthreads();
-  DSPMB_TSTAMP(6);
-  const int n_amb = sm_dup;
-  const int need = num_negative - sm_carry;
-  if (need < 0 || need > n_amb) {  // would mean the error bound was violated
-    if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_INTERNAL);
+    for (int pass = 0; pass < (have_q ? 0 : 4); ++pass) {
+      const int shift = 24 - 8 * pass;
+      const unsigned mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0u;
+      __syncthreads();
+      const unsigned prefix = sm_prefix;
+      // warp-aggregated histogram update (probabilities cluster, so plain atomics would serialise)
+      auto hist_add = [&](unsigned kv, bool in_range) {
+        const bool hit = in_range && (kv & mask) == prefix;
+        const unsigned active = __ballot_sync(kFullMask, hit);
+        if (active == 0u) return;
+        // the digit of the first hit lane is counted for the whole warp with one ballot (probabilities cluster: in the
+        // first pass that is nearly every lane); the other lanes add themselves, and their digits rarely coincide
+        const unsigned digit = (kv >> shift) & 0xffu;
+        const int leader = __ffs(active) - 1;
+        const unsigned d0 = __shfl_sync(kFullMask, digit, leader);
+        const unsigned same = __ballot_sync(kFullMask, hit && digit == d0);
+        if ((int)lane_id() == leader) atomicAdd(&hist[d0], (unsigned)__popc(same));
+        else if (hit && digit != d0) atomicAdd(&hist[digit], 1u);
+      };
+      if (kKeysInSmem && !sh && (A & 3) == 0) {  // four keys per thread and iteration: one LDS.128, four independent updates
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(mk);
+        const int n4 = A >> 2;
+        for (int base = 0; base < n4; base += blockDim.x) {
+          const int j = base + threadIdx.x;
+          const bool in = j < n4;
+          const uint4 kv = in ? s4[j] : make_uint4(0u, 0u, 0u, 0u);
+          hist_add(kv.x, in);
+          hist_add(kv.y, in);
+          hist_add(kv.z, in);
+          hist_add(kv.w, in);
+        }
+      } else {
+        for (int base = 0; base < mn; base += blockDim.x) {
+          const int j = base + threadIdx.x;
+          hist_add(j < mn ? mk[j] : kKeySentinel, j < mn);
+        }
+      }
+      __syncthreads();
+      if (warp_id() == 0) {  // digit search: 8 bins per lane + warp scan
+        const unsigned lane = lane_id();
+        unsigned h[8];
+        int tot = 0;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          h[d] = hist[lane * 8 + d];
+          tot += (int)h[d];
+        }
+        const int incl = warp_scan_incl(tot);
+        const int excl = incl - tot;
+        const int need = sm_need;  // 1 <= need <= number of keys matching the prefix
+        __syncwarp();  // every lane has read sm_need before one lane overwrites it
+        if (excl < need && incl >= need) {
+          int acc = excl;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) {
+            if (acc + (int)h[d] >= need) {
+              sm_need = need - acc;
+              sm_prefix = prefix | ((unsigned)(lane * 8 + d) << shift);
+              break;
+            }
+            acc += (int)h[d];
+          }
+        }
+      }
+      __syncthreads();
+    }
+    DSPMB_TSTAMP(5);
+    const unsigned qkey = sm_prefix;  // the num_negative-th smallest APPROXIMATE key
+    if (qkey == kKeySentinel) {
+      // the num_negative-th smallest key is a non-candidate: CHECK_GE(temp.size(), num_negative) fails
+      // (multibox_target.cc:236)
+      if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_MINING_CANDIDATES);
+      return;
+    }
+    // Keys q approximate the reference's probabilities p with |q - p| <= delta * p, so the exact pivot lies in
+    // [Q/(1+delta), Q/(1-delta)]: keys below Q(1-3 delta) are certainly selected, keys above Q(1+3 delta) certainly
+    // not, and only the band in between is re-evaluated exactly and ranked by (p, anchor) like the stable sort.
+    const float Q = __uint_as_float(qkey);
+    const unsigned klo = __float_as_uint(fmul(Q, 1.0f - 3.0f * a.delta));
+    const unsigned khi = __float_as_uint(fmul(Q, 1.0f + 3.0f * a.delta));
+    if (sh && khi > U) continue;  // the band reaches past the shortlist's bound: keys beyond U could belong to it
+    if (threadIdx.x == 0) {
+      sm_carry = 0;  // surely selected
+      sm_dup = 0;    // ambiguous
+    }
+    __syncthreads();
+    int n_in_local = 0;
+    for (int base = 0; base < mn; base += blockDim.x) {
+      const int i = base + threadIdx.x;
+      const unsigned kv = i < mn ? mk[i] : kKeySentinel;
+      const int j = (sh && i < mn) ? sl_idx[i] : i;
+      if (kv < klo) {
+        ct[j] = 0.0f;
+        ++n_in_local;
+      }
+      const bool amb = kv >= klo && kv <= khi;
+      const unsigned m = __ballot_sync(kFullMask, amb);
+      if (m) {
+        int wbase = 0;
+        if (lane_id() == 0) wbase = atomicAdd(&sm_dup, __popc(m));
+        wbase = __shfl_sync(kFullMask, wbase, 0);
+        if (amb) amb_list[wbase + __popc(m & ((1u << lane_id()) - 1u))] = j;
+      }
+    }
+    n_in_local = warp_sum_i32(n_in_local);
+    if (lane_id() == 0) scan_smem[warp_id()] = n_in_local;  // per-warp partials, summed by every warp after the barrier
+    __syncthreads();
+    DSPMB_TSTAMP(6);
+    const int n_amb = sm_dup;
+    const int need = num_negative - warp_sum_i32(lane_id() < (blockDim.x >> 5) ? scan_smem[lane_id()] : 0);
+    if (need < 0 || need > n_amb) {  // would mean the error bound was violated
+      if (threadIdx.x == 0) atomicMin(&a.header->status, DSPMB_ERR_INTERNAL);
+      return;
+    }
+    if (need == n_amb) {  // the whole band is selected (typically: the pivot is alone in it) -- nothing to rank
+      for (int q = threadIdx.x; q < n_amb; q += blockDim.x) ct[amb_list[q]] = 0.0f;
+      DSPMB_TSTAMP(7);
+      return;
+    }
+    const float *p_cls = a.cls_preds + (size_t)b * a.C * A;
+    if (n_amb <= 4 * (int)(blockDim.x >> 5)) {  // a handful: one warp each (latency); many: one thread each (throughput)
+      for (int q = (int)warp_id(); q < n_amb; q += (int)(blockDim.x >> 5)) {
+        const int j = amb_list[q];
+        const float pe = a.fma_build ? exact_bg_prob_warp<true>(p_cls, j, A, a.C) : exact_bg_prob_warp<false>(p_cls, j, A, a.C);
+        if (lane_id() == 0) amb_key[q] = __float_as_uint(pe);
+      }
+    } else {
+      for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+        const int j = amb_list[q];
+        const float pe = a.fma_build ? exact_bg_prob<true>(p_cls, j, A, a.C) : exact_bg_prob<false>(p_cls, j, A, a.C);
+        amb_key[q] = __float_as_uint(pe);
+      }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
+      const unsigned kq = amb_key[q];
+      const int jq = amb_list[q];
+      int rank = 0;
+      for (int i = 0; i < n_amb; ++i) {
+        const unsigned ki = amb_key[i];
+        rank += (ki < kq || (ki == kq && amb_list[i] < jq)) ? 1 : 0;
+      }
+      if (rank < need) ct[jq] = 0.0f;
+    }
+    DSPMB_TSTAMP(7);
     return;
   }
-  const float *p_cls = a.cls_preds + (size_t)b * a.C * A;
-  if (n_amb <= 4 * (int)(blockDim.x >> 5)) {  // a handful: one warp each (latency); many: one thread each (throughput)
-    for (int q = (int)warp_id(); q < n_amb; q += (int)(blockDim.x >> 5)) {
-      const int j = amb_list[q];
-      const float pe = a.fma_build ? exact_bg_prob_warp<true>(p_cls, j, A, a.C) : exact_bg_prob_warp<false>(p_cls, j, A, a.C);
-      if (lane_id() == 0) amb_key[q] = __float_as_uint(pe);
-    }
-  } else {
-    for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
-      const int j = amb_list[q];
-      const float pe = a.fma_build ? exact_bg_prob<true>(p_cls, j, A, a.C) : exact_bg_prob<false>(p_cls, j, A, a.C);
-      amb_key[q] = __float_as_uint(pe);
-    }
-  }
-  __syncthreads();
-  for (int q = threadIdx.x; q < n_amb; q += blockDim.x) {
-    const unsigned kq = amb_key[q];
-    const int jq = amb_list[q];
-    int rank = 0;
-    for (int i = 0; i < n_amb; ++i) {
-      const unsigned ki = amb_key[i];
-      rank += (ki < kq || (ki == kq && amb_list[i] < jq)) ? 1 : 0;
-    }
-    if (rank < need) ct[jq] = 0.0f;
-  }
-  DSPMB_TSTAMP(7);
 }
 
 
@@ -1861,6 +2005,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   ta.vw = variances[2];
   ta.vh = variances[3];
   ta.fma_build = libm_fma_mode();
+  ta.shortlist = tuning(DSPMB_TUNE_TARGET_SHORTLIST);
 
   const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L +
                        sizeof(unsigned short) * (size_t)L * (kStreamThreads / 32);
@@ -1868,11 +2013,11 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
                        2 * sizeof(int) * (size_t)((L + 3) & ~3) +
                        (size_t)((L + 15) / 16) * 16 + sizeof(unsigned) * (size_t)((((A + 31) / 32) + 3) & ~3);
   const bool keys_in_smem = smem2 + sizeof(unsigned) * (size_t)A <= 170 * 1024;
-  const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)A : 0);
+  const size_t smem2_total = smem2 + (keys_in_smem ? sizeof(unsigned) * (size_t)((A + 3) & ~3) + 2 * sizeof(unsigned) * (size_t)kShortCap : 0);
   DSPMB_REQUIRE(smem1 <= 48 * 1024, "MultiBoxTarget: more than %d label slots are not supported", 48 * 1024 / 36);
   DSPMB_REQUIRE(smem2 <= 190 * 1024, "MultiBoxTarget: A=%d / L=%d exceed the matcher's shared memory", A, L);
-  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 190 * 1024);  // + ~31 KB static
-  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 190 * 1024);
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<true>, 204 * 1024);  // + ~14 KB static
+  DSPMB_ENSURE_DYN_SMEM(target_match_kernel<false>, 204 * 1024);
   const int phases = tuning(DSPMB_TUNE_PHASES);
   dim3 grid1(ta.T, B);
   if (phases & 1) {
@@ -1923,10 +2068,20 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     ++ctx.launches;
   } else if (phases & 2) {
     ProfileScope _p(kSlotTargetMatch, stream);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B);
+    cfg.blockDim = dim3(kMatchThreads);
+    cfg.dynamicSmemBytes = smem2_total;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tuning(DSPMB_TUNE_TARGET_PDL) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     if (keys_in_smem)
-      target_match_kernel<true><<<B, kMatchThreads, smem2_total, stream>>>(ta);
+      DSPMB_CUDA_TRY(cudaLaunchKernelEx(&cfg, target_match_kernel<true>, ta));
     else
-      target_match_kernel<false><<<B, kMatchThreads, smem2_total, stream>>>(ta);
+      DSPMB_CUDA_TRY(cudaLaunchKernelEx(&cfg, target_match_kernel<false>, ta));
     ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());

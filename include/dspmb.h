@@ -265,10 +265,13 @@ const char *dspmb_profile_kernel_name(int slot);
                                            of ~8 dependent global-memory round trips and barriers, not a throughput
                                            problem, so eight times the threads buy nothing)                          */
 #define DSPMB_TUNE_NMS_PIPELINE 8       /* 1 (default): tiled standalone NMS; 0: full-mask kernels                   */
-#define DSPMB_TUNE_DET_PREFETCH 9        /* detection stream kernel: CTA start issues an L2 prefetch for the tile this many
-                                           CTAs ahead in launch order (default 0 = off: measured 54.6 us/step without,
-                                           57.0 us with a distance of one resident wave -- the kernel is not short of
-                                           requests in flight)                                                       */
+#define DSPMB_TUNE_DET_PREFETCH 9        /* detection stream kernel: once a CTA's own tile has landed, one thread issues
+                                           an L2 prefetch for the class tile of the CTA this many launches ahead, so
+                                           that DRAM keeps working while the resident CTAs compute (the CTAs of a wave
+                                           load together and compute together).  Default 600; measured stream kernel
+                                           24.6 us without, 24.3 / 22.9 / 22.6 / 22.6 / 23.8 / 24.7 us at 150 / 300 /
+                                           500 / 700 / 900 / 1332 CTAs.  (Issued at CTA start, as in round 2's first
+                                           attempt, the prefetch cost +2.5 us.)  0 = off                              */
 #define DSPMB_TUNE_TARGET_PREFETCH 10    /* same for the target stream kernel                                        */
 #define DSPMB_TUNE_DET_SPLIT 11           /* detection fork/join pipeline: image groups whose post-processing overlaps the
                                            stream kernel of the next group inside the graph (default 1 = no split, max 4;
@@ -277,13 +280,22 @@ const char *dspmb_profile_kernel_name(int slot);
                                            stream CTAs have drained, and the stream kernel itself slows down)          */
 #define DSPMB_TUNE_DET_LEAN 12            /* 1: the TMA-fed detection stream kernel stages only the class rows; survivors
                                            fetch their loc_pred / anchor values from global memory (9 instead of 7
-                                           CTAs per SM); 2: the same with the class tile as ONE cp.async.bulk.tensor
-                                           2-D copy (tensor map, UTMALDG) instead of NFG 1-D bulk copies; 0: loc_pred
-                                           and anchors are staged by bulk copies as well                             */
+                                           CTAs per SM); 2 (default): the same with the class tile as ONE
+                                           cp.async.bulk.tensor 2-D copy (tensor map, UTMALDG) instead of NFG 1-D bulk
+                                           copies (measured 51.8 vs 53.3 us per step); 0: loc_pred and anchors are
+                                           staged by bulk copies as well                                             */
 #define DSPMB_TUNE_TARGET_SMALL 13        /* target stream kernel with ONE anchor per thread: 0 never, 1 (default) when the
                                            two-anchor grid is at most about two waves of CTAs (latency-bound batches:
                                            55.5 -> 53.0 us at 8 images of SSD-512, 57.5 -> 55.4 us at 16), 2 always       */
-#define DSPMB_NUM_TUNING 14
+#define DSPMB_TUNE_TARGET_SHORTLIST 14    /* 1 (default): the target matcher mines the hard negatives on a shortlist -- a
+                                           2048-key sample bounds the pivot, one pass compacts the keys below the bound
+                                           into shared memory, range / histogram / pivot / final pass run on that list
+                                           (verified by its count; falls back to the full walk); 0: always four passes
+                                           over all A keys                                                            */
+#define DSPMB_TUNE_TARGET_PDL 15          /* 1 (default): the target matcher is a programmatic dependent of the stream
+                                           kernel (resident and through its label-only prologue before the stream
+                                           kernel has drained); 0: plain stream order                                */
+#define DSPMB_NUM_TUNING 16
 int dspmb_set_tuning(int knob, int value);
 
 /* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)

@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, '.')
 from dspnet_b200 import _lib
-for k in range(6):
+for k in range(32):
     v = os.environ.get('TUNE%d' % k)
     if v is not None:
         _lib.lib().dspmb_set_tuning(k, int(v))

@@ -57,6 +57,11 @@ tt = t[ok]
 for k, nme in enumerate(names):
     d = tt[:, k + 1] - tt[:, k]
     print('  %-11s mean %6.2f  max %6.2f us' % (nme, d.mean().item(), d.max().item()))
+if (tt[:, 8] > 0).any():   # shortlist sub-phases of 'pivot' (stamps 8, 9, 10)
+    sub = tt[tt[:, 8] > 0]
+    for a_, b_, nme in ((4, 8, 'sample'), (8, 9, 'compaction'), (9, 10, 'histogram'), (10, 5, 'pivot rank')):
+        d = sub[:, b_] - sub[:, a_]
+        print('    %-11s mean %6.2f  max %6.2f us' % (nme, d.mean().item(), d.max().item()))
 d = tt[:, 7] - tt[:, 0]
 print('  %-11s mean %6.2f  max %6.2f us (image %d)' % ('total', d.mean().item(), d.max().item(), int(d.argmax())))
 print('  span of the kernel: %.2f us' % (tt[:, 7].max() - tt[:, 0].min()).item())

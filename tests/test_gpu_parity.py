@@ -366,6 +366,53 @@ def test_target_mining_band_with_massive_ties(oracle, cuda):
     _check_target(oracle, cuda, anchors, lab, cp2, negative_mining_ratio=3)
 
 
+@pytest.mark.parametrize("shortlist,pdl", [(1, 1), (0, 1), (1, 0)])
+def test_target_mining_shortlist_paths(oracle, cuda, shortlist, pdl):
+    """Hard-negative mining on the sampled shortlist (DSPMB_TUNE_TARGET_SHORTLIST, the default) and on all A keys must
+    agree with the oracle in every regime: a pivot far below the sampled bound (the shortlist decides), a negative
+    count beyond the shortlist's capacity (falls back), probabilities so tightly spaced that the pivot's ambiguity band
+    reaches past the bound (falls back after the selection), and a tie group that holds the pivot."""
+    from dspnet_b200 import _lib
+    L = _lib.lib()
+    old = L.dspmb_set_tuning(_lib.TUNE_TARGET_SHORTLIST, shortlist)
+    old_pdl = L.dspmb_set_tuning(_lib.TUNE_TARGET_PDL, pdl)
+    try:
+        anchors, lab, cp = util.target_inputs(oracle, "ssd512", 3, config_id=41)
+        for ratio in (3, 0.2, 40):
+            _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=ratio)
+        rng = np.random.default_rng(41)
+        A = cp.shape[2]
+        tight = np.zeros_like(cp)
+        for b in range(cp.shape[0]):
+            tight[b, 0] = rng.permutation(np.linspace(-0.01, 0.01, A)).astype(np.float32)
+        _check_target(oracle, cuda, anchors, lab, tight, negative_mining_ratio=3)
+        tied = np.zeros_like(cp)
+        tied[:, 0] = 3.0
+        tied[:, 0, ::37] = -1.0       # 664 anchors share the lowest background probability
+        _check_target(oracle, cuda, anchors, lab, tied, negative_mining_ratio=3)
+        _check_target(oracle, cuda, anchors, lab, tied, negative_mining_ratio=9)
+        anchors, lab, cp = util.target_inputs(oracle, "ssd300", 2, config_id=42)
+        _check_target(oracle, cuda, anchors, lab, cp, negative_mining_ratio=3)
+    finally:
+        L.dspmb_set_tuning(_lib.TUNE_TARGET_SHORTLIST, old)
+        L.dspmb_set_tuning(_lib.TUNE_TARGET_PDL, old_pdl)
+
+
+@pytest.mark.parametrize("lean", [0, 1, 2])
+def test_detection_stream_staging_variants(oracle, cuda, lean):
+    """DSPMB_TUNE_DET_LEAN: loc_pred / anchors staged by bulk copies as well (0), 1-D bulk copies of the class rows (1)
+    and the class tile through one cp.async.bulk.tensor 2-D copy (2, the default) give identical results."""
+    from dspnet_b200 import _lib
+    L = _lib.lib()
+    old = L.dspmb_set_tuning(_lib.TUNE_DET_LEAN, lean)
+    try:
+        for preset, batch in (("ssd512", 3), ("dspnet_cs", 2), ("ssd300", 2)):
+            anchors, prob, lp = util.detection_inputs(oracle, preset, batch, config_id=43)
+            _check_detection(oracle, cuda, anchors, prob, lp, nms_threshold=0.45, nms_topk=400)
+    finally:
+        L.dspmb_set_tuning(_lib.TUNE_DET_LEAN, old)
+
+
 def test_fused_gather_single_rank(oracle, cuda):
     """The fused compaction + peer all-gather kernel with world = 1 (the multi-rank path is exercised by bench.py
     under torchrun): gathered rows equal the surviving rows of the operator output in row order."""
