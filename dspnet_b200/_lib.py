@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdspmb.so")
+# DSPMB_LIB: another build of the same library (A/B of compile-time settings, scripts/ab_build.sh); never a CPU path
+LIB_PATH = os.environ.get("DSPMB_LIB") or os.path.join(_HERE, "libdspmb.so")
 
 OK = 0
 ERR_BAD_ARG = -1

@@ -109,6 +109,7 @@ struct TargetArgs {
   float overlap_threshold, ignore_label, mining_ratio, mining_thresh;
   float vx, vy, vw, vh;
   int fma_build;
+  int prefetch;   // stream kernel: late L2 prefetch distance in CTAs of launch order (0: none)
   int shortlist;  // matcher: mine on a shortlist of the keys below a sampled bound (DSPMB_TUNE_TARGET_SHORTLIST)
 };
 
@@ -320,6 +321,19 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
   if (threadIdx.x == 0) sm_pos = 0;
   __syncthreads();
   DSPMB_SSTAMP(2);
+  if (a.prefetch > 0 && threadIdx.x == 64 && mining) {
+    // late L2 prefetch (DSPMB_TUNE_TARGET_PREFETCH): this CTA's own loads have been issued long ago; ask L2 for the
+    // logits tile of the CTA `prefetch` launches ahead so that DRAM has work while the resident CTAs compute
+    const int lin = b * (int)gridDim.x + t + a.prefetch;
+    const int pb = lin / (int)gridDim.x, pt = lin - pb * (int)gridDim.x;
+    if (pb < (int)gridDim.y) {
+      const int pbegin = pt * kTile, prow = min(kTile, A - pbegin);
+      const float *pp = a.cls_preds + (size_t)pb * C * A + pbegin;
+      if (prow > 0 && (prow & 3) == 0 && (reinterpret_cast<uintptr_t>(pp) & 15) == 0 && (A & 3) == 0)
+        for (int c = 0; c < C; ++c)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pp + (size_t)c * A), "r"(prow * 4) : "memory");
+    }
+  }
 
   float best_iou[VEC], area[VEC];
   int best_k[VEC];
@@ -2006,6 +2020,7 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   ta.vh = variances[3];
   ta.fma_build = libm_fma_mode();
   ta.shortlist = tuning(DSPMB_TUNE_TARGET_SHORTLIST);
+  ta.prefetch = tuning(DSPMB_TUNE_TARGET_PREFETCH);
 
   const size_t smem1 = (sizeof(float4) + sizeof(unsigned long long) + sizeof(float)) * (size_t)L +
                        sizeof(unsigned short) * (size_t)L * (kStreamThreads / 32);

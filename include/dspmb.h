@@ -272,7 +272,10 @@ const char *dspmb_profile_kernel_name(int slot);
                                            24.6 us without, 24.3 / 22.9 / 22.6 / 22.6 / 23.8 / 24.7 us at 150 / 300 /
                                            500 / 700 / 900 / 1332 CTAs.  (Issued at CTA start, as in round 2's first
                                            attempt, the prefetch cost +2.5 us.)  0 = off                              */
-#define DSPMB_TUNE_TARGET_PREFETCH 10    /* same for the target stream kernel                                        */
+#define DSPMB_TUNE_TARGET_PREFETCH 10    /* the same late prefetch (logits tile of the CTA this many launches ahead) in
+                                           the target stream kernel; default 0 = off: measured 47.4 us without, 49.3 /
+                                           49.0 / 49.4 us at 300 / 740 / 1500 CTAs -- that kernel is bound by latency
+                                           and instruction issue, its DRAM queues are never empty                    */
 #define DSPMB_TUNE_DET_SPLIT 11           /* detection fork/join pipeline: image groups whose post-processing overlaps the
                                            stream kernel of the next group inside the graph (default 1 = no split, max 4;
                                            measured at SSD-512 B=32: 54.0 / 56.2 / 61.7 / 69.5 us for 1 / 2 / 3 / 4 groups:
