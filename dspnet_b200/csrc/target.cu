@@ -33,6 +33,9 @@ namespace {
 constexpr int kStreamThreads = 128;
 constexpr int kMatchThreads = 1024;
 constexpr int kShortCap = 4096;  // matcher: capacity of the mining shortlist (keys + anchor ids in shared memory)
+// smallest A the shortlist is used for: below, four passes over the keys cost less than the sample + compaction barriers
+// (SSD-300, 8732 anchors, one image, cold L2: 59.4 us per step without, 61.5 us with)
+constexpr int kShortMinAnchors = 12000;
 #ifndef DSPMB_TARGET_MIN_BLOCKS
 #define DSPMB_TARGET_MIN_BLOCKS 5
 #endif
@@ -1002,7 +1005,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
   unsigned U = 0u, kmin_short = 0u;
   int n_short = 0;
   bool use_short = false;
-  if (kKeysInSmem && a.shortlist && (A & 3) == 0 && A >= 4 * kSampleKeys) {
+  if (kKeysInSmem && a.shortlist && (A & 3) == 0 && A >= kShortMinAnchors) {
     // Sample histogram on the float bits themselves (sign 0, 8 exponent and 4 mantissa bits: 16 buckets per octave of
     // the probability, 2032 buckets up to p = 1): no range pass, and the bound only has to be roughly right.
     // bucket[] was zeroed at kernel start.
@@ -2090,7 +2093,10 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = tuning(DSPMB_TUNE_TARGET_PDL) ? 1 : 0;
+    // programmatic launch pays when the stream kernel has a tail to hide behind (SSD-512: -0.6 us at 64 images, -1.6 us
+    // at 8); with less than one CTA per SM there is none, and the cold single-image step measured 3 us SLOWER
+    attr[0].val.programmaticStreamSerializationAllowed =
+        (tuning(DSPMB_TUNE_TARGET_PDL) && (long long)ta.T * B > kNumSMs) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (keys_in_smem)
