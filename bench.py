@@ -851,6 +851,9 @@ def main():
         prob_sets = [torch.from_numpy(inputs["prob"]).to(dev) for _ in range(rotate)]
         loc_sets = [torch.from_numpy(inputs["loc"]).to(dev) for _ in range(rotate)]
         out_sets = [dplan.new_output() for _ in range(rotate)]
+        # multi-GPU: the gather kernel only scans the rows below the operator's valid count (one per resident set: it
+        # reads them beside the next step); without it every step re-read the whole 22 MB output on the side stream
+        valid_sets = [dplan.new_valid_count() if world > 1 else None for _ in range(rotate)]
     if "target" in ops:
         tplan = TargetPlan(Bg, A, L, C, dev, **TGT_PARAMS)
         lab_d = torch.from_numpy(inputs["lab"]).to(dev)
@@ -875,9 +878,10 @@ def main():
         if tplan is not None:
             tplan.run(an, lab_d, logit_sets[s], tout_sets[s], stats=stat_sets[s])
         if dplan is not None:
-            dplan.run(prob_sets[s], loc_sets[s], an, out_sets[s])
+            dplan.run(prob_sets[s], loc_sets[s], an, out_sets[s], valid=valid_sets[s])
         if gatherer is not None:
             gatherer.submit(out_sets[s] if dplan is not None else None, i,
+                            valid_count=valid_sets[s] if dplan is not None else None,
                             stats=stat_sets[s] if tplan is not None else None)
             if consume:
                 gatherer.gathered(i)

@@ -31,7 +31,8 @@ EXPORTS = (
     "dspmb_status", "dspmb_nms_workspace_bytes", "dspmb_nms_f32", "dspmb_nms_host", "dspmb_test_expf",
     "dspmb_test_logf", "dspmb_profile_enable", "dspmb_profile_read", "dspmb_profile_kernel_name", "dspmb_detection_compact_f32", "dspmb_set_tuning", "dspmb_gather_buffer_bytes", "dspmb_p2p_alloc",
     "dspmb_p2p_open", "dspmb_p2p_close", "dspmb_p2p_free", "dspmb_detection_gather_f32", "dspmb_detection_gather_wait", "dspmb_detection_gather_read",
-    "dspmb_detection_gather_ack", "dspmb_gather_error",
+    "dspmb_detection_gather_ack", "dspmb_gather_error", "dspmb_gather_ctx_create", "dspmb_gather_ctx_side_stream",
+    "dspmb_gather_ctx_destroy", "dspmb_gather_submit",
     "dspmb_bbox_overlaps_f64", "dspmb_detection_postfilter_f32", "dspmb_map_match_f32", "dspmb_last_launch_count",
     "dspmb_debug_trace", "dspmb_detection_heads_workspace_bytes", "dspmb_detection_heads_f32",
     "dspmb_multibox_loss_workspace_bytes", "dspmb_multibox_loss_f32",
@@ -99,6 +100,12 @@ def lib():
                                              ctypes.POINTER(c_void_p), c_int, c_ll, c_void_p]
     L.dspmb_detection_gather_wait.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_void_p]
     L.dspmb_detection_gather_ack.argtypes = [c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p), c_int, c_ll, c_void_p]
+    L.dspmb_gather_ctx_create.restype = c_void_p
+    L.dspmb_gather_ctx_side_stream.argtypes = [c_void_p]
+    L.dspmb_gather_ctx_side_stream.restype = c_void_p
+    L.dspmb_gather_ctx_destroy.argtypes = [c_void_p]
+    L.dspmb_gather_submit.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                      ctypes.POINTER(c_void_p), c_int, c_ll, c_ll, c_int, c_void_p]
     L.dspmb_detection_gather_read.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     L.dspmb_debug_trace.argtypes = [c_void_p]
     L.dspmb_debug_stamps.argtypes = [c_void_p]

@@ -3459,6 +3459,66 @@ extern "C" int dspmb_detection_gather_ack(int B, int K, int stats_width, int ran
   return DSPMB_OK;
 }
 
+// ---- the whole per-step exchange of a rank in ONE host call ----
+// submit() used to be ~10 Python-level calls per step (two event records, two stream waits, up to three kernel launches,
+// each through ctypes / torch): at 50 us per step that host work was as long as the step itself.  The context owns the
+// side stream and the events; dspmb_gather_submit enqueues, in order: compute stream waits for the gather kernel that
+// read `out` two steps ago; (side) bounded wait + acknowledgement of the generation the slot still holds when nobody
+// read it; side stream waits for the compute stream's work so far; gather kernel; `done` event.
+struct GatherCtx {
+  cudaStream_t side;
+  cudaEvent_t ready[2], done[2];
+};
+
+extern "C" void *dspmb_gather_ctx_create(void) {
+  GatherCtx *c = new GatherCtx();
+  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    set_error("gather_ctx_create: cudaStreamCreateWithFlags failed");
+    return nullptr;
+  }
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&c->ready[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
+  }
+  return c;
+}
+
+extern "C" void *dspmb_gather_ctx_side_stream(void *ctx) { return ctx ? (void *)((GatherCtx *)ctx)->side : nullptr; }
+
+extern "C" int dspmb_gather_ctx_destroy(void *ctx) {
+  if (!ctx) return DSPMB_OK;
+  GatherCtx *c = (GatherCtx *)ctx;
+  for (int i = 0; i < 2; ++i) {
+    cudaEventDestroy(c->ready[i]);
+    cudaEventDestroy(c->done[i]);
+  }
+  cudaStreamDestroy(c->side);
+  delete c;
+  return DSPMB_OK;
+}
+
+extern "C" int dspmb_gather_submit(void *ctx, const float *out, const int32_t *valid_count, const int32_t *stats, int B,
+                                   int A, int K, int stats_width, int rank, int world, void *const *peer_bases, int slot,
+                                   long long seq, long long prev_seq, int release_prev, void *compute_stream_) {
+  DSPMB_REQUIRE(ctx && (slot == 0 || slot == 1), "gather_submit: bad argument");
+  GatherCtx *c = (GatherCtx *)ctx;
+  cudaStream_t compute = (cudaStream_t)compute_stream_;
+  if (prev_seq > 0) DSPMB_CUDA_TRY(cudaStreamWaitEvent(compute, c->done[slot], 0));
+  if (prev_seq > 0 && release_prev) {
+    int rc = dspmb_detection_gather_wait(peer_bases[rank], B, K, stats_width, world, slot, prev_seq, c->side);
+    if (rc != DSPMB_OK) return rc;
+    rc = dspmb_detection_gather_ack(B, K, stats_width, rank, world, peer_bases, slot, prev_seq, c->side);
+    if (rc != DSPMB_OK) return rc;
+  }
+  DSPMB_CUDA_TRY(cudaEventRecord(c->ready[slot], compute));
+  DSPMB_CUDA_TRY(cudaStreamWaitEvent(c->side, c->ready[slot], 0));
+  const int rc = dspmb_detection_gather_f32(out, valid_count, stats, B, A, K, stats_width, rank, world, peer_bases, slot, seq, c->side);
+  if (rc != DSPMB_OK) return rc;
+  DSPMB_CUDA_TRY(cudaEventRecord(c->done[slot], c->side));
+  return DSPMB_OK;
+}
+
 extern "C" int dspmb_detection_gather_read(const void *local_base, int B, int K, int stats_width, int world, int slot,
                                            float *rows_out, int32_t *counts_out, int32_t *stats_out, void *stream_) {
   DSPMB_REQUIRE(local_base && (slot == 0 || slot == 1), "detection_gather_read: bad argument");

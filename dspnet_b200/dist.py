@@ -187,9 +187,13 @@ class P2PDetectionGatherer:
                 self._opened.append(p.value)
         self.step_of = [None, None]     # step whose data currently lives in the slot
         self.unacked = [False, False]   # ... and has not been acknowledged by this rank yet
-        self.side = torch.cuda.Stream(self.device)  # the exchange runs beside the next step's kernels
-        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
-        self.done = [torch.cuda.Event(), torch.cuda.Event()]
+        # the exchange runs beside the next step's kernels, on a side stream owned by the library's gather context
+        # (submit() is ONE C call: event edges, acknowledgement of an unread generation, gather kernel)
+        with torch.cuda.device(self.device):
+            self.ctx = self.lib.dspmb_gather_ctx_create()
+        if not self.ctx:
+            raise _lib.DspmbError(_lib.ERR_CUDA, self.lib.dspmb_last_error().decode())
+        self.side = torch.cuda.ExternalStream(self.lib.dspmb_gather_ctx_side_stream(self.ctx), device=self.device)
         self.read = torch.cuda.Event()
         if world > 1:
             dist.barrier(group=group)  # every peer has mapped every buffer before the first store
@@ -216,22 +220,21 @@ class P2PDetectionGatherer:
 
     def submit(self, out, step, valid_count=None, stats=None):
         slot = step & 1
-        assert self.step_of[slot] is None or step == self.step_of[slot] + 2, "submit() must be called for every step"
+        prev = self.step_of[slot]
+        assert prev is None or step == prev + 2, "submit() must be called for every step"
         compute = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device):
-            if self.step_of[slot] is not None:
-                compute.wait_event(self.done[slot])  # the gather kernel that read `out` two steps ago has finished
-            self.release(slot)
-            self.step_of[slot] = step
-            self.unacked[slot] = True
-            self.ready[slot].record(compute)
-            self.side.wait_event(self.ready[slot])
-            _lib.check(self.lib.dspmb_detection_gather_f32(
-                out.data_ptr() if out is not None else None,
+            # one call: compute waits for the gather kernel that read `out` two steps ago; an unread generation in the
+            # slot is acknowledged on the consumer's behalf (after it has arrived); side stream waits for compute;
+            # gather kernel of this step
+            _lib.check(self.lib.dspmb_gather_submit(
+                self.ctx, out.data_ptr() if out is not None else None,
                 valid_count.data_ptr() if valid_count is not None else None,
                 stats.data_ptr() if (stats is not None and self.SW) else None, self.B, self.A, self.K, self.SW,
-                self.rank, self.world, self.peers, slot, step + 1, self._side()))
-            self.done[slot].record(self.side)
+                self.rank, self.world, self.peers, slot, step + 1, 0 if prev is None else prev + 1,
+                1 if (prev is not None and self.unacked[slot]) else 0, ctypes.c_void_p(compute.cuda_stream)))
+        self.step_of[slot] = step
+        self.unacked[slot] = True
 
     def _fetch(self, step, want_rows, want_stats):
         slot = step & 1
@@ -288,6 +291,9 @@ class P2PDetectionGatherer:
             torch.cuda.synchronize(self.device)
             if self.world > 1:
                 dist.barrier()
+            if self.ctx:
+                self.lib.dspmb_gather_ctx_destroy(self.ctx)
+                self.ctx = None
             for p in self._opened:
                 self.lib.dspmb_p2p_close(p)
             self._opened = []

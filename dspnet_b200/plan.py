@@ -36,13 +36,20 @@ class DetectionPlan:
     def new_output(self):
         return torch.empty((self.B, self.A, 7), dtype=torch.float32, device=self.device)
 
-    def run(self, cls_prob, loc_pred, anchor, out, stream=None):
+    def new_valid_count(self):
+        """(B,) int32 -- pass as run(..., valid=): rows at and beyond valid[b] of image b are untouched (-1)."""
+        return torch.empty((self.B,), dtype=torch.int32, device=self.device)
+
+    def run(self, cls_prob, loc_pred, anchor, out, stream=None, valid=None):
+        """``valid``: per-call valid-count tensor instead of the plan's own (callers that keep several outputs in
+        flight, e.g. beside the P2P gather, need one per output)."""
         s = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         if torch.cuda.current_device() != self._index:  # the library keys graphs / streams on the CURRENT device
             with torch.cuda.device(self.device):
-                return self.run(cls_prob, loc_pred, anchor, out, s)
+                return self.run(cls_prob, loc_pred, anchor, out, s, valid)
+        tail = self._tail if valid is None else self._tail[:9] + (valid.data_ptr(),) + self._tail[10:]
         rc = self.lib.dspmb_detection_f32(cls_prob.data_ptr(), loc_pred.data_ptr(), anchor.data_ptr(), out.data_ptr(),
-                                          *self._tail, s)
+                                          *tail, s)
         if rc:
             _lib.check(rc)
         if self.launches_per_run is None:

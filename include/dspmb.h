@@ -171,6 +171,17 @@ int dspmb_detection_gather_wait(void *local_base, int B, int K, int stats_width,
                                 void *stream);
 int dspmb_detection_gather_ack(int B, int K, int stats_width, int rank, int world, void *const *peer_bases, int slot,
                                long long seq, void *stream);
+/* The per-step exchange of a rank in one host call (what P2PDetectionGatherer.submit issues).  The context owns a side
+ * stream and the events that order it against the caller's compute stream.  dspmb_gather_submit enqueues: compute
+ * stream waits for the gather kernel that read `out` two steps ago (prev_seq > 0: the slot has been used before);
+ * release_prev: bounded wait + acknowledgement, on the side stream, of generation prev_seq that this rank never read;
+ * side stream waits for everything enqueued on compute_stream so far; the gather kernel of generation seq. */
+void *dspmb_gather_ctx_create(void);
+void *dspmb_gather_ctx_side_stream(void *ctx);
+int dspmb_gather_ctx_destroy(void *ctx);
+int dspmb_gather_submit(void *ctx, const float *out, const int32_t *valid_count, const int32_t *stats, int B, int A, int K,
+                        int stats_width, int rank, int world, void *const *peer_bases, int slot, long long seq,
+                        long long prev_seq, int release_prev, void *compute_stream);
 /* Copies slot `slot` of this rank's buffer into rows_out (world*B, K, 7), counts_out (world*B) and stats_out
  * (world*B, stats_width) (device, async; NULL pointers are skipped). */
 int dspmb_detection_gather_read(const void *local_base, int B, int K, int stats_width, int world, int slot,

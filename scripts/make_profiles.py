@@ -148,3 +148,21 @@ with open(os.path.join(P, 'sass_%s.txt' % R), 'w') as f:
                 f.write('/*%s*/ %s\n' % (m.group(1), m.group(2).rstrip(' ;')))
 print({k: {kk: round(vv[1] / vv[0], 1) for kk, vv in v.items() if kk.startswith(('det_', 'target_'))} for k, v in shares.items()})
 print('traffic', {k: v for k, v in tj.items() if k not in ('by_kernel', 'source')})
+
+# 6. multi-GPU rows (scripts/scale_run.sh under gpurun --gpus N) next to the N=1 bench lines
+scal = {}
+for wl in ('detection', 'target'):
+    rows = []
+    for n in (1, 2, 4, 8):
+        path = os.path.join(P, 'bench_%s_%s.json' % (wl, R)) if n == 1 else os.path.join(G, 'scale_%s_n%d.json' % (wl, n))
+        if not os.path.exists(path):
+            continue
+        txt = open(path).read().strip()
+        d = json.loads(txt if n == 1 else txt.splitlines()[-1])
+        rows.append({'n_gpus': d['n_gpus'], 'value': d['value'], 'ms_per_step': d['ms_per_step'], 'e2e': d['e2e']['value'],
+                     'parity_check': d['parity_check']['result'], 'gather_check': d.get('gather_check'), 'scaling': d['scaling'],
+                     'parallelism': d['config'].get('parallelism')})
+    scal[wl] = rows
+if any(len(v) > 1 for v in scal.values()):
+    scal['note'] = 'N=1 rows are the bench lines of this directory; N>1: bench.py --gpus N --workload W under torchrun (scripts/scale_run.sh), all from the final library'
+    json.dump(scal, open(os.path.join(P, 'scaling_%s.json' % R), 'w'), indent=1)

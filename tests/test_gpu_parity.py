@@ -433,6 +433,14 @@ def test_fused_gather_single_rank(oracle, cuda):
             assert (rows[b, len(keep):].cpu().numpy() == -1).all()
         r2, c2 = compact_rows(out, 200)
         assert torch.equal(r2, rows) and torch.equal(c2, counts)
+        # the same through the operator's valid counts (the gather kernel then scans only the rows below them)
+        out2, valid = MultiBoxDetection(_t(prob, cuda), _t(lp, cuda), _t(anchors, cuda), nms_threshold=0.45, nms_topk=400,
+                                        return_valid_count=True)
+        g.submit(out2, 1, valid_count=valid)
+        rows1, counts1 = g.gathered(1)
+        torch.cuda.synchronize()
+        assert torch.equal(rows1, rows) and torch.equal(counts1, counts)
+        assert g.check()
     finally:
         g.close()
 
