@@ -126,9 +126,9 @@ for line in sass.splitlines():
 listing = [k for k in blocks if re.match(r'void det_stream_bulk_kernel<20, 128, 2, true, true, true>|void target_stream_kernel<2, 21, true>|void det_stream_heads_kernel<21, true>', k)]
 with open(os.path.join(P, 'sass_%s.txt' % R), 'w') as f:
     f.write('# cuobjdump -sass dspnet_b200/libdspmb.so (sm_100a only).  Part 1: opcode counts per kernel for the mnemonics that matter on this\n'
-            '# path (no tensor-core opcodes anywhere: nothing here is a dense contraction; UBLKCP = cp.async.bulk TMA copy, SYNCS = mbarrier,\n'
+            '# path (no tensor-core opcodes anywhere: nothing here is a dense contraction; UTMALDG / UBLKCP = cp.async.bulk(.tensor) TMA copies, UTMAPF = TMA L2 prefetch, SYNCS = mbarrier,\n'
             '# UCGABAR / ACQBULK = cluster barrier).  Part 2: the full listing of the three streaming kernels.\n\n')
-    keys = ('LDG.E.NA.128', 'LDG.E.NA.64', 'LDG.E.NA', 'STG.E.NA.128', 'LDG.E.128', 'LDG.E.64', 'STG.E.128', 'UBLKCP', 'SYNCS', 'UCGABAR', 'LDS.128',
+    keys = ('LDG.E.NA.128', 'LDG.E.NA.64', 'LDG.E.NA', 'STG.E.NA.128', 'LDG.E.128', 'LDG.E.64', 'STG.E.128', 'UBLKCP', 'UTMALDG', 'UTMAPF', 'UBLKPF', 'SYNCS', 'UCGABAR', 'LDS.128',
             'MUFU.EX2', 'DFMA', 'DMUL', 'DADD', 'MATCH', 'VOTE', 'SHFL', 'REDUX', 'ATOMS', 'ATOMG', 'RED', 'BAR.SYNC', 'HMMA', 'UTCHMMA')
     for k, lines in blocks.items():
         c = collections.Counter()
