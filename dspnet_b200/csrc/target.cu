@@ -274,17 +274,22 @@ __global__ void __launch_bounds__(kStreamThreads, kTargetMinBlocks) target_strea
   for (int v = 0; v < VEC; ++v) an[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
     if (NC > 0 && mining) {
+      // one 64-bit add of the row stride IN BYTES per load: indexing cp + c * A made the compiler carry a 64-bit
+      // element index and scale it for every row (four address instructions per load, 9 % of the kernel)
+      const char *pc = reinterpret_cast<const char *>(cp);
+      const size_t row_bytes = (size_t)A * sizeof(float);
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         if constexpr (VEC == 4) {
-          const float4 q = ld_stream_f4(cp + (size_t)c * A);
+          const float4 q = ld_stream_f4(reinterpret_cast<const float *>(pc));
           xr[c][0] = q.x, xr[c][1] = q.y, xr[c][2] = q.z, xr[c][3] = q.w;
         } else if constexpr (VEC == 2) {
-          const float2 q = ld_stream_f2(cp + (size_t)c * A);
+          const float2 q = ld_stream_f2(reinterpret_cast<const float *>(pc));
           xr[c][0] = q.x, xr[c][1] = q.y;
         } else {
-          xr[c][0] = ld_stream_f1(cp + (size_t)c * A);
+          xr[c][0] = ld_stream_f1(reinterpret_cast<const float *>(pc));
         }
+        pc += row_bytes;
       }
     }
 #pragma unroll
