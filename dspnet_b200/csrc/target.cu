@@ -716,26 +716,18 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
     sm_pb = -1;              // sample bucket of the shortlist bound
   }
   for (int i = threadIdx.x; i < kLowBuckets; i += blockDim.x) bucket[i] = 0u;  // sample histogram of the shortlist
+  __syncthreads();  // shared-memory initialisation complete -- still in front of the wait, where it costs nothing
   asm volatile("griddepcontrol.wait;" ::: "memory");  // the stream kernel's outputs are complete and visible from here
   DSPMB_TSTAMP(0);
-  if (threadIdx.x == 0 && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
   if (G == 0) {  // multibox_target.cc:107 -- outputs stay at their initial values
-    if (threadIdx.x == 0 && stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (threadIdx.x == 0) {
+      if (a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
+      if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    }
     return;
   }
-  // The mining keys are only needed after the matching, but their 100 KB take two microseconds to arrive: start the
-  // copy into shared memory now (cp.async: no registers, nobody waits) and let it fly beside the column reduction and
-  // the bipartite stage; the fix-up below patches the matched anchors' keys in the staged copy.
   const unsigned *gkeys = a.key + (size_t)b * A;
   const bool async_keys = kKeysInSmem && a.mining_ratio > 0.f && (A & 3) == 0 && (reinterpret_cast<uintptr_t>(gkeys) & 15) == 0;
-  if (async_keys) {
-    for (int j = threadIdx.x; j < (A >> 2); j += blockDim.x)
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(skeys + 4 * j)),
-                   "l"(gkeys + 4 * j)
-                   : "memory");
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  }
-  __syncthreads();
   {  // column maxima and positive counts of the image's tiles (each written by its own stream CTA, no atomics there)
     const unsigned long long *tcol = a.colbest + (size_t)b * a.T * L;
     // One warp per gt, lanes over the tiles, warp-wide maximum: no shared-memory atomics (a 64-bit atomicMax is a CAS
@@ -758,6 +750,18 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       if (lane_id() == 0) sm_thr = pos;
     }
   }
+  // The mining keys are only needed after the matching, but their 100 KB take two microseconds to arrive: start the
+  // copy into shared memory now (cp.async: no registers, nobody waits) and let it fly beside the bipartite stage; the
+  // fix-up below patches the matched anchors' keys in the staged copy.  Issued BEHIND the column loads above: those
+  // are the critical path, and six 16-byte copies per thread in front of them kept them waiting in the load queue.
+  if (async_keys) {
+    for (int j = threadIdx.x; j < (A >> 2); j += blockDim.x)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(skeys + 4 * j)),
+                   "l"(gkeys + 4 * j)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  if (threadIdx.x == (blockDim.x >> 1) && a.gcount[a.B + b] != DSPMB_OK) atomicMin(&a.header->status, a.gcount[a.B + b]);
   __syncthreads();
   DSPMB_TSTAMP(1);
 
@@ -1040,6 +1044,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       const int n4 = A >> 2;
       int c = 0;
       unsigned mymin = kKeySentinel;
+#pragma unroll 3
       for (int j = threadIdx.x; j < n4; j += blockDim.x) {
         const uint4 kv = s4[j];
         c += (kv.x <= U ? 1 : 0) + (kv.y <= U ? 1 : 0) + (kv.z <= U ? 1 : 0) + (kv.w <= U ? 1 : 0);
@@ -1062,6 +1067,7 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
       kmin_short = __reduce_min_sync(kFullMask, (int)lane_id() < nw ? wmin_smem[lane_id()] : kKeySentinel);
       int pos = wbase + incl - c;
       if (c) {
+#pragma unroll 3
         for (int j = threadIdx.x; j < n4; j += blockDim.x) {
           const uint4 kv = s4[j];
           if (kv.x <= U) {
@@ -1141,8 +1147,9 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
         kmax = sm_kmax;
       }
       if (kmin != kKeySentinel) {  // CTA-uniform: at least one candidate
-        int shift = 0;
-        while (((kmax - kmin) >> shift) >= (unsigned)kLowBuckets) ++shift;
+        // smallest shift with ((kmax - kmin) >> shift) < kLowBuckets (= 2^11): bit length of the range minus 11
+        const int shift = max(0, 32 - __clz((int)(kmax - kmin)) - 11);
+        static_assert(kLowBuckets == 2048, "shift formula assumes 2^11 buckets");
         for (int j = threadIdx.x; j < mn; j += blockDim.x) {
           const unsigned kv = mk[j];
           if (kv != kKeySentinel) atomicAdd(&bucket[(kv - kmin) >> shift], 1u);
