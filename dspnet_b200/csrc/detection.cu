@@ -705,6 +705,7 @@ template <int NFG, int kThreads, int kVec, bool kV2, bool kLean = false, bool kT
 __global__ void __launch_bounds__(kThreads) det_stream_bulk_kernel(const __grid_constant__ StreamArgs a,
                                                                    const __grid_constant__ CUtensorMap tmap) {
   constexpr int kTile = kThreads * kVec;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sort kernel may be a programmatic dependent
   TraceScope trace_(0);
   extern __shared__ __align__(128) unsigned char bulk_smem_raw[];
   BulkSmem<NFG, kTile, kLean> &sm = *reinterpret_cast<BulkSmem<NFG, kTile, kLean> *>(bulk_smem_raw);
@@ -862,6 +863,7 @@ template <int C, bool kV2>
 __global__ void __launch_bounds__(kHeadThreads) det_stream_heads_kernel(const __grid_constant__ StreamArgs a,
                                                                         const __grid_constant__ HeadsArgs h) {
   constexpr int NFG = C - 1;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the sort kernel may be a programmatic dependent
   TraceScope trace_(0);
   extern __shared__ __align__(128) unsigned char head_smem_raw[];
   HeadSmem<C> &sm = *reinterpret_cast<HeadSmem<C> *>(head_smem_raw);
@@ -1308,8 +1310,13 @@ __global__ void __launch_bounds__(kSortThreads) det_sort_kernel(const __grid_con
   __shared__ unsigned sm_kmin, sm_kmax;
   __shared__ int sm_pivot, sm_need_rows;
   const int b = blockIdx.x;  // image in x: the sort-role CTAs (y == 0) of all images are scheduled first
-  // Programmatic dependent launch: the pair-test kernel enqueued behind this one may start once every CTA of this
-  // grid is resident and has passed this point -- it runs beside the sort and only waits for it before its resolve.
+  // Programmatic dependent launch, twice.  This kernel may itself be a programmatic dependent of the stream kernel
+  // (DSPMB_TUNE_DET_SORT_PDL; the stream kernel triggers on entry): its CTAs then take the SMs the stream kernel's tail
+  // frees and wait here until that grid has completed and flushed -- a no-op under a plain launch.  Only THEN does it
+  // release its own dependent: the pair-test kernel enqueued behind it reads the stream kernel's outputs before its
+  // own griddepcontrol.wait, so it must not start before the stream kernel is complete; it runs beside the sort and
+  // only waits for the sort before its resolve.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   TraceScope trace_(1);
   if (blockIdx.y != 0) {
@@ -3142,10 +3149,22 @@ static int detection_run(const HeadsArgs *heads, const float *cls_prob, const fl
   na.debug = nms_debug;
   if (phases & 2) {
     ProfileScope _p(kSlotDetSort, stream);
+    cudaLaunchConfig_t scfg = {};
+    scfg.gridDim = dim3(B, 1 + so.rank_parts);
+    scfg.blockDim = dim3(kSortThreads);
+    scfg.dynamicSmemBytes = smem2;
+    scfg.stream = stream;
+    cudaLaunchAttribute sattr[1];
+    sattr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    // only behind a stream kernel launched on this very stream (one image group) that has a tail to hide behind
+    sattr[0].val.programmaticStreamSerializationAllowed =
+        (tuning(DSPMB_TUNE_DET_SORT_PDL) && groups == 1 && (phases & 1) && (long long)T * B > kNumSMs) ? 1 : 0;
+    scfg.attrs = sattr;
+    scfg.numAttrs = 1;
     if (keys_in_smem)
-      det_sort_kernel<true><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
+      DSPMB_CUDA_TRY(cudaLaunchKernelEx(&scfg, det_sort_kernel<true>, so));
     else
-      det_sort_kernel<false><<<dim3(B, 1 + so.rank_parts), kSortThreads, smem2, stream>>>(so);
+      DSPMB_CUDA_TRY(cudaLaunchKernelEx(&scfg, det_sort_kernel<false>, so));
     ++ctx.launches;
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
