@@ -154,11 +154,13 @@ scal = {}
 for wl in ('detection', 'target'):
     rows = []
     for n in (1, 2, 4, 8):
-        path = os.path.join(P, 'bench_%s_%s.json' % (wl, R)) if n == 1 else os.path.join(G, 'scale_%s_n%d.json' % (wl, n))
+        path = os.path.join(G, 'scale_%s_n%d.json' % (wl, n))
+        if n == 1 and not os.path.exists(path):  # no N=1 line from the same library state: the bench line of this directory
+            path = os.path.join(P, 'bench_%s_%s.json' % (wl, R))
         if not os.path.exists(path):
             continue
         txt = open(path).read().strip()
-        d = json.loads(txt if n == 1 else txt.splitlines()[-1])
+        d = json.loads(txt.splitlines()[-1] if txt.count('\n') == 0 or n > 1 else txt)
         rows.append({'n_gpus': d['n_gpus'], 'value': d['value'], 'ms_per_step': d['ms_per_step'], 'e2e': d['e2e']['value'],
                      'parity_check': d['parity_check']['result'], 'gather_check': d.get('gather_check'), 'scaling': d['scaling'],
                      'parallelism': d['config'].get('parallelism')})
