@@ -21,7 +21,7 @@ ERR_CUDA = -6
 (TUNE_DET_STREAM_VARIANT, TUNE_NMS_MASK_ROWS, TUNE_NMS_SMEM_ROWS, TUNE_SORT_SMEM_KEYS, TUNE_PHASES, TUNE_GRAPH_CACHE,
  TUNE_DET_PIPELINE, TUNE_TARGET_PIPELINE, TUNE_NMS_PIPELINE, TUNE_DET_PREFETCH, TUNE_TARGET_PREFETCH,
  TUNE_DET_SPLIT, TUNE_DET_LEAN, TUNE_TARGET_SMALL, TUNE_TARGET_SHORTLIST,
- TUNE_TARGET_PDL, TUNE_DET_SORT_PDL) = range(17)
+ TUNE_TARGET_PDL, TUNE_DET_SORT_PDL, TUNE_NMS_PDL) = range(18)
 PHASES_ALL = 31
 
 # every symbol include/dspmb.h declares (tests check that the built library exports all of them)

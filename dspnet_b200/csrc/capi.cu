@@ -40,8 +40,8 @@ static int detect_host_libm_mode() {
 
 constexpr int kNumTuning = DSPMB_NUM_TUNING;
 // knobs may be set from one thread while another launches: relaxed atomics (each call reads a knob once)
-static std::atomic<int> g_tuning[kNumTuning] = {{2}, {320}, {1024}, {8192}, {31}, {1}, {1}, {0}, {1}, {600}, {0}, {1}, {2}, {1}, {1}, {1}, {1}};
-static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 31, 1, 1, 1, 1, 1 << 20, 1 << 20, 4, 2, 2, 1, 1, 1};
+static std::atomic<int> g_tuning[kNumTuning] = {{2}, {320}, {1024}, {8192}, {31}, {1}, {1}, {0}, {1}, {600}, {0}, {1}, {2}, {1}, {1}, {1}, {1}, {1}};
+static const int kTuningMax[kNumTuning] = {256, 320, 1024, 8192, 31, 1, 1, 1, 1, 1 << 20, 1 << 20, 4, 2, 2, 1, 1, 1, 1};
 int tuning(int knob) { return g_tuning[knob].load(std::memory_order_relaxed); }
 
 int libm_fma_mode() {

@@ -418,6 +418,11 @@ __global__ void __launch_bounds__(kCullThreads) nms_cull_kernel(int N, int c0, d
   __shared__ float ca[kChunk], cc[kChunk];
   __shared__ unsigned char cdead[kChunk];
   __shared__ unsigned short queues[kCullThreads / 32][kQueue];
+  // chained launch (launch_chained below): the CTAs of this grid were made resident while the previous kernel of the
+  // chunk loop was still running; everything they read is that kernel's output, so they wait for it here, and only
+  // then let the NEXT kernel of the chain become resident (one successor pending at a time)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int nk = *nkept;
   if ((int)blockIdx.x * kSlab >= nk) return;
   const float thresh_f = (float)thresh;
@@ -477,6 +482,25 @@ __global__ void __launch_bounds__(kCullThreads) nms_cull_kernel(int N, int c0, d
 // suppresses a fraction of a box on average), and after one cluster barrier CTA 0 resolves and appends alone.  With
 // one CTA the 528 units of a full first chunk took 30 us -- at N = 1000 that was most of the call.
 constexpr int kResolveThreads = 1024;
+// Launch as a programmatic dependent of the previous kernel in the stream (DSPMB_TUNE_NMS_PDL): the chunk loop of the
+// standalone NMS is a chain of up to ~400 short dependent kernels, and a plain launch pays the grid launch latency
+// between every two of them.  The kernels launched this way execute griddepcontrol.wait before they touch memory.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = chained ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 constexpr int kResolveCluster = 8;
 template <bool kUseClass>
 __global__ void __cluster_dims__(kResolveCluster, 1, 1) __launch_bounds__(kResolveThreads) nms_resolve_kernel(int N, int c0, double thresh, int mode, int no_filter,
@@ -498,6 +522,8 @@ __global__ void __cluster_dims__(kResolveCluster, 1, 1) __launch_bounds__(kResol
   __shared__ int scan_smem[kResolveThreads / 32 + 1];
   __shared__ unsigned long long rowany[kChunk / 64], remv_sm[kChunk / 64], diagany[kChunk / 64];
   __shared__ unsigned short queues[kResolveThreads / 32][kQueue];
+  asm volatile("griddepcontrol.wait;" ::: "memory");  // chained launch, see nms_cull_kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
@@ -676,6 +702,7 @@ static int nms_pipeline(const float *dets, int N, int dim, double thresh, int mo
   const size_t smem_res = (size_t)kChunk * (16 + 16 + 4 + 4 + 4) + sizeof(unsigned long long) * (size_t)kChunk * (kChunk / 64);
   DSPMB_ENSURE_DYN_SMEM(nms_resolve_kernel<true>, smem_res);
   DSPMB_ENSURE_DYN_SMEM(nms_resolve_kernel<false>, smem_res);
+  const bool chained = tuning(DSPMB_TUNE_NMS_PDL) != 0;
   for (int c0 = 0; c0 < N; c0 += kChunk) {
     if (c0 > 0) {
       // at most c0 boxes can have been kept so far; CTAs whose slab lies beyond the actual count return at once
@@ -683,23 +710,29 @@ static int nms_pipeline(const float *dets, int N, int dim, double thresh, int mo
       if (grid > 4 * kNumSMs) grid = 4 * kNumSMs;
       ProfileScope _p(kSlotNmsTile, stream);
       if (class_col >= 0)
-        nms_cull_kernel<true><<<grid, kCullThreads, 0, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, w.kbox,
-                                                                  w.kraw, w.karea, w.kcls, w.nkept, w.dead);
+        DSPMB_CUDA_TRY(launch_chained(chained, nms_cull_kernel<true>, dim3(grid), dim3(kCullThreads), 0, stream, N, c0, thresh, mode,
+                                      no_filter, (const float4 *)w.box, (const float *)w.area, (const float *)w.cls,
+                                      (const float4 *)w.kbox, (const float4 *)w.kraw, (const float *)w.karea,
+                                      (const float *)w.kcls, (const int *)w.nkept, w.dead));
       else
-        nms_cull_kernel<false><<<grid, kCullThreads, 0, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, w.kbox,
-                                                                   w.kraw, w.karea, w.kcls, w.nkept, w.dead);
+        DSPMB_CUDA_TRY(launch_chained(chained, nms_cull_kernel<false>, dim3(grid), dim3(kCullThreads), 0, stream, N, c0, thresh, mode,
+                                      no_filter, (const float4 *)w.box, (const float *)w.area, (const float *)w.cls,
+                                      (const float4 *)w.kbox, (const float4 *)w.kraw, (const float *)w.karea,
+                                      (const float *)w.kcls, (const int *)w.nkept, w.dead));
     }
     const int last = c0 + kChunk >= N;
     launches += c0 > 0 ? 2 : 1;
     ProfileScope _p(kSlotNmsReduce, stream);
     if (class_col >= 0)
-      nms_resolve_kernel<true><<<kResolveCluster, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
-                                                                         w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
-                                                                         num_keep, last);
+      DSPMB_CUDA_TRY(launch_chained(chained, nms_resolve_kernel<true>, dim3(kResolveCluster), dim3(kResolveThreads), smem_res, stream, N, c0,
+                                    thresh, mode, no_filter, (const float4 *)w.box, (const float *)w.area, (const float *)w.cls,
+                                    (const int *)order, (const unsigned char *)w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept,
+                                    keep, num_keep, last));
     else
-      nms_resolve_kernel<false><<<kResolveCluster, kResolveThreads, smem_res, stream>>>(N, c0, thresh, mode, no_filter, w.box, w.area, w.cls, order,
-                                                                          w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept, keep,
-                                                                          num_keep, last);
+      DSPMB_CUDA_TRY(launch_chained(chained, nms_resolve_kernel<false>, dim3(kResolveCluster), dim3(kResolveThreads), smem_res, stream, N, c0,
+                                    thresh, mode, no_filter, (const float4 *)w.box, (const float *)w.area, (const float *)w.cls,
+                                    (const int *)order, (const unsigned char *)w.dead, w.kbox, w.kraw, w.karea, w.kcls, w.nkept,
+                                    keep, num_keep, last));
   }
   DSPMB_CUDA_TRY(cudaGetLastError());
   note_launches(launches);

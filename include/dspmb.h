@@ -312,7 +312,10 @@ const char *dspmb_profile_kernel_name(int slot);
 #define DSPMB_TUNE_DET_SORT_PDL 16        /* 1 (default): the detection sort kernel is a programmatic dependent of the stream
                                            kernel (resident while that grid drains; it releases the pair-test kernel
                                            only after its own griddepcontrol.wait); 0: plain stream order               */
-#define DSPMB_NUM_TUNING 17
+#define DSPMB_TUNE_NMS_PDL 17             /* 1 (default): the cull / resolve kernels of the standalone NMS chunk loop are
+                                           launched as programmatic dependents of their predecessors (resident before
+                                           it ends, griddepcontrol.wait first); 0: plain launches                       */
+#define DSPMB_NUM_TUNING 18
 int dspmb_set_tuning(int knob, int value);
 
 /* Debug timeline of the detection kernels: device_buffer (16 x 2 uint64, caller-initialised to UINT64_MAX / 0 pairs)
