@@ -321,6 +321,8 @@ __global__ void __launch_bounds__(kSortThreads) nms_sort_small_kernel(const floa
                                                                        float *__restrict__ cls) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(dyn_smem);
+  // the first resolve kernel is a chained launch (launch_chained): let its cluster become resident beside this one CTA
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (threadIdx.x == 0) *nkept = 0;
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
     unsigned long long k = ~0ull;
