@@ -1344,7 +1344,8 @@ __global__ void __launch_bounds__(kMatchThreads) target_match_kernel(const __gri
 
 
 // ----------------------------------------------------------------------------------------------------
-// Cluster version of the matcher (the default): one thread-block CLUSTER of kMatchCluster CTAs per image instead of
+// Cluster version of the matcher (opt-in, DSPMB_TUNE_TARGET_PIPELINE = 1; measured slower than the single-CTA kernel, see
+// include/dspmb.h): one thread-block CLUSTER of kMatchCluster CTAs per image instead of
 // one 1024-thread CTA.  The single-CTA kernel is pure latency (0.43 waves, four passes over the image's A mining keys
 // by one CTA); here every CTA owns a slice of A / kMatchCluster anchors and their keys in its shared memory, and the
 // CTAs talk through distributed shared memory (cluster.map_shared_rank) and the hardware cluster barrier (~0.2 us):
@@ -1991,7 +1992,8 @@ extern "C" int dspmb_target_f32(const float *anchors, const float *labels, const
   const uintptr_t align_or = (uintptr_t)cls_preds | (uintptr_t)loc_target | (uintptr_t)loc_mask |
                              (uintptr_t)cls_target | (uintptr_t)match_out;
   const bool vec4 = (A % 4 == 0) && (align_or & 15) == 0;
-  // register-resident variants: 2 anchors/thread (about 85 registers => 6 CTAs/SM) unless knob 0 says otherwise
+  // register-resident variants: 2 anchors/thread (87 registers => 5 CTAs/SM; compiled for 6 it spills and measured
+  // 48.4 us against 47.4) unless knob 0 says otherwise
   int tvec = (vec4 && (C == 21 || C == 9) && tuning(DSPMB_TUNE_DET_STREAM_VARIANT) != 4) ? 2 : 4;
   // Small batches are latency bound by the CTAs of images with many ground truths (every warp of a large-anchor tile
   // walks the whole gt list, two IoUs per anchor and gt): up to about two waves of CTAs (measured: 8 and 16 images
