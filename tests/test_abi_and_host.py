@@ -47,6 +47,25 @@ def test_argument_checks_return_codes_without_gpu():
     assert L.dspmb_set_tuning(99, 1) == -1
 
 
+def test_tuning_knobs_match_the_header():
+    """Every DSPMB_TUNE_* index of include/dspmb.h has the same value under its Python name, the library accepts exactly
+    DSPMB_NUM_TUNING knobs, and the defaults the header documents are the ones the library starts with."""
+    import os, re
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "dspmb.h")).read()
+    knobs = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define DSPMB_TUNE_(\w+)\s+(\d+)", hdr)}
+    num = int(re.search(r"#define DSPMB_NUM_TUNING\s+(\d+)", hdr).group(1))
+    assert sorted(knobs.values()) == list(range(num))
+    for name, idx in knobs.items():
+        assert getattr(_lib, "TUNE_" + name) == idx, name
+    L = _lib.lib()
+    assert L.dspmb_set_tuning(num, 0) == -1
+    defaults = {"DET_STREAM_VARIANT": 2, "DET_PIPELINE": 1, "TARGET_PIPELINE": 0, "DET_PREFETCH": 600, "TARGET_PREFETCH": 0,
+                "DET_LEAN": 2, "TARGET_SHORTLIST": 1, "TARGET_PDL": 1, "DET_SORT_PDL": 1, "NMS_PDL": 1, "GRAPH_CACHE": 1}
+    for name, want in defaults.items():
+        old = L.dspmb_set_tuning(knobs[name], want)
+        assert old == want, (name, old)
+
+
 def test_ops_fail_loudly_without_gpu():
     import torch
     if torch.cuda.is_available():
